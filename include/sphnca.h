@@ -1,0 +1,134 @@
+/*
+ * sphnca.h -- C ABI of libsphnca.so: the B200 (sm_100a) implementation of SPH-NCA's per-timestep
+ * particle update.  This is the drop-in boundary: every entry point below replaces
+ * one Numba-CUDA kernel launch (plus its host-side bookkeeping) of the reference's `sphops`
+ * package, and is what a binding in the reference (`code/sphops/ops/func.py`, ctypes) would call.
+ *
+ * Conventions
+ *   - plain C, no torch types; all array arguments are DEVICE pointers unless marked "host";
+ *   - the caller owns every buffer (outputs are caller-allocated, nothing is allocated inside);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no device syncs;
+ *   - return value 0 = success, <0 = error (message via sphnca_last_error(), thread local);
+ *   - fp32 particle data, like every shipped configuration of the reference
+ *     (`func.py:12-16` allows fp16/fp64 but nothing uses them);
+ *   - "original order" = the caller's packed particle order (reference `packed_x`);
+ *     "sorted order"   = cell-sorted order: sorted position p holds original particle
+ *                        sorted_id[p]; sections stay contiguous and in order.
+ *
+ * Data layout in HBM: the neighbour sweeps read particle state from physically
+ * cell-sorted arrays (`xv4`: float4 {x,y,z,v} per particle, feature rows contiguous per particle),
+ * so the 3^D neighbouring cells of a run of particles are a handful of contiguous ranges.
+ */
+#ifndef SPHNCA_H
+#define SPHNCA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHNCA_OK 0
+#define SPHNCA_ERR_INVALID -1   /* bad argument */
+#define SPHNCA_ERR_CUDA -2      /* a CUDA runtime call / launch failed */
+#define SPHNCA_ERR_WORKSPACE -3 /* workspace too small */
+
+/* Cell tables of one packed batch, as consumed by every sweep.  Plain struct, passed by pointer.
+ * Replaces the reference's `Hashgrid` dataclass on the device side
+ * (code/sphops/hashgrid/single_impl.py:127-171). */
+typedef struct sphnca_grid {
+    int32_t dim;               /* D: 2 or 3 (reference kernels are specialised on DIM) */
+    int32_t num_sections;      /* B = len(sections) */
+    int64_t num_particles;     /* N = sum(sections) */
+    int64_t cells_per_section; /* total_cells = prod(dims) */
+    int64_t dims[3];           /* cells per axis, x fastest (single_impl.py:34-44) */
+    double h;                  /* cell size == support radius */
+    const int32_t* cell_off;   /* [B*cells + 1] global sorted offset of every cell (exclusive scan) */
+    const int32_t* sorted_id;  /* [N] original (global packed) index of sorted position p */
+    const int32_t* sorted_cell;/* [N] global cell id (section*cells + hash) of sorted position p */
+} sphnca_grid;
+
+int32_t sphnca_abi_version(void);
+const char* sphnca_last_error(void);
+
+/* ---- (1) hash-grid build: replaces sphops.initialize_hashgrid (code/sphops/preprocess.py:11-43),
+ *      i.e. grid_hash_kernel (single_impl.py:62-91) + torch.sort (preprocess.py:36) +
+ *      cell_index_init_kernel (single_impl.py:93-124) for ALL sections in one pass.
+ *      Outputs idx/cell_start/cell_end/num_points are the reference's Hashgrid fields, bit-exact
+ *      (idx ascending inside a cell == stable sort).  cell_off/sorted_id/sorted_cell feed sphnca_grid. */
+int32_t sphnca_hashgrid_workspace_bytes(int64_t N, int32_t B, int64_t cells_per_section, size_t* bytes);
+int32_t sphnca_hashgrid_build(const float* x, int64_t N, int32_t D,
+                              const int64_t* section_sizes_host, int32_t B, double h,
+                              const int64_t* dims_host,
+                              int64_t* idx, int32_t* cell_start, int32_t* cell_end, int32_t* num_points,
+                              int32_t* cell_off, int32_t* sorted_id, int32_t* sorted_cell,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- layout helpers (original <-> sorted order) */
+/* xv4[p] = {x[sorted_id[p]], v ? v[sorted_id[p]] : 0}; x is [N,D] fp32, z = 0 when D == 2 */
+int32_t sphnca_pack_xv(const sphnca_grid* g, const float* x, const float* v, float* xv4, void* stream);
+/* dst[p, :] = src[sorted_id[p], :], rows of `row` floats */
+int32_t sphnca_pack_rows(const sphnca_grid* g, const float* src, int32_t row, float* dst, void* stream);
+/* dst[sorted_id[p], :] = src[p, :] */
+int32_t sphnca_unpack_rows(const sphnca_grid* g, const float* src, int32_t row, float* dst, void* stream);
+/* same for 1-byte rows (fire masks) */
+int32_t sphnca_pack_bytes(const sphnca_grid* g, const uint8_t* src, uint8_t* dst, void* stream);
+
+/* ---- (2) neighbour-sweep operators.  Inputs in sorted order, outputs in original order.
+ *      Each replaces one kernel factory of code/sphops/ops/operators_batch.py. */
+/* volume_forward (:16-77): v_i = 1/(Cw sum_j (h^2-d^2)^3_+).  Writes v (original order) and xv4[p].w */
+int32_t sphnca_volume_fwd(const sphnca_grid* g, float* xv4, float* v, void* stream);
+/* volume_backward (:79-151): dLdx [N,D] original order; dLdv_s sorted order */
+int32_t sphnca_volume_bwd(const sphnca_grid* g, const float* xv4, const float* dLdv_s, float* dLdx, void* stream);
+/* count_forward (:536-597) */
+int32_t sphnca_count_fwd(const sphnca_grid* g, const float* xv4, float* c, void* stream);
+/* gradient_forward (:158-235): A_s [N,F] sorted -> GA [N,F,D] original order */
+int32_t sphnca_gradient_fwd(const sphnca_grid* g, const float* xv4, const float* A_s, int32_t F, float* GA, void* stream);
+/* gradient_backward, dL/dA branch (:237-343): G_s = dL/dGA [N,F,D] sorted -> dLdA [N,F] original order */
+int32_t sphnca_gradient_bwd(const sphnca_grid* g, const float* xv4, const float* G_s, int32_t F, float* dLdA, void* stream);
+/* blur_forward (:600-671): A_s [N,F] -> SA [N,F] */
+int32_t sphnca_blur_fwd(const sphnca_grid* g, const float* xv4, const float* A_s, int32_t F, float* SA, void* stream);
+/* adjoint of blur w.r.t. A (true adjoint; the reference's :673-772 is not) */
+int32_t sphnca_blur_bwd(const sphnca_grid* g, const float* xv4, const float* G_s, int32_t F, float* dLdA, void* stream);
+/* divergence_forward (:346-423): A_s [N,F,D] -> DA [N,F] */
+int32_t sphnca_divergence_fwd(const sphnca_grid* g, const float* xv4, const float* A_s, int32_t F, float* DA, void* stream);
+/* adjoint of divergence w.r.t. A (true adjoint; reference :425-533 indexes the wrong axis) */
+int32_t sphnca_divergence_bwd(const sphnca_grid* g, const float* xv4, const float* G_s, int32_t F, float* dLdA, void* stream);
+
+/* ---- (3) fused NCA step (code/nca.py:87-117 with the default feature process), 16 channels,
+ *      hidden 256.  Everything in sorted order.  See DESIGN.md 5 for the kernel split. */
+typedef struct sphnca_step_params {
+    const float* W1;  /* [256, 48] row-major == model.0.weight */
+    const float* b1;  /* [256] */
+    const float* W2;  /* [n_out, 256] == model.2.weight; n_out = 33 (gated) or 16 (orig) */
+    const float* b2;  /* [n_out] */
+    int32_t update_rule;   /* 0 = gated, 1 = orig (nca.py:102-108) */
+    int32_t use_alpha;     /* nca.py:17-21 */
+    float perception_scale;/* h*normalize_perception if >0 else 1 (nca.py:65-69) */
+    float orig_rate;       /* self.fire_rate / fire_rate, 'orig' rule only (nca.py:108) */
+} sphnca_step_params;
+
+/* workspace needed by step_fwd / step_bwd for N particles */
+int32_t sphnca_step_workspace_bytes(int64_t N, size_t* fwd_bytes, size_t* bwd_bytes);
+
+/* One forward step.  A_s [N,16] -> A_next_s [N,16].
+ * fire_s: uint8 [N] (the `torch.rand(N) <= fire_rate` draw, sorted order).
+ * Saved for backward: Y_s [N,32] (scaled dA/dx, dA/dy), flags_s uint8 [N]
+ * (bit0 prev_mask, bit1 new_mask, bit2 fire). */
+int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s,
+                        const uint8_t* fire_s, const sphnca_step_params* p,
+                        float* A_next_s, float* Y_s, uint8_t* flags_s,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* One backward step.  dA_next_s [N,16] -> dA_s [N,16]; parameter gradients are ACCUMULATED
+ * (+=) into dW1/db1/dW2/db2 deterministically (fixed-order tree, no float atomics). */
+int32_t sphnca_step_bwd(const sphnca_grid* g, const float* xv4, const float* A_s, const float* Y_s,
+                        const uint8_t* flags_s, const float* dA_next_s, const sphnca_step_params* p,
+                        float* dA_s, float* dW1, float* db1, float* dW2, float* db2,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHNCA_H */
