@@ -77,8 +77,9 @@ int32_t sphnca_pack_bytes(const sphnca_grid* g, const uint8_t* src, uint8_t* dst
 
 /* ---- (2) neighbour-sweep operators.  Inputs in sorted order, outputs in original order.
  *      Each replaces one kernel factory of code/sphops/ops/operators_batch.py. */
-/* volume_forward (:16-77): v_i = 1/(Cw sum_j (h^2-d^2)^3_+).  Writes v (original order) and xv4[p].w */
-int32_t sphnca_volume_fwd(const sphnca_grid* g, float* xv4, float* v, void* stream);
+/* volume_forward (:16-77): v_i = 1/(Cw sum_j (h^2-d^2)^3_+).  Reads xyz of xv4; writes v (original
+ * order) and xv4_out[p] = {x,y,z,v} (sorted order; a buffer distinct from xv4). */
+int32_t sphnca_volume_fwd(const sphnca_grid* g, const float* xv4, float* v, float* xv4_out, void* stream);
 /* volume_backward (:79-151): dLdx [N,D] original order; dLdv_s sorted order */
 int32_t sphnca_volume_bwd(const sphnca_grid* g, const float* xv4, const float* dLdv_s, float* dLdx, void* stream);
 /* count_forward (:536-597) */
@@ -114,18 +115,19 @@ int32_t sphnca_step_workspace_bytes(int64_t N, size_t* fwd_bytes, size_t* bwd_by
 
 /* One forward step.  A_s [N,16] -> A_next_s [N,16].
  * fire_s: uint8 [N] (the `torch.rand(N) <= fire_rate` draw, sorted order).
- * Saved for backward: Y_s [N,32] (scaled dA/dx, dA/dy), flags_s uint8 [N]
+ * Saved for backward: Y_s [N,32] (scaled dA/dx | dA/dy), O_s [N,36] (MLP output before the
+ * gate non-linearities, columns >= n_out are zero), flags_s uint8 [N]
  * (bit0 prev_mask, bit1 new_mask, bit2 fire). */
 int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s,
                         const uint8_t* fire_s, const sphnca_step_params* p,
-                        float* A_next_s, float* Y_s, uint8_t* flags_s,
+                        float* A_next_s, float* Y_s, float* O_s, uint8_t* flags_s,
                         void* workspace, size_t workspace_bytes, void* stream);
 
-/* One backward step.  dA_next_s [N,16] -> dA_s [N,16]; parameter gradients are ACCUMULATED
- * (+=) into dW1/db1/dW2/db2 deterministically (fixed-order tree, no float atomics). */
+/* One backward step (data gradient).  dA_next_s [N,16] -> dA_s [N,16], and dO_s [N,36] =
+ * dL/d(MLP output) for the weight-gradient stage.  Gather-based, no float atomics. */
 int32_t sphnca_step_bwd(const sphnca_grid* g, const float* xv4, const float* A_s, const float* Y_s,
-                        const uint8_t* flags_s, const float* dA_next_s, const sphnca_step_params* p,
-                        float* dA_s, float* dW1, float* db1, float* dW2, float* db2,
+                        const float* O_s, const uint8_t* flags_s, const float* dA_next_s,
+                        const sphnca_step_params* p, float* dA_s, float* dO_s,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,142 @@
+// Shared device/host helpers for libsphnca (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sphnca.h"
+
+namespace sphnca {
+
+void set_error(const char* fmt, ...);
+
+#define SPHNCA_CHECK_ARG(cond, ...)        \
+    do {                                   \
+        if (!(cond)) {                     \
+            sphnca::set_error(__VA_ARGS__);\
+            return SPHNCA_ERR_INVALID;     \
+        }                                  \
+    } while (0)
+
+#define SPHNCA_CUDA(call)                                                                   \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            sphnca::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return SPHNCA_ERR_CUDA;                                                         \
+        }                                                                                   \
+    } while (0)
+
+#define SPHNCA_LAUNCH_CHECK() SPHNCA_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr float kPi = 3.14159265358979323846f;
+
+// Device-side copy of the cell tables (passed by value to kernels).
+struct GridView {
+    int dim;
+    int num_sections;
+    int64_t n;
+    int cells;        // cells per section
+    int dims[3];
+    const int32_t* __restrict__ cell_off;
+    const int32_t* __restrict__ sorted_id;
+    const int32_t* __restrict__ sorted_cell;
+};
+
+inline int make_view(const sphnca_grid* g, GridView* v) {
+    if (!g) { set_error("grid is NULL"); return SPHNCA_ERR_INVALID; }
+    if (g->dim != 2 && g->dim != 3) { set_error("grid.dim must be 2 or 3, got %d", g->dim); return SPHNCA_ERR_INVALID; }
+    if (g->num_particles < 0 || g->num_particles >= (int64_t(1) << 31)) { set_error("num_particles out of range"); return SPHNCA_ERR_INVALID; }
+    if (g->cells_per_section <= 0 || g->cells_per_section * g->num_sections >= (int64_t(1) << 31)) {
+        set_error("cell table too large for int32 indexing"); return SPHNCA_ERR_INVALID;
+    }
+    v->dim = g->dim; v->num_sections = g->num_sections; v->n = g->num_particles;
+    v->cells = (int)g->cells_per_section;
+    for (int d = 0; d < 3; ++d) v->dims[d] = d < g->dim ? (int)g->dims[d] : 1;
+    v->cell_off = g->cell_off; v->sorted_id = g->sorted_id; v->sorted_cell = g->sorted_cell;
+    return SPHNCA_OK;
+}
+
+// Normalisation constants, reference kernels_impl.py:20-30 (poly6) and :131-141 (spiky).
+// Evaluated in double on the host like the reference's Python floats, then rounded once.
+inline double poly6_norm(int dim, double h) {
+    const double pi = 3.14159265358979323846;
+    double h2 = h * h, h4 = h2 * h2, h8 = h4 * h4;
+    return dim == 2 ? 4.0 / (pi * h8) : 315.0 / (64.0 * pi * h8 * h);
+}
+inline double spiky_norm(int dim, double h) {
+    const double pi = 3.14159265358979323846;
+    double h2 = h * h, h4 = h2 * h2;
+    return dim == 2 ? 10.0 / (pi * h4 * h) : 15.0 / (pi * h4 * h2);
+}
+
+// ------------------------------------------------------------------------------------------
+// Neighbour enumeration.  For the particle at sorted position p the reference visits the 3^D
+// cells around its own cell, offsets (-1,0,1) per axis with x fastest, each wrapped modulo dims
+// (single_impl.py:46-60, operators_batch.py:57-76).  An axis with dims<3 therefore visits the
+// same cell more than once -- reproduced here because the loop is the same.
+// `fn(q)` is called for every candidate sorted position q, in the reference's order.
+// ------------------------------------------------------------------------------------------
+template <int D, typename Fn>
+__device__ __forceinline__ void for_each_candidate(const GridView& g, int gcell, Fn&& fn) {
+    const int section = gcell / g.cells;
+    const int cell = gcell - section * g.cells;
+    const int base = section * g.cells;
+    const int dx = g.dims[0], dy = g.dims[1];
+    int cx, cy, cz = 0;
+    if (D == 3) {
+        cz = cell / (dx * dy);
+        int rem = cell - cz * dx * dy;
+        cy = rem / dx; cx = rem - cy * dx;
+    } else {
+        cy = cell / dx; cx = cell - cy * dx;
+    }
+    // wrapped neighbour coordinates per axis: (c + dims + d) % dims for d = -1, 0, 1
+    int nx[3], ny[3], nz[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        nx[o] = (cx + dx + o - 1) % dx;
+        ny[o] = (cy + dy + o - 1) % dy;
+        nz[o] = D == 3 ? (cz + g.dims[2] + o - 1) % g.dims[2] : 0;
+    }
+    constexpr int NZ = D == 3 ? 3 : 1;
+#pragma unroll 1
+    for (int oz = 0; oz < NZ; ++oz) {
+#pragma unroll 1
+        for (int oy = 0; oy < 3; ++oy) {
+            const int row = base + (nz[oz] * dy + ny[oy]) * dx;
+            // fast path: the three x-cells are consecutive -> one contiguous run of candidates
+            if (nx[0] + 1 == nx[1] && nx[1] + 1 == nx[2]) {
+                const int q0 = g.cell_off[row + nx[0]];
+                const int q1 = g.cell_off[row + nx[2] + 1];
+                for (int q = q0; q < q1; ++q) fn(q);
+            } else {
+#pragma unroll 1
+                for (int ox = 0; ox < 3; ++ox) {
+                    const int q0 = g.cell_off[row + nx[ox]];
+                    const int q1 = g.cell_off[row + nx[ox] + 1];
+                    for (int q = q0; q < q1; ++q) fn(q);
+                }
+            }
+        }
+    }
+}
+
+// spiky gradient weight 3 (h-d)^2 / d for 0 < d < h, else 0 (kernels_impl.py:143-156).
+// The reference returns exact 0 for r == 0 (`r[i] and mag*r[i]`), also for coincident particles.
+__device__ __forceinline__ float spiky_mag(float d2, float h, float h2) {
+    if (!(d2 < h2) || d2 <= 0.f) return 0.f;
+    const float d = sqrtf(d2);
+    const float hd = h - d;
+    return 3.f * hd * hd / d;
+}
+
+// poly6 smoothing (h^2 - d^2)^3 clamped at 0 (kernels_impl.py:32-39)
+__device__ __forceinline__ float poly6_w(float d2, float h2) {
+    const float t = h2 - d2;
+    return t > 0.f ? t * t * t : 0.f;
+}
+
+}  // namespace sphnca

@@ -1,0 +1,416 @@
+// Fused NCA step (reference code/nca.py:87-117), 16 channels, hidden 256.
+//
+// Forward = 2 kernels (the reference: 3 Numba sweeps + ~25 eager torch kernels + 2 cuBLAS GEMMs):
+//   step_fwd_kernel   one sweep over the 3^D cells computes BOTH the previous life mask
+//                     (blur of alive bits, F=1) and the SPH gradient (x,y components, F=16);
+//                     the 48-wide perception vector stays in registers and feeds the
+//                     48->256->n_out MLP (weights staged once per CTA in shared memory,
+//                     broadcast LDS.128), then the gated/orig update + fire mask.
+//   step_mask_kernel  second life-mask sweep over the NEW alive bits (needs all neighbours'
+//                     updated state -> grid-wide dependency -> separate launch), applies
+//                     prev & new to the state.
+// Backward = 2 kernels: step_bwd_kernel (gate/tanh derivatives, MLP data gradient with recomputed
+// hidden layer) and step_adjoint_kernel (gather adjoint of the gradient sweep; deterministic).
+//
+// All arrays are in cell-sorted order.  v1: the MLP runs on the fp32 CUDA-core pipe.
+#include "common.cuh"
+
+namespace sphnca {
+
+constexpr int NF = 16;        // channels
+constexpr int NIN = 48;       // MLP input  [A | dA/dx | dA/dy]
+constexpr int NH = 256;       // hidden width
+constexpr int NO_PAD = 36;    // MLP output 33 (gated) / 16 (orig), padded for float4 rows
+constexpr int kStepThreads = 256;
+
+struct StepConsts {
+    float h, h2;
+    float cw;          // poly6 normalisation
+    float kg;          // spiky normalisation * perception scale
+    int use_alpha, rule, n_out;
+    float orig_rate;
+};
+
+struct MlpSmem {
+    float W1[NH][NIN];       // row n = weights of hidden unit n (48 KB)
+    float W2t[NH][NO_PAD];   // row n = outgoing weights of hidden unit n (36 KB)
+    float b1[NH];
+    float b2[NO_PAD];
+};
+
+__device__ __forceinline__ void stage_weights(MlpSmem& s, const sphnca_step_params& p, int n_out) {
+    const float4* w1 = reinterpret_cast<const float4*>(p.W1);
+    float4* d1 = reinterpret_cast<float4*>(&s.W1[0][0]);
+    for (int i = threadIdx.x; i < NH * NIN / 4; i += blockDim.x) d1[i] = __ldg(w1 + i);
+    for (int i = threadIdx.x; i < NH * NO_PAD; i += blockDim.x) {
+        const int n = i / NO_PAD, o = i - n * NO_PAD;
+        s.W2t[n][o] = o < n_out ? __ldg(p.W2 + (size_t)o * NH + n) : 0.f;
+    }
+    for (int i = threadIdx.x; i < NH; i += blockDim.x) s.b1[i] = __ldg(p.b1 + i);
+    if (threadIdx.x < NO_PAD) s.b2[threadIdx.x] = threadIdx.x < n_out ? __ldg(p.b2 + threadIdx.x) : 0.f;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int D>
+__device__ __forceinline__ float pair_d2(const float4& a, const float4& b, float& rx, float& ry) {
+    rx = b.x - a.x; ry = b.y - a.y;
+    float d2 = fmaf(ry, ry, rx * rx);
+    if (D == 3) { const float rz = b.z - a.z; d2 = fmaf(rz, rz, d2); }
+    return d2;
+}
+
+__device__ __forceinline__ void load16(const float* __restrict__ p, float (&o)[NF]) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { float4 t = __ldg(p4 + k); o[4*k] = t.x; o[4*k+1] = t.y; o[4*k+2] = t.z; o[4*k+3] = t.w; }
+}
+
+// hidden pre-activation of unit n for perception vector y (48 FMA, broadcast smem reads)
+__device__ __forceinline__ float hidden_pre(const MlpSmem& s, int n, const float (&y)[NIN]) {
+    const float4* w = reinterpret_cast<const float4*>(&s.W1[n][0]);
+    float a0 = s.b1[n], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NIN / 4; ++k) {
+        const float4 t = w[k];
+        a0 = fmaf(t.x, y[4*k], a0); a1 = fmaf(t.y, y[4*k+1], a1);
+        a2 = fmaf(t.z, y[4*k+2], a2); a3 = fmaf(t.w, y[4*k+3], a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kStepThreads, 2)
+step_fwd_kernel(GridView g, const float4* __restrict__ xv4, const float* __restrict__ A_s,
+                const uint8_t* __restrict__ fire_s, sphnca_step_params prm, StepConsts c,
+                float* __restrict__ An_s, float* __restrict__ Y_s, float* __restrict__ O_s,
+                uint8_t* __restrict__ flags_s, uint8_t* __restrict__ alive_s) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MlpSmem& s = *reinterpret_cast<MlpSmem*>(smem_raw);
+    stage_weights(s, prm, c.n_out);
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.n) return;
+
+    // ---- perception sweep: gradient (x,y) of 16 channels + blur of the alive bit ----
+    const float4 xi = xv4[p];
+    float y[NIN];
+    {
+        float Ai[NF];
+        load16(A_s + (size_t)p * NF, Ai);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) { y[f] = Ai[f]; y[NF + f] = 0.f; y[2 * NF + f] = 0.f; }
+    }
+    float blur = 0.f;
+    for_each_candidate<D>(g, g.sorted_cell[p], [&](int q) {
+        float rx, ry;
+        const float4 xj = __ldg(&xv4[q]);
+        const float d2 = pair_d2<D>(xi, xj, rx, ry);
+        if (d2 < c.h2) {
+            float Aj[NF];
+            load16(A_s + (size_t)q * NF, Aj);
+            const float t = c.h2 - d2;
+            const float alive = c.use_alpha ? (Aj[3] > 0.1f ? 1.f : 0.f) : 1.f;
+            blur = fmaf(alive * xj.w, t * t * t, blur);
+            if (d2 > 0.f) {
+                const float d = sqrtf(d2);
+                const float hd = c.h - d;
+                const float m = 3.f * hd * hd / d * xj.w;
+                const float wx = m * rx, wy = m * ry;
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const float dA = Aj[f] - y[f];
+                    y[NF + f] = fmaf(dA, wx, y[NF + f]);
+                    y[2 * NF + f] = fmaf(dA, wy, y[2 * NF + f]);
+                }
+            }
+        }
+    });
+    const bool prev_mask = blur * c.cw > 0.1f;
+#pragma unroll
+    for (int f = 0; f < 2 * NF; ++f) y[NF + f] *= c.kg;
+
+    // ---- MLP 48 -> 256 (ReLU) -> n_out, one particle per thread ----
+    float out[NO_PAD];
+#pragma unroll
+    for (int o = 0; o < NO_PAD; ++o) out[o] = s.b2[o];
+#pragma unroll 2
+    for (int n = 0; n < NH; ++n) {
+        const float hval = fmaxf(hidden_pre(s, n, y), 0.f);
+        const float4* w2 = reinterpret_cast<const float4*>(&s.W2t[n][0]);
+#pragma unroll
+        for (int k = 0; k < NO_PAD / 4; ++k) {
+            const float4 t = w2[k];
+            out[4*k] = fmaf(t.x, hval, out[4*k]); out[4*k+1] = fmaf(t.y, hval, out[4*k+1]);
+            out[4*k+2] = fmaf(t.z, hval, out[4*k+2]); out[4*k+3] = fmaf(t.w, hval, out[4*k+3]);
+        }
+    }
+
+    // ---- update rule + stochastic fire mask (nca.py:100-110) ----
+    const bool fire = fire_s[p] != 0;
+    float nA[NF];
+    if (c.rule == 0) {
+        const float mult = sigmoidf_(out[2 * NF]);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) nA[f] = fmaf(y[f], sigmoidf_(out[f]), tanhf(out[NF + f]) * mult);
+    } else {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) nA[f] = fmaf(out[f], c.orig_rate, y[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) nA[f] = fire ? nA[f] : y[f];
+
+    float4* o4 = reinterpret_cast<float4*>(An_s + (size_t)p * NF);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o4[k] = make_float4(nA[4*k], nA[4*k+1], nA[4*k+2], nA[4*k+3]);
+    float4* y4 = reinterpret_cast<float4*>(Y_s + (size_t)p * 2 * NF);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) y4[k] = make_float4(y[NF+4*k], y[NF+4*k+1], y[NF+4*k+2], y[NF+4*k+3]);
+    float4* oo4 = reinterpret_cast<float4*>(O_s + (size_t)p * NO_PAD);
+#pragma unroll
+    for (int k = 0; k < NO_PAD / 4; ++k) oo4[k] = make_float4(out[4*k], out[4*k+1], out[4*k+2], out[4*k+3]);
+    flags_s[p] = (uint8_t)((prev_mask ? 1 : 0) | (fire ? 4 : 0));
+    alive_s[p] = c.use_alpha ? (nA[3] > 0.1f ? 1 : 0) : 1;
+}
+
+// new life mask = blur(alive bits of the updated state) > 0.1; state *= prev & new   (nca.py:112-115)
+template <int D>
+__global__ void __launch_bounds__(256)
+step_mask_kernel(GridView g, const float4* __restrict__ xv4, const uint8_t* __restrict__ alive_s, StepConsts c,
+                 float* __restrict__ An_s, uint8_t* __restrict__ flags_s) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.n) return;
+    const float4 xi = xv4[p];
+    float blur = 0.f;
+    for_each_candidate<D>(g, g.sorted_cell[p], [&](int q) {
+        float rx, ry;
+        const float4 xj = __ldg(&xv4[q]);
+        const float d2 = pair_d2<D>(xi, xj, rx, ry);
+        if (d2 < c.h2 && alive_s[q]) {
+            const float t = c.h2 - d2;
+            blur = fmaf(xj.w, t * t * t, blur);
+        }
+    });
+    const bool new_mask = blur * c.cw > 0.1f;
+    uint8_t fl = flags_s[p];
+    if (new_mask) fl |= 2;
+    flags_s[p] = fl;
+    if (!((fl & 1) && new_mask)) {
+        float4* a4 = reinterpret_cast<float4*>(An_s + (size_t)p * NF);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { float4 t = a4[k]; a4[k] = make_float4(t.x * 0.f, t.y * 0.f, t.z * 0.f, t.w * 0.f); }
+    }
+}
+
+// Data gradient of everything after the perception sweep, one particle per thread.
+//   in : dA_next (grad of the masked output), saved A, Y, O, flags
+//   out: dO (grad wrt MLP output, for the weight-gradient stage), dY (grad wrt scaled perception),
+//        dAdir (grad reaching A directly: gate path, fire bypass, MLP input columns 0..15)
+__global__ void __launch_bounds__(kStepThreads, 1)
+step_bwd_kernel(int n_total, const float* __restrict__ A_s, const float* __restrict__ Y_s,
+                const float* __restrict__ O_s, const uint8_t* __restrict__ flags_s,
+                const float* __restrict__ dAn_s, sphnca_step_params prm, StepConsts c,
+                float* __restrict__ dO_s, float* __restrict__ dY_s, float* __restrict__ dAdir_s) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MlpSmem& s = *reinterpret_cast<MlpSmem*>(smem_raw);
+    stage_weights(s, prm, c.n_out);
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_total) return;
+
+    float y[NIN], dnA[NF], dO[NO_PAD], dAdir[NF];
+    load16(A_s + (size_t)p * NF, *reinterpret_cast<float(*)[NF]>(&y[0]));
+    load16(Y_s + (size_t)p * 2 * NF, *reinterpret_cast<float(*)[NF]>(&y[NF]));
+    load16(Y_s + (size_t)p * 2 * NF + NF, *reinterpret_cast<float(*)[NF]>(&y[2 * NF]));
+    load16(dAn_s + (size_t)p * NF, dnA);
+    const uint8_t fl = flags_s[p];
+    const bool living = (fl & 1) && (fl & 2), fire = fl & 4;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) dnA[f] = living ? dnA[f] : 0.f;
+#pragma unroll
+    for (int o = 0; o < NO_PAD; ++o) dO[o] = 0.f;
+    if (fire) {
+        const float4* o4 = reinterpret_cast<const float4*>(O_s + (size_t)p * NO_PAD);
+        float out[NO_PAD];
+#pragma unroll
+        for (int k = 0; k < NO_PAD / 4; ++k) { float4 t = __ldg(o4 + k); out[4*k] = t.x; out[4*k+1] = t.y; out[4*k+2] = t.z; out[4*k+3] = t.w; }
+        if (c.rule == 0) {
+            const float mult = sigmoidf_(out[2 * NF]);
+            float dmult = 0.f;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const float gate = sigmoidf_(out[f]);
+                const float delta = tanhf(out[NF + f]);
+                dO[f] = dnA[f] * y[f] * gate * (1.f - gate);
+                dO[NF + f] = dnA[f] * mult * (1.f - delta * delta);
+                dmult = fmaf(dnA[f], delta, dmult);
+                dAdir[f] = dnA[f] * gate;
+            }
+            dO[2 * NF] = dmult * mult * (1.f - mult);
+        } else {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) { dO[f] = dnA[f] * c.orig_rate; dAdir[f] = dnA[f]; }
+        }
+    } else {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) dAdir[f] = dnA[f];
+    }
+    float4* do4 = reinterpret_cast<float4*>(dO_s + (size_t)p * NO_PAD);
+#pragma unroll
+    for (int k = 0; k < NO_PAD / 4; ++k) do4[k] = make_float4(dO[4*k], dO[4*k+1], dO[4*k+2], dO[4*k+3]);
+
+    // dy = W1^T ( relu'(pre) * (W2^T dO) ), hidden layer recomputed.  Warp-uniform skip when no
+    // lane fired (dO == 0 everywhere in the warp).
+    float dy[NIN];
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) dy[k] = 0.f;
+    if (__any_sync(__activemask(), fire)) {
+#pragma unroll 1
+        for (int n = 0; n < NH; ++n) {
+            const float pre = hidden_pre(s, n, y);
+            const float4* w2 = reinterpret_cast<const float4*>(&s.W2t[n][0]);
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < NO_PAD / 4; ++k) {
+                const float4 t = w2[k];
+                d0 = fmaf(t.x, dO[4*k], d0); d1 = fmaf(t.y, dO[4*k+1], d1);
+                d2 = fmaf(t.z, dO[4*k+2], d2); d3 = fmaf(t.w, dO[4*k+3], d3);
+            }
+            const float dh = pre > 0.f ? (d0 + d1) + (d2 + d3) : 0.f;
+            const float4* w1 = reinterpret_cast<const float4*>(&s.W1[n][0]);
+#pragma unroll
+            for (int k = 0; k < NIN / 4; ++k) {
+                const float4 t = w1[k];
+                dy[4*k] = fmaf(t.x, dh, dy[4*k]); dy[4*k+1] = fmaf(t.y, dh, dy[4*k+1]);
+                dy[4*k+2] = fmaf(t.z, dh, dy[4*k+2]); dy[4*k+3] = fmaf(t.w, dh, dy[4*k+3]);
+            }
+        }
+    }
+    float4* d4 = reinterpret_cast<float4*>(dAdir_s + (size_t)p * NF);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        d4[k] = make_float4(dAdir[4*k] + dy[4*k], dAdir[4*k+1] + dy[4*k+1], dAdir[4*k+2] + dy[4*k+2], dAdir[4*k+3] + dy[4*k+3]);
+    float4* g4 = reinterpret_cast<float4*>(dY_s + (size_t)p * 2 * NF);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g4[k] = make_float4(dy[NF+4*k], dy[NF+4*k+1], dy[NF+4*k+2], dy[NF+4*k+3]);
+}
+
+// Gather adjoint of the perception sweep (same algebra as gradient_bwd_kernel, x/y only):
+//   dA_i[f] = dAdir_i[f] - kg ( v_i sum_j m_ij (r_x Gx_j[f] + r_y Gy_j[f]) + Gx_i[f] s_x + Gy_i[f] s_y ),
+//   s = sum_j m_ij v_j r,  G = dL/dY.
+template <int D>
+__global__ void __launch_bounds__(128)
+step_adjoint_kernel(GridView g, const float4* __restrict__ xv4, const float* __restrict__ dY_s,
+                    const float* __restrict__ dAdir_s, StepConsts c, float* __restrict__ dA_s) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.n) return;
+    const float4 xi = xv4[p];
+    float acc[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f] = 0.f;
+    float sx = 0.f, sy = 0.f;
+    for_each_candidate<D>(g, g.sorted_cell[p], [&](int q) {
+        float rx, ry;
+        const float4 xj = __ldg(&xv4[q]);
+        const float d2 = pair_d2<D>(xi, xj, rx, ry);
+        if (d2 < c.h2 && d2 > 0.f) {
+            const float d = sqrtf(d2);
+            const float hd = c.h - d;
+            const float m = 3.f * hd * hd / d;
+            const float wx = m * rx, wy = m * ry;
+            sx = fmaf(wx, xj.w, sx); sy = fmaf(wy, xj.w, sy);
+            float Gx[NF], Gy[NF];
+            load16(dY_s + (size_t)q * 2 * NF, Gx);
+            load16(dY_s + (size_t)q * 2 * NF + NF, Gy);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) acc[f] = fmaf(wx, Gx[f], fmaf(wy, Gy[f], acc[f]));
+        }
+    });
+    float Gx[NF], Gy[NF], dir[NF];
+    load16(dY_s + (size_t)p * 2 * NF, Gx);
+    load16(dY_s + (size_t)p * 2 * NF + NF, Gy);
+    load16(dAdir_s + (size_t)p * NF, dir);
+    float4* o4 = reinterpret_cast<float4*>(dA_s + (size_t)p * NF);
+    float r[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) r[f] = dir[f] - c.kg * fmaf(xi.w, acc[f], fmaf(Gx[f], sx, Gy[f] * sy));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o4[k] = make_float4(r[4*k], r[4*k+1], r[4*k+2], r[4*k+3]);
+}
+
+static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+static int make_consts(const sphnca_grid* g, const sphnca_step_params* p, StepConsts* c) {
+    if (!p || !p->W1 || !p->b1 || !p->W2 || !p->b2) { set_error("step params / weights are NULL"); return SPHNCA_ERR_INVALID; }
+    if (p->update_rule != 0 && p->update_rule != 1) { set_error("update_rule must be 0 (gated) or 1 (orig)"); return SPHNCA_ERR_INVALID; }
+    if (((uintptr_t)p->W1 & 15) != 0) { set_error("W1 must be 16-byte aligned"); return SPHNCA_ERR_INVALID; }
+    c->h = (float)g->h; c->h2 = (float)(g->h * g->h);
+    c->cw = (float)poly6_norm(g->dim, g->h);
+    c->kg = (float)(spiky_norm(g->dim, g->h) * (double)p->perception_scale);
+    c->use_alpha = p->use_alpha; c->rule = p->update_rule; c->n_out = p->update_rule == 0 ? 2 * NF + 1 : NF;
+    c->orig_rate = p->orig_rate;
+    return SPHNCA_OK;
+}
+
+}  // namespace sphnca
+
+using namespace sphnca;
+
+extern "C" {
+
+int32_t sphnca_step_workspace_bytes(int64_t N, size_t* fwd_bytes, size_t* bwd_bytes) {
+    SPHNCA_CHECK_ARG(N >= 0 && fwd_bytes && bwd_bytes, "bad argument");
+    *fwd_bytes = align256((size_t)N);                                             // alive bits
+    *bwd_bytes = align256((size_t)N * 2 * NF * 4) + align256((size_t)N * NF * 4); // dY, dAdir
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s, const uint8_t* fire_s,
+                        const sphnca_step_params* p, float* A_next_s, float* Y_s, float* O_s, uint8_t* flags_s,
+                        void* workspace, size_t workspace_bytes, void* stream_) {
+    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
+    cudaStream_t stream = as_stream(stream_);
+    if (gv.n == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(xv4 && A_s && fire_s && A_next_s && Y_s && O_s && flags_s, "NULL argument");
+    if (!workspace || workspace_bytes < align256((size_t)gv.n)) { set_error("step_fwd workspace too small"); return SPHNCA_ERR_WORKSPACE; }
+    uint8_t* alive = reinterpret_cast<uint8_t*>(workspace);
+    const int blocks = (int)((gv.n + kStepThreads - 1) / kStepThreads);
+    const size_t smem = sizeof(MlpSmem);
+    if (gv.dim == 3) {
+        SPHNCA_CUDA(cudaFuncSetAttribute(step_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        step_fwd_kernel<3><<<blocks, kStepThreads, smem, stream>>>(gv, (const float4*)xv4, A_s, fire_s, *p, c, A_next_s, Y_s, O_s, flags_s, alive);
+        step_mask_kernel<3><<<(int)((gv.n + 255) / 256), 256, 0, stream>>>(gv, (const float4*)xv4, alive, c, A_next_s, flags_s);
+    } else {
+        SPHNCA_CUDA(cudaFuncSetAttribute(step_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        step_fwd_kernel<2><<<blocks, kStepThreads, smem, stream>>>(gv, (const float4*)xv4, A_s, fire_s, *p, c, A_next_s, Y_s, O_s, flags_s, alive);
+        step_mask_kernel<2><<<(int)((gv.n + 255) / 256), 256, 0, stream>>>(gv, (const float4*)xv4, alive, c, A_next_s, flags_s);
+    }
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_step_bwd(const sphnca_grid* g, const float* xv4, const float* A_s, const float* Y_s,
+                        const float* O_s, const uint8_t* flags_s, const float* dA_next_s,
+                        const sphnca_step_params* p, float* dA_s, float* dO_s,
+                        void* workspace, size_t workspace_bytes, void* stream_) {
+    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
+    cudaStream_t stream = as_stream(stream_);
+    if (gv.n == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(xv4 && A_s && Y_s && O_s && flags_s && dA_next_s && dA_s && dO_s, "NULL argument");
+    const size_t off_dir = align256((size_t)gv.n * 2 * NF * 4);
+    if (!workspace || workspace_bytes < off_dir + align256((size_t)gv.n * NF * 4)) { set_error("step_bwd workspace too small"); return SPHNCA_ERR_WORKSPACE; }
+    float* dY = reinterpret_cast<float*>(workspace);
+    float* dAdir = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + off_dir);
+    const size_t smem = sizeof(MlpSmem);
+    SPHNCA_CUDA(cudaFuncSetAttribute(step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    step_bwd_kernel<<<(int)((gv.n + kStepThreads - 1) / kStepThreads), kStepThreads, smem, stream>>>(
+        (int)gv.n, A_s, Y_s, O_s, flags_s, dA_next_s, *p, c, dO_s, dY, dAdir);
+    if (gv.dim == 3) step_adjoint_kernel<3><<<(int)((gv.n + 127) / 128), 128, 0, stream>>>(gv, (const float4*)xv4, dY, dAdir, c, dA_s);
+    else step_adjoint_kernel<2><<<(int)((gv.n + 127) / 128), 128, 0, stream>>>(gv, (const float4*)xv4, dY, dAdir, c, dA_s);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+"""ctypes binding of libsphnca.so (C ABI declared in include/sphnca.h).
+
+The library is built in-tree by `make -C sph-nca_b200/csrc` (or `__graft_entry__.build()`).
+There is NO fallback: if the shared library is missing, importing `sphops` fails, and every
+operator refuses non-CUDA tensors.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("SPHNCA_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libsphnca.so"))
+
+
+class SphncaError(RuntimeError):
+    pass
+
+
+class CGrid(C.Structure):
+    """struct sphnca_grid (include/sphnca.h)."""
+    _fields_ = [
+        ("dim", C.c_int32), ("num_sections", C.c_int32), ("num_particles", C.c_int64),
+        ("cells_per_section", C.c_int64), ("dims", C.c_int64 * 3), ("h", C.c_double),
+        ("cell_off", C.c_void_p), ("sorted_id", C.c_void_p), ("sorted_cell", C.c_void_p),
+    ]
+
+
+class CStepParams(C.Structure):
+    """struct sphnca_step_params (include/sphnca.h)."""
+    _fields_ = [
+        ("W1", C.c_void_p), ("b1", C.c_void_p), ("W2", C.c_void_p), ("b2", C.c_void_p),
+        ("update_rule", C.c_int32), ("use_alpha", C.c_int32),
+        ("perception_scale", C.c_float), ("orig_rate", C.c_float),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"libsphnca.so not found at {LIB_PATH}: build it with `make -C sph-nca_b200/csrc` "
+            "(or __graft_entry__.build()).  sphops has no CPU / eager fallback.")
+    lib = C.CDLL(LIB_PATH)
+    P, I32, I64, D, G = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.POINTER(CGrid)
+    SP = C.POINTER(CStepParams)
+    sigs = {
+        "sphnca_abi_version": ([], I32),
+        "sphnca_last_error": ([], C.c_char_p),
+        "sphnca_hashgrid_workspace_bytes": ([I64, I32, I64, C.POINTER(C.c_size_t)], I32),
+        "sphnca_hashgrid_build": ([P, I64, I32, C.POINTER(I64), I32, D, C.POINTER(I64),
+                                   P, P, P, P, P, P, P, P, C.c_size_t, P], I32),
+        "sphnca_pack_xv": ([G, P, P, P, P], I32),
+        "sphnca_pack_rows": ([G, P, I32, P, P], I32),
+        "sphnca_unpack_rows": ([G, P, I32, P, P], I32),
+        "sphnca_pack_bytes": ([G, P, P, P], I32),
+        "sphnca_volume_fwd": ([G, P, P, P, P], I32),
+        "sphnca_volume_bwd": ([G, P, P, P, P], I32),
+        "sphnca_count_fwd": ([G, P, P, P], I32),
+        "sphnca_gradient_fwd": ([G, P, P, I32, P, P], I32),
+        "sphnca_gradient_bwd": ([G, P, P, I32, P, P], I32),
+        "sphnca_blur_fwd": ([G, P, P, I32, P, P], I32),
+        "sphnca_blur_bwd": ([G, P, P, I32, P, P], I32),
+        "sphnca_divergence_fwd": ([G, P, P, I32, P, P], I32),
+        "sphnca_divergence_bwd": ([G, P, P, I32, P, P], I32),
+        "sphnca_step_workspace_bytes": ([I64, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)], I32),
+        "sphnca_step_fwd": ([G, P, P, P, SP, P, P, P, P, C.c_size_t, P], I32),
+        "sphnca_step_bwd": ([G, P, P, P, P, P, SP, P, P, P, P, P, P, C.c_size_t, P], I32),
+    }
+    missing = []
+    for name, (args, res) in sigs.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.argtypes = args
+        fn.restype = res
+    return lib, tuple(sigs), tuple(missing)
+
+
+lib, DECLARED_SYMBOLS, MISSING_SYMBOLS = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise SphncaError(f"libsphnca error {rc}: {lib.sphnca_last_error().decode()}")
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def require_cuda_f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: sphops runs only on the GPU (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {t.dtype}); the reference's dtype map "
+                        "(func.py:12-16) also lists fp16/fp64 but only fp32 is implemented")
+    return t.detach().contiguous()

@@ -1,0 +1,98 @@
+"""Fused NCA step (B200 extension of the `sphops` package; no counterpart module in the reference).
+
+`nca_step` computes one `SPHNCA.forward` (reference code/nca.py:87-117, default feature process,
+16 channels, hidden width 256) with three kernels instead of ~30 launches:
+perception sweep (+ previous life mask), MLP + gated update, life-mask sweep (+ masking).
+Backward: MLP backward (+ parameter gradients, deterministic) and the gather adjoint of the
+perception sweep.  All state is handled in cell-sorted order inside; inputs/outputs are in the
+caller's original particle order like every other sphops operator.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, require_cuda_f32, stream_ptr
+
+_RULES = {"gated": 0, "orig": 1}
+
+
+def _step_params(W1, b1, W2, b2, update_rule, use_alpha, perception_scale, orig_rate):
+    p = _lib.CStepParams()
+    p.W1, p.b1, p.W2, p.b2 = W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr()
+    p.update_rule = _RULES[update_rule]
+    p.use_alpha = int(bool(use_alpha))
+    p.perception_scale = float(perception_scale)
+    p.orig_rate = float(orig_rate)
+    return p
+
+
+def _workspace(N, device):
+    f, b = C.c_size_t(0), C.c_size_t(0)
+    check(lib.sphnca_step_workspace_bytes(N, C.byref(f), C.byref(b)))
+    return f.value, b.value
+
+
+class _NCAStep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, v, A, update_mask, W1, b1, W2, b2, h, grid, update_rule, use_alpha, perception_scale, orig_rate):
+        x = require_cuda_f32(x, "x"); v = require_cuda_f32(v, "v"); A_ = require_cuda_f32(A, "A")
+        W1c, b1c, W2c, b2c = [require_cuda_f32(t, n) for t, n in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"))]
+        N = x.shape[0]
+        n_out = 33 if update_rule == "gated" else 16
+        if A_.shape != (N, 16) or W1c.shape != (256, 48) or W2c.shape != (n_out, 256):
+            raise ValueError("fused step needs A [N,16], W1 [256,48], W2 [33|16,256]")
+        dev = x.device
+        xv4 = grid.sorted_xv(x, v)
+        A_s = grid.pack_rows(A_, 16)
+        fire_s = grid.pack_bytes(update_mask.to(torch.uint8).contiguous())
+        An_s = torch.empty((N, 16), dtype=torch.float32, device=dev)
+        Y_s = torch.empty((N, 32), dtype=torch.float32, device=dev)
+        flags_s = torch.empty((N,), dtype=torch.uint8, device=dev)
+        fwd_b, _ = _workspace(N, dev)
+        ws = torch.empty((max(fwd_b, 1),), dtype=torch.uint8, device=dev)
+        p = _step_params(W1c, b1c, W2c, b2c, update_rule, use_alpha, perception_scale, orig_rate)
+        if N:
+            check(lib.sphnca_step_fwd(grid.c_grid(), ptr(xv4), ptr(A_s), ptr(fire_s), C.byref(p),
+                                      ptr(An_s), ptr(Y_s), ptr(flags_s), ptr(ws), fwd_b, stream_ptr()))
+        out = grid.unpack_rows(An_s, 16)
+        ctx.grid = grid
+        ctx.cfg = (update_rule, use_alpha, perception_scale, orig_rate)
+        ctx.save_for_backward(xv4, A_s, Y_s, flags_s, W1c, b1c, W2c, b2c)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dA_next):
+        xv4, A_s, Y_s, flags_s, W1, b1, W2, b2 = ctx.saved_tensors
+        grid = ctx.grid
+        N = A_s.shape[0]
+        dev = A_s.device
+        dAn_s = grid.pack_rows(require_cuda_f32(dA_next, "dA_next"), 16)
+        dA_s = torch.empty((N, 16), dtype=torch.float32, device=dev)
+        dW1 = torch.zeros_like(W1); db1 = torch.zeros_like(b1)
+        dW2 = torch.zeros_like(W2); db2 = torch.zeros_like(b2)
+        _, bwd_b = _workspace(N, dev)
+        ws = torch.empty((max(bwd_b, 1),), dtype=torch.uint8, device=dev)
+        p = _step_params(W1, b1, W2, b2, *ctx.cfg)
+        if N:
+            check(lib.sphnca_step_bwd(grid.c_grid(), ptr(xv4), ptr(A_s), ptr(Y_s), ptr(flags_s), ptr(dAn_s),
+                                      C.byref(p), ptr(dA_s), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2),
+                                      ptr(ws), bwd_b, stream_ptr()))
+        dA = grid.unpack_rows(dA_s, 16)
+        g = ctx.needs_input_grad
+        return (None, None, dA if g[2] else None, None,
+                dW1 if g[4] else None, db1 if g[5] else None, dW2 if g[6] else None, db2 if g[7] else None,
+                None, None, None, None, None, None)
+
+
+def nca_step(x, v, A, update_mask, W1, b1, W2, b2, h, grid, update_rule="gated", use_alpha=True,
+             perception_scale=1.0, orig_rate=1.0):
+    """One NCA step.  x [N,3], v [N], A [N,16], update_mask bool [N] (the fire draw) -> new A [N,16]."""
+    if "sphnca_step_fwd" in _lib.MISSING_SYMBOLS:
+        raise RuntimeError("libsphnca.so was built without the fused step (step.cu)")
+    hval = h.item() if isinstance(h, torch.Tensor) else float(h)
+    if abs(hval - grid.h) > 1e-9 * abs(grid.h):
+        raise ValueError(f"h={hval} differs from the grid's cell size {grid.h}")
+    return _NCAStep.apply(x, v, A, update_mask, W1, b1, W2, b2, h, grid, update_rule, use_alpha,
+                          perception_scale, orig_rate)

@@ -1,0 +1,126 @@
+"""Hash-grid container with the reference's field names (code/sphops/hashgrid/single_impl.py:127-171)."""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+
+INTTYPE = torch.int32
+
+
+class Hashgrid:
+    """Cell tables of one packed batch.
+
+    Reference-visible fields (same meaning as single_impl.py:127-171 after `merge()`):
+      h: float, dims: i64[D] (device), total_cells: int,
+      idx: i64[N]  section-local sorted->original index, concatenated over sections,
+      cell_start / cell_end: i32[B*total_cells] section-local positions, -1 = empty cell,
+      num_points: i32[B], occupied_cells / points_per_cells: list[tensor] (lazy; unused by kernels).
+    Internal (consumed by libsphnca): cell_off, sorted_id, sorted_cell and a cache of the
+    cell-sorted {x,y,z,v} array.
+    """
+
+    def __init__(self, h, dims, total_cells, sections, device):
+        self.h = float(h)
+        self.dims = dims
+        self.total_cells = int(total_cells)
+        self.sections = tuple(int(s) for s in sections)
+        self.device = device
+        self.idx = self.cell_start = self.cell_end = self.num_points = None
+        self.cell_off = self.sorted_id = self.sorted_cell = None
+        self._c = None
+        self._occupied = None
+        self._xv_key = None
+        self._xv4 = None
+        self._xyz_key = None
+        self._xyz4 = None
+
+    # -- reference API -------------------------------------------------------------------
+    def get_num_blocks(self, block_size):
+        return torch.ceil(self.num_points / block_size).to(INTTYPE)
+
+    def _occupancy(self):
+        if self._occupied is None:
+            occ, cnt = [], []
+            B = len(self.sections)
+            cs = self.cell_start.view(B, self.total_cells)
+            ce = self.cell_end.view(B, self.total_cells)
+            for b in range(B):
+                cells = torch.nonzero(cs[b] >= 0).flatten()
+                occ.append(cells.to(INTTYPE))
+                cnt.append((ce[b][cells] - cs[b][cells]).to(torch.int64))
+            self._occupied = (occ, cnt)
+        return self._occupied
+
+    @property
+    def occupied_cells(self):
+        return self._occupancy()[0]
+
+    @property
+    def points_per_cells(self):
+        return self._occupancy()[1]
+
+    # -- libsphnca side ------------------------------------------------------------------
+    @property
+    def num_particles(self):
+        return sum(self.sections)
+
+    def c_grid(self):
+        if self._c is None:
+            g = _lib.CGrid()
+            D = int(self.dims.shape[0])
+            g.dim = D
+            g.num_sections = len(self.sections)
+            g.num_particles = self.num_particles
+            g.cells_per_section = self.total_cells
+            for d in range(3):
+                g.dims[d] = self._dims_host[d] if d < D else 1
+            g.h = self.h
+            g.cell_off = self.cell_off.data_ptr()
+            g.sorted_id = self.sorted_id.data_ptr()
+            g.sorted_cell = self.sorted_cell.data_ptr()
+            self._c = g
+        return C.byref(self._c)
+
+    @staticmethod
+    def _key(t):
+        return (t.data_ptr(), t._version, tuple(t.shape))
+
+    def sorted_xyz(self, x):
+        """float4 {x,y,z,0} in cell-sorted order (cached per position tensor)."""
+        key = self._key(x)
+        if self._xyz_key != key:
+            out = torch.empty((x.shape[0], 4), dtype=torch.float32, device=x.device)
+            _lib.check(_lib.lib.sphnca_pack_xv(self.c_grid(), _lib.ptr(x), None, _lib.ptr(out), _lib.stream_ptr()))
+            self._xyz_key, self._xyz4, self._xyz_ref = key, out, x   # the ref pins the storage address
+        return self._xyz4
+
+    def sorted_xv(self, x, v):
+        """float4 {x,y,z,v} in cell-sorted order (cached per (x, v) pair)."""
+        key = (self._key(x), self._key(v))
+        if self._xv_key != key:
+            out = torch.empty((x.shape[0], 4), dtype=torch.float32, device=x.device)
+            _lib.check(_lib.lib.sphnca_pack_xv(self.c_grid(), _lib.ptr(x), _lib.ptr(v), _lib.ptr(out), _lib.stream_ptr()))
+            self._xv_key, self._xv4, self._xv_ref = key, out, (x, v)
+        return self._xv4
+
+    def remember_xv(self, x, v, xv4):
+        self._xv_key, self._xv4, self._xv_ref = (self._key(x), self._key(v)), xv4, (x, v)
+
+    def pack_rows(self, t, row):
+        out = torch.empty((self.num_particles, row), dtype=torch.float32, device=t.device)
+        if self.num_particles:
+            _lib.check(_lib.lib.sphnca_pack_rows(self.c_grid(), _lib.ptr(t), row, _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    def unpack_rows(self, t, row):
+        out = torch.empty((self.num_particles, row), dtype=torch.float32, device=t.device)
+        if self.num_particles:
+            _lib.check(_lib.lib.sphnca_unpack_rows(self.c_grid(), _lib.ptr(t), row, _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    def pack_bytes(self, t):
+        out = torch.empty((self.num_particles,), dtype=torch.uint8, device=t.device)
+        if self.num_particles:
+            _lib.check(_lib.lib.sphnca_pack_bytes(self.c_grid(), _lib.ptr(t), _lib.ptr(out), _lib.stream_ptr()))
+        return out
