@@ -48,42 +48,57 @@ class _NCAStep(torch.autograd.Function):
         fire_s = grid.pack_bytes(update_mask.to(torch.uint8).contiguous())
         An_s = torch.empty((N, 16), dtype=torch.float32, device=dev)
         Y_s = torch.empty((N, 32), dtype=torch.float32, device=dev)
+        O_s = torch.empty((N, 36), dtype=torch.float32, device=dev)
         flags_s = torch.empty((N,), dtype=torch.uint8, device=dev)
         fwd_b, _ = _workspace(N, dev)
         ws = torch.empty((max(fwd_b, 1),), dtype=torch.uint8, device=dev)
         p = _step_params(W1c, b1c, W2c, b2c, update_rule, use_alpha, perception_scale, orig_rate)
         if N:
             check(lib.sphnca_step_fwd(grid.c_grid(), ptr(xv4), ptr(A_s), ptr(fire_s), C.byref(p),
-                                      ptr(An_s), ptr(Y_s), ptr(flags_s), ptr(ws), fwd_b, stream_ptr()))
+                                      ptr(An_s), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(ws), fwd_b, stream_ptr()))
         out = grid.unpack_rows(An_s, 16)
         ctx.grid = grid
         ctx.cfg = (update_rule, use_alpha, perception_scale, orig_rate)
-        ctx.save_for_backward(xv4, A_s, Y_s, flags_s, W1c, b1c, W2c, b2c)
+        ctx.save_for_backward(xv4, A_s, Y_s, O_s, flags_s, W1c, b1c, W2c, b2c)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dA_next):
-        xv4, A_s, Y_s, flags_s, W1, b1, W2, b2 = ctx.saved_tensors
+        xv4, A_s, Y_s, O_s, flags_s, W1, b1, W2, b2 = ctx.saved_tensors
         grid = ctx.grid
         N = A_s.shape[0]
         dev = A_s.device
+        n_out = W2.shape[0]
         dAn_s = grid.pack_rows(require_cuda_f32(dA_next, "dA_next"), 16)
         dA_s = torch.empty((N, 16), dtype=torch.float32, device=dev)
-        dW1 = torch.zeros_like(W1); db1 = torch.zeros_like(b1)
-        dW2 = torch.zeros_like(W2); db2 = torch.zeros_like(b2)
+        dO_s = torch.empty((N, 36), dtype=torch.float32, device=dev)
         _, bwd_b = _workspace(N, dev)
         ws = torch.empty((max(bwd_b, 1),), dtype=torch.uint8, device=dev)
         p = _step_params(W1, b1, W2, b2, *ctx.cfg)
         if N:
-            check(lib.sphnca_step_bwd(grid.c_grid(), ptr(xv4), ptr(A_s), ptr(Y_s), ptr(flags_s), ptr(dAn_s),
-                                      C.byref(p), ptr(dA_s), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2),
-                                      ptr(ws), bwd_b, stream_ptr()))
-        dA = grid.unpack_rows(dA_s, 16)
+            check(lib.sphnca_step_bwd(grid.c_grid(), ptr(xv4), ptr(A_s), ptr(Y_s), ptr(O_s), ptr(flags_s),
+                                      ptr(dAn_s), C.byref(p), ptr(dA_s), ptr(dO_s), ptr(ws), bwd_b, stream_ptr()))
         g = ctx.needs_input_grad
-        return (None, None, dA if g[2] else None, None,
-                dW1 if g[4] else None, db1 if g[5] else None, dW2 if g[6] else None, db2 if g[7] else None,
-                None, None, None, None, None, None)
+        dA = grid.unpack_rows(dA_s, 16) if g[2] else None
+        dW1 = db1 = dW2 = db2 = None
+        if any(g[4:8]):
+            dW1, db1, dW2, db2 = _weight_grads(A_s, Y_s, dO_s[:, :n_out], W1, b1, W2)
+        return (None, None, dA, None, dW1 if g[4] else None, db1 if g[5] else None,
+                dW2 if g[6] else None, db2 if g[7] else None, None, None, None, None, None, None)
+
+
+def _weight_grads(A_s, Y_s, dO, W1, b1, W2):
+    """Parameter gradients of the 48->256->n_out MLP from the saved perception and dL/d(output).
+
+    v1: the hidden layer is recomputed and the four reductions over particles are library GEMMs
+    (torch/cuBLAS fp32).  They are the only library calls on the step path; the hand-written
+    tcgen05 weight-gradient kernel replaces them."""
+    Yfull = torch.cat([A_s, Y_s], dim=1)                    # [N,48]
+    pre = torch.addmm(b1, Yfull, W1.t())                    # [N,256]
+    dH = (dO @ W2) * (pre > 0)                              # [N,256]
+    H = torch.relu_(pre)
+    return dH.t() @ Yfull, dH.sum(0), dO.t() @ H, dO.sum(0)
 
 
 def nca_step(x, v, A, update_mask, W1, b1, W2, b2, h, grid, update_rule="gated", use_alpha=True,

