@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- particle-NCA-steps/s (fwd+bwd) of the SPH-NCA per-timestep particle update on B200.
+
+One bench "step" = one training iteration of the reference's public API on one synthetic batch:
+`nca.sample_plane(model, x0, A0, sections, h, dims, iter_n=K_nca, loss_fn, optimizer)`, i.e.
+hash-grid build + volume + K_nca NCA steps forward + loss + backward + normalize_grads + Adam step
+(reference code/nca.py:124-164, code/train.py:295-305).  Units processed per step =
+particles x K_nca ("particle-NCA-steps").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+N>1 is launched by the driver with torch.distributed.run (one rank per GPU, NCCL): batches shard
+data-parallel over sections (each rank its own equally sized batch = weak scaling) and the 84 KB
+parameter gradient is all-reduced before `normalize_grads`.
+
+JSON keys beyond the base contract: `roofline` (dominant kernel, CUDA-event timed inside the timed
+region), `kernels` (per-kernel share of the step), `cpu_baseline` (the CPU oracle port on a bounded
+sample, rank 0, N=1), `e2e` (same metric with host buffers: pinned H2D of the inputs and D2H of
+the final state + loss inside the timed region).  `--impl reference` times the CPU oracle port
+(the reference itself is Numba-CUDA Python with no CPU build).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "sph-nca_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# workload name -> (description, dim of the lattice, n_side, batch, K_nca, h factor)
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on at N=1
+    "train2d_b8x65k_k64": dict(desc="2D texture training, batch 8 x 65,536 jittered particles (256^2, zero-padded to 3-D), "
+                                    "16 channels, 64 NCA steps fwd+bwd", lattice_dim=2, n_side=256, batch=8, k_nca=64, hf=3.2),
+    # BASELINE.json configs[2]
+    "train3d_250k_k96": dict(desc="3D point cloud, 250,047 jittered particles (63^3), 96 NCA steps fwd+bwd",
+                             lattice_dim=3, n_side=63, batch=1, k_nca=96, hf=1.97),
+    # reduced sizes for quick checks (not a bench line)
+    "tiny": dict(desc="tiny 2D, batch 2 x 4,096, 8 steps", lattice_dim=2, n_side=64, batch=2, k_nca=8, hf=3.2),
+}
+DEFAULT_WORKLOAD = "train2d_b8x65k_k64"
+METRIC = "particle-NCA-steps/sec (fwd+bwd)"
+UNIT = "particle-steps/s"
+ALGO_BYTES = {  # algorithmic HBM bytes per particle per launch
+    "step_fwd": 152.0, "step_mask": 24.0, "step_bwd": 208.0, "step_adjoint": 336.0,
+}
+
+
+def jittered_lattice(n_side, dim, gen):
+    s = 2.0 / n_side
+    axes = [(torch.arange(n_side, dtype=torch.float32) + 0.5) * s - 1.0 for _ in range(dim)]
+    mesh = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, dim)
+    return mesh + (torch.rand(mesh.shape, generator=gen) - 0.5) * s
+
+
+def make_inputs(wl, seed):
+    """Synthetic batch: jittered lattices in [-1,1]^d, A ~ U[0,1), CPU generator."""
+    gen = torch.Generator().manual_seed(seed)
+    xs = [jittered_lattice(wl["n_side"], wl["lattice_dim"], gen) for _ in range(wl["batch"])]
+    x = torch.cat(xs)
+    sections = tuple(t.shape[0] for t in xs)
+    A = torch.rand(x.shape[0], 16, generator=gen)
+    h = wl["hf"] * 2.0 / wl["n_side"]
+    return x, A, sections, h, math.ceil(2.0 / h)
+
+
+def load_weights():
+    w = np.load(os.path.join(ROOT, "tests", "golden", "weights_zebra.npz"))
+    return [torch.from_numpy(w[k]) for k in ("W1", "b1", "W2", "b2")]
+
+
+def bench_loss(x, A, img, A0=None):
+    return (A[:, :4] ** 2).mean()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [t.strip() for t in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(wl, steps, warmup, sample_sections=1, sample_k=4):
+    """The CPU oracle port on a bounded sample of the workload: `sample_sections` batch elements,
+    `sample_k` NCA steps, grid build + volume + fwd + loss + bwd, all host threads torch uses."""
+    from oracle import sphnca_oracle as O
+    sub = dict(wl, batch=sample_sections, k_nca=sample_k)
+    x, A, sections, h, dims = make_inputs(sub, 0)
+    if x.shape[1] == 2:
+        x = torch.nn.functional.pad(x, (0, 1))
+    params = load_weights()
+    cfg = O.StepConfig(use_alpha=False, normalize_perception=1.0 / h)
+    gen = torch.Generator().manual_seed(1)
+    times = []
+    for it in range(warmup + steps):
+        masks = torch.rand(sample_k, x.shape[0], generator=gen) <= 0.5
+        t0 = time.perf_counter()
+        O.rollout_fwd_bwd(x, sections, h, dims, A, params, masks, cfg)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    units = x.shape[0] * sample_k
+    sample = (f"{sample_sections} of {wl['batch']} batch elements ({x.shape[0]} particles) x {sample_k} of "
+              f"{wl['k_nca']} NCA steps, grid build + volume + fwd + bwd, fp64 oracle (oracle/sphnca_oracle.py)")
+    return units / (sum(times) / len(times)), sum(times) / len(times), sample
+
+
+def run_reference(args, wl, rank):
+    """--impl reference: the reference's path on the host cores = the CPU oracle port (kind 'port')."""
+    if rank != 0:
+        return
+    steps, warmup = max(args.steps, 1), min(args.warmup, 1)
+    rate, sec, sample = cpu_oracle_rate(wl, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": {"workload": args.workload, "description": wl["desc"]},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--nca-steps", type=int, default=0, help="override the workload's NCA steps per rollout (profiling runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="operator-by-operator path (sphops ops + torch MLP)")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.nca_steps > 0:
+        wl["k_nca"] = args.nca_steps
+        wl["desc"] += f" [NCA steps overridden to {args.nca_steps}]"
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, wl, rank)
+        return
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU oracle)")
+
+    import nca
+    import sphops
+    from sphops import _lib, fused
+    import multigpu
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+
+    nca.USE_3D = True
+    nca.USE_FUSED_STEP = not args.no_fused
+    torch.manual_seed(1234 + rank)
+    x_cpu, A_cpu, sections, h, dims = make_inputs(wl, seed=rank)
+    N, K_nca = x_cpu.shape[0], wl["k_nca"]
+    model = multigpu.DataParallelSPHNCA(16, 0.5, update_rule="gated", normalize_grad=True, use_alpha=False,
+                                        normalize_perception=1.0 / h).to(dev)
+    with torch.no_grad():
+        for t, src in zip((model.model[0].weight, model.model[0].bias, model.model[2].weight, model.model[2].bias), load_weights()):
+            t.copy_(src)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=0)
+
+    x_pin, A_pin = x_cpu.pin_memory(), A_cpu.pin_memory()
+    out_pin = torch.empty_like(A_pin).pin_memory()
+    x_dev, A_dev = x_pin.to(dev), A_pin.to(dev)
+
+    def one_step(x0, A0):
+        return nca.sample_plane(model, x0, A0, sections, h, dims, iter_n=K_nca, loss_fn=bench_loss, img=None, optimizer=opt)
+
+    def one_step_e2e():
+        x0 = x_pin.to(dev, non_blocking=True)
+        A0 = A_pin.to(dev, non_blocking=True)
+        loss, _, A = one_step(x0, A0)
+        out_pin.copy_(A.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(x_dev, A_dev)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib.sphnca_launch_count()
+    fused.PROFILE = {}
+    ms = timed(lambda: one_step(x_dev, A_dev), args.steps)
+    prof, fused.PROFILE = fused.PROFILE, None
+    launches = int(_lib.lib.sphnca_launch_count() - launches0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    for _ in range(2):
+        one_step_e2e()
+    ms_e2e = timed(one_step_e2e, args.steps)
+
+    units_per_step = N * K_nca * world
+    value = units_per_step * args.steps / (ms * 1e-3)
+    e2e_value = units_per_step * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    hbm, bf16_burst, bf16_sust, which = peaks()
+    kernels, dominant = {}, None
+    for name, evs in prof.items():
+        tot = sum(a.elapsed_time(b) for a, b in evs)
+        kernels[name] = {"launches": len(evs), "avg_ms": tot / len(evs), "share_of_step": tot / ms}
+        if dominant is None or tot > kernels[dominant]["avg_ms"] * kernels[dominant]["launches"]:
+            dominant = name
+    roofline = None
+    if dominant:
+        avg_s = kernels[dominant]["avg_ms"] * 1e-3
+        achieved = ALGO_BYTES[dominant] * N / avg_s / 1e9
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                    "frac": achieved / hbm, "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
+                    "algorithmic_bytes_per_particle": ALGO_BYTES[dominant], "particles_per_launch": N,
+                    "avg_launch_ms": kernels[dominant]["avg_ms"],
+                    "note": "v1 step_fwd runs its MLP on the fp32 CUDA-core pipe: 2*(48*256+256*33)=41,472 FLOP/particle "
+                            "=> the kernel is fp32-pipe bound, not HBM bound (DESIGN.md 5); fp32 fraction below"}
+        if dominant in ("step_fwd", "step_bwd"):
+            flops = {"step_fwd": 41472.0 + 5500.0, "step_bwd": 2 * (48 * 256 * 2 + 256 * 36)}[dominant]
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+            roofline["fp32_pipe"] = {"achieved_tflops": flops * N / avg_s / 1e12, "peak_tflops_at_sampled_clock": fp32_peak,
+                                     "frac": flops * N / avg_s / 1e12 / fp32_peak}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": wl["desc"], "particles_per_gpu": N, "nca_steps": K_nca,
+                   "h": h, "dims": dims, "weights": "zebra (trained, tests/golden/weights_zebra.npz)", "optimizer": "Adam lr=1e-5",
+                   "path": "fused" if nca.USE_FUSED_STEP else "ops", "parallelism": f"dp{world}",
+                   "l2": "no flush needed: ~340 B/particle/NCA-step of saved state => working set "
+                         f"{340 * N * K_nca / 1e9:.1f} GB per step >> 126 MB L2"},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": x_pin.numel() * 4 + A_pin.numel() * 4, "d2h_bytes_per_step": out_pin.numel() * 4 + 4},
+        "roofline": roofline, "kernels": kernels,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        rate, sec, sample = cpu_oracle_rate(wl, 1, 0)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

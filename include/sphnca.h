@@ -51,6 +51,8 @@ typedef struct sphnca_grid {
 
 int32_t sphnca_abi_version(void);
 const char* sphnca_last_error(void);
+/* number of kernels this library has launched so far in this process (all threads) */
+int64_t sphnca_launch_count(void);
 
 /* ---- (1) hash-grid build: replaces sphops.initialize_hashgrid (code/sphops/preprocess.py:11-43),
  *      i.e. grid_hash_kernel (single_impl.py:62-91) + torch.sort (preprocess.py:36) +
@@ -110,25 +112,34 @@ typedef struct sphnca_step_params {
     float orig_rate;       /* self.fire_rate / fire_rate, 'orig' rule only (nca.py:108) */
 } sphnca_step_params;
 
-/* workspace needed by step_fwd / step_bwd for N particles */
-int32_t sphnca_step_workspace_bytes(int64_t N, size_t* fwd_bytes, size_t* bwd_bytes);
-
-/* One forward step.  A_s [N,16] -> A_next_s [N,16].
- * fire_s: uint8 [N] (the `torch.rand(N) <= fire_rate` draw, sorted order).
- * Saved for backward: Y_s [N,32] (scaled dA/dx | dA/dy), O_s [N,36] (MLP output before the
- * gate non-linearities, columns >= n_out are zero), flags_s uint8 [N]
- * (bit0 prev_mask, bit1 new_mask, bit2 fire). */
+/* One forward step = sphnca_step_fwd then sphnca_step_mask (one kernel each).
+ *
+ * sphnca_step_fwd: perception sweep (SPH gradient x,y of 16 channels + previous life mask) fused
+ * with the 48->256->n_out MLP, the gated/orig update and the fire mask.
+ *   in : xv4, A_s [N,16], fire_s uint8 [N] (the `torch.rand(N) <= fire_rate` draw)
+ *   out: A_new_s [N,16] (not yet life-masked), alive_s uint8 [N] (activity(A_new) > 0.1),
+ *        saved for backward: Y_s [N,32] (scaled dA/dx | dA/dy), O_s [N,36] (MLP output before the
+ *        gate non-linearities, columns >= n_out zero), flags_s uint8 [N] (bit0 prev_mask, bit2 fire). */
 int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s,
                         const uint8_t* fire_s, const sphnca_step_params* p,
-                        float* A_next_s, float* Y_s, float* O_s, uint8_t* flags_s,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        float* A_new_s, uint8_t* alive_s, float* Y_s, float* O_s, uint8_t* flags_s,
+                        void* stream);
+/* sphnca_step_mask: new life mask = blur(alive_s) > 0.1 (nca.py:112); A_new_s *= prev & new in
+ * place; flags_s bit1 = new_mask. */
+int32_t sphnca_step_mask(const sphnca_grid* g, const float* xv4, const uint8_t* alive_s,
+                         float* A_new_s, uint8_t* flags_s, void* stream);
 
-/* One backward step (data gradient).  dA_next_s [N,16] -> dA_s [N,16], and dO_s [N,36] =
- * dL/d(MLP output) for the weight-gradient stage.  Gather-based, no float atomics. */
-int32_t sphnca_step_bwd(const sphnca_grid* g, const float* xv4, const float* A_s, const float* Y_s,
-                        const float* O_s, const uint8_t* flags_s, const float* dA_next_s,
-                        const sphnca_step_params* p, float* dA_s, float* dO_s,
-                        void* workspace, size_t workspace_bytes, void* stream);
+/* One backward step = sphnca_step_bwd then sphnca_step_adjoint (one kernel each), gather-based,
+ * no float atomics.
+ * sphnca_step_bwd: everything after the perception sweep.  dA_next_s [N,16] ->
+ *   dO_s [N,36] = dL/d(MLP output) (for the weight-gradient stage), dY_s [N,32] = dL/dY,
+ *   dAdir_s [N,16] = the part of dL/dA that does not pass through the sweep. */
+int32_t sphnca_step_bwd(int64_t N, const float* A_s, const float* Y_s, const float* O_s,
+                        const uint8_t* flags_s, const float* dA_next_s, const sphnca_step_params* p,
+                        float* dO_s, float* dY_s, float* dAdir_s, void* stream);
+/* sphnca_step_adjoint: dA_s = dAdir_s + (adjoint of the perception sweep applied to dY_s). */
+int32_t sphnca_step_adjoint(const sphnca_grid* g, const float* xv4, const float* dY_s, const float* dAdir_s,
+                            const sphnca_step_params* p, float* dA_s, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,7 @@
 namespace sphnca {
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // bookkeeping for sphnca_launch_count()
 
 #define SPHNCA_CHECK_ARG(cond, ...)        \
     do {                                   \
@@ -28,6 +29,9 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 #define SPHNCA_LAUNCH_CHECK() SPHNCA_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro so that launches can be counted
+#define SPHNCA_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    do { kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); sphnca::count_launches(1); } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -26,6 +26,10 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+static unsigned long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+long long launches() { return (long long)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 constexpr int kScanThreads = 512;
 constexpr int kScanItems = 8;                       // per thread
 constexpr int kScanTile = kScanThreads * kScanItems;
@@ -279,6 +283,7 @@ extern "C" {
 
 int32_t sphnca_abi_version(void) { return 1; }
 const char* sphnca_last_error(void) { return sphnca::last_error(); }
+int64_t sphnca_launch_count(void) { return sphnca::launches(); }
 
 int32_t sphnca_hashgrid_workspace_bytes(int64_t N, int32_t B, int64_t cells, size_t* bytes) {
     SPHNCA_CHECK_ARG(bytes != nullptr, "bytes is NULL");
@@ -321,20 +326,20 @@ int32_t sphnca_hashgrid_build(const float* x, int64_t N, int32_t D, const int64_
 
     const int nN = (int)((N + 255) / 256);
     const int nb = (int)((M + kScanTile - 1) / kScanTile);
-    num_points_kernel<<<(B + 127) / 128, 128, 0, stream>>>(w.sec_off, B, num_points);
+    SPHNCA_LAUNCH(num_points_kernel, (B + 127) / 128, 128, 0, stream, w.sec_off, B, num_points);
     if (N > 0) {
         if (D == 3)
-            hash_count_kernel<3><<<nN, 256, 0, stream>>>(x, (int)N, w.sec_off, B, h, (int)dims[0], (int)dims[1], (int)dims[2], (int)cells, w.hi, w.cnt);
+            SPHNCA_LAUNCH(hash_count_kernel<3>, nN, 256, 0, stream, x, (int)N, w.sec_off, B, h, (int)dims[0], (int)dims[1], (int)dims[2], (int)cells, w.hi, w.cnt);
         else
-            hash_count_kernel<2><<<nN, 256, 0, stream>>>(x, (int)N, w.sec_off, B, h, (int)dims[0], (int)dims[1], 1, (int)cells, w.hi, w.cnt);
+            SPHNCA_LAUNCH(hash_count_kernel<2>, nN, 256, 0, stream, x, (int)N, w.sec_off, B, h, (int)dims[0], (int)dims[1], 1, (int)cells, w.hi, w.cnt);
     }
-    scan_reduce_kernel<<<nb, kScanThreads, 0, stream>>>(w.cnt, (int)M, w.block_sums);
-    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(w.block_sums, nb);
-    scan_write_kernel<<<nb, kScanThreads, 0, stream>>>(w.cnt, (int)M, w.block_sums, w.sec_off, (int)cells, (int)N,
+    SPHNCA_LAUNCH(scan_reduce_kernel, nb, kScanThreads, 0, stream, w.cnt, (int)M, w.block_sums);
+    SPHNCA_LAUNCH(scan_block_sums_kernel, 1, 1024, 0, stream, w.block_sums, nb);
+    SPHNCA_LAUNCH(scan_write_kernel, nb, kScanThreads, 0, stream, w.cnt, (int)M, w.block_sums, w.sec_off, (int)cells, (int)N,
                                                        cell_off, cell_start, cell_end);
     if (N > 0) {
-        scatter_kernel<<<nN, 256, 0, stream>>>(w.hi, (int)N, cell_off, w.cnt, w.tmp);
-        rank_kernel<<<nN, 256, 0, stream>>>(w.hi, w.tmp, (int)N, cell_off, w.sec_off, (int)cells, sorted_id, sorted_cell, idx);
+        SPHNCA_LAUNCH(scatter_kernel, nN, 256, 0, stream, w.hi, (int)N, cell_off, w.cnt, w.tmp);
+        SPHNCA_LAUNCH(rank_kernel, nN, 256, 0, stream, w.hi, w.tmp, (int)N, cell_off, w.sec_off, (int)cells, sorted_id, sorted_cell, idx);
     }
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
@@ -344,7 +349,7 @@ int32_t sphnca_pack_xv(const sphnca_grid* g, const float* x, const float* v, flo
     GridView gv; int rc = make_view(g, &gv); if (rc) return rc;
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(x && xv4, "x/xv4 is NULL");
-    pack_xv_kernel<<<(int)((gv.n + 255) / 256), 256, 0, as_stream(stream)>>>(x, v, gv.sorted_id, (int)gv.n, gv.dim, (float4*)xv4);
+    SPHNCA_LAUNCH(pack_xv_kernel, (int)((gv.n + 255) / 256), 256, 0, as_stream(stream), x, v, gv.sorted_id, (int)gv.n, gv.dim, (float4*)xv4);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }
@@ -358,14 +363,14 @@ static int32_t permute_rows(const sphnca_grid* g, const float* src, int32_t row,
     if (vec) {
         int64_t total = gv.n * (row / 4);
         int blocks = (int)((total + 255) / 256);
-        if (pack) permute_rows4_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>((const float4*)src, (float4*)dst, gv.sorted_id, total, row / 4);
-        else permute_rows4_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>((const float4*)src, (float4*)dst, gv.sorted_id, total, row / 4);
+        if (pack) SPHNCA_LAUNCH(permute_rows4_kernel<true>, blocks, 256, 0, as_stream(stream), (const float4*)src, (float4*)dst, gv.sorted_id, total, row / 4);
+        else SPHNCA_LAUNCH(permute_rows4_kernel<false>, blocks, 256, 0, as_stream(stream), (const float4*)src, (float4*)dst, gv.sorted_id, total, row / 4);
     } else {
         int64_t total = gv.n * row;
         int64_t blocks = (total + 255) / 256;
         SPHNCA_CHECK_ARG(blocks < (int64_t(1) << 31), "too many elements");
-        if (pack) permute_rows_kernel<true><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, dst, gv.sorted_id, total, row);
-        else permute_rows_kernel<false><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, dst, gv.sorted_id, total, row);
+        if (pack) SPHNCA_LAUNCH(permute_rows_kernel<true>, (unsigned)blocks, 256, 0, as_stream(stream), src, dst, gv.sorted_id, total, row);
+        else SPHNCA_LAUNCH(permute_rows_kernel<false>, (unsigned)blocks, 256, 0, as_stream(stream), src, dst, gv.sorted_id, total, row);
     }
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
@@ -380,7 +385,7 @@ int32_t sphnca_unpack_rows(const sphnca_grid* g, const float* src, int32_t row, 
 int32_t sphnca_pack_bytes(const sphnca_grid* g, const uint8_t* src, uint8_t* dst, void* stream) {
     GridView gv; int rc = make_view(g, &gv); if (rc) return rc;
     if (gv.n == 0) return SPHNCA_OK;
-    pack_bytes_kernel<<<(int)((gv.n + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, gv.sorted_id, (int)gv.n);
+    SPHNCA_LAUNCH(pack_bytes_kernel, (int)((gv.n + 255) / 256), 256, 0, as_stream(stream), src, dst, gv.sorted_id, (int)gv.n);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

@@ -338,8 +338,6 @@ step_adjoint_kernel(GridView g, const float4* __restrict__ xv4, const float* __r
     for (int k = 0; k < 4; ++k) o4[k] = make_float4(r[4*k], r[4*k+1], r[4*k+2], r[4*k+3]);
 }
 
-static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
-
 static int make_consts(const sphnca_grid* g, const sphnca_step_params* p, StepConsts* c) {
     if (!p || !p->W1 || !p->b1 || !p->W2 || !p->b2) { set_error("step params / weights are NULL"); return SPHNCA_ERR_INVALID; }
     if (p->update_rule != 0 && p->update_rule != 1) { set_error("update_rule must be 0 (gated) or 1 (orig)"); return SPHNCA_ERR_INVALID; }
@@ -358,57 +356,69 @@ using namespace sphnca;
 
 extern "C" {
 
-int32_t sphnca_step_workspace_bytes(int64_t N, size_t* fwd_bytes, size_t* bwd_bytes) {
-    SPHNCA_CHECK_ARG(N >= 0 && fwd_bytes && bwd_bytes, "bad argument");
-    *fwd_bytes = align256((size_t)N);                                             // alive bits
-    *bwd_bytes = align256((size_t)N * 2 * NF * 4) + align256((size_t)N * NF * 4); // dY, dAdir
-    return SPHNCA_OK;
-}
-
 int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s, const uint8_t* fire_s,
-                        const sphnca_step_params* p, float* A_next_s, float* Y_s, float* O_s, uint8_t* flags_s,
-                        void* workspace, size_t workspace_bytes, void* stream_) {
+                        const sphnca_step_params* p, float* A_new_s, uint8_t* alive_s, float* Y_s, float* O_s,
+                        uint8_t* flags_s, void* stream_) {
     GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
     StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
     cudaStream_t stream = as_stream(stream_);
     if (gv.n == 0) return SPHNCA_OK;
-    SPHNCA_CHECK_ARG(xv4 && A_s && fire_s && A_next_s && Y_s && O_s && flags_s, "NULL argument");
-    if (!workspace || workspace_bytes < align256((size_t)gv.n)) { set_error("step_fwd workspace too small"); return SPHNCA_ERR_WORKSPACE; }
-    uint8_t* alive = reinterpret_cast<uint8_t*>(workspace);
+    SPHNCA_CHECK_ARG(xv4 && A_s && fire_s && A_new_s && alive_s && Y_s && O_s && flags_s, "NULL argument");
     const int blocks = (int)((gv.n + kStepThreads - 1) / kStepThreads);
     const size_t smem = sizeof(MlpSmem);
     if (gv.dim == 3) {
         SPHNCA_CUDA(cudaFuncSetAttribute(step_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        step_fwd_kernel<3><<<blocks, kStepThreads, smem, stream>>>(gv, (const float4*)xv4, A_s, fire_s, *p, c, A_next_s, Y_s, O_s, flags_s, alive);
-        step_mask_kernel<3><<<(int)((gv.n + 255) / 256), 256, 0, stream>>>(gv, (const float4*)xv4, alive, c, A_next_s, flags_s);
+        SPHNCA_LAUNCH(step_fwd_kernel<3>, blocks, kStepThreads, smem, stream, gv, (const float4*)xv4, A_s, fire_s, *p, c, A_new_s, Y_s, O_s, flags_s, alive_s);
     } else {
         SPHNCA_CUDA(cudaFuncSetAttribute(step_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        step_fwd_kernel<2><<<blocks, kStepThreads, smem, stream>>>(gv, (const float4*)xv4, A_s, fire_s, *p, c, A_next_s, Y_s, O_s, flags_s, alive);
-        step_mask_kernel<2><<<(int)((gv.n + 255) / 256), 256, 0, stream>>>(gv, (const float4*)xv4, alive, c, A_next_s, flags_s);
+        SPHNCA_LAUNCH(step_fwd_kernel<2>, blocks, kStepThreads, smem, stream, gv, (const float4*)xv4, A_s, fire_s, *p, c, A_new_s, Y_s, O_s, flags_s, alive_s);
     }
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }
 
-int32_t sphnca_step_bwd(const sphnca_grid* g, const float* xv4, const float* A_s, const float* Y_s,
-                        const float* O_s, const uint8_t* flags_s, const float* dA_next_s,
-                        const sphnca_step_params* p, float* dA_s, float* dO_s,
-                        void* workspace, size_t workspace_bytes, void* stream_) {
+int32_t sphnca_step_mask(const sphnca_grid* g, const float* xv4, const uint8_t* alive_s, float* A_new_s,
+                         uint8_t* flags_s, void* stream_) {
+    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    cudaStream_t stream = as_stream(stream_);
+    if (gv.n == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(xv4 && alive_s && A_new_s && flags_s, "NULL argument");
+    StepConsts c{};
+    c.h = (float)g->h; c.h2 = (float)(g->h * g->h); c.cw = (float)poly6_norm(g->dim, g->h);
+    const int blocks = (int)((gv.n + 255) / 256);
+    if (gv.dim == 3) SPHNCA_LAUNCH(step_mask_kernel<3>, blocks, 256, 0, stream, gv, (const float4*)xv4, alive_s, c, A_new_s, flags_s);
+    else SPHNCA_LAUNCH(step_mask_kernel<2>, blocks, 256, 0, stream, gv, (const float4*)xv4, alive_s, c, A_new_s, flags_s);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_step_bwd(int64_t N, const float* A_s, const float* Y_s, const float* O_s, const uint8_t* flags_s,
+                        const float* dA_next_s, const sphnca_step_params* p, float* dO_s, float* dY_s,
+                        float* dAdir_s, void* stream_) {
+    SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
+    sphnca_grid fake{}; fake.dim = 3; fake.h = 1.0;      // only the rule / rates of the constants are used here
+    StepConsts c; { int rc = make_consts(&fake, p, &c); if (rc) return rc; }
+    cudaStream_t stream = as_stream(stream_);
+    if (N == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(A_s && Y_s && O_s && flags_s && dA_next_s && dO_s && dY_s && dAdir_s, "NULL argument");
+    const size_t smem = sizeof(MlpSmem);
+    SPHNCA_CUDA(cudaFuncSetAttribute(step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPHNCA_LAUNCH(step_bwd_kernel, (int)((N + kStepThreads - 1) / kStepThreads), kStepThreads, smem, stream,
+                  (int)N, A_s, Y_s, O_s, flags_s, dA_next_s, *p, c, dO_s, dY_s, dAdir_s);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_step_adjoint(const sphnca_grid* g, const float* xv4, const float* dY_s, const float* dAdir_s,
+                            const sphnca_step_params* p, float* dA_s, void* stream_) {
     GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
     StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
     cudaStream_t stream = as_stream(stream_);
     if (gv.n == 0) return SPHNCA_OK;
-    SPHNCA_CHECK_ARG(xv4 && A_s && Y_s && O_s && flags_s && dA_next_s && dA_s && dO_s, "NULL argument");
-    const size_t off_dir = align256((size_t)gv.n * 2 * NF * 4);
-    if (!workspace || workspace_bytes < off_dir + align256((size_t)gv.n * NF * 4)) { set_error("step_bwd workspace too small"); return SPHNCA_ERR_WORKSPACE; }
-    float* dY = reinterpret_cast<float*>(workspace);
-    float* dAdir = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + off_dir);
-    const size_t smem = sizeof(MlpSmem);
-    SPHNCA_CUDA(cudaFuncSetAttribute(step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    step_bwd_kernel<<<(int)((gv.n + kStepThreads - 1) / kStepThreads), kStepThreads, smem, stream>>>(
-        (int)gv.n, A_s, Y_s, O_s, flags_s, dA_next_s, *p, c, dO_s, dY, dAdir);
-    if (gv.dim == 3) step_adjoint_kernel<3><<<(int)((gv.n + 127) / 128), 128, 0, stream>>>(gv, (const float4*)xv4, dY, dAdir, c, dA_s);
-    else step_adjoint_kernel<2><<<(int)((gv.n + 127) / 128), 128, 0, stream>>>(gv, (const float4*)xv4, dY, dAdir, c, dA_s);
+    SPHNCA_CHECK_ARG(xv4 && dY_s && dAdir_s && dA_s, "NULL argument");
+    const int blocks = (int)((gv.n + 127) / 128);
+    if (gv.dim == 3) SPHNCA_LAUNCH(step_adjoint_kernel<3>, blocks, 128, 0, stream, gv, (const float4*)xv4, dY_s, dAdir_s, c, dA_s);
+    else SPHNCA_LAUNCH(step_adjoint_kernel<2>, blocks, 128, 0, stream, gv, (const float4*)xv4, dY_s, dAdir_s, c, dA_s);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

@@ -337,8 +337,8 @@ int32_t sphnca_volume_fwd(const sphnca_grid* g, const float* xv4, float* v, floa
     SPHNCA_PROLOGUE();
     SPHNCA_CHECK_ARG(xv4 && v && xv4_out, "NULL argument");
     const double norm = poly6_norm(gv.dim, hd);
-    if (gv.dim == 3) volume_fwd_kernel<3><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, hd * hd, norm, v, (float4*)xv4_out);
-    else volume_fwd_kernel<2><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, hd * hd, norm, v, (float4*)xv4_out);
+    if (gv.dim == 3) SPHNCA_LAUNCH(volume_fwd_kernel<3>, blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, hd * hd, norm, v, (float4*)xv4_out);
+    else SPHNCA_LAUNCH(volume_fwd_kernel<2>, blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, hd * hd, norm, v, (float4*)xv4_out);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }
@@ -347,8 +347,8 @@ int32_t sphnca_volume_bwd(const sphnca_grid* g, const float* xv4, const float* d
     SPHNCA_PROLOGUE();
     SPHNCA_CHECK_ARG(xv4 && dLdv_s && dLdx, "NULL argument");
     const float norm = (float)poly6_norm(gv.dim, hd);
-    if (gv.dim == 3) volume_bwd_kernel<3><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, dLdv_s, h2, norm, dLdx);
-    else volume_bwd_kernel<2><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, dLdv_s, h2, norm, dLdx);
+    if (gv.dim == 3) SPHNCA_LAUNCH(volume_bwd_kernel<3>, blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, dLdv_s, h2, norm, dLdx);
+    else SPHNCA_LAUNCH(volume_bwd_kernel<2>, blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, dLdv_s, h2, norm, dLdx);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }
@@ -356,8 +356,8 @@ int32_t sphnca_volume_bwd(const sphnca_grid* g, const float* xv4, const float* d
 int32_t sphnca_count_fwd(const sphnca_grid* g, const float* xv4, float* c, void* stream_) {
     SPHNCA_PROLOGUE();
     SPHNCA_CHECK_ARG(xv4 && c, "NULL argument");
-    if (gv.dim == 3) count_fwd_kernel<3><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, hd * hd, c);
-    else count_fwd_kernel<2><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, hd * hd, c);
+    if (gv.dim == 3) SPHNCA_LAUNCH(count_fwd_kernel<3>, blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, hd * hd, c);
+    else SPHNCA_LAUNCH(count_fwd_kernel<2>, blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, hd * hd, c);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }
@@ -371,11 +371,11 @@ int32_t sphnca_gradient_fwd(const sphnca_grid* g, const float* xv4, const float*
         const bool vec = vec_ok && fc >= 4;
         SPHNCA_DISPATCH_FC(fc,
             if (gv.dim == 3) {
-                if (vec) gradient_fwd_kernel<3, FC, (FC >= 4)><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, A_s, F, f0, h, h2, norm, GA);
-                else gradient_fwd_kernel<3, FC, false><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, A_s, F, f0, h, h2, norm, GA);
+                if (vec) SPHNCA_LAUNCH((gradient_fwd_kernel<3, FC, (FC >= 4)>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, A_s, F, f0, h, h2, norm, GA);
+                else SPHNCA_LAUNCH((gradient_fwd_kernel<3, FC, false>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, A_s, F, f0, h, h2, norm, GA);
             } else {
-                if (vec) gradient_fwd_kernel<2, FC, (FC >= 4)><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, A_s, F, f0, h, h2, norm, GA);
-                else gradient_fwd_kernel<2, FC, false><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, A_s, F, f0, h, h2, norm, GA);
+                if (vec) SPHNCA_LAUNCH((gradient_fwd_kernel<2, FC, (FC >= 4)>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, A_s, F, f0, h, h2, norm, GA);
+                else SPHNCA_LAUNCH((gradient_fwd_kernel<2, FC, false>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, A_s, F, f0, h, h2, norm, GA);
             })
     });
     SPHNCA_LAUNCH_CHECK();
@@ -391,11 +391,11 @@ int32_t sphnca_gradient_bwd(const sphnca_grid* g, const float* xv4, const float*
         const bool vec = vec_ok && ((f0 * gv.dim) % 4 == 0) && ((fc * gv.dim) % 4 == 0);
         SPHNCA_DISPATCH_FC(fc,
             if (gv.dim == 3) {
-                if (vec) gradient_bwd_kernel<3, FC, (FC * 3 % 4 == 0)><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, G_s, F, f0, h, h2, norm, dLdA);
-                else gradient_bwd_kernel<3, FC, false><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, G_s, F, f0, h, h2, norm, dLdA);
+                if (vec) SPHNCA_LAUNCH((gradient_bwd_kernel<3, FC, (FC * 3 % 4 == 0)>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, G_s, F, f0, h, h2, norm, dLdA);
+                else SPHNCA_LAUNCH((gradient_bwd_kernel<3, FC, false>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, G_s, F, f0, h, h2, norm, dLdA);
             } else {
-                if (vec) gradient_bwd_kernel<2, FC, (FC * 2 % 4 == 0)><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, G_s, F, f0, h, h2, norm, dLdA);
-                else gradient_bwd_kernel<2, FC, false><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, G_s, F, f0, h, h2, norm, dLdA);
+                if (vec) SPHNCA_LAUNCH((gradient_bwd_kernel<2, FC, (FC * 2 % 4 == 0)>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, G_s, F, f0, h, h2, norm, dLdA);
+                else SPHNCA_LAUNCH((gradient_bwd_kernel<2, FC, false>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, G_s, F, f0, h, h2, norm, dLdA);
             })
     });
     SPHNCA_LAUNCH_CHECK();
@@ -414,11 +414,11 @@ static int32_t blur_impl(const sphnca_grid* g, const float* xv4, const float* A_
         const bool vec = vec_ok && fc >= 4;
         SPHNCA_DISPATCH_FC(fc,
             if (gv.dim == 3) {
-                if (vec) blur_kernel<3, FC, (FC >= 4), ADJ><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, A_s, F, f0, h2, norm, SA);
-                else blur_kernel<3, FC, false, ADJ><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, A_s, F, f0, h2, norm, SA);
+                if (vec) SPHNCA_LAUNCH((blur_kernel<3, FC, (FC >= 4), ADJ>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, A_s, F, f0, h2, norm, SA);
+                else SPHNCA_LAUNCH((blur_kernel<3, FC, false, ADJ>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, A_s, F, f0, h2, norm, SA);
             } else {
-                if (vec) blur_kernel<2, FC, (FC >= 4), ADJ><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, A_s, F, f0, h2, norm, SA);
-                else blur_kernel<2, FC, false, ADJ><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, A_s, F, f0, h2, norm, SA);
+                if (vec) SPHNCA_LAUNCH((blur_kernel<2, FC, (FC >= 4), ADJ>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, A_s, F, f0, h2, norm, SA);
+                else SPHNCA_LAUNCH((blur_kernel<2, FC, false, ADJ>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, A_s, F, f0, h2, norm, SA);
             })
     });
     SPHNCA_LAUNCH_CHECK();
@@ -444,8 +444,8 @@ int32_t sphnca_divergence_fwd(const sphnca_grid* g, const float* xv4, const floa
         int fc = rem >= 8 ? 8 : rem >= 4 ? 4 : rem >= 2 ? 2 : 1;
         SPHNCA_DISPATCH_FC(fc,
             if (FC <= 8) {
-                if (gv.dim == 3) divergence_fwd_kernel<3, (FC <= 8 ? FC : 8)><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, A_s, F, f0, h, h2, norm, DA);
-                else divergence_fwd_kernel<2, (FC <= 8 ? FC : 8)><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, A_s, F, f0, h, h2, norm, DA);
+                if (gv.dim == 3) SPHNCA_LAUNCH((divergence_fwd_kernel<3, (FC <= 8 ? FC : 8)>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, A_s, F, f0, h, h2, norm, DA);
+                else SPHNCA_LAUNCH((divergence_fwd_kernel<2, (FC <= 8 ? FC : 8)>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, A_s, F, f0, h, h2, norm, DA);
             })
         f0 += fc;
     }
@@ -463,8 +463,8 @@ int32_t sphnca_divergence_bwd(const sphnca_grid* g, const float* xv4, const floa
         int fc = rem >= 8 ? 8 : rem >= 4 ? 4 : rem >= 2 ? 2 : 1;
         SPHNCA_DISPATCH_FC(fc,
             if (FC <= 8) {
-                if (gv.dim == 3) divergence_bwd_kernel<3, (FC <= 8 ? FC : 8)><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, G_s, F, f0, h, h2, norm, dLdA);
-                else divergence_bwd_kernel<2, (FC <= 8 ? FC : 8)><<<blocks, kSweepThreads, 0, stream>>>(gv, (const float4*)xv4, G_s, F, f0, h, h2, norm, dLdA);
+                if (gv.dim == 3) SPHNCA_LAUNCH((divergence_bwd_kernel<3, (FC <= 8 ? FC : 8)>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, G_s, F, f0, h, h2, norm, dLdA);
+                else SPHNCA_LAUNCH((divergence_bwd_kernel<2, (FC <= 8 ? FC : 8)>), blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, G_s, F, f0, h, h2, norm, dLdA);
             })
         f0 += fc;
     }

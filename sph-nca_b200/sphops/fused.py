@@ -27,10 +27,20 @@ def _step_params(W1, b1, W2, b2, update_rule, use_alpha, perception_scale, orig_
     return p
 
 
-def _workspace(N, device):
-    f, b = C.c_size_t(0), C.c_size_t(0)
-    check(lib.sphnca_step_workspace_bytes(N, C.byref(f), C.byref(b)))
-    return f.value, b.value
+# Optional per-kernel timing hook used by bench.py: a dict name -> list of (start, end) CUDA events
+# recorded on the launching (current) stream around each C-ABI call.  None = off (default).
+PROFILE = None
+
+
+def _timed(name, fn, *args):
+    if PROFILE is None:
+        check(fn(*args))
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    check(fn(*args))
+    b.record()
+    PROFILE.setdefault(name, []).append((a, b))
 
 
 class _NCAStep(torch.autograd.Function):
@@ -43,19 +53,21 @@ class _NCAStep(torch.autograd.Function):
         if A_.shape != (N, 16) or W1c.shape != (256, 48) or W2c.shape != (n_out, 256):
             raise ValueError("fused step needs A [N,16], W1 [256,48], W2 [33|16,256]")
         dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
         xv4 = grid.sorted_xv(x, v)
         A_s = grid.pack_rows(A_, 16)
         fire_s = grid.pack_bytes(update_mask.to(torch.uint8).contiguous())
-        An_s = torch.empty((N, 16), dtype=torch.float32, device=dev)
-        Y_s = torch.empty((N, 32), dtype=torch.float32, device=dev)
-        O_s = torch.empty((N, 36), dtype=torch.float32, device=dev)
+        An_s = torch.empty((N, 16), **f32)
+        Y_s = torch.empty((N, 32), **f32)
+        O_s = torch.empty((N, 36), **f32)
         flags_s = torch.empty((N,), dtype=torch.uint8, device=dev)
-        fwd_b, _ = _workspace(N, dev)
-        ws = torch.empty((max(fwd_b, 1),), dtype=torch.uint8, device=dev)
+        alive_s = torch.empty((N,), dtype=torch.uint8, device=dev)
         p = _step_params(W1c, b1c, W2c, b2c, update_rule, use_alpha, perception_scale, orig_rate)
         if N:
-            check(lib.sphnca_step_fwd(grid.c_grid(), ptr(xv4), ptr(A_s), ptr(fire_s), C.byref(p),
-                                      ptr(An_s), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(ws), fwd_b, stream_ptr()))
+            g, st = grid.c_grid(), stream_ptr()
+            _timed("step_fwd", lib.sphnca_step_fwd, g, ptr(xv4), ptr(A_s), ptr(fire_s), C.byref(p), ptr(An_s),
+                   ptr(alive_s), ptr(Y_s), ptr(O_s), ptr(flags_s), st)
+            _timed("step_mask", lib.sphnca_step_mask, g, ptr(xv4), ptr(alive_s), ptr(An_s), ptr(flags_s), st)
         out = grid.unpack_rows(An_s, 16)
         ctx.grid = grid
         ctx.cfg = (update_rule, use_alpha, perception_scale, orig_rate)
@@ -69,16 +81,20 @@ class _NCAStep(torch.autograd.Function):
         grid = ctx.grid
         N = A_s.shape[0]
         dev = A_s.device
+        f32 = dict(dtype=torch.float32, device=dev)
         n_out = W2.shape[0]
         dAn_s = grid.pack_rows(require_cuda_f32(dA_next, "dA_next"), 16)
-        dA_s = torch.empty((N, 16), dtype=torch.float32, device=dev)
-        dO_s = torch.empty((N, 36), dtype=torch.float32, device=dev)
-        _, bwd_b = _workspace(N, dev)
-        ws = torch.empty((max(bwd_b, 1),), dtype=torch.uint8, device=dev)
+        dA_s = torch.empty((N, 16), **f32)
+        dO_s = torch.empty((N, 36), **f32)
+        dY_s = torch.empty((N, 32), **f32)
+        dAdir_s = torch.empty((N, 16), **f32)
         p = _step_params(W1, b1, W2, b2, *ctx.cfg)
         if N:
-            check(lib.sphnca_step_bwd(grid.c_grid(), ptr(xv4), ptr(A_s), ptr(Y_s), ptr(O_s), ptr(flags_s),
-                                      ptr(dAn_s), C.byref(p), ptr(dA_s), ptr(dO_s), ptr(ws), bwd_b, stream_ptr()))
+            st = stream_ptr()
+            _timed("step_bwd", lib.sphnca_step_bwd, N, ptr(A_s), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(dAn_s),
+                   C.byref(p), ptr(dO_s), ptr(dY_s), ptr(dAdir_s), st)
+            _timed("step_adjoint", lib.sphnca_step_adjoint, grid.c_grid(), ptr(xv4), ptr(dY_s), ptr(dAdir_s),
+                   C.byref(p), ptr(dA_s), st)
         g = ctx.needs_input_grad
         dA = grid.unpack_rows(dA_s, 16) if g[2] else None
         dW1 = db1 = dW2 = db2 = None

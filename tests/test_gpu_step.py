@@ -162,7 +162,7 @@ def test_fused_rollout_matches_oracle_midsize(dim3, use_alpha, n_side):
         frac = (gerr > 5e-5).mean()
         assert frac <= 2e-2 and gerr.max() <= 2e-2, f"dL/dA0: {frac:.3%} rows > 5e-5, worst {gerr.max():.2e}"
         for t, r, nm in zip((m.model[0].weight, m.model[0].bias, m.model[2].weight, m.model[2].bias), dP_ref, ("dW1", "db1", "dW2", "db2")):
-            assert_close(t.grad, r, rtol=2e-4, what=nm)
+            assert_close(t.grad, r, rtol=5e-4, what=nm)
 
 
 def test_fused_equals_ops_path_bitwise_masks():

@@ -1,0 +1,53 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: section sharding and the flat
+gradient all-reduce that makes `sample_plane` data-parallel."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import multigpu
+    torch.manual_seed(0)
+    model = multigpu.DataParallelSPHNCA(16, 0.5, normalize_grad=True)
+    # rank-dependent gradients; model.2.bias left without a gradient on rank 1 only
+    for i, p in enumerate(model.parameters()):
+        if not (rank == 1 and i == 3):
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    nbytes = multigpu.allreduce_gradients(model.parameters())
+    grads = [p.grad.clone() for p in model.parameters()]
+    model.normalize_grads()            # all-reduces again (idempotent on equal grads), then normalises
+    norms = [float(p.grad.norm()) for p in model.parameters()]
+    ret[rank] = (nbytes, [float(g.flatten()[0]) for g in grads], norms)
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0][0] == ret[1][0] == 21025 * 4                      # one flat 84,100-byte buffer
+    expect = [(1 * (i + 1) + 2 * (i + 1)) / 2 for i in range(3)] + [(1 * 4 + 0) / 2]
+    for r in range(world):
+        assert ret[r][1] == expect                                  # average over ranks, identical on both
+        assert all(abs(n - 1.0) < 1e-5 for n in ret[r][2])          # normalize_grads ran after the reduce
+
+
+def test_shard_sections():
+    import multigpu
+    sections = (5, 7, 3, 9, 2)
+    got = [multigpu.shard_sections(sections, 2, r) for r in range(2)]
+    assert got == [(0, 3, 0, 15), (3, 5, 15, 26)]
+    got8 = [multigpu.shard_sections((4,) * 8, 8, r) for r in range(8)]
+    assert [g[2] for g in got8] == [4 * r for r in range(8)] and all(g[1] - g[0] == 1 for g in got8)
+    # more ranks than sections: trailing ranks get empty shards
+    assert multigpu.shard_sections((4, 4), 4, 3) == (2, 2, 8, 8)
