@@ -51,6 +51,8 @@ METRIC = "particle-NCA-steps/sec (fwd+bwd)"
 UNIT = "particle-steps/s"
 ALGO_BYTES = {  # algorithmic HBM bytes per particle per launch
     "step_fwd": 152.0, "step_mask": 24.0, "step_bwd": 208.0, "step_adjoint": 336.0,
+    # weight-gradient stage: streams the transposed hidden activations H^T, dH^T (2 x 256 x 4 B) + y (192) + dO (132)
+    "mlp_wgrad": 2372.0,
 }
 
 

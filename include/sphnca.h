@@ -124,6 +124,10 @@ int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s
                         const uint8_t* fire_s, const sphnca_step_params* p,
                         float* A_new_s, uint8_t* alive_s, float* Y_s, float* O_s, uint8_t* flags_s,
                         void* stream);
+/* Implementation switch for sphnca_step_fwd: 1 (default) = tcgen05 tensor-core MLP with the 3xTF32
+ * split (csrc/step_tc.cu), 0 = fp32 CUDA-core MLP (csrc/step.cu).  Both produce the same outputs
+ * to fp32 rounding; the switch exists for A/B tests. */
+int32_t sphnca_set_mlp_path(int32_t path);
 /* sphnca_step_mask: new life mask = blur(alive_s) > 0.1 (nca.py:112); A_new_s *= prev & new in
  * place; flags_s bit1 = new_mask. */
 int32_t sphnca_step_mask(const sphnca_grid* g, const float* xv4, const uint8_t* alive_s,
@@ -136,7 +140,18 @@ int32_t sphnca_step_mask(const sphnca_grid* g, const float* xv4, const uint8_t* 
  *   dAdir_s [N,16] = the part of dL/dA that does not pass through the sweep. */
 int32_t sphnca_step_bwd(int64_t N, const float* A_s, const float* Y_s, const float* O_s,
                         const uint8_t* flags_s, const float* dA_next_s, const sphnca_step_params* p,
-                        float* dO_s, float* dY_s, float* dAdir_s, void* stream);
+                        float* dO_s, float* dY_s, float* dAdir_s, float* Ht, float* dHt, void* stream);
+/*   Ht, dHt (both or neither, may be NULL): hidden activations relu(pre) and dL/d(pre), transposed and
+ *   tile-blocked for sphnca_mlp_wgrad: float [ceil(N/32)][256][32], element (p, n) at
+ *   ((p/32)*256 + n)*32 + p%32. */
+
+/* Weight gradients of the MLP, ACCUMULATED (+=) into dW1 [256,48], db1 [256], dW2 [n_out,256],
+ * db2 [n_out] (replaces torch autograd's GEMMs over `model.0` / `model.2`, code/nca.py:96,151).
+ * Deterministic two-stage reduction.  n_out = 33 (gated) or 16 (orig). */
+int32_t sphnca_mlp_wgrad_workspace_bytes(int64_t N, size_t* bytes);
+int32_t sphnca_mlp_wgrad(int64_t N, const float* A_s, const float* Y_s, const float* dO_s, const float* Ht,
+                         const float* dHt, int32_t n_out, float* dW1, float* db1, float* dW2, float* db2,
+                         void* workspace, size_t workspace_bytes, void* stream);
 /* sphnca_step_adjoint: dA_s = dAdir_s + (adjoint of the perception sweep applied to dY_s). */
 int32_t sphnca_step_adjoint(const sphnca_grid* g, const float* xv4, const float* dY_s, const float* dAdir_s,
                             const sphnca_step_params* p, float* dA_s, void* stream);

@@ -83,8 +83,10 @@ inline double spiky_norm(int dim, double h) {
 // same cell more than once -- reproduced here because the loop is the same.
 // `fn(q)` is called for every candidate sorted position q, in the reference's order.
 // ------------------------------------------------------------------------------------------
+// `fn(q0, q1)` is called for every contiguous run [q0,q1) of candidate sorted positions, in the
+// reference's visiting order.  The three x-cells of a stencil row are one run when they do not wrap.
 template <int D, typename Fn>
-__device__ __forceinline__ void for_each_candidate(const GridView& g, int gcell, Fn&& fn) {
+__device__ __forceinline__ void for_each_run(const GridView& g, int gcell, Fn&& fn) {
     const int section = gcell / g.cells;
     const int cell = gcell - section * g.cells;
     const int base = section * g.cells;
@@ -98,34 +100,33 @@ __device__ __forceinline__ void for_each_candidate(const GridView& g, int gcell,
         cy = cell / dx; cx = cell - cy * dx;
     }
     // wrapped neighbour coordinates per axis: (c + dims + d) % dims for d = -1, 0, 1
-    int nx[3], ny[3], nz[3];
-#pragma unroll
-    for (int o = 0; o < 3; ++o) {
-        nx[o] = (cx + dx + o - 1) % dx;
-        ny[o] = (cy + dy + o - 1) % dy;
-        nz[o] = D == 3 ? (cz + g.dims[2] + o - 1) % g.dims[2] : 0;
-    }
+    const int x0 = (cx + dx - 1) % dx, x2 = (cx + 1) % dx;
+    const bool contiguous = (x0 + 1 == cx) && (cx + 1 == x2);
     constexpr int NZ = D == 3 ? 3 : 1;
 #pragma unroll 1
     for (int oz = 0; oz < NZ; ++oz) {
+        const int z = D == 3 ? (cz + g.dims[2] + oz - 1) % g.dims[2] : 0;
 #pragma unroll 1
         for (int oy = 0; oy < 3; ++oy) {
-            const int row = base + (nz[oz] * dy + ny[oy]) * dx;
-            // fast path: the three x-cells are consecutive -> one contiguous run of candidates
-            if (nx[0] + 1 == nx[1] && nx[1] + 1 == nx[2]) {
-                const int q0 = g.cell_off[row + nx[0]];
-                const int q1 = g.cell_off[row + nx[2] + 1];
-                for (int q = q0; q < q1; ++q) fn(q);
+            const int y = (cy + dy + oy - 1) % dy;
+            const int row = base + (z * dy + y) * dx;
+            if (contiguous) {
+                fn(g.cell_off[row + x0], g.cell_off[row + x2 + 1]);
             } else {
-#pragma unroll 1
-                for (int ox = 0; ox < 3; ++ox) {
-                    const int q0 = g.cell_off[row + nx[ox]];
-                    const int q1 = g.cell_off[row + nx[ox] + 1];
-                    for (int q = q0; q < q1; ++q) fn(q);
-                }
+                fn(g.cell_off[row + x0], g.cell_off[row + x0 + 1]);
+                fn(g.cell_off[row + cx], g.cell_off[row + cx + 1]);
+                fn(g.cell_off[row + x2], g.cell_off[row + x2 + 1]);
             }
         }
     }
+}
+
+// `fn(q)` for every candidate sorted position q, in the reference's order.
+template <int D, typename Fn>
+__device__ __forceinline__ void for_each_candidate(const GridView& g, int gcell, Fn&& fn) {
+    for_each_run<D>(g, gcell, [&](int q0, int q1) {
+        for (int q = q0; q < q1; ++q) fn(q);
+    });
 }
 
 // spiky gradient weight 3 (h-d)^2 / d for 0 < d < h, else 0 (kernels_impl.py:143-156).

@@ -13,23 +13,9 @@
 // hidden layer) and step_adjoint_kernel (gather adjoint of the gradient sweep; deterministic).
 //
 // All arrays are in cell-sorted order.  v1: the MLP runs on the fp32 CUDA-core pipe.
-#include "common.cuh"
+#include "step_common.cuh"
 
 namespace sphnca {
-
-constexpr int NF = 16;        // channels
-constexpr int NIN = 48;       // MLP input  [A | dA/dx | dA/dy]
-constexpr int NH = 256;       // hidden width
-constexpr int NO_PAD = 36;    // MLP output 33 (gated) / 16 (orig), padded for float4 rows
-constexpr int kStepThreads = 256;
-
-struct StepConsts {
-    float h, h2;
-    float cw;          // poly6 normalisation
-    float kg;          // spiky normalisation * perception scale
-    int use_alpha, rule, n_out;
-    float orig_rate;
-};
 
 struct MlpSmem {
     float W1[NH][NIN];       // row n = weights of hidden unit n (48 KB)
@@ -48,22 +34,6 @@ __device__ __forceinline__ void stage_weights(MlpSmem& s, const sphnca_step_para
     }
     for (int i = threadIdx.x; i < NH; i += blockDim.x) s.b1[i] = __ldg(p.b1 + i);
     if (threadIdx.x < NO_PAD) s.b2[threadIdx.x] = threadIdx.x < n_out ? __ldg(p.b2 + threadIdx.x) : 0.f;
-}
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-
-template <int D>
-__device__ __forceinline__ float pair_d2(const float4& a, const float4& b, float& rx, float& ry) {
-    rx = b.x - a.x; ry = b.y - a.y;
-    float d2 = fmaf(ry, ry, rx * rx);
-    if (D == 3) { const float rz = b.z - a.z; d2 = fmaf(rz, rz, d2); }
-    return d2;
-}
-
-__device__ __forceinline__ void load16(const float* __restrict__ p, float (&o)[NF]) {
-    const float4* p4 = reinterpret_cast<const float4*>(p);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { float4 t = __ldg(p4 + k); o[4*k] = t.x; o[4*k+1] = t.y; o[4*k+2] = t.z; o[4*k+3] = t.w; }
 }
 
 // hidden pre-activation of unit n for perception vector y (48 FMA, broadcast smem reads)
@@ -210,7 +180,8 @@ __global__ void __launch_bounds__(kStepThreads, 1)
 step_bwd_kernel(int n_total, const float* __restrict__ A_s, const float* __restrict__ Y_s,
                 const float* __restrict__ O_s, const uint8_t* __restrict__ flags_s,
                 const float* __restrict__ dAn_s, sphnca_step_params prm, StepConsts c,
-                float* __restrict__ dO_s, float* __restrict__ dY_s, float* __restrict__ dAdir_s) {
+                float* __restrict__ dO_s, float* __restrict__ dY_s, float* __restrict__ dAdir_s,
+                float* __restrict__ Ht, float* __restrict__ dHt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MlpSmem& s = *reinterpret_cast<MlpSmem*>(smem_raw);
     stage_weights(s, prm, c.n_out);
@@ -277,6 +248,11 @@ step_bwd_kernel(int n_total, const float* __restrict__ A_s, const float* __restr
                 d2 = fmaf(t.z, dO[4*k+2], d2); d3 = fmaf(t.w, dO[4*k+3], d3);
             }
             const float dh = pre > 0.f ? (d0 + d1) + (d2 + d3) : 0.f;
+            if (Ht) {   // tile-blocked [p/32][256][32]: a warp writes 128 contiguous bytes per hidden unit
+                const size_t o = ((size_t)(p >> 5) * NH + n) * 32 + (p & 31);
+                Ht[o] = fmaxf(pre, 0.f);
+                dHt[o] = dh;
+            }
             const float4* w1 = reinterpret_cast<const float4*>(&s.W1[n][0]);
 #pragma unroll
             for (int k = 0; k < NIN / 4; ++k) {
@@ -284,6 +260,13 @@ step_bwd_kernel(int n_total, const float* __restrict__ A_s, const float* __restr
                 dy[4*k] = fmaf(t.x, dh, dy[4*k]); dy[4*k+1] = fmaf(t.y, dh, dy[4*k+1]);
                 dy[4*k+2] = fmaf(t.z, dh, dy[4*k+2]); dy[4*k+3] = fmaf(t.w, dh, dy[4*k+3]);
             }
+        }
+    } else if (Ht) {
+        // no lane of this warp fired: dO == 0, so dH == 0 and H is multiplied by zero downstream
+#pragma unroll 4
+        for (int n = 0; n < NH; ++n) {
+            const size_t o = ((size_t)(p >> 5) * NH + n) * 32 + (p & 31);
+            Ht[o] = 0.f; dHt[o] = 0.f;
         }
     }
     float4* d4 = reinterpret_cast<float4*>(dAdir_s + (size_t)p * NF);
@@ -338,18 +321,6 @@ step_adjoint_kernel(GridView g, const float4* __restrict__ xv4, const float* __r
     for (int k = 0; k < 4; ++k) o4[k] = make_float4(r[4*k], r[4*k+1], r[4*k+2], r[4*k+3]);
 }
 
-static int make_consts(const sphnca_grid* g, const sphnca_step_params* p, StepConsts* c) {
-    if (!p || !p->W1 || !p->b1 || !p->W2 || !p->b2) { set_error("step params / weights are NULL"); return SPHNCA_ERR_INVALID; }
-    if (p->update_rule != 0 && p->update_rule != 1) { set_error("update_rule must be 0 (gated) or 1 (orig)"); return SPHNCA_ERR_INVALID; }
-    if (((uintptr_t)p->W1 & 15) != 0) { set_error("W1 must be 16-byte aligned"); return SPHNCA_ERR_INVALID; }
-    c->h = (float)g->h; c->h2 = (float)(g->h * g->h);
-    c->cw = (float)poly6_norm(g->dim, g->h);
-    c->kg = (float)(spiky_norm(g->dim, g->h) * (double)p->perception_scale);
-    c->use_alpha = p->use_alpha; c->rule = p->update_rule; c->n_out = p->update_rule == 0 ? 2 * NF + 1 : NF;
-    c->orig_rate = p->orig_rate;
-    return SPHNCA_OK;
-}
-
 }  // namespace sphnca
 
 using namespace sphnca;
@@ -364,6 +335,8 @@ int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s
     cudaStream_t stream = as_stream(stream_);
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(xv4 && A_s && fire_s && A_new_s && alive_s && Y_s && O_s && flags_s, "NULL argument");
+    if (mlp_path() >= 1)
+        return launch_step_fwd_tc(gv, c, p, xv4, A_s, fire_s, A_new_s, alive_s, Y_s, O_s, flags_s, stream);
     const int blocks = (int)((gv.n + kStepThreads - 1) / kStepThreads);
     const size_t smem = sizeof(MlpSmem);
     if (gv.dim == 3) {
@@ -394,17 +367,18 @@ int32_t sphnca_step_mask(const sphnca_grid* g, const float* xv4, const uint8_t* 
 
 int32_t sphnca_step_bwd(int64_t N, const float* A_s, const float* Y_s, const float* O_s, const uint8_t* flags_s,
                         const float* dA_next_s, const sphnca_step_params* p, float* dO_s, float* dY_s,
-                        float* dAdir_s, void* stream_) {
+                        float* dAdir_s, float* Ht, float* dHt, void* stream_) {
     SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
     sphnca_grid fake{}; fake.dim = 3; fake.h = 1.0;      // only the rule / rates of the constants are used here
     StepConsts c; { int rc = make_consts(&fake, p, &c); if (rc) return rc; }
     cudaStream_t stream = as_stream(stream_);
     if (N == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(A_s && Y_s && O_s && flags_s && dA_next_s && dO_s && dY_s && dAdir_s, "NULL argument");
+    SPHNCA_CHECK_ARG((Ht == nullptr) == (dHt == nullptr), "Ht and dHt must be given together");
     const size_t smem = sizeof(MlpSmem);
     SPHNCA_CUDA(cudaFuncSetAttribute(step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPHNCA_LAUNCH(step_bwd_kernel, (int)((N + kStepThreads - 1) / kStepThreads), kStepThreads, smem, stream,
-                  (int)N, A_s, Y_s, O_s, flags_s, dA_next_s, *p, c, dO_s, dY_s, dAdir_s);
+                  (int)N, A_s, Y_s, O_s, flags_s, dA_next_s, *p, c, dO_s, dY_s, dAdir_s, Ht, dHt);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

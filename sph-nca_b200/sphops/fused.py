@@ -89,32 +89,41 @@ class _NCAStep(torch.autograd.Function):
         dY_s = torch.empty((N, 32), **f32)
         dAdir_s = torch.empty((N, 16), **f32)
         p = _step_params(W1, b1, W2, b2, *ctx.cfg)
+        g = ctx.needs_input_grad
+        want_w = any(g[4:8])
+        dW1 = db1 = dW2 = db2 = None
+        if want_w:
+            dW1, db1, dW2, db2 = torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2), torch.zeros_like(b2)
         if N:
             st = stream_ptr()
-            _timed("step_bwd", lib.sphnca_step_bwd, N, ptr(A_s), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(dAn_s),
-                   C.byref(p), ptr(dO_s), ptr(dY_s), ptr(dAdir_s), st)
+            # particles are processed in chunks so that the transposed hidden activations
+            # (2 x [chunk/32][256][32] fp32, 2 KB per particle) stay bounded for very large clouds
+            chunk = min(N, WGRAD_CHUNK)
+            Ht = dHt = ws = None
+            if want_w:
+                tiles = (chunk + 31) // 32          # [tiles][256][32], see include/sphnca.h
+                Ht = torch.empty((tiles, 256, 32), **f32)
+                dHt = torch.empty((tiles, 256, 32), **f32)
+                nb = C.c_size_t(0)
+                check(lib.sphnca_mlp_wgrad_workspace_bytes(chunk, C.byref(nb)))
+                ws = torch.empty((nb.value,), dtype=torch.uint8, device=dev)
+            for lo in range(0, N, chunk):
+                n = min(chunk, N - lo)
+                Hc, dHc = Ht, dHt
+                _timed("step_bwd", lib.sphnca_step_bwd, n, ptr(A_s[lo:]), ptr(Y_s[lo:]), ptr(O_s[lo:]), ptr(flags_s[lo:]),
+                       ptr(dAn_s[lo:]), C.byref(p), ptr(dO_s[lo:]), ptr(dY_s[lo:]), ptr(dAdir_s[lo:]), ptr(Hc), ptr(dHc), st)
+                if want_w:
+                    _timed("mlp_wgrad", lib.sphnca_mlp_wgrad, n, ptr(A_s[lo:]), ptr(Y_s[lo:]), ptr(dO_s[lo:]), ptr(Hc), ptr(dHc),
+                           n_out, ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value, st)
             _timed("step_adjoint", lib.sphnca_step_adjoint, grid.c_grid(), ptr(xv4), ptr(dY_s), ptr(dAdir_s),
                    C.byref(p), ptr(dA_s), st)
-        g = ctx.needs_input_grad
         dA = grid.unpack_rows(dA_s, 16) if g[2] else None
-        dW1 = db1 = dW2 = db2 = None
-        if any(g[4:8]):
-            dW1, db1, dW2, db2 = _weight_grads(A_s, Y_s, dO_s[:, :n_out], W1, b1, W2)
         return (None, None, dA, None, dW1 if g[4] else None, db1 if g[5] else None,
                 dW2 if g[6] else None, db2 if g[7] else None, None, None, None, None, None, None)
 
 
-def _weight_grads(A_s, Y_s, dO, W1, b1, W2):
-    """Parameter gradients of the 48->256->n_out MLP from the saved perception and dL/d(output).
-
-    v1: the hidden layer is recomputed and the four reductions over particles are library GEMMs
-    (torch/cuBLAS fp32).  They are the only library calls on the step path; the hand-written
-    tcgen05 weight-gradient kernel replaces them."""
-    Yfull = torch.cat([A_s, Y_s], dim=1)                    # [N,48]
-    pre = torch.addmm(b1, Yfull, W1.t())                    # [N,256]
-    dH = (dO @ W2) * (pre > 0)                              # [N,256]
-    H = torch.relu_(pre)
-    return dH.t() @ Yfull, dH.sum(0), dO.t() @ H, dO.sum(0)
+# particles per backward chunk (bounds the [256][chunk] x 2 fp32 scratch to 8 GB)
+WGRAD_CHUNK = 4 * 1024 * 1024
 
 
 def nca_step(x, v, A, update_mask, W1, b1, W2, b2, h, grid, update_rule="gated", use_alpha=True,

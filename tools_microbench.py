@@ -1,0 +1,34 @@
+"""Kernel micro-benchmark through the C ABI (development aid): times sphnca_step_fwd variants with CUDA events."""
+import ctypes as C, math, sys, os
+ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "sph-nca_b200"))
+import torch, numpy as np
+import sphops
+from sphops import _lib, fused
+from bench import make_inputs, WORKLOADS, load_weights
+dev = "cuda"
+wl = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "train2d_b8x65k_k64"]
+x, A, sections, h, dims = make_inputs(wl, 0)
+if x.shape[1] == 2: x = torch.nn.functional.pad(x, (0, 1))
+x = x.to(dev); A = A.to(dev); N = x.shape[0]
+grid = sphops.initialize_hashgrid(x, sections, h, dims)
+v = sphops.volume(x, h, grid)
+W = [t.to(dev) for t in load_weights()]
+xv4 = grid.sorted_xv(x, v); A_s = grid.pack_rows(A, 16)
+fire_s = grid.pack_bytes((torch.rand(N, device=dev) <= 0.5).to(torch.uint8))
+An = torch.zeros(N, 16, device=dev); Y = torch.zeros(N, 32, device=dev); O = torch.zeros(N, 36, device=dev)
+fl = torch.zeros(N, dtype=torch.uint8, device=dev); al = torch.zeros(N, dtype=torch.uint8, device=dev)
+p = fused._step_params(*W, "gated", False, 1.0 / h, 1.0)
+def run():
+    _lib.check(_lib.lib.sphnca_step_fwd(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(A_s), _lib.ptr(fire_s), C.byref(p),
+               _lib.ptr(An), _lib.ptr(al), _lib.ptr(Y), _lib.ptr(O), _lib.ptr(fl), _lib.stream_ptr()))
+for path, name in ((0, "simt"), (1, "tcgen05"), (2, "tcgen05, neighbour loop skipped (debug)")):
+    _lib.check(_lib.lib.sphnca_set_mlp_path(path))
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10): run()
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    print(f"step_fwd [{name}]: {ms:.4f} ms  ({N/ms/1e6:.2f} G particles/s, {ms*1e-3*1.965e9*148/N:.0f} clk*SM/particle)")
+_lib.check(_lib.lib.sphnca_set_mlp_path(1))
