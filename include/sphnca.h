@@ -119,11 +119,12 @@ typedef struct sphnca_step_params {
  *   in : xv4, A_s [N,16], fire_s uint8 [N] (the `torch.rand(N) <= fire_rate` draw)
  *   out: A_new_s [N,16] (not yet life-masked), alive_s uint8 [N] (activity(A_new) > 0.1),
  *        saved for backward: Y_s [N,32] (scaled dA/dx | dA/dy), O_s [N,36] (MLP output before the
- *        gate non-linearities, columns >= n_out zero), flags_s uint8 [N] (bit0 prev_mask, bit2 fire). */
+ *        gate non-linearities, columns >= n_out zero), flags_s uint8 [N] (bit0 prev_mask, bit2 fire),
+ *        relu_s uint32 [N,8] (bit n%32 of word n/32 = hidden unit n is active, i.e. pre-activation > 0). */
 int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s,
                         const uint8_t* fire_s, const sphnca_step_params* p,
                         float* A_new_s, uint8_t* alive_s, float* Y_s, float* O_s, uint8_t* flags_s,
-                        void* stream);
+                        uint32_t* relu_s, void* stream);
 /* Implementation switch for sphnca_step_fwd: 1 (default) = tcgen05 tensor-core MLP with the 3xTF32
  * split (csrc/step_tc.cu), 0 = fp32 CUDA-core MLP (csrc/step.cu).  Both produce the same outputs
  * to fp32 rounding; the switch exists for A/B tests. */
@@ -139,19 +140,23 @@ int32_t sphnca_step_mask(const sphnca_grid* g, const float* xv4, const uint8_t* 
  *   dO_s [N,36] = dL/d(MLP output) (for the weight-gradient stage), dY_s [N,32] = dL/dY,
  *   dAdir_s [N,16] = the part of dL/dA that does not pass through the sweep. */
 int32_t sphnca_step_bwd(int64_t N, const float* A_s, const float* Y_s, const float* O_s,
-                        const uint8_t* flags_s, const float* dA_next_s, const sphnca_step_params* p,
-                        float* dO_s, float* dY_s, float* dAdir_s, float* Ht, float* dHt, void* stream);
+                        const uint8_t* flags_s, const uint32_t* relu_s, const float* dA_next_s,
+                        const sphnca_step_params* p, float* dO_s, float* dY_s, float* dAdir_s,
+                        float* Ht, float* dHt, void* stream);
+/*   relu_s: the ReLU bits saved by sphnca_step_fwd (used by the tensor-core path, which needs no recompute). */
 /*   Ht, dHt (both or neither, may be NULL): hidden activations relu(pre) and dL/d(pre), transposed and
  *   tile-blocked for sphnca_mlp_wgrad: float [ceil(N/32)][256][32], element (p, n) at
  *   ((p/32)*256 + n)*32 + p%32. */
 
 /* Weight gradients of the MLP, ACCUMULATED (+=) into dW1 [256,48], db1 [256], dW2 [n_out,256],
  * db2 [n_out] (replaces torch autograd's GEMMs over `model.0` / `model.2`, code/nca.py:96,151).
- * Deterministic two-stage reduction.  n_out = 33 (gated) or 16 (orig). */
+ * Deterministic two-stage reduction.  With Ht == dHt == NULL (default) the hidden layer is recomputed
+ * on the tensor cores from (A_s, Y_s, dO_s) and the weights in `p`; with Ht/dHt given (the CUDA-core
+ * sphnca_step_bwd wrote them) they are streamed instead. */
 int32_t sphnca_mlp_wgrad_workspace_bytes(int64_t N, size_t* bytes);
 int32_t sphnca_mlp_wgrad(int64_t N, const float* A_s, const float* Y_s, const float* dO_s, const float* Ht,
-                         const float* dHt, int32_t n_out, float* dW1, float* db1, float* dW2, float* db2,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         const float* dHt, const sphnca_step_params* p, float* dW1, float* db1, float* dW2,
+                         float* db2, void* workspace, size_t workspace_bytes, void* stream);
 /* sphnca_step_adjoint: dA_s = dAdir_s + (adjoint of the perception sweep applied to dY_s). */
 int32_t sphnca_step_adjoint(const sphnca_grid* g, const float* xv4, const float* dY_s, const float* dAdir_s,
                             const sphnca_step_params* p, float* dA_s, void* stream);

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kStepThreads, 2)
 step_fwd_kernel(GridView g, const float4* __restrict__ xv4, const float* __restrict__ A_s,
                 const uint8_t* __restrict__ fire_s, sphnca_step_params prm, StepConsts c,
                 float* __restrict__ An_s, float* __restrict__ Y_s, float* __restrict__ O_s,
-                uint8_t* __restrict__ flags_s, uint8_t* __restrict__ alive_s) {
+                uint8_t* __restrict__ flags_s, uint8_t* __restrict__ alive_s, uint32_t* __restrict__ relu_s) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MlpSmem& s = *reinterpret_cast<MlpSmem*>(smem_raw);
     stage_weights(s, prm, c.n_out);
@@ -104,16 +104,25 @@ step_fwd_kernel(GridView g, const float4* __restrict__ xv4, const float* __restr
     float out[NO_PAD];
 #pragma unroll
     for (int o = 0; o < NO_PAD; ++o) out[o] = s.b2[o];
+    uint32_t* rm = relu_s + (size_t)p * (NH / 32);
+#pragma unroll 1
+    for (int nw = 0; nw < NH / 32; ++nw) {
+        uint32_t bits = 0;
 #pragma unroll 2
-    for (int n = 0; n < NH; ++n) {
-        const float hval = fmaxf(hidden_pre(s, n, y), 0.f);
-        const float4* w2 = reinterpret_cast<const float4*>(&s.W2t[n][0]);
+        for (int nb = 0; nb < 32; ++nb) {
+            const int n = nw * 32 + nb;
+            const float pre = hidden_pre(s, n, y);
+            bits |= (pre > 0.f ? 1u : 0u) << nb;
+            const float hval = fmaxf(pre, 0.f);
+            const float4* w2 = reinterpret_cast<const float4*>(&s.W2t[n][0]);
 #pragma unroll
-        for (int k = 0; k < NO_PAD / 4; ++k) {
-            const float4 t = w2[k];
-            out[4*k] = fmaf(t.x, hval, out[4*k]); out[4*k+1] = fmaf(t.y, hval, out[4*k+1]);
-            out[4*k+2] = fmaf(t.z, hval, out[4*k+2]); out[4*k+3] = fmaf(t.w, hval, out[4*k+3]);
+            for (int k = 0; k < NO_PAD / 4; ++k) {
+                const float4 t = w2[k];
+                out[4*k] = fmaf(t.x, hval, out[4*k]); out[4*k+1] = fmaf(t.y, hval, out[4*k+1]);
+                out[4*k+2] = fmaf(t.z, hval, out[4*k+2]); out[4*k+3] = fmaf(t.w, hval, out[4*k+3]);
+            }
         }
+        rm[nw] = bits;        // ReLU activity bits of hidden units 32*nw .. 32*nw+31 (saved for backward)
     }
 
     // ---- update rule + stochastic fire mask (nca.py:100-110) ----
@@ -329,22 +338,22 @@ extern "C" {
 
 int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s, const uint8_t* fire_s,
                         const sphnca_step_params* p, float* A_new_s, uint8_t* alive_s, float* Y_s, float* O_s,
-                        uint8_t* flags_s, void* stream_) {
+                        uint8_t* flags_s, uint32_t* relu_s, void* stream_) {
     GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
     StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
     cudaStream_t stream = as_stream(stream_);
     if (gv.n == 0) return SPHNCA_OK;
-    SPHNCA_CHECK_ARG(xv4 && A_s && fire_s && A_new_s && alive_s && Y_s && O_s && flags_s, "NULL argument");
+    SPHNCA_CHECK_ARG(xv4 && A_s && fire_s && A_new_s && alive_s && Y_s && O_s && flags_s && relu_s, "NULL argument");
     if (mlp_path() >= 1)
-        return launch_step_fwd_tc(gv, c, p, xv4, A_s, fire_s, A_new_s, alive_s, Y_s, O_s, flags_s, stream);
+        return launch_step_fwd_tc(gv, c, p, xv4, A_s, fire_s, A_new_s, alive_s, Y_s, O_s, flags_s, relu_s, stream);
     const int blocks = (int)((gv.n + kStepThreads - 1) / kStepThreads);
     const size_t smem = sizeof(MlpSmem);
     if (gv.dim == 3) {
         SPHNCA_CUDA(cudaFuncSetAttribute(step_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SPHNCA_LAUNCH(step_fwd_kernel<3>, blocks, kStepThreads, smem, stream, gv, (const float4*)xv4, A_s, fire_s, *p, c, A_new_s, Y_s, O_s, flags_s, alive_s);
+        SPHNCA_LAUNCH(step_fwd_kernel<3>, blocks, kStepThreads, smem, stream, gv, (const float4*)xv4, A_s, fire_s, *p, c, A_new_s, Y_s, O_s, flags_s, alive_s, relu_s);
     } else {
         SPHNCA_CUDA(cudaFuncSetAttribute(step_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SPHNCA_LAUNCH(step_fwd_kernel<2>, blocks, kStepThreads, smem, stream, gv, (const float4*)xv4, A_s, fire_s, *p, c, A_new_s, Y_s, O_s, flags_s, alive_s);
+        SPHNCA_LAUNCH(step_fwd_kernel<2>, blocks, kStepThreads, smem, stream, gv, (const float4*)xv4, A_s, fire_s, *p, c, A_new_s, Y_s, O_s, flags_s, alive_s, relu_s);
     }
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
@@ -366,8 +375,8 @@ int32_t sphnca_step_mask(const sphnca_grid* g, const float* xv4, const uint8_t* 
 }
 
 int32_t sphnca_step_bwd(int64_t N, const float* A_s, const float* Y_s, const float* O_s, const uint8_t* flags_s,
-                        const float* dA_next_s, const sphnca_step_params* p, float* dO_s, float* dY_s,
-                        float* dAdir_s, float* Ht, float* dHt, void* stream_) {
+                        const uint32_t* relu_s, const float* dA_next_s, const sphnca_step_params* p, float* dO_s,
+                        float* dY_s, float* dAdir_s, float* Ht, float* dHt, void* stream_) {
     SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
     sphnca_grid fake{}; fake.dim = 3; fake.h = 1.0;      // only the rule / rates of the constants are used here
     StepConsts c; { int rc = make_consts(&fake, p, &c); if (rc) return rc; }
@@ -375,6 +384,10 @@ int32_t sphnca_step_bwd(int64_t N, const float* A_s, const float* Y_s, const flo
     if (N == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(A_s && Y_s && O_s && flags_s && dA_next_s && dO_s && dY_s && dAdir_s, "NULL argument");
     SPHNCA_CHECK_ARG((Ht == nullptr) == (dHt == nullptr), "Ht and dHt must be given together");
+    if (mlp_path() >= 1 && Ht == nullptr) {
+        SPHNCA_CHECK_ARG(relu_s != nullptr, "relu_s is required by the tensor-core data-gradient path");
+        return launch_step_bwd_tc(N, c, p, A_s, O_s, flags_s, relu_s, dA_next_s, dO_s, dY_s, dAdir_s, stream);
+    }
     const size_t smem = sizeof(MlpSmem);
     SPHNCA_CUDA(cudaFuncSetAttribute(step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPHNCA_LAUNCH(step_bwd_kernel, (int)((N + kStepThreads - 1) / kStepThreads), kStepThreads, smem, stream,

@@ -51,6 +51,13 @@ inline int make_consts(const sphnca_grid* g, const sphnca_step_params* p, StepCo
 int mlp_path();
 int launch_step_fwd_tc(const GridView& gv, const StepConsts& c, const sphnca_step_params* p, const float* xv4,
                        const float* A_s, const uint8_t* fire_s, float* A_new_s, uint8_t* alive_s, float* Y_s,
-                       float* O_s, uint8_t* flags_s, cudaStream_t stream);
+                       float* O_s, uint8_t* flags_s, uint32_t* relu_s, cudaStream_t stream);
+
+int launch_step_bwd_tc(int64_t N, const StepConsts& c, const sphnca_step_params* p, const float* A_s, const float* O_s,
+                       const uint8_t* flags_s, const uint32_t* relu_s, const float* dA_next_s, float* dO_s, float* dY_s,
+                       float* dAdir_s, cudaStream_t stream);
+int wgrad_tc_streams(int64_t N);
+int launch_mlp_wgrad_tc(int64_t N, const float* A_s, const float* Y_s, const float* dO_s, const sphnca_step_params* p,
+                        int n_out, float* partial, int part_floats, int streams, cudaStream_t stream);
 
 }  // namespace sphnca

@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 step_fwd_tc_kernel(GridView g, const float4* __restrict__ xv4, const float* __restrict__ A_s,
                    const uint8_t* __restrict__ fire_s, sphnca_step_params prm, StepConsts c,
                    float* __restrict__ An_s, float* __restrict__ Y_s, float* __restrict__ O_s,
-                   uint8_t* __restrict__ flags_s, uint8_t* __restrict__ alive_s, int num_tiles, int dbg) {
+                   uint8_t* __restrict__ flags_s, uint8_t* __restrict__ alive_s, uint32_t* __restrict__ relu_s,
+                   int num_tiles, int dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -103,6 +104,7 @@ step_fwd_tc_kernel(GridView g, const float4* __restrict__ xv4, const float* __re
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int p = tile * TILE + m;
             const bool valid = p < g.n;
+            if (st == 0) SPHNCA_TL(0);
             float Ai[NF], gx[NF], gy[NF];
             float blur = 0.f;
 #pragma unroll
@@ -137,6 +139,7 @@ step_fwd_tc_kernel(GridView g, const float4* __restrict__ xv4, const float* __re
                     }
                 });
             }
+            if (st == 0) SPHNCA_TL(1);
             // butterfly over the 4 lanes of a particle: every lane ends with the full sums
 #pragma unroll
             for (int o = 1; o < SWEEP_LANES; o <<= 1) {
@@ -151,6 +154,7 @@ step_fwd_tc_kernel(GridView g, const float4* __restrict__ xv4, const float* __re
             for (int f = 0; f < NF; ++f) { gx[f] *= c.kg; gy[f] *= c.kg; }
 
             mbar_wait(&s.bar[Y_EMPTY], (it & 1) ^ 1);      // GEMM1 of the previous tile has consumed Y
+            if (st == 0) SPHNCA_TL(2);
             // perception row y = [A | gx | gy] = 12 chunks of 4; lane `sub` writes chunks 3*sub .. 3*sub+2
 #pragma unroll
             for (int ch = 0; ch < NIN / 4; ++ch) {
@@ -182,6 +186,7 @@ step_fwd_tc_kernel(GridView g, const float4* __restrict__ xv4, const float* __re
             if (sub == 0) s.prev[it & 1][m] = (blur * c.cw > 0.1f) ? 1 : 0;
             fence_proxy_async_smem();
             mbar_arrive(&s.bar[Y_FULL]);
+            if (st == 0) SPHNCA_TL(3);
         }
     } else if (warp == MMA_WARP) {
         // =========================== tensor-core issue (one lane) ===========================
@@ -192,9 +197,10 @@ step_fwd_tc_kernel(GridView g, const float4* __restrict__ xv4, const float* __re
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 mbar_wait(&s.bar[Y_FULL], it & 1);
                 fence_after_sync();
+                SPHNCA_TL(4);
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
-                    if (half == 1) { mbar_wait(&s.bar[D1_EMPTY], 0); fence_after_sync(); }
+                    if (half == 1) { mbar_wait(&s.bar[D1_EMPTY], 0); fence_after_sync(); SPHNCA_TL(6); }
                     else if (it > 0) { mbar_wait(&s.bar[D1_EMPTY], 1); fence_after_sync(); }
                     const uint32_t wh = smem_u32(s.W1_hi[half]), wl = smem_u32(s.W1_lo[half]);
 #pragma unroll
@@ -208,6 +214,7 @@ step_fwd_tc_kernel(GridView g, const float4* __restrict__ xv4, const float* __re
                         mma_tf32_ss(tbase + COL_D1, a_hi, b_hi, idesc1, true);
                     }
                     mma_commit(&s.bar[D1_FULL]);
+                    SPHNCA_TL(5 + 2 * half);
                 }
                 mma_commit(&s.bar[Y_EMPTY]);                  // all GEMM1 reads of the Y tile are done
                 mbar_wait(&s.bar[D2_EMPTY], (it & 1) ^ 1);    // epilogue drained D2 of the previous tile
@@ -215,6 +222,7 @@ step_fwd_tc_kernel(GridView g, const float4* __restrict__ xv4, const float* __re
                 for (int half = 0; half < 2; ++half) {
                     mbar_wait(&s.bar[H_FULL], half);
                     fence_after_sync();
+                    SPHNCA_TL(8 + 2 * half);
                     const uint32_t wh = smem_u32(s.W2_hi[half]), wl = smem_u32(s.W2_lo[half]);
 #pragma unroll
                     for (int ks = 0; ks < 128 / 8; ++ks) {
@@ -225,6 +233,7 @@ step_fwd_tc_kernel(GridView g, const float4* __restrict__ xv4, const float* __re
                         mma_tf32_ts(tbase + COL_D2, tbase + COL_HHI + 8 * ks, b_hi, idesc2, true);
                     }
                     mma_commit(&s.bar[H_EMPTY]);
+                    SPHNCA_TL(9 + 2 * half);
                 }
                 mma_commit(&s.bar[D2_FULL]);
             }
@@ -238,24 +247,32 @@ step_fwd_tc_kernel(GridView g, const float4* __restrict__ xv4, const float* __re
             const int p = tile * TILE + m;
             const bool valid = p < g.n;
             float o32 = 0.f;
-#pragma unroll 1
+            uint32_t rmask[NH / 32];
+#pragma unroll
+            for (int wd = 0; wd < NH / 32; ++wd) rmask[wd] = 0u;
+#pragma unroll
             for (int half = 0; half < 2; ++half) {
                 mbar_wait(&s.bar[D1_FULL], half);
                 mbar_wait(&s.bar[H_EMPTY], half ^ 1);        // GEMM2 finished with the previous H
                 fence_after_sync();
-#pragma unroll 1
+                if (tid == 0) SPHNCA_TL(12 + half);
+#pragma unroll
                 for (int cc = 0; cc < 128; cc += 16) {
                     uint32_t r[16], hi[16], lo[16];
                     tmem_ld16(lane_addr + COL_D1 + cc, r);
                     wait_ld();
+                    uint32_t bits = 0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int n = half * 128 + cc + j;
-                        const float hv = fmaxf(__uint_as_float(r[j]) + s.b1[n], 0.f);
+                        const float pre = __uint_as_float(r[j]) + s.b1[n];
+                        bits |= (pre > 0.f ? 1u : 0u) << j;
+                        const float hv = fmaxf(pre, 0.f);
                         o32 = fmaf(hv, s.w2_last[n], o32);
                         float h_, l_; split_tf32(hv, h_, l_);
                         hi[j] = __float_as_uint(h_); lo[j] = __float_as_uint(l_);
                     }
+                    rmask[(half * 128 + cc) >> 5] |= bits << (cc & 16);
                     tmem_st16(lane_addr + COL_HHI + cc, hi);
                     tmem_st16(lane_addr + COL_HLO + cc, lo);
                 }
@@ -266,6 +283,7 @@ step_fwd_tc_kernel(GridView g, const float4* __restrict__ xv4, const float* __re
             }
             mbar_wait(&s.bar[D2_FULL], it & 1);
             fence_after_sync();
+            if (tid == 0) SPHNCA_TL(14);
             float out[NO_PAD];
             {
                 uint32_t r[16];
@@ -303,9 +321,13 @@ step_fwd_tc_kernel(GridView g, const float4* __restrict__ xv4, const float* __re
                 float4* oo4 = reinterpret_cast<float4*>(O_s + (size_t)p * NO_PAD);
 #pragma unroll
                 for (int k = 0; k < NO_PAD / 4; ++k) oo4[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+                uint4* rm4 = reinterpret_cast<uint4*>(relu_s + (size_t)p * (NH / 32));
+                rm4[0] = make_uint4(rmask[0], rmask[1], rmask[2], rmask[3]);
+                rm4[1] = make_uint4(rmask[4], rmask[5], rmask[6], rmask[7]);
                 flags_s[p] = (uint8_t)((s.prev[it & 1][m] ? 1 : 0) | (fire ? 4 : 0));
                 alive_s[p] = c.use_alpha ? (nA[3] > 0.1f ? 1 : 0) : 1;
             }
+            if (tid == 0) SPHNCA_TL(15);
         }
     }
     fence_before_sync();
@@ -318,7 +340,7 @@ int mlp_path() { return g_mlp_path; }
 
 int launch_step_fwd_tc(const GridView& gv, const StepConsts& c, const sphnca_step_params* p, const float* xv4,
                        const float* A_s, const uint8_t* fire_s, float* A_new_s, uint8_t* alive_s, float* Y_s,
-                       float* O_s, uint8_t* flags_s, cudaStream_t stream) {
+                       float* O_s, uint8_t* flags_s, uint32_t* relu_s, cudaStream_t stream) {
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -331,11 +353,11 @@ int launch_step_fwd_tc(const GridView& gv, const StepConsts& c, const sphnca_ste
     if (gv.dim == 3) {
         SPHNCA_CUDA(cudaFuncSetAttribute(step_fwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SPHNCA_LAUNCH(step_fwd_tc_kernel<3>, blocks, TC_THREADS, smem, stream, gv, (const float4*)xv4, A_s, fire_s, *p, c,
-                      A_new_s, Y_s, O_s, flags_s, alive_s, num_tiles, g_mlp_path);
+                      A_new_s, Y_s, O_s, flags_s, alive_s, relu_s, num_tiles, g_mlp_path);
     } else {
         SPHNCA_CUDA(cudaFuncSetAttribute(step_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SPHNCA_LAUNCH(step_fwd_tc_kernel<2>, blocks, TC_THREADS, smem, stream, gv, (const float4*)xv4, A_s, fire_s, *p, c,
-                      A_new_s, Y_s, O_s, flags_s, alive_s, num_tiles, g_mlp_path);
+                      A_new_s, Y_s, O_s, flags_s, alive_s, relu_s, num_tiles, g_mlp_path);
     }
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
@@ -348,3 +370,5 @@ extern "C" int32_t sphnca_set_mlp_path(int32_t path) {
     sphnca::g_mlp_path = path;
     return SPHNCA_OK;
 }
+
+SPHNCA_TIMELINE_READER(sphnca_debug_timeline_fwd)

@@ -117,4 +117,14 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 }
 
 }  // namespace tc
+
+// development aid: per-role clock64 timestamps of CTA 0, 16 slots per tile/chunk iteration.  One buffer
+// per translation unit (no relocatable device code); each kernel file exports its own reader.
+static __device__ long long g_timeline[64 * 16];
+#define SPHNCA_TL(slot) do { if (blockIdx.x == 0 && it < 64) sphnca::g_timeline[it * 16 + (slot)] = clock64(); } while (0)
+#define SPHNCA_TIMELINE_READER(name)                                                              \
+    extern "C" int32_t name(long long* out_host, int32_t n) {                                     \
+        if (n > 64 * 16) n = 64 * 16;                                                             \
+        return cudaMemcpyFromSymbol(out_host, sphnca::g_timeline, sizeof(long long) * n) == cudaSuccess ? 0 : -2; \
+    }
 }  // namespace sphnca

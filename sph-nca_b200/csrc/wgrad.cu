@@ -155,16 +155,31 @@ extern "C" {
 
 int32_t sphnca_mlp_wgrad_workspace_bytes(int64_t N, size_t* bytes) {
     SPHNCA_CHECK_ARG(N >= 0 && bytes, "bad argument");
-    *bytes = (size_t)wg_grid(N) * WG_PART * sizeof(float);
+    const int a = wg_grid(N), b = wgrad_tc_streams(N);
+    *bytes = (size_t)(a > b ? a : b) * WG_PART * sizeof(float);
     return SPHNCA_OK;
 }
 
 int32_t sphnca_mlp_wgrad(int64_t N, const float* A_s, const float* Y_s, const float* dO_s, const float* Ht,
-                         const float* dHt, int32_t n_out, float* dW1, float* db1, float* dW2, float* db2,
+                         const float* dHt, const sphnca_step_params* p, float* dW1, float* db1, float* dW2, float* db2,
                          void* workspace, size_t workspace_bytes, void* stream_) {
-    SPHNCA_CHECK_ARG(N >= 0 && (n_out == 33 || n_out == 16), "bad N / n_out");
+    SPHNCA_CHECK_ARG(N >= 0 && p && (p->update_rule == 0 || p->update_rule == 1), "bad N / params");
+    const int n_out = p->update_rule == 0 ? 2 * NF + 1 : NF;
     if (N == 0) return SPHNCA_OK;
-    SPHNCA_CHECK_ARG(A_s && Y_s && dO_s && Ht && dHt && dW1 && db1 && dW2 && db2, "NULL argument");
+    SPHNCA_CHECK_ARG(A_s && Y_s && dO_s && dW1 && db1 && dW2 && db2, "NULL argument");
+    SPHNCA_CHECK_ARG((Ht == nullptr) == (dHt == nullptr), "Ht and dHt must be given together");
+    if (Ht == nullptr) {
+        // tensor-core path: hidden layer recomputed in the transposed orientation (wgrad_tc.cu)
+        SPHNCA_CHECK_ARG(p->W1 && p->b1 && p->W2, "weights are required by the recompute path");
+        const int streams = wgrad_tc_streams(N);
+        if (!workspace || workspace_bytes < (size_t)streams * WG_PART * sizeof(float)) { set_error("wgrad workspace too small"); return SPHNCA_ERR_WORKSPACE; }
+        float* partial = reinterpret_cast<float*>(workspace);
+        int rc = launch_mlp_wgrad_tc(N, A_s, Y_s, dO_s, p, n_out, partial, WG_PART, streams, as_stream(stream_));
+        if (rc) return rc;
+        SPHNCA_LAUNCH(mlp_wgrad_reduce_kernel, (WG_PART + 255) / 256, 256, 0, as_stream(stream_), partial, streams, n_out, dW1, db1, dW2, db2);
+        SPHNCA_LAUNCH_CHECK();
+        return SPHNCA_OK;
+    }
     const int grid = wg_grid(N);
     if (!workspace || workspace_bytes < (size_t)grid * WG_PART * sizeof(float)) { set_error("wgrad workspace too small"); return SPHNCA_ERR_WORKSPACE; }
     cudaStream_t stream = as_stream(stream_);

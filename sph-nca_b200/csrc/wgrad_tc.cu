@@ -1,0 +1,386 @@
+// Weight gradients of the 48->256->n_out MLP on the Blackwell tensor path, from (y, dO) only:
+// the hidden layer is RECOMPUTED in the transposed orientation so that the contraction over
+// particles lands on the MMA K dimension with the A operand in TMEM:
+//
+//   recompute   D1t[128h x 64p] = W1_half[128h x 48] . y[64p x 48]^T          (pre-activations^T)
+//               D3t[128h x 64p] = W2t_half[128h x 32] . dO[64p x 32]^T        (dL/dH^T before the mask)
+//   epilogue    thread = hidden unit: H^T = relu(D1t + b1), dH^T = (D1t + b1 > 0) * (D3t + dO[:,32] W2[32][h]);
+//               tf32 hi/lo, written back IN PLACE as TMEM A operands [lanes = h][columns = p]
+//   accumulate  dW1_half[128h x 64] += dH^T . [y | 1 | 0]   (column 48 of the result = db1)
+//               dW2t_half[128h x 48] += H^T . dO            (B operands = K-major TRANSPOSED copies yT, dOT)
+//   the two accumulators (112 TMEM columns) live in TMEM for the whole CTA; one partial per CTA pair
+//   is written at the end and reduced in fixed order by mlp_wgrad_reduce_kernel (wgrad.cu).
+//
+// A CTA owns ONE hidden half (blockIdx.x & 1) and a contiguous range of 64-particle chunks, so the
+// weights it stages are halves: W1 48 KB + W2^T 32 KB (hi/lo); chunk operand tiles 96 KB.
+// No float atomics, fixed order everywhere: deterministic.
+#include "step_common.cuh"
+#include "tc_common.cuh"
+
+namespace sphnca {
+
+using namespace tc;
+
+
+namespace wg {
+constexpr int CH = 64;                                       // particles per chunk (MMA N / K)
+// epilogue warps 0..7: warp & 3 = TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31),
+// warp >> 2 = which half of the chunk's 64 particle columns it converts
+constexpr int EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP0 = 9, LOAD_WARPS = 4;
+constexpr int THREADS = (LOAD_WARP0 + LOAD_WARPS) * 32;      // 416
+constexpr int LOADERS = LOAD_WARPS * 32;                     // 128
+constexpr int KO = 32;                                       // dO columns on the tensor core in the recompute
+constexpr int NY = 64;                                       // rows of yT: 48 inputs + ones + pad
+constexpr int NOUT = 48;                                     // rows of dOT: 36 outputs + pad
+constexpr int ROW = NF + 2 * NF + NO_PAD;                    // 84 floats = 21 float4 per particle
+constexpr uint32_t COL_R1 = 0, COL_HLO = 64, COL_R3 = 128, COL_DHLO = 192, COL_ACC1 = 256, COL_ACC2 = 320, TMEM_COLS = 512;
+enum { K_FULL = 0, K_EMPTY, T_FULL, T_EMPTY, R_FULL, HT_FULL, ACC_FULL, NUM_BARS };
+
+struct Smem {
+    float W1_hi[128 * NIN], W1_lo[128 * NIN];      // rows = h (this half), K = k
+    float W2t_hi[128 * KO], W2t_lo[128 * KO];      // rows = h, K = o
+    float yK_hi[CH * NIN], yK_lo[CH * NIN];        // rows = p, K = k        (B of D1t)
+    float dOK_hi[CH * KO], dOK_lo[CH * KO];        // rows = p, K = o        (B of D3t)
+    float yT_hi[NY * CH], yT_lo[NY * CH];          // rows = k (+ones), K = p (B of dW1)
+    float dOT_hi[NOUT * CH], dOT_lo[NOUT * CH];    // rows = o, K = p        (B of dW2t)
+    float stage[2][CH][ROW];                       // raw fp32 rows [A 16 | Y 32 | dO 36] of a chunk, filled by cp.async (double buffered)
+    float dO32[2][CH];                             // scalar-gate column dO[:,32] for the epilogue (double buffered)
+    float b1[128], w2_last[128];
+    uint64_t bar[NUM_BARS];
+    uint32_t tmem_base;
+};
+__device__ __forceinline__ uint32_t fidx(uint32_t rows, uint32_t m, uint32_t k) { return chunk_off(rows, m, k >> 2) / 4 + (k & 3); }
+}  // namespace wg
+
+__global__ void __launch_bounds__(wg::THREADS, 1)
+mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float* __restrict__ Y_s,
+                    const float* __restrict__ dO_s, sphnca_step_params prm, int n_out, float* __restrict__ partial,
+                    int part_floats) {
+    using namespace wg;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int hh = blockIdx.x & 1;                            // hidden half of this CTA
+    const int stream_id = blockIdx.x >> 1, num_streams = gridDim.x >> 1;
+    const int64_t chunks_total = (n_total + CH - 1) / CH;
+    const int64_t c0 = chunks_total * stream_id / num_streams, c1 = chunks_total * (stream_id + 1) / num_streams;
+    const int n_mma = n_out < KO ? n_out : KO;
+
+    for (int i = tid; i < 128 * NIN; i += THREADS) {
+        const int h = i / NIN, k = i - h * NIN;
+        float hi, lo; split_tf32(__ldg(prm.W1 + (size_t)(hh * 128 + h) * NIN + k), hi, lo);
+        const uint32_t o = fidx(128, h, k);
+        s.W1_hi[o] = hi; s.W1_lo[o] = lo;
+    }
+    for (int i = tid; i < KO * 128; i += THREADS) {
+        const int o_ = i / 128, h = i - o_ * 128;
+        float hi, lo; split_tf32(o_ < n_mma ? __ldg(prm.W2 + (size_t)o_ * NH + hh * 128 + h) : 0.f, hi, lo);
+        const uint32_t o = fidx(128, h, o_);
+        s.W2t_hi[o] = hi; s.W2t_lo[o] = lo;
+    }
+    for (int i = tid; i < 128; i += THREADS) {
+        s.b1[i] = __ldg(prm.b1 + hh * 128 + i);
+        s.w2_last[i] = n_out > KO ? __ldg(prm.W2 + (size_t)KO * NH + hh * 128 + i) : 0.f;
+    }
+    // constant rows of the transposed B tiles: yT rows 49..63 and dOT rows 36..47 are zero (row 48 of yT,
+    // the ones column that yields db1, is rewritten per chunk because of the ragged last chunk)
+    for (int i = tid; i < (NY - NIN) * CH; i += THREADS) {
+        const int row = NIN + i / CH, pl = i - (i / CH) * CH;
+        s.yT_hi[fidx(NY, row, pl)] = 0.f; s.yT_lo[fidx(NY, row, pl)] = 0.f;
+    }
+    for (int i = tid; i < (NOUT - NO_PAD) * CH; i += THREADS) {
+        const int row = NO_PAD + i / CH, pl = i - (i / CH) * CH;
+        s.dOT_hi[fidx(NOUT, row, pl)] = 0.f; s.dOT_lo[fidx(NOUT, row, pl)] = 0.f;
+    }
+    if (tid == 0) {
+        mbar_init(&s.bar[K_FULL], LOADERS); mbar_init(&s.bar[K_EMPTY], 1);
+        mbar_init(&s.bar[T_FULL], LOADERS); mbar_init(&s.bar[T_EMPTY], 1);
+        mbar_init(&s.bar[R_FULL], 1);       mbar_init(&s.bar[HT_FULL], EPI_WARPS * 32);
+        mbar_init(&s.bar[ACC_FULL], 1);
+        mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(&s.tmem_base, TMEM_COLS);
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = s.tmem_base;
+
+    if (warp >= LOAD_WARP0) {
+        // ============================ loader: chunk operand tiles ============================
+        const int lt = tid - LOAD_WARP0 * 32;                 // 0..127
+        float db2[NO_PAD];
+#pragma unroll
+        for (int o = 0; o < NO_PAD; ++o) db2[o] = 0.f;
+        // cp.async staging: all 1344 16-byte pieces of a chunk (64 particles x 21 float4) are in flight at
+        // once and land in smem without passing through registers; they are issued one chunk ahead so the
+        // HBM/L2 latency overlaps the MMAs / epilogue of the current chunk.
+        auto issue_copy = [&](int64_t chn, int buf) {
+            for (int i = lt; i < CH * 21; i += LOADERS) {
+                const int pl = i / 21, q = i - pl * 21;
+                const int64_t p = chn * CH + pl;
+                float* dst = &s.stage[buf][pl][4 * q];
+                if (p < n_total) {
+                    const float* src = q < 4 ? A_s + p * NF + 4 * q : (q < 12 ? Y_s + p * 2 * NF + 4 * (q - 4) : dO_s + p * NO_PAD + 4 * (q - 12));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+                } else {
+                    *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (c0 < c1) issue_copy(c0, 0);
+        int it = 0;
+        for (int64_t ch = c0; ch < c1; ++ch, ++it) {
+            const int buf = it & 1;
+            float (*stg)[ROW] = s.stage[buf];
+            // the other staging buffer was last read in phase 2 of the previous chunk (all loaders passed the
+            // barrier at the end of that iteration): refill it now, a full chunk ahead
+            if (ch + 1 < c1) {
+                issue_copy(ch + 1, buf ^ 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");     // this chunk's group has landed
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            asm volatile("bar.sync 1, %0;" :: "r"(LOADERS) : "memory");  // ... for every loader thread
+            // phase 1 (K-major tiles).  Lanes vary over particles: stage rows are 336 B apart (8 lanes cover
+            // all 32 banks), tile chunks of consecutive particles are consecutive 16 B -> conflict-free
+            mbar_wait(&s.bar[K_EMPTY], (it & 1) ^ 1);         // recompute MMAs of the previous chunk are done
+            if (lt == 0) SPHNCA_TL(0);
+#pragma unroll
+            for (int r = 0; r < CH * (NIN / 4) / LOADERS; ++r) {
+                const int i = lt + r * LOADERS;
+                const int q = i / CH, pl = i - q * CH;
+                const float4 v = *reinterpret_cast<const float4*>(&stg[pl][4 * q]);
+                float hi[4], lo[4];
+                split_tf32(v.x, hi[0], lo[0]); split_tf32(v.y, hi[1], lo[1]);
+                split_tf32(v.z, hi[2], lo[2]); split_tf32(v.w, hi[3], lo[3]);
+                const uint32_t o = chunk_off(CH, pl, q) / 4;
+                *reinterpret_cast<float4*>(&s.yK_hi[o]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(&s.yK_lo[o]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+#pragma unroll
+            for (int r = 0; r < CH * (KO / 4) / LOADERS; ++r) {
+                const int i = lt + r * LOADERS;
+                const int qo = i / CH, pl = i - qo * CH;
+                const float4 v = *reinterpret_cast<const float4*>(&stg[pl][3 * NF + 4 * qo]);
+                float hi[4], lo[4];
+                split_tf32(v.x, hi[0], lo[0]); split_tf32(v.y, hi[1], lo[1]);
+                split_tf32(v.z, hi[2], lo[2]); split_tf32(v.w, hi[3], lo[3]);
+                const uint32_t o = chunk_off(CH, pl, qo) / 4;
+                *reinterpret_cast<float4*>(&s.dOK_hi[o]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(&s.dOK_lo[o]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            if (lt < CH) s.dO32[it & 1][lt] = stg[lt][3 * NF + KO];
+            fence_proxy_async_smem();
+            mbar_arrive(&s.bar[K_FULL]);
+            if (lt == 0) SPHNCA_TL(1);
+            if (hh == 0 && lt < CH) {                         // db2 partial sums (one CTA of the pair)
+#pragma unroll
+                for (int o = 0; o < NO_PAD; ++o) db2[o] += stg[lt][3 * NF + o];
+            }
+            // phase 2 (transposed K-major tiles): one 16-byte piece = 4 consecutive particles of one row.
+            // Lanes vary over rows: consecutive words of a stage row, consecutive 16 B of the tile.
+            mbar_wait(&s.bar[T_EMPTY], (it & 1) ^ 1);         // accumulate MMAs of the previous chunk are done
+            if (lt == 0) SPHNCA_TL(2);
+            constexpr int ROWS2 = NIN + NO_PAD;               // 48 y rows + 36 dO rows = 84 = the stage row
+#pragma unroll 3
+            for (int i = lt; i < ROWS2 * (CH / 4); i += LOADERS) {
+                const int pg = i / ROWS2, row = i - pg * ROWS2;
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) split_tf32(stg[4 * pg + j][row], hi[j], lo[j]);
+                const bool isy = row < NIN;
+                float* th = isy ? s.yT_hi : s.dOT_hi;
+                float* tl = isy ? s.yT_lo : s.dOT_lo;
+                const uint32_t o = (isy ? chunk_off(NY, row, pg) : chunk_off(NOUT, row - NIN, pg)) / 4;
+                *reinterpret_cast<float4*>(&th[o]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(&tl[o]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            if (lt < CH / 4) {                                // ones row (-> db1): 1 for real particles
+                float one[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) one[j] = (ch * CH + 4 * lt + j < n_total) ? 1.f : 0.f;
+                *reinterpret_cast<float4*>(&s.yT_hi[chunk_off(NY, NIN, lt) / 4]) = make_float4(one[0], one[1], one[2], one[3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&s.bar[T_FULL]);
+            if (lt == 0) SPHNCA_TL(3);
+            // every loader is done reading this staging buffer before it is refilled two iterations later
+            asm volatile("bar.sync 1, %0;" :: "r"(LOADERS) : "memory");
+        }
+        // db2: fixed-order tree over the 64 row-owning loader threads, written by the hh == 0 CTA
+        if (hh == 0) {
+            // scratch for the tree: the staging buffer (idle now; rows of 84 floats, 64 rows used)
+            float (*red)[ROW] = s.stage[0];
+            if (lt < CH) {
+#pragma unroll
+                for (int o = 0; o < NO_PAD; ++o) red[lt][o] = db2[o];
+            }
+            asm volatile("bar.sync 1, %0;" :: "r"(LOADERS) : "memory");
+            for (int stride = CH / 2; stride > 0; stride >>= 1) {
+                if (lt < stride) {
+#pragma unroll
+                    for (int o = 0; o < NO_PAD; ++o) red[lt][o] += red[lt + stride][o];
+                }
+                asm volatile("bar.sync 1, %0;" :: "r"(LOADERS) : "memory");
+            }
+            if (lt < NO_PAD) partial[(size_t)stream_id * part_floats + NH * NIN + NH + NO_PAD * NH + lt] = red[0][lt];
+        }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t idR = make_idesc_tf32(128, CH), idA1 = make_idesc_tf32(128, NY), idA2 = make_idesc_tf32(128, NOUT);
+            int it = 0;
+            for (int64_t ch = c0; ch < c1; ++ch, ++it) {
+                mbar_wait(&s.bar[K_FULL], it & 1);
+                fence_after_sync();
+                SPHNCA_TL(4);
+                // recompute (the TMEM chunk regions were last read by the accumulate MMAs issued before: in order)
+#pragma unroll
+                for (int ks = 0; ks < NIN / 8; ++ks) {
+                    const uint64_t a_hi = make_smem_desc(smem_u32(s.W1_hi) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
+                    const uint64_t a_lo = make_smem_desc(smem_u32(s.W1_lo) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
+                    const uint64_t b_hi = make_smem_desc(smem_u32(s.yK_hi) + chunk_off(CH, 0, 2 * ks), CH * 16, 128);
+                    const uint64_t b_lo = make_smem_desc(smem_u32(s.yK_lo) + chunk_off(CH, 0, 2 * ks), CH * 16, 128);
+                    mma_tf32_ss(tbase + COL_R1, a_lo, b_hi, idR, ks > 0);
+                    mma_tf32_ss(tbase + COL_R1, a_hi, b_lo, idR, true);
+                    mma_tf32_ss(tbase + COL_R1, a_hi, b_hi, idR, true);
+                }
+#pragma unroll
+                for (int ks = 0; ks < KO / 8; ++ks) {
+                    const uint64_t a_hi = make_smem_desc(smem_u32(s.W2t_hi) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
+                    const uint64_t a_lo = make_smem_desc(smem_u32(s.W2t_lo) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
+                    const uint64_t b_hi = make_smem_desc(smem_u32(s.dOK_hi) + chunk_off(CH, 0, 2 * ks), CH * 16, 128);
+                    const uint64_t b_lo = make_smem_desc(smem_u32(s.dOK_lo) + chunk_off(CH, 0, 2 * ks), CH * 16, 128);
+                    mma_tf32_ss(tbase + COL_R3, a_lo, b_hi, idR, ks > 0);
+                    mma_tf32_ss(tbase + COL_R3, a_hi, b_lo, idR, true);
+                    mma_tf32_ss(tbase + COL_R3, a_hi, b_hi, idR, true);
+                }
+                mma_commit(&s.bar[R_FULL]);
+                mma_commit(&s.bar[K_EMPTY]);
+                SPHNCA_TL(5);
+                mbar_wait(&s.bar[HT_FULL], it & 1);
+                SPHNCA_TL(6);
+                mbar_wait(&s.bar[T_FULL], it & 1);
+                fence_after_sync();
+                SPHNCA_TL(7);
+#pragma unroll
+                for (int ks = 0; ks < CH / 8; ++ks) {
+                    const uint64_t y_hi = make_smem_desc(smem_u32(s.yT_hi) + chunk_off(NY, 0, 2 * ks), NY * 16, 128);
+                    const uint64_t y_lo = make_smem_desc(smem_u32(s.yT_lo) + chunk_off(NY, 0, 2 * ks), NY * 16, 128);
+                    const uint64_t o_hi = make_smem_desc(smem_u32(s.dOT_hi) + chunk_off(NOUT, 0, 2 * ks), NOUT * 16, 128);
+                    const uint64_t o_lo = make_smem_desc(smem_u32(s.dOT_lo) + chunk_off(NOUT, 0, 2 * ks), NOUT * 16, 128);
+                    const bool acc = (it | ks) > 0;
+                    mma_tf32_ts(tbase + COL_ACC1, tbase + COL_DHLO + 8 * ks, y_hi, idA1, acc);
+                    mma_tf32_ts(tbase + COL_ACC1, tbase + COL_R3 + 8 * ks, y_lo, idA1, true);
+                    mma_tf32_ts(tbase + COL_ACC1, tbase + COL_R3 + 8 * ks, y_hi, idA1, true);
+                    mma_tf32_ts(tbase + COL_ACC2, tbase + COL_HLO + 8 * ks, o_hi, idA2, acc);
+                    mma_tf32_ts(tbase + COL_ACC2, tbase + COL_R1 + 8 * ks, o_lo, idA2, true);
+                    mma_tf32_ts(tbase + COL_ACC2, tbase + COL_R1 + 8 * ks, o_hi, idA2, true);
+                }
+                mma_commit(&s.bar[T_EMPTY]);
+                SPHNCA_TL(8);
+            }
+            mma_commit(&s.bar[ACC_FULL]);
+        }
+    } else {
+        // ============================ epilogue: thread = hidden unit ============================
+        const int h = (warp & 3) * 32 + lane;                 // 0..127 within the half == TMEM lane
+        const int col0 = (warp >> 2) * (CH / 2);              // this warp's particle columns [col0, col0 + 32)
+        const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        const float b1h = s.b1[h], w2l = s.w2_last[h];
+        int it = 0;
+        for (int64_t ch = c0; ch < c1; ++ch, ++it) {
+            mbar_wait(&s.bar[R_FULL], it & 1);
+            fence_after_sync();
+            if (tid == 0) SPHNCA_TL(9);
+#pragma unroll
+            for (int cc = col0; cc < col0 + CH / 2; cc += 16) {
+                uint32_t r1[16], r3[16], hhi[16], hlo[16], dhi[16], dlo[16];
+                tmem_ld16(lane_addr + COL_R1 + cc, r1);
+                tmem_ld16(lane_addr + COL_R3 + cc, r3);
+                wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float pre = __uint_as_float(r1[j]) + b1h;
+                    const bool on = pre > 0.f;
+                    const float hv = on ? pre : 0.f;
+                    const float dh = on ? fmaf(s.dO32[it & 1][cc + j], w2l, __uint_as_float(r3[j])) : 0.f;
+                    float a, b;
+                    split_tf32(hv, a, b); hhi[j] = __float_as_uint(a); hlo[j] = __float_as_uint(b);
+                    split_tf32(dh, a, b); dhi[j] = __float_as_uint(a); dlo[j] = __float_as_uint(b);
+                }
+                tmem_st16(lane_addr + COL_R1 + cc, hhi);
+                tmem_st16(lane_addr + COL_HLO + cc, hlo);
+                tmem_st16(lane_addr + COL_R3 + cc, dhi);
+                tmem_st16(lane_addr + COL_DHLO + cc, dlo);
+            }
+            wait_st();
+            fence_before_sync();
+            mbar_arrive(&s.bar[HT_FULL]);
+            if (tid == 0) SPHNCA_TL(10);
+        }
+        // the accumulators: dW1 row h (48) | db1 (column 48)   and   dW2[o][h] (column o of ACC2)
+        float* out = partial + (size_t)stream_id * part_floats;
+        const int hg = hh * 128 + h;
+        if (warp >= 4) {
+            // second column-half warps have no share in the final dump
+        } else if (c0 < c1) {
+            mbar_wait(&s.bar[ACC_FULL], 0);
+            fence_after_sync();
+#pragma unroll
+            for (int cc = 0; cc < NY; cc += 16) {
+                uint32_t r[16];
+                tmem_ld16(lane_addr + COL_ACC1 + cc, r); wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int k = cc + j;
+                    if (k < NIN) out[hg * NIN + k] = __uint_as_float(r[j]);
+                    else if (k == NIN) out[NH * NIN + hg] = __uint_as_float(r[j]);
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < NOUT; cc += 16) {
+                uint32_t r[16];
+                tmem_ld16(lane_addr + COL_ACC2 + cc, r); wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int o = cc + j;
+                    if (o < NO_PAD) out[NH * NIN + NH + o * NH + hg] = __uint_as_float(r[j]);
+                }
+            }
+        } else {
+            for (int k = 0; k < NIN; ++k) out[hg * NIN + k] = 0.f;
+            out[NH * NIN + hg] = 0.f;
+            for (int o = 0; o < NO_PAD; ++o) out[NH * NIN + NH + o * NH + hg] = 0.f;
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tbase, wg::TMEM_COLS);
+}
+
+int wgrad_tc_streams(int64_t N) {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) num_sms = 148;
+    }
+    int64_t chunks = (N + wg::CH - 1) / wg::CH;
+    int64_t st = num_sms / 2;
+    if (st > chunks) st = chunks;
+    return (int)(st < 1 ? 1 : st);
+}
+
+int launch_mlp_wgrad_tc(int64_t N, const float* A_s, const float* Y_s, const float* dO_s, const sphnca_step_params* p,
+                        int n_out, float* partial, int part_floats, int streams, cudaStream_t stream) {
+    const size_t smem = sizeof(wg::Smem);
+    SPHNCA_CUDA(cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPHNCA_LAUNCH(mlp_wgrad_tc_kernel, 2 * streams, wg::THREADS, smem, stream, N, A_s, Y_s, dO_s, *p, n_out, partial, part_floats);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+}  // namespace sphnca
+
+SPHNCA_TIMELINE_READER(sphnca_debug_timeline_wgrad)

@@ -62,11 +62,11 @@ def _load():
         "sphnca_blur_bwd": ([G, P, P, I32, P, P], I32),
         "sphnca_divergence_fwd": ([G, P, P, I32, P, P], I32),
         "sphnca_divergence_bwd": ([G, P, P, I32, P, P], I32),
-        "sphnca_step_fwd": ([G, P, P, P, SP, P, P, P, P, P, P], I32),
+        "sphnca_step_fwd": ([G, P, P, P, SP, P, P, P, P, P, P, P], I32),
         "sphnca_step_mask": ([G, P, P, P, P, P], I32),
-        "sphnca_step_bwd": ([I64, P, P, P, P, P, SP, P, P, P, P, P, P], I32),
+        "sphnca_step_bwd": ([I64, P, P, P, P, P, P, SP, P, P, P, P, P, P], I32),
         "sphnca_mlp_wgrad_workspace_bytes": ([I64, C.POINTER(C.c_size_t)], I32),
-        "sphnca_mlp_wgrad": ([I64, P, P, P, P, P, I32, P, P, P, P, P, C.c_size_t, P], I32),
+        "sphnca_mlp_wgrad": ([I64, P, P, P, P, P, SP, P, P, P, P, P, C.c_size_t, P], I32),
         "sphnca_step_adjoint": ([G, P, P, P, SP, P, P], I32),
         "sphnca_launch_count": ([], I64),
         "sphnca_set_mlp_path": ([I32], I32),

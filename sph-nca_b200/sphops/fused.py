@@ -62,22 +62,23 @@ class _NCAStep(torch.autograd.Function):
         O_s = torch.empty((N, 36), **f32)
         flags_s = torch.empty((N,), dtype=torch.uint8, device=dev)
         alive_s = torch.empty((N,), dtype=torch.uint8, device=dev)
+        relu_s = torch.empty((N, 8), dtype=torch.int32, device=dev)
         p = _step_params(W1c, b1c, W2c, b2c, update_rule, use_alpha, perception_scale, orig_rate)
         if N:
             g, st = grid.c_grid(), stream_ptr()
             _timed("step_fwd", lib.sphnca_step_fwd, g, ptr(xv4), ptr(A_s), ptr(fire_s), C.byref(p), ptr(An_s),
-                   ptr(alive_s), ptr(Y_s), ptr(O_s), ptr(flags_s), st)
+                   ptr(alive_s), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
             _timed("step_mask", lib.sphnca_step_mask, g, ptr(xv4), ptr(alive_s), ptr(An_s), ptr(flags_s), st)
         out = grid.unpack_rows(An_s, 16)
         ctx.grid = grid
         ctx.cfg = (update_rule, use_alpha, perception_scale, orig_rate)
-        ctx.save_for_backward(xv4, A_s, Y_s, O_s, flags_s, W1c, b1c, W2c, b2c)
+        ctx.save_for_backward(xv4, A_s, Y_s, O_s, flags_s, relu_s, W1c, b1c, W2c, b2c)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dA_next):
-        xv4, A_s, Y_s, O_s, flags_s, W1, b1, W2, b2 = ctx.saved_tensors
+        xv4, A_s, Y_s, O_s, flags_s, relu_s, W1, b1, W2, b2 = ctx.saved_tensors
         grid = ctx.grid
         N = A_s.shape[0]
         dev = A_s.device
@@ -98,12 +99,14 @@ class _NCAStep(torch.autograd.Function):
             st = stream_ptr()
             # particles are processed in chunks so that the transposed hidden activations
             # (2 x [chunk/32][256][32] fp32, 2 KB per particle) stay bounded for very large clouds
-            chunk = min(N, WGRAD_CHUNK)
+            simt = SIMT_BACKWARD
+            chunk = min(N, WGRAD_CHUNK) if simt else N
             Ht = dHt = ws = None
             if want_w:
-                tiles = (chunk + 31) // 32          # [tiles][256][32], see include/sphnca.h
-                Ht = torch.empty((tiles, 256, 32), **f32)
-                dHt = torch.empty((tiles, 256, 32), **f32)
+                if simt:
+                    tiles = (chunk + 31) // 32      # [tiles][256][32], see include/sphnca.h
+                    Ht = torch.empty((tiles, 256, 32), **f32)
+                    dHt = torch.empty((tiles, 256, 32), **f32)
                 nb = C.c_size_t(0)
                 check(lib.sphnca_mlp_wgrad_workspace_bytes(chunk, C.byref(nb)))
                 ws = torch.empty((nb.value,), dtype=torch.uint8, device=dev)
@@ -111,10 +114,11 @@ class _NCAStep(torch.autograd.Function):
                 n = min(chunk, N - lo)
                 Hc, dHc = Ht, dHt
                 _timed("step_bwd", lib.sphnca_step_bwd, n, ptr(A_s[lo:]), ptr(Y_s[lo:]), ptr(O_s[lo:]), ptr(flags_s[lo:]),
-                       ptr(dAn_s[lo:]), C.byref(p), ptr(dO_s[lo:]), ptr(dY_s[lo:]), ptr(dAdir_s[lo:]), ptr(Hc), ptr(dHc), st)
+                       ptr(relu_s[lo:]), ptr(dAn_s[lo:]), C.byref(p), ptr(dO_s[lo:]), ptr(dY_s[lo:]), ptr(dAdir_s[lo:]),
+                       ptr(Hc), ptr(dHc), st)
                 if want_w:
                     _timed("mlp_wgrad", lib.sphnca_mlp_wgrad, n, ptr(A_s[lo:]), ptr(Y_s[lo:]), ptr(dO_s[lo:]), ptr(Hc), ptr(dHc),
-                           n_out, ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value, st)
+                           C.byref(p), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value, st)
             _timed("step_adjoint", lib.sphnca_step_adjoint, grid.c_grid(), ptr(xv4), ptr(dY_s), ptr(dAdir_s),
                    C.byref(p), ptr(dA_s), st)
         dA = grid.unpack_rows(dA_s, 16) if g[2] else None
@@ -122,7 +126,10 @@ class _NCAStep(torch.autograd.Function):
                 dW2 if g[6] else None, db2 if g[7] else None, None, None, None, None, None, None)
 
 
-# particles per backward chunk (bounds the [256][chunk] x 2 fp32 scratch to 8 GB)
+# True: CUDA-core backward (step_bwd_kernel streams transposed hidden activations to mlp_wgrad_kernel);
+# False (default): tensor-core backward (step_bwd_tc_kernel + mlp_wgrad_tc_kernel, no scratch).
+SIMT_BACKWARD = False
+# particles per backward chunk on the CUDA-core path (bounds the 2 KB/particle scratch to 8 GB)
 WGRAD_CHUNK = 4 * 1024 * 1024
 
 

@@ -57,23 +57,27 @@ def run_case(g, fused):
 @pytest.fixture(autouse=True)
 def _default_mlp_path():
     """every test starts (and leaves) with the default tcgen05 MLP path"""
-    from sphops import _lib
+    from sphops import _lib, fused
     _lib.check(_lib.lib.sphnca_set_mlp_path(1))
+    fused.SIMT_BACKWARD = False
     yield
     _lib.check(_lib.lib.sphnca_set_mlp_path(1))
+    fused.SIMT_BACKWARD = False
 
 
 @pytest.mark.parametrize("path", ["ops", "fused_simt", "fused_tc"])
 @pytest.mark.parametrize("name", STEP_CASES)
 def test_step_matches_reference(name, path):
-    """ops = general sphops operators + torch MLP; fused_simt = fused step with the fp32 CUDA-core MLP;
-    fused_tc = fused step with the tcgen05 (3xTF32) MLP, the default."""
+    """ops = general sphops operators + torch MLP; fused_simt = fused step with the fp32 CUDA-core MLP
+    (forward, data gradient, weight gradient); fused_tc = fused step with the tcgen05 (3xTF32) MLP kernels
+    for all three, the default."""
     import sphops
-    from sphops import _lib
+    from sphops import _lib, fused as fused_mod
     fused = path != "ops"
     if fused:
         assert sphops.fused_available(), "libsphnca.so lacks the fused step"
         _lib.check(_lib.lib.sphnca_set_mlp_path(1 if path == "fused_tc" else 0))
+        fused_mod.SIMT_BACKWARD = path == "fused_simt"
     g = load_golden(name)
     model, A0, states, loss = run_case(g, fused)
     K = g["masks"].shape[0]
@@ -248,12 +252,16 @@ def test_tc_forward_equals_simt_forward(n_particles):
         _lib.check(_lib.lib.sphnca_set_mlp_path(path))
         An = torch.zeros(N, 16, device=DEV); Y = torch.zeros(N, 32, device=DEV); O = torch.zeros(N, 36, device=DEV)
         fl = torch.zeros(N, dtype=torch.uint8, device=DEV); al = torch.zeros(N, dtype=torch.uint8, device=DEV)
+        rl = torch.zeros(N, 8, dtype=torch.int32, device=DEV)
         p = fused._step_params(*W, "gated", True, 1.0 / h, 1.0)
         _lib.check(_lib.lib.sphnca_step_fwd(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(A_s), _lib.ptr(fire_s), C.byref(p),
-                                            _lib.ptr(An), _lib.ptr(al), _lib.ptr(Y), _lib.ptr(O), _lib.ptr(fl), _lib.stream_ptr()))
+                                            _lib.ptr(An), _lib.ptr(al), _lib.ptr(Y), _lib.ptr(O), _lib.ptr(fl), _lib.ptr(rl), _lib.stream_ptr()))
         torch.cuda.synchronize()
-        res.append((An, Y, O, fl, al))
-    for a, b, nm in zip(res[1], res[0], ("A_new", "Y", "O", "flags", "alive")):
+        res.append((An, Y, O, fl, al, rl.view(torch.uint8)))
+    # ReLU bits: a pre-activation within fp32 noise of 0 may land on either side in the two kernels
+    nbits = int(torch.tensor([bin(v).count("1") for v in (res[0][5] ^ res[1][5]).flatten().tolist()]).sum()) if N <= 6000 else 0
+    assert nbits <= max(4, N // 200), f"relu masks differ in {nbits} bits"
+    for a, b, nm in zip(res[1][:5], res[0][:5], ("A_new", "Y", "O", "flags", "alive")):
         if a.dtype == torch.uint8:
             # a `> 0.1` decision on a value within fp32 noise of 0.1 may differ between the two kernels
             assert int((a != b).sum()) <= max(2, N // 10000), f"{nm}: {int((a != b).sum())} bytes differ"
@@ -268,6 +276,7 @@ def test_backward_chunking_is_equivalent(monkeypatch):
     from sphops import fused
     g = load_golden("rollout_gecko_alpha_k3")
     res = []
+    monkeypatch.setattr(fused, "SIMT_BACKWARD", True)
     for chunk in (4 * 1024 * 1024, 61):
         monkeypatch.setattr(fused, "WGRAD_CHUNK", chunk)
         model, A0, states, loss = run_case(g, True)
@@ -276,3 +285,68 @@ def test_backward_chunking_is_equivalent(monkeypatch):
         assert_close(a, b, rtol=2e-6, what="chunked vs unchunked")
     for t, key in zip(res[1][1:], ("dW1", "db1", "dW2", "db2")):
         assert_close(t, g[key], rtol=GRAD_RTOL, what=key)
+
+
+@pytest.mark.parametrize("n_particles", [1, 63, 64, 65, 129, 5000, 148 * 128 * 2 + 77])
+def test_tc_backward_equals_simt_backward(n_particles):
+    """tcgen05 data-gradient (step_bwd_tc_kernel) and weight-gradient (mlp_wgrad_tc_kernel) kernels against the
+    CUDA-core kernels and an fp64 torch evaluation of the same formulas, on ragged tile / chunk counts."""
+    import ctypes as C
+    import sphops
+    from sphops import _lib, fused
+    gen = torch.Generator().manual_seed(100 + n_particles)
+    N = n_particles
+    side = max(int(math.ceil(N ** 0.5)), 1)
+    x = torch.nn.functional.pad(jittered_lattice(side, 2, gen)[:N], (0, 1))
+    h = max(3.2 * 2 / side, 0.02)
+    dims = max(math.ceil(2 / h), 1)
+    xd = x.to(DEV)
+    grid = sphops.initialize_hashgrid(xd, (N,), h, (dims, dims, 3))
+    v = sphops.volume(xd, h, grid)
+    w = load_golden("weights_gecko")
+    W = [torch.from_numpy(w[k]).to(DEV) for k in ("W1", "b1", "W2", "b2")]
+    d2 = (x ** 2).sum(-1)
+    A = ((torch.clamp(1 - d2 / 0.6 ** 2, 0, 1) ** 3)[:, None].repeat(1, 16) + 0.05 * torch.rand(N, 16, generator=gen)).to(DEV)
+    fire = (torch.rand(N, generator=gen) <= 0.5).to(DEV)
+    xv4 = grid.sorted_xv(xd, v); A_s = grid.pack_rows(A, 16); fire_s = grid.pack_bytes(fire.to(torch.uint8))
+    f32 = dict(dtype=torch.float32, device=DEV)
+    An = torch.zeros(N, 16, **f32); Y = torch.zeros(N, 32, **f32); O = torch.zeros(N, 36, **f32)
+    fl = torch.zeros(N, dtype=torch.uint8, device=DEV); al = torch.zeros(N, dtype=torch.uint8, device=DEV)
+    rl = torch.zeros(N, 8, dtype=torch.int32, device=DEV)
+    p = fused._step_params(*W, "gated", True, 1.0 / h, 1.0)
+    st = _lib.stream_ptr()
+    _lib.check(_lib.lib.sphnca_set_mlp_path(0))
+    _lib.check(_lib.lib.sphnca_step_fwd(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(A_s), _lib.ptr(fire_s), C.byref(p), _lib.ptr(An),
+                                        _lib.ptr(al), _lib.ptr(Y), _lib.ptr(O), _lib.ptr(fl), _lib.ptr(rl), st))
+    _lib.check(_lib.lib.sphnca_step_mask(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(al), _lib.ptr(An), _lib.ptr(fl), st))
+    dAn = torch.randn(N, 16, generator=gen).to(DEV)
+    nb = C.c_size_t(0); _lib.check(_lib.lib.sphnca_mlp_wgrad_workspace_bytes(N, C.byref(nb)))
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=DEV)
+    tiles = (N + 31) // 32
+    out = {}
+    for path in (0, 1):
+        _lib.check(_lib.lib.sphnca_set_mlp_path(path))
+        dO = torch.zeros(N, 36, **f32); dY = torch.zeros(N, 32, **f32); dAd = torch.zeros(N, 16, **f32)
+        Ht = torch.empty(tiles, 256, 32, **f32) if path == 0 else None
+        dHt = torch.empty(tiles, 256, 32, **f32) if path == 0 else None
+        _lib.check(_lib.lib.sphnca_step_bwd(N, _lib.ptr(A_s), _lib.ptr(Y), _lib.ptr(O), _lib.ptr(fl), _lib.ptr(rl), _lib.ptr(dAn),
+                                            C.byref(p), _lib.ptr(dO), _lib.ptr(dY), _lib.ptr(dAd), _lib.ptr(Ht), _lib.ptr(dHt), st))
+        dW = [torch.zeros_like(t) for t in W]
+        _lib.check(_lib.lib.sphnca_mlp_wgrad(N, _lib.ptr(A_s), _lib.ptr(Y), _lib.ptr(dO), _lib.ptr(Ht), _lib.ptr(dHt), C.byref(p),
+                                             *[_lib.ptr(t) for t in dW], _lib.ptr(ws), nb.value, st))
+        torch.cuda.synchronize()
+        out[path] = (dO, dY, dAd, dW)
+    # fp64 evaluation of the same formulas from the saved tensors
+    Yf = torch.cat([A_s, Y], 1).double(); W1, b1, W2, b2 = [t.double() for t in W]
+    pre = Yf @ W1.t() + b1
+    dOd = out[0][0][:, :33].double()
+    dH = (dOd @ W2) * (pre > 0)
+    ref = dict(dY=(dH @ W1)[:, 16:], dW1=dH.t() @ Yf, db1=dH.sum(0), dW2=dOd.t() @ torch.relu(pre), db2=dOd.sum(0))
+    for path in (0, 1):
+        dO, dY, dAd, dW = out[path]
+        tol = 2e-5
+        assert_close(dO, out[0][0], rtol=1e-6, what=f"dO path {path}")
+        assert_close(dY, ref["dY"], rtol=tol, what=f"dY path {path}")
+        for t, nm in zip(dW, ("dW1", "db1", "dW2", "db2")):
+            assert_close(t, ref[nm], rtol=tol, what=f"{nm} path {path}")
+    assert_close(out[1][2], out[0][2], rtol=2e-5, what="dAdir tc vs simt")

@@ -17,10 +17,11 @@ xv4 = grid.sorted_xv(x, v); A_s = grid.pack_rows(A, 16)
 fire_s = grid.pack_bytes((torch.rand(N, device=dev) <= 0.5).to(torch.uint8))
 An = torch.zeros(N, 16, device=dev); Y = torch.zeros(N, 32, device=dev); O = torch.zeros(N, 36, device=dev)
 fl = torch.zeros(N, dtype=torch.uint8, device=dev); al = torch.zeros(N, dtype=torch.uint8, device=dev)
+rl = torch.zeros(N, 8, dtype=torch.int32, device=dev)
 p = fused._step_params(*W, "gated", False, 1.0 / h, 1.0)
 def run():
     _lib.check(_lib.lib.sphnca_step_fwd(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(A_s), _lib.ptr(fire_s), C.byref(p),
-               _lib.ptr(An), _lib.ptr(al), _lib.ptr(Y), _lib.ptr(O), _lib.ptr(fl), _lib.stream_ptr()))
+               _lib.ptr(An), _lib.ptr(al), _lib.ptr(Y), _lib.ptr(O), _lib.ptr(fl), _lib.ptr(rl), _lib.stream_ptr()))
 for path, name in ((0, "simt"), (1, "tcgen05"), (2, "tcgen05, neighbour loop skipped (debug)")):
     _lib.check(_lib.lib.sphnca_set_mlp_path(path))
     for _ in range(3): run()
