@@ -125,9 +125,11 @@ int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s
                         const uint8_t* fire_s, const sphnca_step_params* p,
                         float* A_new_s, uint8_t* alive_s, float* Y_s, float* O_s, uint8_t* flags_s,
                         uint32_t* relu_s, void* stream);
-/* Implementation switch for sphnca_step_fwd: 1 (default) = tcgen05 tensor-core MLP with the 3xTF32
- * split (csrc/step_tc.cu), 0 = fp32 CUDA-core MLP (csrc/step.cu).  Both produce the same outputs
- * to fp32 rounding; the switch exists for A/B tests. */
+/* Implementation switch of the step kernels (A/B tests; all produce the same tensors to fp32 rounding):
+ *   1 (default) tcgen05 MLP with the 3xTF32 split; forward split into a full-L1 perception sweep
+ *               kernel + the tensor-core MLP kernel (csrc/step.cu:step_perceive_kernel, step_mlp_tc.cu);
+ *   2           same, forward fused into one persistent kernel (csrc/step_tc.cu);
+ *   0           fp32 CUDA-core MLP (csrc/step.cu). */
 int32_t sphnca_set_mlp_path(int32_t path);
 /* sphnca_step_mask: new life mask = blur(alive_s) > 0.1 (nca.py:112); A_new_s *= prev & new in
  * place; flags_s bit1 = new_mask. */

@@ -129,6 +129,40 @@ __device__ __forceinline__ void for_each_candidate(const GridView& g, int gcell,
     });
 }
 
+// In-radius compaction.  Only ~35% (padded 2-D) / ~15% (3-D) of the candidates of a 3^D-cell sweep lie
+// inside the support radius, but a warp executes a branch body whenever ANY lane takes it, so a heavy body
+// (16-channel FMAs) would run for every candidate.  Two passes instead: a light pass tests every candidate
+// and appends the in-radius sorted positions to a per-thread list in shared memory (layout [slot][thread]:
+// conflict-free), a heavy pass `fn(q, xj)` walks only the list (trip count = the lane's neighbour count).
+// A full list is flushed in place, so any neighbour count works.  Visiting order is unchanged.
+constexpr int kNbrSlots = 64;
+template <int D, int THREADS, typename Fn>
+__device__ __forceinline__ void for_each_neighbor(const GridView& g, int gcell, const float4* __restrict__ xv4,
+                                                  const float4& xi, float h2, int* __restrict__ list, Fn&& fn) {
+    int* mine = list + threadIdx.x;
+    int cnt = 0;
+    auto flush = [&]() {
+        for (int k = 0; k < cnt; ++k) {
+            const int q = mine[k * THREADS];
+            fn(q, __ldg(&xv4[q]));
+        }
+        cnt = 0;
+    };
+    for_each_run<D>(g, gcell, [&](int q0, int q1) {
+        for (int q = q0; q < q1; ++q) {
+            const float4 xj = __ldg(&xv4[q]);
+            const float rx = xj.x - xi.x, ry = xj.y - xi.y;
+            float d2 = fmaf(ry, ry, rx * rx);
+            if (D == 3) { const float rz = xj.z - xi.z; d2 = fmaf(rz, rz, d2); }
+            if (d2 < h2) {
+                mine[cnt * THREADS] = q;
+                if (++cnt == kNbrSlots) flush();
+            }
+        }
+    });
+    flush();
+}
+
 // spiky gradient weight 3 (h-d)^2 / d for 0 < d < h, else 0 (kernels_impl.py:143-156).
 // The reference returns exact 0 for r == 0 (`r[i] and mag*r[i]`), also for coincident particles.
 __device__ __forceinline__ float spiky_mag(float d2, float h, float h2) {

@@ -152,6 +152,52 @@ step_fwd_kernel(GridView g, const float4* __restrict__ xv4, const float* __restr
     alive_s[p] = c.use_alpha ? (nA[3] > 0.1f ? 1 : 0) : 1;
 }
 
+// Perception sweep only (split forward path): SPH gradient (x,y; 16 channels, scaled) + previous life mask.
+// No shared memory -> the whole 228 KB of the SM serve as L1 for the neighbour gathers; 128-thread CTAs.
+template <int D>
+__global__ void __launch_bounds__(128)
+step_perceive_kernel(GridView g, const float4* __restrict__ xv4, const float* __restrict__ A_s, StepConsts c,
+                     float* __restrict__ Y_s, uint8_t* __restrict__ flags_s) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.n) return;
+    const float4 xi = xv4[p];
+    float Ai[NF], gx[NF], gy[NF];
+    load16(A_s + (size_t)p * NF, Ai);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) { gx[f] = 0.f; gy[f] = 0.f; }
+    float blur = 0.f;
+    for_each_candidate<D>(g, g.sorted_cell[p], [&](int q) {
+        float rx, ry;
+        const float4 xj = __ldg(&xv4[q]);
+        const float d2 = pair_d2<D>(xi, xj, rx, ry);
+        if (d2 < c.h2) {
+            float Aj[NF];
+            load16(A_s + (size_t)q * NF, Aj);
+            const float t = c.h2 - d2;
+            const float alive = c.use_alpha ? (Aj[3] > 0.1f ? 1.f : 0.f) : 1.f;
+            blur = fmaf(alive * xj.w, t * t * t, blur);
+            if (d2 > 0.f) {
+                const float d = sqrtf(d2);
+                const float hd = c.h - d;
+                const float m = 3.f * hd * hd / d * xj.w;
+                const float wx = m * rx, wy = m * ry;
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const float dA = Aj[f] - Ai[f];
+                    gx[f] = fmaf(dA, wx, gx[f]);
+                    gy[f] = fmaf(dA, wy, gy[f]);
+                }
+            }
+        }
+    });
+    float4* y4 = reinterpret_cast<float4*>(Y_s + (size_t)p * 2 * NF);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y4[k] = make_float4(gx[4*k] * c.kg, gx[4*k+1] * c.kg, gx[4*k+2] * c.kg, gx[4*k+3] * c.kg);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y4[4 + k] = make_float4(gy[4*k] * c.kg, gy[4*k+1] * c.kg, gy[4*k+2] * c.kg, gy[4*k+3] * c.kg);
+    flags_s[p] = blur * c.cw > 0.1f ? 1 : 0;
+}
+
 // new life mask = blur(alive bits of the updated state) > 0.1; state *= prev & new   (nca.py:112-115)
 template <int D>
 __global__ void __launch_bounds__(256)
@@ -344,8 +390,15 @@ int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s
     cudaStream_t stream = as_stream(stream_);
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(xv4 && A_s && fire_s && A_new_s && alive_s && Y_s && O_s && flags_s && relu_s, "NULL argument");
-    if (mlp_path() >= 1)
+    if (mlp_path() == 2)      // fused tcgen05 kernel (sweep + MLP in one persistent kernel)
         return launch_step_fwd_tc(gv, c, p, xv4, A_s, fire_s, A_new_s, alive_s, Y_s, O_s, flags_s, relu_s, stream);
+    if (mlp_path() == 1) {    // split: full-L1 sweep kernel, then the tcgen05 MLP kernel (default)
+        const int pblocks = (int)((gv.n + 127) / 128);
+        if (gv.dim == 3) SPHNCA_LAUNCH(step_perceive_kernel<3>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+        else SPHNCA_LAUNCH(step_perceive_kernel<2>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+        SPHNCA_LAUNCH_CHECK();
+        return launch_step_mlp_tc(gv.n, c, p, A_s, Y_s, fire_s, A_new_s, alive_s, O_s, flags_s, relu_s, stream);
+    }
     const int blocks = (int)((gv.n + kStepThreads - 1) / kStepThreads);
     const size_t smem = sizeof(MlpSmem);
     if (gv.dim == 3) {

@@ -47,12 +47,16 @@ inline int make_consts(const sphnca_grid* g, const sphnca_step_params* p, StepCo
 }
 
 
-// which implementation sphnca_step_fwd uses: 0 = CUDA-core MLP (step.cu), 1 = tcgen05 (step_tc.cu)
+// which implementation the step uses: 0 = CUDA-core MLP (step.cu), 1 = tcgen05, split forward
+// (step_perceive_kernel + step_mlp_tc.cu; default), 2 = tcgen05, fused forward (step_tc.cu)
 int mlp_path();
 int launch_step_fwd_tc(const GridView& gv, const StepConsts& c, const sphnca_step_params* p, const float* xv4,
                        const float* A_s, const uint8_t* fire_s, float* A_new_s, uint8_t* alive_s, float* Y_s,
                        float* O_s, uint8_t* flags_s, uint32_t* relu_s, cudaStream_t stream);
 
+int launch_step_mlp_tc(int64_t N, const StepConsts& c, const sphnca_step_params* p, const float* A_s, const float* Y_s,
+                       const uint8_t* fire_s, float* A_new_s, uint8_t* alive_s, float* O_s, uint8_t* flags_s,
+                       uint32_t* relu_s, cudaStream_t stream);
 int launch_step_bwd_tc(int64_t N, const StepConsts& c, const sphnca_step_params* p, const float* A_s, const float* O_s,
                        const uint8_t* flags_s, const uint32_t* relu_s, const float* dA_next_s, float* dO_s, float* dY_s,
                        float* dAdir_s, cudaStream_t stream);

@@ -1,0 +1,303 @@
+// NCA step forward, split form: this kernel is the MLP + update half (tcgen05), fed from HBM.
+//
+//   step_perceive_kernel (step.cu)   neighbour sweep only: full L1 (no shared memory), high occupancy;
+//                                    writes the scaled perception Y_s [N,32] (needed by backward anyway)
+//                                    and the previous-life-mask bit.
+//   step_mlp_tc_kernel (this file)   loader warps pull rows [A | Y] (192 B / particle) one tile ahead into
+//                                    registers and write the tf32 hi/lo MMA A tile; MMA warp and TMEM
+//                                    pipeline as in step_tc.cu; 8 epilogue warps (two per TMEM lane
+//                                    quarter, half of the hidden columns each).
+//
+// Why split: the fused kernel (step_tc.cu) needs 215 KB of shared memory, which leaves ~13 KB of L1 per SM,
+// so its neighbour gathers all go to L2 and the sweep (41-58 k cycles per 128-particle tile, measured with
+// the in-kernel timeline) hides the whole MLP chain.  The extra HBM traffic of the split is one 192-byte
+// row read per particle.  Both paths are kept (sphnca_set_mlp_path) and produce identical tensors.
+#include "step_common.cuh"
+#include "tc_common.cuh"
+
+namespace sphnca {
+
+using namespace tc;
+
+namespace mt {
+constexpr int TILE = 128;
+constexpr int EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP0 = 9, LOAD_WARPS = 4;
+constexpr int THREADS = (LOAD_WARP0 + LOAD_WARPS) * 32;        // 416
+constexpr int N2 = 32;
+constexpr uint32_t COL_D1 = 0, COL_HHI = 128, COL_HLO = 256, COL_D2 = 384, TMEM_COLS = 512;
+enum { Y_FULL = 0, Y_EMPTY, D1_FULL, D1_EMPTY, H_FULL, H_EMPTY, D2_FULL, D2_EMPTY, NUM_BARS };
+
+struct Smem {
+    float W1_hi[2][128 * NIN], W1_lo[2][128 * NIN];
+    float W2_hi[2][N2 * 128], W2_lo[2][N2 * 128];
+    float Y_hi[TILE * NIN], Y_lo[TILE * NIN];
+    float b1[NH], w2_last[NH], b2[NO_PAD];
+    float o32[2][TILE];                 // partial scalar-gate sums of the second column-half warps
+    uint32_t relu[2][TILE][NH / 64];    // ReLU words of the second column-half warps (4 of the 8 words)
+    uint64_t bar[NUM_BARS];
+    uint32_t tmem_base;
+};
+__device__ __forceinline__ uint32_t fidx(uint32_t rows, uint32_t m, uint32_t k) { return chunk_off(rows, m, k >> 2) / 4 + (k & 3); }
+// gates: fast exponential (2 ulp) -> |error| ~1e-7 on sigmoid / tanh, far inside the 1e-5 parity bar
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float e = __expf(-2.f * fabsf(x));
+    const float t = __fdividef(1.f - e, 1.f + e);
+    return copysignf(t, x);
+}
+}  // namespace mt
+
+__global__ void __launch_bounds__(mt::THREADS, 1)
+step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __restrict__ Y_s,
+                   const uint8_t* __restrict__ fire_s, sphnca_step_params prm, StepConsts c,
+                   float* __restrict__ An_s, float* __restrict__ O_s, uint8_t* __restrict__ flags_s,
+                   uint8_t* __restrict__ alive_s, uint32_t* __restrict__ relu_s, int num_tiles) {
+    using namespace mt;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int i = tid; i < NH * NIN; i += THREADS) {
+        const int n = i / NIN, k = i - n * NIN;
+        float hi, lo; split_tf32(__ldg(prm.W1 + i), hi, lo);
+        const uint32_t o = fidx(128, n & 127, k);
+        s.W1_hi[n >> 7][o] = hi; s.W1_lo[n >> 7][o] = lo;
+    }
+    const int n_mma = c.n_out < N2 ? c.n_out : N2;
+    for (int i = tid; i < N2 * NH; i += THREADS) {
+        const int o_ = i / NH, k = i - o_ * NH;
+        float hi, lo; split_tf32(o_ < n_mma ? __ldg(prm.W2 + (size_t)o_ * NH + k) : 0.f, hi, lo);
+        const uint32_t o = fidx(N2, o_, k & 127);
+        s.W2_hi[k >> 7][o] = hi; s.W2_lo[k >> 7][o] = lo;
+    }
+    for (int i = tid; i < NH; i += THREADS) {
+        s.b1[i] = __ldg(prm.b1 + i);
+        s.w2_last[i] = c.n_out > N2 ? __ldg(prm.W2 + (size_t)N2 * NH + i) : 0.f;
+    }
+    if (tid < NO_PAD) s.b2[tid] = tid < c.n_out ? __ldg(prm.b2 + tid) : 0.f;
+    if (tid == 0) {
+        mbar_init(&s.bar[Y_FULL], LOAD_WARPS * 32); mbar_init(&s.bar[Y_EMPTY], 1);
+        mbar_init(&s.bar[D1_FULL], 1);              mbar_init(&s.bar[D1_EMPTY], EPI_WARPS * 32);
+        mbar_init(&s.bar[H_FULL], EPI_WARPS * 32);  mbar_init(&s.bar[H_EMPTY], 1);
+        mbar_init(&s.bar[D2_FULL], 1);              mbar_init(&s.bar[D2_EMPTY], 4 * 32);
+        mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(&s.tmem_base, TMEM_COLS);
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = s.tmem_base;
+
+    if (warp >= LOAD_WARP0) {
+        // ===================== loader: rows [A | Y] -> tf32 hi/lo A tile, one tile ahead =====================
+        const int m = tid - LOAD_WARP0 * 32;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int p = tile * TILE + m;
+            float4 v[NIN / 4];
+            if (p < n_total) {
+                const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)p * NF);
+                const float4* y4 = reinterpret_cast<const float4*>(Y_s + (size_t)p * 2 * NF);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = __ldg(a4 + k);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[4 + k] = __ldg(y4 + k);
+            } else {
+#pragma unroll
+                for (int k = 0; k < NIN / 4; ++k) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            mbar_wait(&s.bar[Y_EMPTY], (it & 1) ^ 1);
+#pragma unroll
+            for (int ch = 0; ch < NIN / 4; ++ch) {
+                float hi[4], lo[4];
+                split_tf32(v[ch].x, hi[0], lo[0]); split_tf32(v[ch].y, hi[1], lo[1]);
+                split_tf32(v[ch].z, hi[2], lo[2]); split_tf32(v[ch].w, hi[3], lo[3]);
+                const uint32_t o = chunk_off(TILE, m, ch) / 4;
+                *reinterpret_cast<float4*>(&s.Y_hi[o]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(&s.Y_lo[o]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&s.bar[Y_FULL]);
+        }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc_tf32(TILE, 128), idesc2 = make_idesc_tf32(TILE, N2);
+            const uint32_t yh = smem_u32(s.Y_hi), yl = smem_u32(s.Y_lo);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                mbar_wait(&s.bar[Y_FULL], it & 1);
+                fence_after_sync();
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    if (half == 1) { mbar_wait(&s.bar[D1_EMPTY], 0); fence_after_sync(); }
+                    else if (it > 0) { mbar_wait(&s.bar[D1_EMPTY], 1); fence_after_sync(); }
+                    const uint32_t wh = smem_u32(s.W1_hi[half]), wl = smem_u32(s.W1_lo[half]);
+#pragma unroll
+                    for (int ks = 0; ks < NIN / 8; ++ks) {
+                        const uint64_t a_hi = make_smem_desc(yh + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
+                        const uint64_t a_lo = make_smem_desc(yl + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
+                        const uint64_t b_hi = make_smem_desc(wh + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
+                        const uint64_t b_lo = make_smem_desc(wl + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
+                        mma_tf32_ss(tbase + COL_D1, a_lo, b_hi, idesc1, ks > 0);
+                        mma_tf32_ss(tbase + COL_D1, a_hi, b_lo, idesc1, true);
+                        mma_tf32_ss(tbase + COL_D1, a_hi, b_hi, idesc1, true);
+                    }
+                    mma_commit(&s.bar[D1_FULL]);
+                }
+                mma_commit(&s.bar[Y_EMPTY]);
+                mbar_wait(&s.bar[D2_EMPTY], (it & 1) ^ 1);
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait(&s.bar[H_FULL], half);
+                    fence_after_sync();
+                    const uint32_t wh = smem_u32(s.W2_hi[half]), wl = smem_u32(s.W2_lo[half]);
+#pragma unroll
+                    for (int ks = 0; ks < 128 / 8; ++ks) {
+                        const uint64_t b_hi = make_smem_desc(wh + chunk_off(N2, 0, 2 * ks), N2 * 16, 128);
+                        const uint64_t b_lo = make_smem_desc(wl + chunk_off(N2, 0, 2 * ks), N2 * 16, 128);
+                        mma_tf32_ts(tbase + COL_D2, tbase + COL_HLO + 8 * ks, b_hi, idesc2, (half | ks) > 0);
+                        mma_tf32_ts(tbase + COL_D2, tbase + COL_HHI + 8 * ks, b_lo, idesc2, true);
+                        mma_tf32_ts(tbase + COL_D2, tbase + COL_HHI + 8 * ks, b_hi, idesc2, true);
+                    }
+                    mma_commit(&s.bar[H_EMPTY]);
+                }
+                mma_commit(&s.bar[D2_FULL]);
+            }
+        }
+    } else {
+        // ===================== epilogue: 8 warps; warp & 3 = TMEM lane quarter, warp >> 2 = column half =====================
+        const int m = (warp & 3) * 32 + lane;                 // tile row == TMEM lane
+        const int chalf = warp >> 2;                          // hidden columns [64*chalf, 64*chalf+64) of each 128 half
+        const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int p = tile * TILE + m;
+            const bool valid = p < n_total;
+            // operands of the final update, fetched early (L2) so their latency hides behind the MMAs
+            float Ai[NF];
+            bool fire = false;
+            uint8_t prevbit = 0;
+            if (chalf == 0) {
+                if (valid) { load16(A_s + (size_t)p * NF, Ai); fire = fire_s[p] != 0; prevbit = flags_s[p] & 1; }
+                else {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) Ai[f] = 0.f;
+                }
+            }
+            float o32 = 0.f;
+            uint32_t rmask[NH / 64];                          // this warp's 4 ReLU words: (half, chalf) -> word 4*half + 2*chalf + {0,1}
+#pragma unroll
+            for (int wd = 0; wd < NH / 64; ++wd) rmask[wd] = 0u;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                mbar_wait(&s.bar[D1_FULL], half);
+                mbar_wait(&s.bar[H_EMPTY], half ^ 1);
+                fence_after_sync();
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int cc = chalf * 64 + c4 * 16;
+                    uint32_t r[16], hi[16], lo[16];
+                    tmem_ld16(lane_addr + COL_D1 + cc, r);
+                    wait_ld();
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = half * 128 + cc + j;
+                        const float pre = __uint_as_float(r[j]) + s.b1[n];
+                        bits |= (pre > 0.f ? 1u : 0u) << j;
+                        const float hv = fmaxf(pre, 0.f);
+                        o32 = fmaf(hv, s.w2_last[n], o32);
+                        float h_, l_; split_tf32(hv, h_, l_);
+                        hi[j] = __float_as_uint(h_); lo[j] = __float_as_uint(l_);
+                    }
+                    rmask[2 * half + (c4 >> 1)] |= bits << ((c4 & 1) * 16);
+                    tmem_st16(lane_addr + COL_HHI + cc, hi);
+                    tmem_st16(lane_addr + COL_HLO + cc, lo);
+                }
+                wait_st();
+                fence_before_sync();
+                mbar_arrive(&s.bar[D1_EMPTY]);
+                mbar_arrive(&s.bar[H_FULL]);
+            }
+            const int slot = it & 1;
+            if (chalf == 1) {
+                // hand the partial scalar-gate sum and ReLU words to the row's first-half warp
+                s.o32[slot][m] = o32;
+#pragma unroll
+                for (int wd = 0; wd < NH / 64; ++wd) s.relu[slot][m][wd] = rmask[wd];
+                asm volatile("bar.sync 2, 256;" ::: "memory");   // epilogue-only barrier (8 warps)
+            } else {
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                mbar_wait(&s.bar[D2_FULL], it & 1);
+                fence_after_sync();
+                float out[NO_PAD];
+                {
+                    uint32_t r[16];
+                    tmem_ld16(lane_addr + COL_D2, r); wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) out[j] = __uint_as_float(r[j]) + s.b2[j];
+                    tmem_ld16(lane_addr + COL_D2 + 16, r); wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) out[16 + j] = __uint_as_float(r[j]) + s.b2[16 + j];
+                }
+                fence_before_sync();
+                mbar_arrive(&s.bar[D2_EMPTY]);
+                out[32] = o32 + s.o32[slot][m] + s.b2[32]; out[33] = 0.f; out[34] = 0.f; out[35] = 0.f;
+                if (c.rule != 0) {
+#pragma unroll
+                    for (int o = NF; o < NO_PAD; ++o) out[o] = 0.f;
+                }
+                if (valid) {
+                    float nA[NF];
+                    if (c.rule == 0) {
+                        const float mult = fast_sigmoid(out[2 * NF]);
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) nA[f] = fmaf(Ai[f], fast_sigmoid(out[f]), fast_tanh(out[NF + f]) * mult);
+                    } else {
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) nA[f] = fmaf(out[f], c.orig_rate, Ai[f]);
+                    }
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) nA[f] = fire ? nA[f] : Ai[f];
+                    float4* o4 = reinterpret_cast<float4*>(An_s + (size_t)p * NF);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o4[k] = make_float4(nA[4 * k], nA[4 * k + 1], nA[4 * k + 2], nA[4 * k + 3]);
+                    float4* oo4 = reinterpret_cast<float4*>(O_s + (size_t)p * NO_PAD);
+#pragma unroll
+                    for (int k = 0; k < NO_PAD / 4; ++k) oo4[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+                    // relu words: hidden 0..63 -> words 0,1 (mine) ; 64..127 -> 2,3 (partner) ; 128..191 -> 4,5 (mine) ; 192..255 -> 6,7 (partner)
+                    uint4* rm4 = reinterpret_cast<uint4*>(relu_s + (size_t)p * (NH / 32));
+                    rm4[0] = make_uint4(rmask[0], rmask[1], s.relu[slot][m][0], s.relu[slot][m][1]);
+                    rm4[1] = make_uint4(rmask[2], rmask[3], s.relu[slot][m][2], s.relu[slot][m][3]);
+                    flags_s[p] = (uint8_t)(prevbit | (fire ? 4 : 0));
+                    alive_s[p] = c.use_alpha ? (nA[3] > 0.1f ? 1 : 0) : 1;
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tbase, mt::TMEM_COLS);
+}
+
+int launch_step_mlp_tc(int64_t N, const StepConsts& c, const sphnca_step_params* p, const float* A_s, const float* Y_s,
+                       const uint8_t* fire_s, float* A_new_s, uint8_t* alive_s, float* O_s, uint8_t* flags_s,
+                       uint32_t* relu_s, cudaStream_t stream) {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        SPHNCA_CUDA(cudaGetDevice(&dev));
+        SPHNCA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int num_tiles = (int)((N + mt::TILE - 1) / mt::TILE);
+    const int blocks = num_tiles < num_sms ? num_tiles : num_sms;
+    const size_t smem = sizeof(mt::Smem);
+    SPHNCA_CUDA(cudaFuncSetAttribute(step_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPHNCA_LAUNCH(step_mlp_tc_kernel, blocks, mt::THREADS, smem, stream, (int)N, A_s, Y_s, fire_s, *p, c, A_new_s, O_s, flags_s,
+                  alive_s, relu_s, num_tiles);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+}  // namespace sphnca

@@ -353,11 +353,11 @@ int launch_step_fwd_tc(const GridView& gv, const StepConsts& c, const sphnca_ste
     if (gv.dim == 3) {
         SPHNCA_CUDA(cudaFuncSetAttribute(step_fwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SPHNCA_LAUNCH(step_fwd_tc_kernel<3>, blocks, TC_THREADS, smem, stream, gv, (const float4*)xv4, A_s, fire_s, *p, c,
-                      A_new_s, Y_s, O_s, flags_s, alive_s, relu_s, num_tiles, g_mlp_path);
+                      A_new_s, Y_s, O_s, flags_s, alive_s, relu_s, num_tiles, 0);
     } else {
         SPHNCA_CUDA(cudaFuncSetAttribute(step_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SPHNCA_LAUNCH(step_fwd_tc_kernel<2>, blocks, TC_THREADS, smem, stream, gv, (const float4*)xv4, A_s, fire_s, *p, c,
-                      A_new_s, Y_s, O_s, flags_s, alive_s, relu_s, num_tiles, g_mlp_path);
+                      A_new_s, Y_s, O_s, flags_s, alive_s, relu_s, num_tiles, 0);
     }
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;

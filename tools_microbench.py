@@ -22,7 +22,7 @@ p = fused._step_params(*W, "gated", False, 1.0 / h, 1.0)
 def run():
     _lib.check(_lib.lib.sphnca_step_fwd(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(A_s), _lib.ptr(fire_s), C.byref(p),
                _lib.ptr(An), _lib.ptr(al), _lib.ptr(Y), _lib.ptr(O), _lib.ptr(fl), _lib.ptr(rl), _lib.stream_ptr()))
-for path, name in ((0, "simt"), (1, "tcgen05"), (2, "tcgen05, neighbour loop skipped (debug)")):
+for path, name in ((0, "simt fused"), (2, "tcgen05 fused"), (1, "tcgen05 split (perceive + mlp)")):
     _lib.check(_lib.lib.sphnca_set_mlp_path(path))
     for _ in range(3): run()
     torch.cuda.synchronize()
