@@ -125,6 +125,14 @@ int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s
                         const uint8_t* fire_s, const sphnca_step_params* p,
                         float* A_new_s, uint8_t* alive_s, float* Y_s, float* O_s, uint8_t* flags_s,
                         uint32_t* relu_s, void* stream);
+/* The two halves of the default (split) forward, callable on their own:
+ *   sphnca_step_perceive  neighbour sweep: Y_s [N,32] (scaled dA/dx | dA/dy), flags_s bit0 = previous life mask;
+ *   sphnca_step_mlp       tcgen05 MLP + gated/orig update + fire mask from (A_s, Y_s); reads flags_s bit0,
+ *                         writes A_new_s, alive_s, O_s, flags_s (bit0 | fire << 2), relu_s. */
+int32_t sphnca_step_perceive(const sphnca_grid* g, const float* xv4, const float* A_s, const sphnca_step_params* p,
+                             float* Y_s, uint8_t* flags_s, void* stream);
+int32_t sphnca_step_mlp(int64_t N, const float* A_s, const float* Y_s, const uint8_t* fire_s, const sphnca_step_params* p,
+                        float* A_new_s, uint8_t* alive_s, float* O_s, uint8_t* flags_s, uint32_t* relu_s, void* stream);
 /* Implementation switch of the step kernels (A/B tests; all produce the same tensors to fp32 rounding):
  *   1 (default) tcgen05 MLP with the 3xTF32 split; forward split into a full-L1 perception sweep
  *               kernel + the tensor-core MLP kernel (csrc/step.cu:step_perceive_kernel, step_mlp_tc.cu);

@@ -382,6 +382,30 @@ using namespace sphnca;
 
 extern "C" {
 
+int32_t sphnca_step_perceive(const sphnca_grid* g, const float* xv4, const float* A_s, const sphnca_step_params* p,
+                             float* Y_s, uint8_t* flags_s, void* stream_) {
+    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
+    cudaStream_t stream = as_stream(stream_);
+    if (gv.n == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(xv4 && A_s && Y_s && flags_s, "NULL argument");
+    const int pblocks = (int)((gv.n + 127) / 128);
+    if (gv.dim == 3) SPHNCA_LAUNCH(step_perceive_kernel<3>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+    else SPHNCA_LAUNCH(step_perceive_kernel<2>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_step_mlp(int64_t N, const float* A_s, const float* Y_s, const uint8_t* fire_s, const sphnca_step_params* p,
+                        float* A_new_s, uint8_t* alive_s, float* O_s, uint8_t* flags_s, uint32_t* relu_s, void* stream_) {
+    SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
+    sphnca_grid fake{}; fake.dim = 3; fake.h = 1.0;      // geometry constants are unused by the MLP half
+    StepConsts c; { int rc = make_consts(&fake, p, &c); if (rc) return rc; }
+    if (N == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(A_s && Y_s && fire_s && A_new_s && alive_s && O_s && flags_s && relu_s, "NULL argument");
+    return launch_step_mlp_tc(N, c, p, A_s, Y_s, fire_s, A_new_s, alive_s, O_s, flags_s, relu_s, as_stream(stream_));
+}
+
 int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s, const uint8_t* fire_s,
                         const sphnca_step_params* p, float* A_new_s, uint8_t* alive_s, float* Y_s, float* O_s,
                         uint8_t* flags_s, uint32_t* relu_s, void* stream_) {
@@ -393,11 +417,9 @@ int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s
     if (mlp_path() == 2)      // fused tcgen05 kernel (sweep + MLP in one persistent kernel)
         return launch_step_fwd_tc(gv, c, p, xv4, A_s, fire_s, A_new_s, alive_s, Y_s, O_s, flags_s, relu_s, stream);
     if (mlp_path() == 1) {    // split: full-L1 sweep kernel, then the tcgen05 MLP kernel (default)
-        const int pblocks = (int)((gv.n + 127) / 128);
-        if (gv.dim == 3) SPHNCA_LAUNCH(step_perceive_kernel<3>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
-        else SPHNCA_LAUNCH(step_perceive_kernel<2>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
-        SPHNCA_LAUNCH_CHECK();
-        return launch_step_mlp_tc(gv.n, c, p, A_s, Y_s, fire_s, A_new_s, alive_s, O_s, flags_s, relu_s, stream);
+        int rc = sphnca_step_perceive(g, xv4, A_s, p, Y_s, flags_s, stream_);
+        if (rc) return rc;
+        return sphnca_step_mlp(gv.n, A_s, Y_s, fire_s, p, A_new_s, alive_s, O_s, flags_s, relu_s, stream_);
     }
     const int blocks = (int)((gv.n + kStepThreads - 1) / kStepThreads);
     const size_t smem = sizeof(MlpSmem);

@@ -23,8 +23,9 @@ using namespace tc;
 
 namespace bw {
 constexpr int TILE = 128;
-constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP0 = 5, LOAD_WARPS = 4;
-constexpr int THREADS = (LOAD_WARP0 + LOAD_WARPS) * 32;      // 288
+// epilogue warps 0..7: warp & 3 = TMEM lane quarter, warp >> 2 = which 64 of a half's 128 hidden columns
+constexpr int EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP0 = 9, LOAD_WARPS = 4;
+constexpr int THREADS = (LOAD_WARP0 + LOAD_WARPS) * 32;      // 416
 constexpr int KO = 32;                                       // outputs handled by the tensor core
 constexpr uint32_t COL_D3 = 0, COL_DHLO = 128, COL_DY = 256, TMEM_COLS = 512;
 enum { DO_FULL = 0, DO_EMPTY, D3_FULL, DH_FULL, DY_FULL, DY_EMPTY, NUM_BARS };
@@ -70,7 +71,7 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     if (tid == 0) {
         mbar_init(&s.bar[DO_FULL], LOAD_WARPS * 32); mbar_init(&s.bar[DO_EMPTY], 1);
         mbar_init(&s.bar[D3_FULL], 1);               mbar_init(&s.bar[DH_FULL], EPI_WARPS * 32);
-        mbar_init(&s.bar[DY_FULL], 1);               mbar_init(&s.bar[DY_EMPTY], EPI_WARPS * 32);
+        mbar_init(&s.bar[DY_FULL], 1);               mbar_init(&s.bar[DY_EMPTY], 4 * 32);
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc(&s.tmem_base, TMEM_COLS);
@@ -109,12 +110,14 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
 #pragma unroll
                     for (int k = 0; k < NO_PAD / 4; ++k) { float4 t = __ldg(o4 + k); out[4*k] = t.x; out[4*k+1] = t.y; out[4*k+2] = t.z; out[4*k+3] = t.w; }
                     if (c.rule == 0) {
-                        const float mult = sigmoidf_(out[2 * NF]);
+                        // fast exponential (2 ulp): |error| ~1e-7 on the gates, far inside the parity bar
+                        const float mult = __fdividef(1.f, 1.f + __expf(-out[2 * NF]));
                         float dmult = 0.f;
 #pragma unroll
                         for (int f = 0; f < NF; ++f) {
-                            const float gate = sigmoidf_(out[f]);
-                            const float delta = tanhf(out[NF + f]);
+                            const float gate = __fdividef(1.f, 1.f + __expf(-out[f]));
+                            const float e2 = __expf(-2.f * fabsf(out[NF + f]));
+                            const float delta = copysignf(__fdividef(1.f - e2, 1.f + e2), out[NF + f]);
                             dO[f] = dnA[f] * Ai[f] * gate * (1.f - gate);
                             dO[NF + f] = dnA[f] * mult * (1.f - delta * delta);
                             dmult = fmaf(dnA[f], delta, dmult);
@@ -207,8 +210,9 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
         }
     } else {
         // ======================= epilogue =======================
-        const int m = tid;
-        const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+        const int m = (warp & 3) * 32 + lane;
+        const int chalf = warp >> 2;
+        const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int p = tile * TILE + m;
@@ -220,7 +224,8 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 fence_after_sync();
                 const float d32 = s.dO32[slot][m];
 #pragma unroll
-                for (int cc = 0; cc < 128; cc += 16) {
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int cc = chalf * 64 + c4 * 16;
                     uint32_t r[16], hi[16], lo[16];
                     tmem_ld16(lane_addr + COL_D3 + cc, r);
                     wait_ld();
@@ -239,6 +244,7 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 fence_before_sync();
                 mbar_arrive(&s.bar[DH_FULL]);
             }
+            if (chalf != 0) continue;                         // the final part belongs to the first column-half warps
             mbar_wait(&s.bar[DY_FULL], it & 1);
             fence_after_sync();
             float dy[NIN];

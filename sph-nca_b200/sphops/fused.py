@@ -66,8 +66,13 @@ class _NCAStep(torch.autograd.Function):
         p = _step_params(W1c, b1c, W2c, b2c, update_rule, use_alpha, perception_scale, orig_rate)
         if N:
             g, st = grid.c_grid(), stream_ptr()
-            _timed("step_fwd", lib.sphnca_step_fwd, g, ptr(xv4), ptr(A_s), ptr(fire_s), C.byref(p), ptr(An_s),
-                   ptr(alive_s), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
+            if SPLIT_FORWARD:
+                _timed("step_perceive", lib.sphnca_step_perceive, g, ptr(xv4), ptr(A_s), C.byref(p), ptr(Y_s), ptr(flags_s), st)
+                _timed("step_mlp", lib.sphnca_step_mlp, N, ptr(A_s), ptr(Y_s), ptr(fire_s), C.byref(p), ptr(An_s),
+                       ptr(alive_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
+            else:
+                _timed("step_fwd", lib.sphnca_step_fwd, g, ptr(xv4), ptr(A_s), ptr(fire_s), C.byref(p), ptr(An_s),
+                       ptr(alive_s), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
             _timed("step_mask", lib.sphnca_step_mask, g, ptr(xv4), ptr(alive_s), ptr(An_s), ptr(flags_s), st)
         out = grid.unpack_rows(An_s, 16)
         ctx.grid = grid
@@ -126,6 +131,9 @@ class _NCAStep(torch.autograd.Function):
                 dW2 if g[6] else None, db2 if g[7] else None, None, None, None, None, None, None)
 
 
+# True (default): call the two halves of the split forward (perception sweep, tcgen05 MLP) as separate
+# C-ABI entries; False: one sphnca_step_fwd call, whose implementation follows sphnca_set_mlp_path.
+SPLIT_FORWARD = True
 # True: CUDA-core backward (step_bwd_kernel streams transposed hidden activations to mlp_wgrad_kernel);
 # False (default): tensor-core backward (step_bwd_tc_kernel + mlp_wgrad_tc_kernel, no scratch).
 SIMT_BACKWARD = False

@@ -60,9 +60,11 @@ def _default_mlp_path():
     from sphops import _lib, fused
     _lib.check(_lib.lib.sphnca_set_mlp_path(1))
     fused.SIMT_BACKWARD = False
+    fused.SPLIT_FORWARD = True
     yield
     _lib.check(_lib.lib.sphnca_set_mlp_path(1))
     fused.SIMT_BACKWARD = False
+    fused.SPLIT_FORWARD = True
 
 
 @pytest.mark.parametrize("path", ["ops", "fused_simt", "fused_tc", "fused_tc_onekernel"])
@@ -79,6 +81,7 @@ def test_step_matches_reference(name, path):
         assert sphops.fused_available(), "libsphnca.so lacks the fused step"
         _lib.check(_lib.lib.sphnca_set_mlp_path({"fused_tc": 1, "fused_tc_onekernel": 2, "fused_simt": 0}[path]))
         fused_mod.SIMT_BACKWARD = path == "fused_simt"
+        fused_mod.SPLIT_FORWARD = path == "fused_tc"
     g = load_golden(name)
     model, A0, states, loss = run_case(g, fused)
     K = g["masks"].shape[0]
