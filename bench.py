@@ -49,10 +49,22 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "train2d_b8x65k_k64"
 METRIC = "particle-NCA-steps/sec (fwd+bwd)"
 UNIT = "particle-steps/s"
-ALGO_BYTES = {  # algorithmic HBM bytes per particle per launch
-    "step_fwd": 152.0, "step_mask": 24.0, "step_bwd": 208.0, "step_adjoint": 336.0,
-    # weight-gradient stage: streams the transposed hidden activations H^T, dH^T (2 x 256 x 4 B) + y (192) + dO (132)
-    "mlp_wgrad": 2372.0,
+# Per-kernel roofline bookkeeping.  bytes = algorithmic HBM bytes per particle per launch
+# (compulsory traffic of that kernel's interface), flops = algorithmic FLOPs per particle (FMA = 2),
+# bound = which roof applies: "hbm" (sweeps: memory/latency side) or "tensor" (tcgen05 MLP kernels).
+KERNELS = {
+    # sweep: read x,v,A (80) + write scaled dA/dx|dA/dy (128) + 1 flag byte; ~12 FLOP/candidate + ~137 FLOP/neighbour
+    "step_perceive": dict(bytes=209.0, flops=5500.0, bound="hbm"),
+    # MLP + update: read A,Y (192) + fire (1) ; write A' (64), O (144), relu bits (32), flags/alive (2); 2*(48*256+256*33) FLOP
+    "step_mlp": dict(bytes=435.0, flops=41472.0, bound="tensor"),
+    "step_fwd": dict(bytes=152.0, flops=41472.0 + 5500.0, bound="tensor"),   # fused forward (A/B path)
+    "step_mask": dict(bytes=24.0, flops=1300.0, bound="hbm"),
+    # data gradient: read A,O,dA',relu,flags (64+144+64+32+1) ; write dO (144), dY (128), dAdir (64); 2*(33*256+256*48) FLOP
+    "step_bwd": dict(bytes=641.0, flops=41472.0, bound="tensor"),
+    # weight gradient with transposed recompute: read A,Y,dO (336); recompute 2*(48*256+33*256) + accumulate the same
+    "mlp_wgrad": dict(bytes=336.0, flops=82944.0, bound="tensor"),
+    # gather adjoint: read x,v (16), dY (128), dAdir (64) ; write dA (64)
+    "step_adjoint": dict(bytes=272.0, flops=5000.0, bound="hbm"),
 }
 
 
@@ -286,25 +298,36 @@ def main():
     kernels, dominant = {}, None
     for name, evs in prof.items():
         tot = sum(a.elapsed_time(b) for a, b in evs)
-        kernels[name] = {"launches": len(evs), "avg_ms": tot / len(evs), "share_of_step": tot / ms}
+        k = {"launches": len(evs), "avg_ms": tot / len(evs), "share_of_step": tot / ms}
+        info = KERNELS.get(name)
+        if info:
+            sec = k["avg_ms"] * 1e-3
+            k["hbm_gbs"] = info["bytes"] * N / sec / 1e9
+            k["hbm_frac"] = k["hbm_gbs"] / hbm
+            k["tflops"] = info["flops"] * N / sec / 1e12
+            k["bound"] = info["bound"]
+        kernels[name] = k
         if dominant is None or tot > kernels[dominant]["avg_ms"] * kernels[dominant]["launches"]:
             dominant = name
     roofline = None
-    if dominant:
-        avg_s = kernels[dominant]["avg_ms"] * 1e-3
-        achieved = ALGO_BYTES[dominant] * N / avg_s / 1e9
-        roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                    "frac": achieved / hbm, "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
-                    "algorithmic_bytes_per_particle": ALGO_BYTES[dominant], "particles_per_launch": N,
-                    "avg_launch_ms": kernels[dominant]["avg_ms"],
-                    "note": "v1 step_fwd runs its MLP on the fp32 CUDA-core pipe: 2*(48*256+256*33)=41,472 FLOP/particle "
-                            "=> the kernel is fp32-pipe bound, not HBM bound (DESIGN.md 5); fp32 fraction below"}
-        if dominant in ("step_fwd", "step_bwd"):
-            flops = {"step_fwd": 41472.0 + 5500.0, "step_bwd": 2 * (48 * 256 * 2 + 256 * 36)}[dominant]
-            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-            fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-            roofline["fp32_pipe"] = {"achieved_tflops": flops * N / avg_s / 1e12, "peak_tflops_at_sampled_clock": fp32_peak,
-                                     "frac": flops * N / avg_s / 1e12 / fp32_peak}
+    if dominant and dominant in KERNELS:
+        info, k = KERNELS[dominant], kernels[dominant]
+        if info["bound"] == "tensor":
+            # kernels timed inside a long step -> sustained bf16 figure; kind::tf32 runs at half the bf16 rate and the
+            # 3xTF32 split issues 3 MMAs per product, so 1/6 of this peak is the ceiling of an fp32-accurate kernel
+            roofline = {"kernel": dominant, "bound": "tensor", "achieved": k["tflops"], "peak": bf16_sust, "unit": "TFLOP/s",
+                        "frac": k["tflops"] / bf16_sust, "traffic": None,
+                        "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({which})",
+                        "algorithmic_flops_per_particle": info["flops"], "particles_per_launch": N, "avg_launch_ms": k["avg_ms"],
+                        "note": "fp32-accurate MLP on tcgen05 kind::tf32 with the 3xTF32 split: ceiling = peak/6 "
+                                f"= {bf16_sust / 6:.0f} TFLOP/s of algorithmic FLOPs; frac_of_3xtf32_ceiling below",
+                        "frac_of_3xtf32_ceiling": k["tflops"] / (bf16_sust / 6)}
+        else:
+            roofline = {"kernel": dominant, "bound": "hbm", "achieved": k["hbm_gbs"], "peak": hbm, "unit": "GB/s",
+                        "frac": k["hbm_frac"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
+                        "algorithmic_bytes_per_particle": info["bytes"], "particles_per_launch": N, "avg_launch_ms": k["avg_ms"],
+                        "note": "neighbour sweep: ~32 gathered 64-byte rows per particle out of L1/L2; latency/issue bound, "
+                                "not HBM bound (DESIGN.md 4)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -51,3 +51,46 @@ def test_shard_sections():
     assert [g[2] for g in got8] == [4 * r for r in range(8)] and all(g[1] - g[0] == 1 for g in got8)
     # more ranks than sections: trailing ranks get empty shards
     assert multigpu.shard_sections((4, 4), 4, 3) == (2, 2, 8, 8)
+
+
+def _slab_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import math
+    import multigpu
+    from oracle import sphnca_oracle as O
+    from tests.util import jittered_lattice
+    gen = torch.Generator().manual_seed(0)
+    n = 40
+    x = torch.nn.functional.pad(jittered_lattice(n, 2, gen), (0, 1))
+    h = 3.2 * 2 / n
+    dims = (math.ceil(2 / h), math.ceil(2 / h), 3)
+    A = torch.rand(x.shape[0], 4, generator=gen)
+    # global reference: blur of A over the whole cloud (oracle)
+    og, pairs, v = O.prepare(x, (x.shape[0],), h, dims)
+    ref = O.blur(pairs, v, A)
+    # sharded: each rank computes the same operator on [interior | halo] and keeps its interior
+    part = multigpu.SlabPartition(x, h, dims, axis=1, rank=rank, world=world)
+    x_loc = part.local_from_global(x)
+    A_loc = part.local_from_global(A)
+    v_loc = part.local_from_global(v[:, None].contiguous())[:, 0]
+    lg = O.build_hashgrid(x_loc, (part.n_local,), h, dims)
+    lp = O.make_pairs(x_loc, lg)
+    out = O.blur(lp, v_loc, A_loc)[:part.n_own]
+    err = float((out - ref[part.own_idx]).abs().max() / ref.abs().max())
+    ret[rank] = (err, part.n_own, part.n_halo_prev, part.n_halo_next, part.row_lo, part.row_hi)
+    dist.destroy_process_group()
+
+
+def test_slab_partition_halo_world2():
+    """One cell layer of halo from the ring neighbours reproduces the global neighbour sums on every interior."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_slab_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0][1] + ret[1][1] == 40 * 40                        # every particle owned exactly once
+    for r in range(world):
+        err, n_own, hp, hn, lo, hi = ret[r]
+        assert err < 1e-12, err                                      # identical neighbour sets -> identical fp64 sums
+        assert hp > 0 and hn > 0 and hi > lo
+    assert ret[0][5] == ret[1][4]                                    # contiguous row ranges
