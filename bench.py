@@ -43,6 +43,10 @@ WORKLOADS = {
     # BASELINE.json configs[2]
     "train3d_250k_k96": dict(desc="3D point cloud, 250,047 jittered particles (63^3), 96 NCA steps fwd+bwd",
                              lattice_dim=3, n_side=63, batch=1, k_nca=96, hf=1.97),
+    # BASELINE.json configs[3]: one cloud, forward only, slab shard + NVLink halo (strong scaling over GPUs)
+    "infer2d_16m_slab": dict(desc="discretization-agnostic inference on 16,000,000 jittered 2D particles (4000^2, zero-padded to 3-D, "
+                                  "dims (1250,1250,3)), 16 NCA steps forward, spatial slab shard + halo exchange",
+                             lattice_dim=2, n_side=4000, batch=1, k_nca=16, hf=3.2, slab=True),
     # reduced sizes for quick checks (not a bench line)
     "tiny": dict(desc="tiny 2D, batch 2 x 4,096, 8 steps", lattice_dim=2, n_side=64, batch=2, k_nca=8, hf=3.2),
 }
@@ -166,6 +170,71 @@ def cpu_oracle_rate(wl, steps, warmup, sample_sections=1, sample_k=4):
     return units / (sum(times) / len(times)), sum(times) / len(times), sample
 
 
+def run_slab(args, wl, rank, world, local_rank):
+    """Forward-only rollout of ONE cloud sharded into slabs of cell rows (multigpu.SlabShardedNCA)."""
+    import nca
+    import multigpu
+    from sphops import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    n_side, K = wl["n_side"], wl["k_nca"]
+    s_ = 2.0 / n_side
+    h = wl["hf"] * s_
+    d = math.ceil(2.0 / h)
+    dims = (d, d, 3)
+    gen = torch.Generator(device=dev).manual_seed(0)               # every rank builds the same cloud on its GPU
+    ax = (torch.arange(n_side, dtype=torch.float32, device=dev) + 0.5) * s_ - 1.0
+    x = torch.stack(torch.meshgrid(ax, ax, indexing="ij"), dim=-1).reshape(-1, 2)
+    x = x + (torch.rand(x.shape, generator=gen, device=dev) - 0.5) * s_
+    x = torch.nn.functional.pad(x, (0, 1))
+    N = x.shape[0]
+    model = nca.SPHNCA(16, 0.5, update_rule="gated", use_alpha=False, normalize_perception=-1).to(dev)
+    with torch.no_grad():
+        for t, src in zip((model.model[0].weight, model.model[0].bias, model.model[2].weight, model.model[2].bias), load_weights()):
+            t.copy_(src)
+    sh = multigpu.SlabShardedNCA(model, x, h, dims, axis=1)
+    n_own = sh.part.n_own
+    del x
+    torch.manual_seed(1234 + rank)
+    A0 = torch.rand(n_own, 16, device=dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        sh.rollout(A0, 2)
+    barrier()
+    l0 = _lib.lib.sphnca_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = sh.rollout(A0, K)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = int(_lib.lib.sphnca_launch_count() - l0)
+    if rank == 0:
+        line = {"metric": "particle-NCA-steps/sec (fwd)", "value": N * K * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "description": wl["desc"], "particles_total": N, "particles_rank0": n_own,
+                           "halo_rank0": sh.part.n_halo_prev + sh.part.n_halo_next, "nca_steps": K, "h": h, "dims": list(dims),
+                           "parallelism": f"slab{world}", "halo_bytes_per_nca_step_rank0": sh.bytes_per_step,
+                           "l2": "state per rank >> 126 MB L2"},
+                "gpu_launches": launches}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def run_reference(args, wl, rank):
     """--impl reference: the reference's path on the host cores = the CPU oracle port (kind 'port')."""
     if rank != 0:
@@ -211,6 +280,9 @@ def main():
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU oracle)")
+    if wl.get("slab"):
+        run_slab(args, wl, rank, world, local_rank)
+        return
 
     import nca
     import sphops

@@ -114,17 +114,27 @@ class SlabPartition:
         `out_local` has n_local rows.  Blocking; one batched NCCL/gloo P2P round with the two ring neighbours."""
         if self.world == 1:
             return 0
-        to_prev = own_rows_tensor[self.send_prev].contiguous()
-        to_next = own_rows_tensor[self.send_next].contiguous()
-        shape = own_rows_tensor.shape[1:]
-        from_prev = torch.empty((self.n_halo_prev,) + tuple(shape), dtype=own_rows_tensor.dtype, device=own_rows_tensor.device)
-        from_next = torch.empty((self.n_halo_next,) + tuple(shape), dtype=own_rows_tensor.dtype, device=own_rows_tensor.device)
+        n = self.n_own
+        halo_prev = torch.arange(n, n + self.n_halo_prev, device=out_local.device)
+        halo_next = torch.arange(n + self.n_halo_prev, self.n_local, device=out_local.device)
+        return self.exchange_indexed(own_rows_tensor, self.send_prev, self.send_next, out_local, halo_prev, halo_next)
+
+    def exchange_indexed(self, src, send_prev_idx, send_next_idx, dst, halo_prev_idx, halo_next_idx):
+        """Generic form: rows src[send_*_idx] go to the ring neighbours, received rows land in dst[halo_*_idx].
+        Only halo-sized gathers / scatters are performed (the tensors may be in any order, e.g. cell-sorted)."""
+        if self.world == 1:
+            return 0
+        to_prev = src[send_prev_idx].contiguous()
+        to_next = src[send_next_idx].contiguous()
+        shape = tuple(src.shape[1:])
+        from_prev = torch.empty((self.n_halo_prev,) + shape, dtype=src.dtype, device=src.device)
+        from_next = torch.empty((self.n_halo_next,) + shape, dtype=src.dtype, device=src.device)
         ops = [dist.P2POp(dist.isend, to_prev, self.prev, self.group), dist.P2POp(dist.isend, to_next, self.next, self.group),
                dist.P2POp(dist.irecv, from_next, self.next, self.group), dist.P2POp(dist.irecv, from_prev, self.prev, self.group)]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-        out_local[self.halo_prev] = from_prev
-        out_local[self.halo_next] = from_next
+        dst[halo_prev_idx] = from_prev
+        dst[halo_next_idx] = from_next
         return (to_prev.numel() + to_next.numel()) * to_prev.element_size()
 
     def local_from_global(self, t_global):
@@ -171,19 +181,16 @@ class SlabShardedNCA:
         inv = torch.empty_like(sid); inv[sid] = torch.arange(sid.numel(), device=sid.device)
         self.pos_of_local = inv                                   # sorted position of local particle i
         self.own_pos = inv[:p.n_own]
+        # sorted positions of what is sent / received each step (halo-sized index sets)
+        self.send_prev_pos = self.own_pos[p.send_prev]
+        self.send_next_pos = self.own_pos[p.send_next]
+        self.halo_prev_pos = inv[p.n_own:p.n_own + p.n_halo_prev]
+        self.halo_next_pos = inv[p.n_own + p.n_halo_prev:]
         self.bytes_per_step = 0
 
     def _exchange_sorted(self, t_s):
-        """halo exchange of a tensor held in sorted order (rows = local particles)."""
-        p = self.part
-        if p.world == 1:
-            return 0
-        own = t_s[self.own_pos]
-        loc = torch.empty((p.n_local,) + tuple(t_s.shape[1:]), dtype=t_s.dtype, device=t_s.device)
-        nbytes = p.exchange(own, loc)
-        halo_pos = self.pos_of_local[p.n_own:]
-        t_s[halo_pos] = loc[p.n_own:]
-        return nbytes
+        """halo exchange, in place, of a tensor held in cell-sorted order (rows = local particles)."""
+        return self.part.exchange_indexed(t_s, self.send_prev_pos, self.send_next_pos, t_s, self.halo_prev_pos, self.halo_next_pos)
 
     @torch.no_grad()
     def rollout(self, A_global_own, steps, fire_masks=None, fire_rate=None):
