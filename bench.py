@@ -382,6 +382,14 @@ def main():
         if dominant is None or tot > kernels[dominant]["avg_ms"] * kernels[dominant]["launches"]:
             dominant = name
     roofline = None
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if dominant and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if dominant in tj.get("bytes_per_launch", {}):
+            # measured once under `ncu --set full` (never during a timed run); scaled to this launch size
+            traffic = tj["bytes_per_launch"][dominant] * N / tj["particles"]
+            traffic_src = tj["source"]
     if dominant and dominant in KERNELS:
         info, k = KERNELS[dominant], kernels[dominant]
         if info["bound"] == "tensor":
@@ -393,7 +401,8 @@ def main():
                         "algorithmic_flops_per_particle": info["flops"], "particles_per_launch": N, "avg_launch_ms": k["avg_ms"],
                         "note": "fp32-accurate MLP on tcgen05 kind::tf32 with the 3xTF32 split: ceiling = peak/6 "
                                 f"= {bf16_sust / 6:.0f} TFLOP/s of algorithmic FLOPs; frac_of_3xtf32_ceiling below",
-                        "frac_of_3xtf32_ceiling": k["tflops"] / (bf16_sust / 6)}
+                        "frac_of_3xtf32_ceiling": k["tflops"] / (bf16_sust / 6),
+                        "algorithmic_bytes_per_launch": info["bytes"] * N}
         else:
             roofline = {"kernel": dominant, "bound": "hbm", "achieved": k["hbm_gbs"], "peak": hbm, "unit": "GB/s",
                         "frac": k["hbm_frac"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
@@ -401,6 +410,9 @@ def main():
                         "note": "neighbour sweep: ~32 gathered 64-byte rows per particle out of L1/L2; latency/issue bound, "
                                 "not HBM bound (DESIGN.md 4)"}
 
+    if roofline is not None:
+        roofline["traffic"] = traffic
+        roofline["traffic_source"] = traffic_src
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
