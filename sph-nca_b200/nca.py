@@ -193,3 +193,268 @@ def sample_plane(model, x, A, sections, h, dims, out_steps=False, iter_n=None, l
     if out_steps:
         return loss, x, out
     return loss, x, A
+
+
+# =====================================================================================================
+# Periodic ("wrapped") planes -- reference code/nca.py:167-299
+# =====================================================================================================
+def get_wrapped_points_index(x, A, sections, gmin, gsize, h):
+    """Per section, the 9 ghost index lists of the reference (None at slot 4 = the plane itself): particles
+    within h of the left/right (x) and bottom/top (y) edges and the four corner intersections, each list in
+    ascending particle order.  Device-side (the reference round-trips through numpy)."""
+    gmin = torch.as_tensor(gmin, dtype=x.dtype, device=x.device)
+    gmax = gmin + torch.as_tensor(gsize, dtype=x.dtype, device=x.device)
+    out, off = [], 0
+    for n in sections:
+        xs = x[off:off + n]
+        lo_x, hi_x = xs[:, 0] <= gmin[0] + h, xs[:, 0] >= gmax[0] - h
+        lo_y, hi_y = xs[:, 1] <= gmin[1] + h, xs[:, 1] >= gmax[1] - h
+        pick = lambda m: torch.nonzero(m).flatten()
+        out.append([pick(lo_x & lo_y), pick(lo_x), pick(lo_x & hi_y), pick(lo_y), None, pick(hi_y),
+                    pick(hi_x & lo_y), pick(hi_x), pick(hi_x & hi_y)])
+        off += n
+    return out
+
+
+class _WrapPlan:
+    """One gather that performs the reference's wrap (and unwrap+wrap) for a whole packed batch.
+
+    wrapped row r of the packed batch = original row src[r], positions shifted by shift[r];
+    own[i] = wrapped row of original particle i (the reference's `unwrap_tensors` keeps exactly these)."""
+
+    def __init__(self, sections, idxs, gsize, device):
+        src, shift, own, new_sections = [], [], [], []
+        off, woff = 0, 0
+        gs = torch.as_tensor(gsize, dtype=torch.float32, device=device)
+        for n, idx in zip(sections, idxs):
+            parts = [torch.arange(n, device=device)]
+            shifts = [torch.zeros((n, 2), device=device)]
+            for k in range(9):
+                if idx[k] is None:
+                    continue
+                sx, sy = 1 - (k // 3), 1 - (k % 3)        # ghost offset signs (reference nca.py:214-217)
+                parts.append(idx[k])
+                shifts.append(torch.tensor([sx, sy], dtype=torch.float32, device=device).expand(idx[k].numel(), 2) * gs[:2])
+            p = torch.cat(parts)
+            src.append(p + off)
+            shift.append(torch.cat(shifts))
+            own.append(torch.arange(n, device=device) + woff)
+            new_sections.append(int(p.numel()))
+            off += n
+            woff += int(p.numel())
+        self.src, self.shift, self.own = torch.cat(src), torch.cat(shift), torch.cat(own)
+        self.sections = new_sections
+        self.rewrap = self.own[self.src]                   # unwrap followed by wrap, as one gather
+
+    def wrap_positions(self, x):
+        xw = x[self.src].clone()
+        xw[:, :2] += self.shift.to(x.dtype)
+        return xw
+
+
+def wrap_tensors(tensors, sections, idxs, gsize, x=None):
+    """API of reference nca.py:200-227: ghost-pad every tensor (and shift the ghost positions of `x`)."""
+    dev = tensors[0].device if tensors else x.device
+    plan = _WrapPlan(sections, idxs, gsize, dev)
+    new = [t[plan.src] for t in tensors]
+    if x is not None:
+        return new, plan.sections, plan.wrap_positions(x)
+    return new, plan.sections
+
+
+def unwrap_tensors(tensors, sections, orig_sections):
+    """API of reference nca.py:229-242: keep the first `orig_sections[b]` rows of every wrapped section."""
+    keep, off = [], 0
+    for n_w, n in zip(sections, orig_sections):
+        keep.append(torch.arange(n) + off)
+        off += n_w
+    keep = torch.cat(keep)
+    return [t[keep.to(t.device)] for t in tensors]
+
+
+def sample_plane_wrapped(model, x, A, sections, h, dims, gmin, gsize, out_steps=False, iter_n=None, loss_fn=None,
+                         img=None, optimizer=None, scheduler=None, out_wrapped=False, fire_rate=None):
+    """Rollout on a periodic plane (reference nca.py:245-299): ghost copies of the particles within h of an
+    edge are appended, the grid/volume are built on the wrapped set once, and after every step the ghosts are
+    refreshed from their sources.  Here wrap / unwrap+wrap are single device-side gathers."""
+    iter_n = _draw_steps(iter_n, (32, 48))
+    xdim = x.shape[-1]
+    if USE_3D and xdim == 2:
+        x = F.pad(x, (0, 1))
+    idxs = get_wrapped_points_index(x, A, sections, gmin, gsize, h)
+    plan = _WrapPlan(sections, idxs, gsize, x.device)
+    x_w = plan.wrap_positions(x)
+    A_w = A[plan.src]
+    grid, v_w = model.init_grid(x_w, plan.sections, h, dims)
+
+    out, out_w = [], []
+    for _ in range(iter_n):
+        out.append(A.clone())
+        out_w.append(A_w.clone())
+        x_w, A_w = model(x_w, v_w, A_w, h, grid, fire_rate=fire_rate, feature_process=None)
+        A = A_w[plan.own]
+        A_w = A_w[plan.rewrap]
+    out.append(A.clone())
+    out_w.append(A_w.clone())
+
+    loss = 0.0
+    if loss_fn is not None:
+        if xdim == 2:
+            x = x[..., :2]
+        loss = _train_on(loss_fn, x, A, img, out, model, optimizer, scheduler)
+    if USE_3D and xdim == 2:
+        x = x[..., :2]
+    if out_steps:
+        if out_w:       # the reference's `out_wrapped` flag is shadowed by its list of the same name (always truthy)
+            return loss, x, out, x_w, out_w
+        return loss, x, out
+    return loss, x, A
+
+
+# =====================================================================================================
+# Surface meshes: tangent frames -- reference code/nca.py:303-398 (SURVEY.md 8f row 2)
+# =====================================================================================================
+def normalize(v):
+    return v / (1e-8 + torch.linalg.norm(v, dim=-1, keepdims=True))
+
+
+def orthogonalize(N, T):
+    """Remove the component of T along N and renormalise."""
+    return normalize(T - N * (N * T).sum(-1, keepdims=True))
+
+
+_DIFFUSE_GRIDS = {}
+
+
+def diffuse(N, T, x, A, sections, h, dims, v=None, grid=None, lerp_multiplier=1.0, w_multiplier=1.0):
+    """Spread the tangent field over the surface with an activity-weighted SPH blur (reference nca.py:312-323).
+    The reference rebuilds the hash grid and volumes on every call; positions do not change during a rollout,
+    so they are cached per position tensor (same data pointer / version / h / dims)."""
+    if v is None or grid is None:
+        key = (x.data_ptr(), x._version, tuple(x.shape), float(h), str(dims), tuple(sections))
+        hit = _DIFFUSE_GRIDS.get("last")
+        if hit is None or hit[0] != key:
+            g = sphops.initialize_hashgrid(x, sections, h, dims)
+            hit = (key, g, sphops.volume(x, h, g), x)       # keeping x alive pins its address
+            _DIFFUSE_GRIDS["last"] = hit
+        grid, v = hit[1], hit[2]
+    w = torch.clip(cell_activity(A)[..., None], 0, 1)
+    m = torch.lerp(torch.ones_like(w), w, w_multiplier)
+    blurred = sphops.blur(x, v, torch.cat([m, m * T], dim=-1), h, grid)
+    T2 = blurred[..., 1:] / (1e-8 + blurred[..., [0]])
+    return orthogonalize(N, torch.lerp(T2, T, w * lerp_multiplier))
+
+
+def project_tangent_space(Av, N, T):
+    """Av [n,C,3] expressed in the local frame (T, N x T, N)."""
+    frame = torch.stack([T, torch.linalg.cross(N, T), N], dim=-1)
+    return torch.matmul(Av, frame)
+
+
+def feature_process_tangent(N, T):
+    def func(features):
+        return [(As, project_tangent_space(Av, N, T)) for As, Av in features]
+    return func
+
+
+def sample_mesh(model, x, A, N, T, sections, h, dims, out_steps=False, iter_n=None, loss_fn=None, img=None,
+                optimizer=None, scheduler=None, lerp_multiplier=1.0, w_multiplier=1.0, out_np=False, iter_wrapper=None,
+                fire_rate=None):
+    """Rollout on a surface point cloud (reference nca.py:338-381): perception is projected onto the tangent
+    frame, and the tangent field T is diffused (in place) after every step."""
+    iter_n = _draw_steps(iter_n, (32, 48))
+    xdim = x.shape[-1]
+    if USE_3D and xdim == 2:
+        x = F.pad(x, (0, 1))
+    grid, v = model.init_grid(x, sections, h, dims)
+    steps = range(iter_n)
+    if iter_wrapper is not None:
+        steps = iter_wrapper(steps)
+    out = []
+    for _ in steps:
+        out.append(A.clone())
+        x, A = model(x, v, A, h, grid, fire_rate=fire_rate, feature_process=feature_process_tangent(N, T))
+        T[:, :] = diffuse(N, T, x, A, sections, 0.1, 20, lerp_multiplier=lerp_multiplier, w_multiplier=w_multiplier).detach()
+    out.append(A.clone())
+
+    loss = 0.0
+    if loss_fn is not None:
+        if xdim == 2:
+            x = x[..., :2]
+        loss = _train_on(loss_fn, x, A, img, out, model, optimizer, scheduler)
+    if out_np:
+        out = [a.cpu().numpy() for a in out]
+    if out_steps:
+        return loss, x, out
+    return loss, x, A
+
+
+def add_radial_seed(x3, A3, N=None, T=None, R=0.2, idx=None, center=None):
+    """Add a smooth bump (1 - d^2/R^2)^3 around a particle or a given centre to every channel, in place
+    (reference nca.py:383-398); optionally seed the tangent of the closest particle."""
+    if idx is None:
+        idx = int(torch.randint(0, x3.shape[0], (1,)))
+    c = x3[idx, :] if center is None else center
+    d2 = ((x3 - c) ** 2).sum(dim=-1)
+    A3 += (torch.clamp(1 - d2 / R ** 2, 0, 1) ** 3)[..., None]
+    if N is not None:
+        i = torch.argmin(d2)
+        T[i, :] = orthogonalize(N[i, :], torch.randn((x3.shape[-1],), device=T.device))
+
+
+def get_rgba(A, margin=None):
+    rgba = A[..., :4].clone()
+    if margin is not None:
+        rgba = rgba + (torch.clamp(rgba, -margin, 1 + margin) - rgba).detach()
+    return rgba
+
+
+class Pool:
+    """Sample pool of NCA states (reference nca.py:400-460): `sample` draws a batch (optionally sorted by loss,
+    worst one re-seeded), `update` writes the evolved states back.  States stay on the CPU like the reference."""
+
+    def __init__(self, seed, total_size, randomized_feat=False, feature_process=None):
+        self.total_size, self.seed = total_size, seed
+        self.num_points = seed[0].shape[0]
+        self.randomized_feat, self.feature_process = randomized_feat, feature_process
+        self.x = seed[0].cpu().repeat((total_size, 1, 1))
+        self.A = seed[1].cpu().repeat((total_size, 1, 1))
+        self.num_features = self.A.shape[-1]
+        if feature_process:
+            x, A = self.get_initial_feature()
+            self.x[:] = x.cpu()
+            self.A[:] = A.cpu()
+        else:
+            for i in range(total_size):
+                x, A = self.get_initial_feature()
+                self.x[i], self.A[i] = x.cpu(), A.cpu()
+
+    def get_initial_feature(self):
+        x, A = self.seed
+        if self.randomized_feat:
+            A = torch.rand_like(A)
+        elif self.feature_process:
+            x, A = self.feature_process(x, A)
+        return x, A
+
+    def sample(self, batch_size, device, replace_worst=False, loss_fn=None, img=None, degrade_prob=0.0, erase_R=0.0):
+        idx = torch.randperm(self.total_size)[:batch_size]
+        x, A = self.x[idx].to(device), self.A[idx].to(device)
+        if replace_worst:
+            import numpy as np
+            order = torch.from_numpy(np.array(loss_fn(x, A, img)).argsort()[::-1].copy())
+            x, A, idx = x[order], A[order], idx[order]
+            x[0], A[0] = self.get_initial_feature()
+        if degrade_prob > 0.0:
+            hit = torch.rand_like(A[..., 0]) < degrade_prob
+            A[hit, :] = torch.rand_like(A[hit, :])
+        if erase_R > 0.0:
+            for b in range(x.shape[0]):
+                c = x[b, int(torch.randint(0, x.shape[1], (1,)))]
+                A[b, ((x[b] - c) ** 2).sum(-1) < erase_R ** 2, :] = 0.0
+        return x.view(-1, 2), A.view(-1, self.num_features), (self.num_points,) * batch_size, idx
+
+    def update(self, x, A, idx):
+        b = idx.shape[0]
+        self.x[idx] = x.view(b, -1, 2).detach().cpu()
+        self.A[idx] = A.view(b, -1, self.num_features).detach().cpu()
