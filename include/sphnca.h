@@ -139,6 +139,10 @@ int32_t sphnca_step_mlp(int64_t N, const float* A_s, const float* Y_s, const uin
  *   2           same, forward fused into one persistent kernel (csrc/step_tc.cu);
  *   0           fp32 CUDA-core MLP (csrc/step.cu). */
 int32_t sphnca_set_mlp_path(int32_t path);
+/* Implementation switch of the two hot sweeps (sphnca_step_perceive, sphnca_step_adjoint): 0 (default) =
+ * one-thread-per-particle gathers out of L1/L2 with packed-pair FMAs, 1 = shared-memory tile engine with
+ * in-radius compaction (csrc/sweep_tile.cuh; measured slower on B200, kept for A/B). */
+int32_t sphnca_set_sweep_path(int32_t path);
 /* sphnca_step_mask: new life mask = blur(alive_s) > 0.1 (nca.py:112); A_new_s *= prev & new in
  * place; flags_s bit1 = new_mask. */
 int32_t sphnca_step_mask(const sphnca_grid* g, const float* xv4, const uint8_t* alive_s,

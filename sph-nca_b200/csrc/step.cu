@@ -14,6 +14,7 @@
 //
 // All arrays are in cell-sorted order.  v1: the MLP runs on the fp32 CUDA-core pipe.
 #include "step_common.cuh"
+#include "sweep_tile.cuh"
 
 namespace sphnca {
 
@@ -161,18 +162,74 @@ step_perceive_kernel(GridView g, const float4* __restrict__ xv4, const float* __
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= g.n) return;
     const float4 xi = xv4[p];
-    float Ai[NF], gx[NF], gy[NF];
-    load16(A_s + (size_t)p * NF, Ai);
+    float2 Ai[NF / 2], gx[NF / 2], gy[NF / 2];            // channel pairs (FFMA2 / FADD2)
+    {
+        const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)p * NF);
 #pragma unroll
-    for (int f = 0; f < NF; ++f) { gx[f] = 0.f; gy[f] = 0.f; }
+        for (int k = 0; k < 4; ++k) { const float4 t = __ldg(a4 + k); Ai[2*k] = make_float2(t.x, t.y); Ai[2*k+1] = make_float2(t.z, t.w); }
+    }
+#pragma unroll
+    for (int f = 0; f < NF / 2; ++f) { gx[f] = make_float2(0.f, 0.f); gy[f] = make_float2(0.f, 0.f); }
     float blur = 0.f;
     for_each_candidate<D>(g, g.sorted_cell[p], [&](int q) {
         float rx, ry;
         const float4 xj = __ldg(&xv4[q]);
         const float d2 = pair_d2<D>(xi, xj, rx, ry);
         if (d2 < c.h2) {
+            const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)q * NF);
+            float2 Aj[NF / 2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float4 t = __ldg(a4 + k); Aj[2*k] = make_float2(t.x, t.y); Aj[2*k+1] = make_float2(t.z, t.w); }
+            const float t = c.h2 - d2;
+            const float alive = c.use_alpha ? (Aj[1].y > 0.1f ? 1.f : 0.f) : 1.f;      // channel 3
+            blur = fmaf(alive * xj.w, t * t * t, blur);
+            if (d2 > 0.f) {
+                // 3 (h-d)^2 / d with d = d2 * rsqrt(d2): MUFU.RSQ (2 ulp) instead of IEEE sqrt + divide
+                const float inv = rsqrtf(d2);
+                const float hd = c.h - d2 * inv;
+                const float m = 3.f * hd * hd * inv * xj.w;
+                const float2 wx = make_float2(m * rx, m * rx), wy = make_float2(m * ry, m * ry);
+#pragma unroll
+                for (int f = 0; f < NF / 2; ++f) {
+                    const float2 dA = fsub2(Aj[f], Ai[f]);
+                    gx[f] = ffma2(dA, wx, gx[f]);
+                    gy[f] = ffma2(dA, wy, gy[f]);
+                }
+            }
+        }
+    });
+    float4* y4 = reinterpret_cast<float4*>(Y_s + (size_t)p * 2 * NF);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y4[k] = make_float4(gx[2*k].x * c.kg, gx[2*k].y * c.kg, gx[2*k+1].x * c.kg, gx[2*k+1].y * c.kg);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y4[4 + k] = make_float4(gy[2*k].x * c.kg, gy[2*k].y * c.kg, gy[2*k+1].x * c.kg, gy[2*k+1].y * c.kg);
+    flags_s[p] = blur * c.cw > 0.1f ? 1 : 0;
+}
+
+// ---- shared-memory tile versions of the two hot sweeps (sweep_tile.cuh) ---------------------------------
+template <int D>
+__global__ void __launch_bounds__(128)
+step_perceive_tile_kernel(GridView g, const float4* __restrict__ xv4, const float* __restrict__ A_s, StepConsts c,
+                          float* __restrict__ Y_s, uint8_t* __restrict__ flags_s) {
+    __shared__ TileSweepSmem<128, NF> sm;
+    const int p0 = blockIdx.x * 128, p = p0 + threadIdx.x;
+    const bool valid = p < g.n;
+    const float4 xi = valid ? xv4[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float Ai[NF], gx[NF], gy[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) { Ai[f] = 0.f; gx[f] = 0.f; gy[f] = 0.f; }
+    if (valid) load16(A_s + (size_t)p * NF, Ai);
+    float blur = 0.f;
+    tile_sweep<D, 128, NF, 128, 48>(g, xv4, A_s, sm, p0, c.h2, xi, valid, valid ? g.sorted_cell[p] : 0,
+        [&](const float4& xj, const float* row) {
+            float rx, ry;
+            const float d2 = pair_d2<D>(xi, xj, rx, ry);
             float Aj[NF];
-            load16(A_s + (size_t)q * NF, Aj);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 t = *reinterpret_cast<const float4*>(row + 4 * k);
+                Aj[4*k] = t.x; Aj[4*k+1] = t.y; Aj[4*k+2] = t.z; Aj[4*k+3] = t.w;
+            }
             const float t = c.h2 - d2;
             const float alive = c.use_alpha ? (Aj[3] > 0.1f ? 1.f : 0.f) : 1.f;
             blur = fmaf(alive * xj.w, t * t * t, blur);
@@ -188,14 +245,60 @@ step_perceive_kernel(GridView g, const float4* __restrict__ xv4, const float* __
                     gy[f] = fmaf(dA, wy, gy[f]);
                 }
             }
-        }
-    });
+        });
+    if (!valid) return;
     float4* y4 = reinterpret_cast<float4*>(Y_s + (size_t)p * 2 * NF);
 #pragma unroll
     for (int k = 0; k < 4; ++k) y4[k] = make_float4(gx[4*k] * c.kg, gx[4*k+1] * c.kg, gx[4*k+2] * c.kg, gx[4*k+3] * c.kg);
 #pragma unroll
     for (int k = 0; k < 4; ++k) y4[4 + k] = make_float4(gy[4*k] * c.kg, gy[4*k+1] * c.kg, gy[4*k+2] * c.kg, gy[4*k+3] * c.kg);
     flags_s[p] = blur * c.cw > 0.1f ? 1 : 0;
+}
+
+template <int D>
+__global__ void __launch_bounds__(128)
+step_adjoint_tile_kernel(GridView g, const float4* __restrict__ xv4, const float* __restrict__ dY_s,
+                         const float* __restrict__ dAdir_s, StepConsts c, float* __restrict__ dA_s) {
+    __shared__ TileSweepSmem<128, 2 * NF> sm;
+    const int p0 = blockIdx.x * 128, p = p0 + threadIdx.x;
+    const bool valid = p < g.n;
+    const float4 xi = valid ? xv4[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f] = 0.f;
+    float sx = 0.f, sy = 0.f;
+    tile_sweep<D, 128, 2 * NF, 128, 48>(g, xv4, dY_s, sm, p0, c.h2, xi, valid, valid ? g.sorted_cell[p] : 0,
+        [&](const float4& xj, const float* row) {
+            float rx, ry;
+            const float d2 = pair_d2<D>(xi, xj, rx, ry);
+            if (d2 > 0.f) {
+                const float d = sqrtf(d2);
+                const float hd = c.h - d;
+                const float m = 3.f * hd * hd / d;
+                const float wx = m * rx, wy = m * ry;
+                sx = fmaf(wx, xj.w, sx); sy = fmaf(wy, xj.w, sy);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 a = *reinterpret_cast<const float4*>(row + 4 * k);
+                    const float4 b = *reinterpret_cast<const float4*>(row + NF + 4 * k);
+                    acc[4*k] = fmaf(wx, a.x, fmaf(wy, b.x, acc[4*k]));
+                    acc[4*k+1] = fmaf(wx, a.y, fmaf(wy, b.y, acc[4*k+1]));
+                    acc[4*k+2] = fmaf(wx, a.z, fmaf(wy, b.z, acc[4*k+2]));
+                    acc[4*k+3] = fmaf(wx, a.w, fmaf(wy, b.w, acc[4*k+3]));
+                }
+            }
+        });
+    if (!valid) return;
+    float Gx[NF], Gy[NF], dir[NF];
+    load16(dY_s + (size_t)p * 2 * NF, Gx);
+    load16(dY_s + (size_t)p * 2 * NF + NF, Gy);
+    load16(dAdir_s + (size_t)p * NF, dir);
+    float4* o4 = reinterpret_cast<float4*>(dA_s + (size_t)p * NF);
+    float r[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) r[f] = dir[f] - c.kg * fmaf(xi.w, acc[f], fmaf(Gx[f], sx, Gy[f] * sy));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o4[k] = make_float4(r[4*k], r[4*k+1], r[4*k+2], r[4*k+3]);
 }
 
 // new life mask = blur(alive bits of the updated state) > 0.1; state *= prev & new   (nca.py:112-115)
@@ -343,25 +446,28 @@ step_adjoint_kernel(GridView g, const float4* __restrict__ xv4, const float* __r
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= g.n) return;
     const float4 xi = xv4[p];
-    float acc[NF];
+    float2 acc[NF / 2];                                   // channel pairs (FFMA2)
 #pragma unroll
-    for (int f = 0; f < NF; ++f) acc[f] = 0.f;
+    for (int f = 0; f < NF / 2; ++f) acc[f] = make_float2(0.f, 0.f);
     float sx = 0.f, sy = 0.f;
     for_each_candidate<D>(g, g.sorted_cell[p], [&](int q) {
         float rx, ry;
         const float4 xj = __ldg(&xv4[q]);
         const float d2 = pair_d2<D>(xi, xj, rx, ry);
         if (d2 < c.h2 && d2 > 0.f) {
-            const float d = sqrtf(d2);
-            const float hd = c.h - d;
-            const float m = 3.f * hd * hd / d;
-            const float wx = m * rx, wy = m * ry;
-            sx = fmaf(wx, xj.w, sx); sy = fmaf(wy, xj.w, sy);
-            float Gx[NF], Gy[NF];
-            load16(dY_s + (size_t)q * 2 * NF, Gx);
-            load16(dY_s + (size_t)q * 2 * NF + NF, Gy);
+            const float inv = rsqrtf(d2);
+            const float hd = c.h - d2 * inv;
+            const float m = 3.f * hd * hd * inv;
+            const float wxs = m * rx, wys = m * ry;
+            sx = fmaf(wxs, xj.w, sx); sy = fmaf(wys, xj.w, sy);
+            const float2 wx = make_float2(wxs, wxs), wy = make_float2(wys, wys);
+            const float4* g4 = reinterpret_cast<const float4*>(dY_s + (size_t)q * 2 * NF);
 #pragma unroll
-            for (int f = 0; f < NF; ++f) acc[f] = fmaf(wx, Gx[f], fmaf(wy, Gy[f], acc[f]));
+            for (int k = 0; k < 4; ++k) {
+                const float4 a = __ldg(g4 + k), b = __ldg(g4 + 4 + k);
+                acc[2*k] = ffma2(wx, make_float2(a.x, a.y), ffma2(wy, make_float2(b.x, b.y), acc[2*k]));
+                acc[2*k+1] = ffma2(wx, make_float2(a.z, a.w), ffma2(wy, make_float2(b.z, b.w), acc[2*k+1]));
+            }
         }
     });
     float Gx[NF], Gy[NF], dir[NF];
@@ -371,7 +477,10 @@ step_adjoint_kernel(GridView g, const float4* __restrict__ xv4, const float* __r
     float4* o4 = reinterpret_cast<float4*>(dA_s + (size_t)p * NF);
     float r[NF];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) r[f] = dir[f] - c.kg * fmaf(xi.w, acc[f], fmaf(Gx[f], sx, Gy[f] * sy));
+    for (int f = 0; f < NF; ++f) {
+        const float a = (f & 1) ? acc[f >> 1].y : acc[f >> 1].x;
+        r[f] = dir[f] - c.kg * fmaf(xi.w, a, fmaf(Gx[f], sx, Gy[f] * sy));
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) o4[k] = make_float4(r[4*k], r[4*k+1], r[4*k+2], r[4*k+3]);
 }
@@ -380,7 +489,15 @@ step_adjoint_kernel(GridView g, const float4* __restrict__ xv4, const float* __r
 
 using namespace sphnca;
 
+static int g_sweep_path = 0;
+
 extern "C" {
+
+int32_t sphnca_set_sweep_path(int32_t path) {
+    if (path != 0 && path != 1) { set_error("sweep path must be 0 (per-thread gathers) or 1 (shared-memory tiles)"); return SPHNCA_ERR_INVALID; }
+    g_sweep_path = path;
+    return SPHNCA_OK;
+}
 
 int32_t sphnca_step_perceive(const sphnca_grid* g, const float* xv4, const float* A_s, const sphnca_step_params* p,
                              float* Y_s, uint8_t* flags_s, void* stream_) {
@@ -390,8 +507,13 @@ int32_t sphnca_step_perceive(const sphnca_grid* g, const float* xv4, const float
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(xv4 && A_s && Y_s && flags_s, "NULL argument");
     const int pblocks = (int)((gv.n + 127) / 128);
-    if (gv.dim == 3) SPHNCA_LAUNCH(step_perceive_kernel<3>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
-    else SPHNCA_LAUNCH(step_perceive_kernel<2>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+    if (g_sweep_path == 1) {
+        if (gv.dim == 3) SPHNCA_LAUNCH(step_perceive_tile_kernel<3>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+        else SPHNCA_LAUNCH(step_perceive_tile_kernel<2>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+    } else {
+        if (gv.dim == 3) SPHNCA_LAUNCH(step_perceive_kernel<3>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+        else SPHNCA_LAUNCH(step_perceive_kernel<2>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+    }
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }
@@ -479,7 +601,10 @@ int32_t sphnca_step_adjoint(const sphnca_grid* g, const float* xv4, const float*
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(xv4 && dY_s && dAdir_s && dA_s, "NULL argument");
     const int blocks = (int)((gv.n + 127) / 128);
-    if (gv.dim == 3) SPHNCA_LAUNCH(step_adjoint_kernel<3>, blocks, 128, 0, stream, gv, (const float4*)xv4, dY_s, dAdir_s, c, dA_s);
+    if (g_sweep_path == 1) {
+        if (gv.dim == 3) SPHNCA_LAUNCH(step_adjoint_tile_kernel<3>, blocks, 128, 0, stream, gv, (const float4*)xv4, dY_s, dAdir_s, c, dA_s);
+        else SPHNCA_LAUNCH(step_adjoint_tile_kernel<2>, blocks, 128, 0, stream, gv, (const float4*)xv4, dY_s, dAdir_s, c, dA_s);
+    } else if (gv.dim == 3) SPHNCA_LAUNCH(step_adjoint_kernel<3>, blocks, 128, 0, stream, gv, (const float4*)xv4, dY_s, dAdir_s, c, dA_s);
     else SPHNCA_LAUNCH(step_adjoint_kernel<2>, blocks, 128, 0, stream, gv, (const float4*)xv4, dY_s, dAdir_s, c, dA_s);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;

@@ -72,6 +72,7 @@ def _load():
         "sphnca_step_adjoint": ([G, P, P, P, SP, P, P], I32),
         "sphnca_launch_count": ([], I64),
         "sphnca_set_mlp_path": ([I32], I32),
+        "sphnca_set_sweep_path": ([I32], I32),
     }
     missing = []
     for name, (args, res) in sigs.items():
@@ -86,6 +87,11 @@ def _load():
 
 
 lib, DECLARED_SYMBOLS, MISSING_SYMBOLS = _load()
+
+# optional implementation switches for A/B runs (see include/sphnca.h)
+for _env, _fn in (("SPHNCA_MLP_PATH", "sphnca_set_mlp_path"), ("SPHNCA_SWEEP_PATH", "sphnca_set_sweep_path")):
+    if os.environ.get(_env) is not None and _fn not in MISSING_SYMBOLS:
+        getattr(lib, _fn)(int(os.environ[_env]))
 
 
 def check(rc):

@@ -357,3 +357,58 @@ def test_tc_backward_equals_simt_backward(n_particles):
         for t, nm in zip(dW, ("dW1", "db1", "dW2", "db2")):
             assert_close(t, ref[nm], rtol=tol, what=f"{nm} path {path}")
     assert_close(out[1][2], out[0][2], rtol=2e-5, what="dAdir tc vs simt")
+
+
+def _sweep_inputs(kind):
+    gen = torch.Generator().manual_seed(7)
+    if kind.startswith("golden:"):
+        g = load_golden(kind.split(":")[1])
+        return torch.from_numpy(g["x"]), tuple(int(s) for s in g["sections"]), float(g["h"]), tuple(int(d) for d in g["dims"])
+    if kind == "one_cell_dense":           # 400 particles in ONE cell: chunking (CAP=128) and hit-list flushes (SLOTS=48)
+        return torch.rand(400, 3, generator=gen) * 0.2 + 0.1, (400,), 0.5, (4, 4, 4)
+    if kind == "lattice3d":
+        x = jittered_lattice(30, 3, gen)
+        return x, (9000, 27000 - 9000), 1.97 * 2 / 30, (31, 31, 31)
+    if kind == "lattice2d_padded":
+        x = torch.nn.functional.pad(jittered_lattice(150, 2, gen), (0, 1))
+        return x, (150 * 150,), 3.2 * 2 / 150, (47, 47, 47)
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind", ["golden:ops_3d_ragged", "golden:ops_padded2d", "golden:ops_thin_axis", "golden:ops_single_layer",
+                                  "golden:ops_2d", "one_cell_dense", "lattice3d", "lattice2d_padded"])
+def test_tile_sweeps_equal_gather_sweeps(kind):
+    """Shared-memory tile engine (segments per cell row, wrapped-cell runs, chunked staging, hit lists) against the
+    one-thread-per-particle gather sweeps: perception + previous life mask, and the gather adjoint.  Covers ragged
+    sections, coordinates outside the box (modulo wrap), axes with dims < 3 (double / triple counting), true 2-D,
+    a cell holding more particles than a chunk, and BASELINE-like lattices."""
+    import ctypes as C
+    import sphops
+    from sphops import _lib, fused
+    x, sections, h, dims = _sweep_inputs(kind)
+    N, D = x.shape
+    xd = x.to(DEV)
+    grid = sphops.initialize_hashgrid(xd, sections, h, dims)
+    v = sphops.volume(xd, h, grid)
+    gen = torch.Generator().manual_seed(3)
+    A = torch.rand(N, 16, generator=gen).to(DEV)
+    dY = torch.randn(N, 32, generator=gen).to(DEV)
+    dAd = torch.randn(N, 16, generator=gen).to(DEV)
+    xv4 = grid.sorted_xv(xd, v)
+    A_s = grid.pack_rows(A, 16); dY_s = grid.pack_rows(dY, 32); dAd_s = grid.pack_rows(dAd, 16)
+    w = load_golden("weights_gecko")
+    W = [torch.from_numpy(w[k]).to(DEV) for k in ("W1", "b1", "W2", "b2")]
+    p = fused._step_params(*W, "gated", True, 1.7, 1.0)
+    st = _lib.stream_ptr()
+    res = []
+    for path in (0, 1):
+        _lib.check(_lib.lib.sphnca_set_sweep_path(path))
+        Y = torch.zeros(N, 32, device=DEV); fl = torch.zeros(N, dtype=torch.uint8, device=DEV); dA = torch.zeros(N, 16, device=DEV)
+        _lib.check(_lib.lib.sphnca_step_perceive(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), st))
+        _lib.check(_lib.lib.sphnca_step_adjoint(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(dY_s), _lib.ptr(dAd_s), C.byref(p), _lib.ptr(dA), st))
+        torch.cuda.synchronize()
+        res.append((Y, fl, dA))
+    _lib.check(_lib.lib.sphnca_set_sweep_path(0))
+    assert_close(res[1][0], res[0][0], rtol=2e-5 if kind != "one_cell_dense" else 2e-4, what="perception")
+    assert int((res[1][1] != res[0][1]).sum()) <= max(1, N // 5000), "previous life mask"
+    assert_close(res[1][2], res[0][2], rtol=2e-5 if kind != "one_cell_dense" else 2e-4, what="adjoint")

@@ -1,6 +1,6 @@
 """Micro-benchmark of the backward kernels through the C ABI (development aid)."""
 import ctypes as C, math, sys, os
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "sph-nca_b200"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "sph-nca_b200"))
 import torch
 import sphops
 from sphops import _lib, fused

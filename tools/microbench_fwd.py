@@ -1,6 +1,6 @@
 """Kernel micro-benchmark through the C ABI (development aid): times sphnca_step_fwd variants with CUDA events."""
 import ctypes as C, math, sys, os
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "sph-nca_b200"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "sph-nca_b200"))
 import torch, numpy as np
 import sphops
 from sphops import _lib, fused

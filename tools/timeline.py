@@ -1,7 +1,7 @@
 import ctypes as C, sys, os
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "sph-nca_b200"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "sph-nca_b200"))
 import runpy
-g = runpy.run_path(os.path.join(ROOT, "tools_microbench_bwd.py"))
+g = runpy.run_path(os.path.join(ROOT, "tools", "microbench_bwd.py"))
 from sphops import _lib
 import torch
 g["wgrad_tc"](); torch.cuda.synchronize()
@@ -17,7 +17,7 @@ for it in range(2, 8):
 
 print("---- step_fwd_tc timeline (cycles, CTA 0)")
 import runpy as _r
-g2 = _r.run_path(os.path.join(ROOT, "tools_microbench.py"))
+g2 = _r.run_path(os.path.join(ROOT, "tools", "microbench_fwd.py"))
 g2["run"](); torch.cuda.synchronize()
 _lib.check(_lib.lib.sphnca_set_mlp_path(1)); g2["run"](); torch.cuda.synchronize()
 _lib.lib.sphnca_debug_timeline_fwd(buf, 64 * 16)
