@@ -43,6 +43,11 @@ WORKLOADS = {
     # BASELINE.json configs[2]
     "train3d_250k_k96": dict(desc="3D point cloud, 250,047 jittered particles (63^3), 96 NCA steps fwd+bwd",
                              lattice_dim=3, n_side=63, batch=1, k_nca=96, hf=1.97),
+    # BASELINE.json configs[4]: 64 clouds of 1,000,000 3-D particles, split data-parallel over the GPUs
+    # (batch_total / n_gpus clouds per GPU = strong scaling; 3 NCA steps keep the saved state of 64 M particles in HBM)
+    "train3d_b64x1m_k3": dict(desc="3D training, batch 64 x 1,000,000 jittered particles (100^3), 3 NCA steps fwd+bwd, "
+                                   "data-parallel over batch elements + NCCL gradient all-reduce",
+                              lattice_dim=3, n_side=100, batch=64, batch_total=64, k_nca=3, hf=1.97),
     # BASELINE.json configs[3]: one cloud, forward only, slab shard + NVLink halo (strong scaling over GPUs)
     "infer2d_16m_slab": dict(desc="discretization-agnostic inference on 16,000,000 jittered 2D particles (4000^2, zero-padded to 3-D, "
                                   "dims (1250,1250,3)), 16 NCA steps forward, spatial slab shard + halo exchange",
@@ -295,6 +300,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=dev)
 
+    if wl.get("batch_total"):                     # strong scaling: the batch is split over the ranks
+        if wl["batch_total"] % world:
+            raise SystemExit("batch_total must be divisible by the number of GPUs")
+        wl["batch"] = wl["batch_total"] // world
     nca.USE_3D = True
     nca.USE_FUSED_STEP = not args.no_fused
     torch.manual_seed(1234 + rank)
@@ -415,8 +424,8 @@ def main():
         roofline["traffic_source"] = traffic_src
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if wl.get("batch_total") else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "description": wl["desc"], "particles_per_gpu": N, "nca_steps": K_nca,
                    "h": h, "dims": dims, "weights": "zebra (trained, tests/golden/weights_zebra.npz)", "optimizer": "Adam lr=1e-5",
                    "path": "fused" if nca.USE_FUSED_STEP else "ops", "parallelism": f"dp{world}",
