@@ -161,7 +161,8 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             mbar_arrive(&s.bar[DO_FULL]);
         }
     } else if (warp == MMA_WARP) {
-        if (lane == 0) {
+        {   // warp-uniform issue: every lane runs the loop, one elected lane issues (tc_common.cuh)
+            const uint32_t go = elect_one();
             const uint32_t idesc3 = make_idesc_tf32(TILE, 128), idesc4 = make_idesc_tf32(TILE, NIN);
             const uint32_t ah = smem_u32(s.dO_hi), al = smem_u32(s.dO_lo);
             auto gemm3 = [&](int half) {
@@ -172,9 +173,9 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                     const uint64_t a_lo = make_smem_desc(al + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
                     const uint64_t b_hi = make_smem_desc(wh + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
                     const uint64_t b_lo = make_smem_desc(wl + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                    mma_tf32_ss(tbase + COL_D3, a_lo, b_hi, idesc3, ks > 0);
-                    mma_tf32_ss(tbase + COL_D3, a_hi, b_lo, idesc3, true);
-                    mma_tf32_ss(tbase + COL_D3, a_hi, b_hi, idesc3, true);
+                    mma_tf32_ss_e(tbase + COL_D3, a_lo, b_hi, idesc3, ks > 0, go);
+                    mma_tf32_ss_e(tbase + COL_D3, a_hi, b_lo, idesc3, true, go);
+                    mma_tf32_ss_e(tbase + COL_D3, a_hi, b_hi, idesc3, true, go);
                 }
             };
             auto gemm4 = [&](int half) {
@@ -183,9 +184,9 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 for (int ks = 0; ks < 128 / 8; ++ks) {
                     const uint64_t b_hi = make_smem_desc(wh + chunk_off(NIN, 0, 2 * ks), NIN * 16, 128);
                     const uint64_t b_lo = make_smem_desc(wl + chunk_off(NIN, 0, 2 * ks), NIN * 16, 128);
-                    mma_tf32_ts(tbase + COL_DY, tbase + COL_DHLO + 8 * ks, b_hi, idesc4, (half | ks) > 0);
-                    mma_tf32_ts(tbase + COL_DY, tbase + COL_D3 + 8 * ks, b_lo, idesc4, true);
-                    mma_tf32_ts(tbase + COL_DY, tbase + COL_D3 + 8 * ks, b_hi, idesc4, true);
+                    mma_tf32_ts_e(tbase + COL_DY, tbase + COL_DHLO + 8 * ks, b_hi, idesc4, (half | ks) > 0, go);
+                    mma_tf32_ts_e(tbase + COL_DY, tbase + COL_D3 + 8 * ks, b_lo, idesc4, true, go);
+                    mma_tf32_ts_e(tbase + COL_DY, tbase + COL_D3 + 8 * ks, b_hi, idesc4, true, go);
                 }
             };
             int it = 0;
@@ -193,19 +194,19 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 mbar_wait(&s.bar[DO_FULL], it & 1);
                 fence_after_sync();
                 gemm3(0);
-                mma_commit(&s.bar[D3_FULL]);
+                mma_commit_e(&s.bar[D3_FULL], go);
                 mbar_wait(&s.bar[DH_FULL], 0);
                 fence_after_sync();
                 mbar_wait(&s.bar[DY_EMPTY], (it & 1) ^ 1);    // epilogue drained Dy of the previous tile
                 fence_after_sync();
                 gemm4(0);
                 gemm3(1);                                     // in issue order behind GEMM4(0) on the same columns
-                mma_commit(&s.bar[D3_FULL]);
-                mma_commit(&s.bar[DO_EMPTY]);
+                mma_commit_e(&s.bar[D3_FULL], go);
+                mma_commit_e(&s.bar[DO_EMPTY], go);
                 mbar_wait(&s.bar[DH_FULL], 1);
                 fence_after_sync();
                 gemm4(1);
-                mma_commit(&s.bar[DY_FULL]);
+                mma_commit_e(&s.bar[DY_FULL], go);
             }
         }
     } else {

@@ -121,7 +121,8 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             mbar_arrive(&s.bar[Y_FULL]);
         }
     } else if (warp == MMA_WARP) {
-        if (lane == 0) {
+        {   // warp-uniform issue: every lane runs the loop, one elected lane issues (tc_common.cuh)
+            const uint32_t go = elect_one();
             const uint32_t idesc1 = make_idesc_tf32(TILE, 128), idesc2 = make_idesc_tf32(TILE, N2);
             const uint32_t yh = smem_u32(s.Y_hi), yl = smem_u32(s.Y_lo);
             int it = 0;
@@ -139,13 +140,13 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                         const uint64_t a_lo = make_smem_desc(yl + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
                         const uint64_t b_hi = make_smem_desc(wh + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
                         const uint64_t b_lo = make_smem_desc(wl + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                        mma_tf32_ss(tbase + COL_D1, a_lo, b_hi, idesc1, ks > 0);
-                        mma_tf32_ss(tbase + COL_D1, a_hi, b_lo, idesc1, true);
-                        mma_tf32_ss(tbase + COL_D1, a_hi, b_hi, idesc1, true);
+                        mma_tf32_ss_e(tbase + COL_D1, a_lo, b_hi, idesc1, ks > 0, go);
+                        mma_tf32_ss_e(tbase + COL_D1, a_hi, b_lo, idesc1, true, go);
+                        mma_tf32_ss_e(tbase + COL_D1, a_hi, b_hi, idesc1, true, go);
                     }
-                    mma_commit(&s.bar[D1_FULL]);
+                    mma_commit_e(&s.bar[D1_FULL], go);
                 }
-                mma_commit(&s.bar[Y_EMPTY]);
+                mma_commit_e(&s.bar[Y_EMPTY], go);
                 mbar_wait(&s.bar[D2_EMPTY], (it & 1) ^ 1);
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
@@ -156,13 +157,13 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                     for (int ks = 0; ks < 128 / 8; ++ks) {
                         const uint64_t b_hi = make_smem_desc(wh + chunk_off(N2, 0, 2 * ks), N2 * 16, 128);
                         const uint64_t b_lo = make_smem_desc(wl + chunk_off(N2, 0, 2 * ks), N2 * 16, 128);
-                        mma_tf32_ts(tbase + COL_D2, tbase + COL_HLO + 8 * ks, b_hi, idesc2, (half | ks) > 0);
-                        mma_tf32_ts(tbase + COL_D2, tbase + COL_HHI + 8 * ks, b_lo, idesc2, true);
-                        mma_tf32_ts(tbase + COL_D2, tbase + COL_HHI + 8 * ks, b_hi, idesc2, true);
+                        mma_tf32_ts_e(tbase + COL_D2, tbase + COL_HLO + 8 * ks, b_hi, idesc2, (half | ks) > 0, go);
+                        mma_tf32_ts_e(tbase + COL_D2, tbase + COL_HHI + 8 * ks, b_lo, idesc2, true, go);
+                        mma_tf32_ts_e(tbase + COL_D2, tbase + COL_HHI + 8 * ks, b_hi, idesc2, true, go);
                     }
-                    mma_commit(&s.bar[H_EMPTY]);
+                    mma_commit_e(&s.bar[H_EMPTY], go);
                 }
-                mma_commit(&s.bar[D2_FULL]);
+                mma_commit_e(&s.bar[D2_FULL], go);
             }
         }
     } else {

@@ -228,7 +228,8 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
             if (lt < NO_PAD) partial[(size_t)stream_id * part_floats + NH * NIN + NH + NO_PAD * NH + lt] = red[0][lt];
         }
     } else if (warp == MMA_WARP) {
-        if (lane == 0) {
+        {   // warp-uniform issue: every lane runs the loop, one elected lane issues (tc_common.cuh)
+            const uint32_t go = elect_one();
             const uint32_t idR = make_idesc_tf32(128, CH), idA1 = make_idesc_tf32(128, NY), idA2 = make_idesc_tf32(128, NOUT);
             int it = 0;
             for (int64_t ch = c0; ch < c1; ++ch, ++it) {
@@ -242,9 +243,9 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                     const uint64_t a_lo = make_smem_desc(smem_u32(s.W1_lo) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
                     const uint64_t b_hi = make_smem_desc(smem_u32(s.yK_hi) + chunk_off(CH, 0, 2 * ks), CH * 16, 128);
                     const uint64_t b_lo = make_smem_desc(smem_u32(s.yK_lo) + chunk_off(CH, 0, 2 * ks), CH * 16, 128);
-                    mma_tf32_ss(tbase + COL_R1, a_lo, b_hi, idR, ks > 0);
-                    mma_tf32_ss(tbase + COL_R1, a_hi, b_lo, idR, true);
-                    mma_tf32_ss(tbase + COL_R1, a_hi, b_hi, idR, true);
+                    mma_tf32_ss_e(tbase + COL_R1, a_lo, b_hi, idR, ks > 0, go);
+                    mma_tf32_ss_e(tbase + COL_R1, a_hi, b_lo, idR, true, go);
+                    mma_tf32_ss_e(tbase + COL_R1, a_hi, b_hi, idR, true, go);
                 }
 #pragma unroll
                 for (int ks = 0; ks < KO / 8; ++ks) {
@@ -252,12 +253,12 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                     const uint64_t a_lo = make_smem_desc(smem_u32(s.W2t_lo) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
                     const uint64_t b_hi = make_smem_desc(smem_u32(s.dOK_hi) + chunk_off(CH, 0, 2 * ks), CH * 16, 128);
                     const uint64_t b_lo = make_smem_desc(smem_u32(s.dOK_lo) + chunk_off(CH, 0, 2 * ks), CH * 16, 128);
-                    mma_tf32_ss(tbase + COL_R3, a_lo, b_hi, idR, ks > 0);
-                    mma_tf32_ss(tbase + COL_R3, a_hi, b_lo, idR, true);
-                    mma_tf32_ss(tbase + COL_R3, a_hi, b_hi, idR, true);
+                    mma_tf32_ss_e(tbase + COL_R3, a_lo, b_hi, idR, ks > 0, go);
+                    mma_tf32_ss_e(tbase + COL_R3, a_hi, b_lo, idR, true, go);
+                    mma_tf32_ss_e(tbase + COL_R3, a_hi, b_hi, idR, true, go);
                 }
-                mma_commit(&s.bar[R_FULL]);
-                mma_commit(&s.bar[K_EMPTY]);
+                mma_commit_e(&s.bar[R_FULL], go);
+                mma_commit_e(&s.bar[K_EMPTY], go);
                 SPHNCA_TL(5);
                 mbar_wait(&s.bar[HT_FULL], it & 1);
                 SPHNCA_TL(6);
@@ -271,17 +272,17 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                     const uint64_t o_hi = make_smem_desc(smem_u32(s.dOT_hi) + chunk_off(NOUT, 0, 2 * ks), NOUT * 16, 128);
                     const uint64_t o_lo = make_smem_desc(smem_u32(s.dOT_lo) + chunk_off(NOUT, 0, 2 * ks), NOUT * 16, 128);
                     const bool acc = (it | ks) > 0;
-                    mma_tf32_ts(tbase + COL_ACC1, tbase + COL_DHLO + 8 * ks, y_hi, idA1, acc);
-                    mma_tf32_ts(tbase + COL_ACC1, tbase + COL_R3 + 8 * ks, y_lo, idA1, true);
-                    mma_tf32_ts(tbase + COL_ACC1, tbase + COL_R3 + 8 * ks, y_hi, idA1, true);
-                    mma_tf32_ts(tbase + COL_ACC2, tbase + COL_HLO + 8 * ks, o_hi, idA2, acc);
-                    mma_tf32_ts(tbase + COL_ACC2, tbase + COL_R1 + 8 * ks, o_lo, idA2, true);
-                    mma_tf32_ts(tbase + COL_ACC2, tbase + COL_R1 + 8 * ks, o_hi, idA2, true);
+                    mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_DHLO + 8 * ks, y_hi, idA1, acc, go);
+                    mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_R3 + 8 * ks, y_lo, idA1, true, go);
+                    mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_R3 + 8 * ks, y_hi, idA1, true, go);
+                    mma_tf32_ts_e(tbase + COL_ACC2, tbase + COL_HLO + 8 * ks, o_hi, idA2, acc, go);
+                    mma_tf32_ts_e(tbase + COL_ACC2, tbase + COL_R1 + 8 * ks, o_lo, idA2, true, go);
+                    mma_tf32_ts_e(tbase + COL_ACC2, tbase + COL_R1 + 8 * ks, o_hi, idA2, true, go);
                 }
-                mma_commit(&s.bar[T_EMPTY]);
+                mma_commit_e(&s.bar[T_EMPTY], go);
                 SPHNCA_TL(8);
             }
-            mma_commit(&s.bar[ACC_FULL]);
+            mma_commit_e(&s.bar[ACC_FULL], go);
         }
     } else {
         // ============================ epilogue: thread = hidden unit ============================

@@ -23,6 +23,9 @@ import sphops
 USE_3D = False
 # set to False to force the operator-by-operator path (used by the parity tests)
 USE_FUSED_STEP = True
+# set to False to run rollouts as K separate fused steps (one autograd node per step, states permuted back
+# to particle order after every step) instead of one cell-sorted-resident K-step node
+USE_FUSED_ROLLOUT = True
 
 
 def cell_activity(A, use_alpha=True):
@@ -135,6 +138,20 @@ class SPHNCA(nn.Module):
         new_mask = self.life_mask(x, v, cell_activity(nA, self.use_alpha)[..., None], h, grid)
         return x, nA * (prev_mask & new_mask).float()
 
+    def rollout(self, x, v, A, h, grid, steps, fire_rate=None, keep_all=True):
+        """`steps` chained `forward` calls as one autograd node with the state kept cell-sorted on the
+        device (sphops.fused.nca_rollout); returns the sequence of the steps+1 states, or None when the
+        configuration is not the fused one (callers then loop over `forward`)."""
+        if not (USE_FUSED_ROLLOUT and self._fusable(x, A, None)):
+            return None
+        if fire_rate is None:
+            fire_rate = self.fire_rate
+        lin1, lin2 = self.model[0], self.model[2]
+        return sphops.fused.nca_rollout(
+            x, v, A, lin1.weight, lin1.bias, lin2.weight, lin2.bias, h, grid, steps, fire_rate,
+            update_rule=self.update_rule, use_alpha=self.use_alpha,
+            perception_scale=self.perception_scale(h), orig_rate=self.fire_rate / fire_rate, keep_all=keep_all)
+
     def normalize_grads(self):
         if not self.normalize_grad:
             return
@@ -177,11 +194,16 @@ def sample_plane(model, x, A, sections, h, dims, out_steps=False, iter_n=None, l
         x = F.pad(x, (0, 1))
 
     grid, v = model.init_grid(x, sections, h, dims)
-    out = []
-    for _ in range(iter_n):
+    out = model.rollout(x, v, A, h, grid, iter_n, fire_rate, keep_all=out_steps or loss_fn is not None) \
+        if hasattr(model, "rollout") else None
+    if out is not None:
+        A = out[-1]
+    else:
+        out = []
+        for _ in range(iter_n):
+            out.append(A.clone())
+            x, A = model(x, v, A, h, grid, fire_rate=fire_rate, feature_process=None)
         out.append(A.clone())
-        x, A = model(x, v, A, h, grid, fire_rate=fire_rate, feature_process=None)
-    out.append(A.clone())
 
     loss = 0.0
     if loss_fn is not None:

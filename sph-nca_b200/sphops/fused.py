@@ -131,6 +131,169 @@ class _NCAStep(torch.autograd.Function):
                 dW2 if g[6] else None, db2 if g[7] else None, None, None, None, None, None, None)
 
 
+class _UnpackRows(torch.autograd.Function):
+    """cell-sorted rows -> the caller's particle order (adjoint: the inverse permutation)."""
+
+    @staticmethod
+    def forward(ctx, S, grid):
+        ctx.grid = grid
+        return grid.unpack_rows(S, S.shape[1])
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dA):
+        return ctx.grid.pack_rows(require_cuda_f32(dA, "dA"), dA.shape[1]), None
+
+
+class _NCARollout(torch.autograd.Function):
+    """K chained NCA steps as ONE autograd node (replaces the K-node tape the
+    reference builds in the loop of code/nca.py:141-145).  The state never leaves cell-sorted order:
+    per step the forward is perceive -> MLP -> mask, the backward data-gradient -> weight-gradient ->
+    sweep adjoint, with the parameter gradients accumulated in place over all steps (fixed order:
+    deterministic).  Outputs: the K+1 states S_0..S_K in SORTED order (unpack lazily, `RolloutStates`);
+    a loss may read any subset of them -- missing output gradients are skipped, not materialised.
+    The fire mask of step k is drawn here by `torch.rand(N) <= fire_rate`, the same call, in the same
+    order, as the reference's `SPHNCA.forward` (nca.py:100)."""
+
+    @staticmethod
+    def forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_rate, keep_all, taped):
+        update_rule, use_alpha, perception_scale, orig_rate = cfg
+        x = require_cuda_f32(x, "x"); v = require_cuda_f32(v, "v"); A0 = require_cuda_f32(A0, "A")
+        W1c, b1c, W2c, b2c = [require_cuda_f32(t, n) for t, n in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"))]
+        N = x.shape[0]
+        n_out = 33 if update_rule == "gated" else 16
+        if A0.shape != (N, 16) or W1c.shape != (256, 48) or W2c.shape != (n_out, 256):
+            raise ValueError("fused rollout needs A [N,16], W1 [256,48], W2 [33|16,256]")
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        ctx.set_materialize_grads(False)
+        xv4 = grid.sorted_xv(x, v)
+        p = _step_params(W1c, b1c, W2c, b2c, update_rule, use_alpha, perception_scale, orig_rate)
+        g, st = grid.c_grid(), stream_ptr()
+        S = grid.pack_rows(A0, 16)
+        states, saved = [S], []
+        alive_s = torch.empty((N,), **u8)
+        Y_s = O_s = flags_s = relu_s = None
+        for _ in range(steps):
+            fire = torch.rand(N, device=dev) <= fire_rate
+            fire_s = grid.pack_bytes(fire.view(torch.uint8))
+            if taped or Y_s is None:
+                Y_s = torch.empty((N, 32), **f32); O_s = torch.empty((N, 36), **f32)
+                flags_s = torch.empty((N,), **u8); relu_s = torch.empty((N, 8), dtype=torch.int32, device=dev)
+            Sn = torch.empty((N, 16), **f32)
+            if N:
+                if SPLIT_FORWARD:
+                    _timed("step_perceive", lib.sphnca_step_perceive, g, ptr(xv4), ptr(S), C.byref(p), ptr(Y_s), ptr(flags_s), st)
+                    _timed("step_mlp", lib.sphnca_step_mlp, N, ptr(S), ptr(Y_s), ptr(fire_s), C.byref(p), ptr(Sn),
+                           ptr(alive_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
+                else:
+                    _timed("step_fwd", lib.sphnca_step_fwd, g, ptr(xv4), ptr(S), ptr(fire_s), C.byref(p), ptr(Sn),
+                           ptr(alive_s), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
+                _timed("step_mask", lib.sphnca_step_mask, g, ptr(xv4), ptr(alive_s), ptr(Sn), ptr(flags_s), st)
+            if taped:
+                saved += [Y_s, O_s, flags_s, relu_s]
+            if keep_all or taped:
+                states.append(Sn)
+            else:
+                states = [states[0], Sn] if len(states) else [Sn]
+            S = Sn
+        ctx.grid, ctx.cfg, ctx.steps = grid, cfg, steps
+        if taped:
+            ctx.save_for_backward(xv4, W1c, b1c, W2c, b2c, *states, *saved)
+        return tuple(states)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *dstates):
+        K = ctx.steps
+        t = ctx.saved_tensors
+        xv4, W1, b1, W2, b2 = t[:5]
+        states, saved = t[5:5 + K + 1], t[5 + K + 1:]
+        grid = ctx.grid
+        N = xv4.shape[0]
+        dev = xv4.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad
+        want_w = any(need[3:7])
+        p = _step_params(W1, b1, W2, b2, *ctx.cfg)
+        dW1 = db1 = dW2 = db2 = None
+        ws, nb = None, C.c_size_t(0)
+        if want_w:
+            dW1, db1, dW2, db2 = torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2), torch.zeros_like(b2)
+            check(lib.sphnca_mlp_wgrad_workspace_bytes(max(N, 1), C.byref(nb)))
+            ws = torch.empty((nb.value,), dtype=torch.uint8, device=dev)
+        dO_s = torch.empty((N, 36), **f32)
+        dY_s = torch.empty((N, 32), **f32)
+        dAdir_s = torch.empty((N, 16), **f32)
+        own = [torch.empty((N, 16), **f32), torch.empty((N, 16), **f32)]   # gradient ping-pong (never write autograd's buffers)
+        st = stream_ptr()
+        gcur = dstates[K]
+        if gcur is not None:
+            gcur = require_cuda_f32(gcur, "dS")
+        for k in range(K - 1, -1, -1):
+            if gcur is not None and N:          # steps after the last state a loss reads carry no gradient
+                Y_s, O_s, flags_s, relu_s = saved[4 * k:4 * k + 4]
+                _timed("step_bwd", lib.sphnca_step_bwd, N, ptr(states[k]), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(relu_s),
+                       ptr(gcur), C.byref(p), ptr(dO_s), ptr(dY_s), ptr(dAdir_s), None, None, st)
+                if want_w:
+                    _timed("mlp_wgrad", lib.sphnca_mlp_wgrad, N, ptr(states[k]), ptr(Y_s), ptr(dO_s), None, None,
+                           C.byref(p), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value, st)
+                out = own[k & 1]
+                _timed("step_adjoint", lib.sphnca_step_adjoint, grid.c_grid(), ptr(xv4), ptr(dY_s), ptr(dAdir_s),
+                       C.byref(p), ptr(out), st)
+                gcur = out
+            if dstates[k] is not None:
+                dk = require_cuda_f32(dstates[k], "dS")
+                gcur = dk if gcur is None else gcur.add_(dk)
+        dA0 = None
+        if need[2]:
+            dA0 = grid.unpack_rows(gcur, 16) if gcur is not None else torch.zeros((N, 16), **f32)
+        return (None, None, dA0, dW1 if need[3] else None, db1 if need[4] else None, dW2 if need[5] else None,
+                db2 if need[6] else None, None, None, None, None, None, None)
+
+
+class RolloutStates:
+    """The `out` list of the reference's rollout drivers (nca.py:140-146: one `A.clone()` per step) as a lazy
+    sequence: states live cell-sorted on the device and item k is permuted back to particle order -- through
+    autograd -- only when somebody reads it (the loss reads 5 of K+1)."""
+
+    def __init__(self, sorted_states, grid):
+        self._s, self._grid, self._cache = list(sorted_states), grid, {}
+
+    def __len__(self):
+        return len(self._s)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self._s)))]
+        if k < 0:
+            k += len(self._s)
+        if not 0 <= k < len(self._s):
+            raise IndexError(k)
+        if k not in self._cache:
+            self._cache[k] = _UnpackRows.apply(self._s[k], self._grid)
+        return self._cache[k]
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self._s)))
+
+
+def nca_rollout(x, v, A, W1, b1, W2, b2, h, grid, steps, fire_rate, update_rule="gated", use_alpha=True,
+                perception_scale=1.0, orig_rate=1.0, keep_all=True):
+    """`steps` NCA steps from state A [N,16] as one autograd node -> RolloutStates (K+1 states if `keep_all`
+    or anything requires grad, else [first, last])."""
+    if "sphnca_step_fwd" in _lib.MISSING_SYMBOLS:
+        raise RuntimeError("libsphnca.so was built without the fused step (step.cu)")
+    hval = h.item() if isinstance(h, torch.Tensor) else float(h)
+    if abs(hval - grid.h) > 1e-9 * abs(grid.h):
+        raise ValueError(f"h={hval} differs from the grid's cell size {grid.h}")
+    taped = torch.is_grad_enabled() and any(t.requires_grad for t in (A, W1, b1, W2, b2))
+    states = _NCARollout.apply(x, v, A, W1, b1, W2, b2, grid, (update_rule, use_alpha, perception_scale, orig_rate),
+                               int(steps), fire_rate, keep_all, taped)
+    return RolloutStates(states, grid)
+
+
 # True (default): call the two halves of the split forward (perception sweep, tcgen05 MLP) as separate
 # C-ABI entries; False: one sphnca_step_fwd call, whose implementation follows sphnca_set_mlp_path.
 SPLIT_FORWARD = True

@@ -442,3 +442,108 @@ def test_rollout_is_bit_reproducible_at_config_size():
         assert torch.equal(a, b)
     # and the size-independent sanity of the result: finite, masks not degenerate
     assert bool(torch.isfinite(runs[0][0]).all()) and bool(torch.isfinite(runs[0][1]).all())
+
+
+# ---- K-step rollout as one autograd node ---------------------------------------
+def _rollout_model(use_alpha, h):
+    import nca
+    from bench import load_weights
+    nca.USE_3D, nca.USE_FUSED_STEP = True, True
+    w = load_golden("weights_gecko" if use_alpha else "weights_zebra")
+    m = nca.SPHNCA(16, 0.5, use_alpha=use_alpha, normalize_perception=1.0 / h).to(DEV)
+    with torch.no_grad():
+        for t, k in zip((m.model[0].weight, m.model[0].bias, m.model[2].weight, m.model[2].bias), ("W1", "b1", "W2", "b2")):
+            t.copy_(torch.from_numpy(w[k]))
+    return m
+
+
+def _multi_state_loss(out, picks):
+    loss = (out[-1][:, :4] ** 2).mean() + 0.3 * (out[0][:, 4:8] ** 2).mean()
+    for k in picks:
+        loss = loss + 0.1 * (out[k][:, :4] - 0.25).abs().mean()
+    return loss
+
+
+@pytest.mark.parametrize("use_alpha", [False, True], ids=["noalpha", "alpha"])
+@pytest.mark.parametrize("picks", [(1, 3, 3), ()], ids=["multi_state_loss", "final_only"])
+def test_rollout_node_equals_stepwise_tape(use_alpha, picks):
+    """One K-step node (sorted-resident state, in-place accumulated parameter gradients) == K fused single-step
+    nodes: states bit-identical, gradients to fp32 summation order."""
+    import nca
+    K = 5
+    x, sections, h, dims, A0, params, masks, cfg = oracle_case(64, False, use_alpha, K, seed=5)
+    m = _rollout_model(use_alpha, h)
+    xd = x.to(DEV)
+    res = []
+    for fused_rollout in (False, True):
+        m.zero_grad()
+        grid, v = m.init_grid(xd, sections, h, dims)
+        A = A0.to(DEV).requires_grad_(True)
+        with forced_fire_masks(list(masks)):
+            if fused_rollout:
+                out = m.rollout(xd, v, A, h, grid, K)
+                assert out is not None and len(out) == K + 1
+            else:
+                out, cur = [], A
+                for _ in range(K):
+                    out.append(cur.clone())
+                    _, cur = m(xd, v, cur, h, grid)
+                out.append(cur.clone())
+        _multi_state_loss(out, picks).backward()
+        res.append(([o.detach().clone() for o in out], A.grad.clone(), [p.grad.clone() for p in m.parameters()]))
+    for k, (a, b) in enumerate(zip(res[0][0], res[1][0])):
+        assert torch.equal(a, b), f"state {k}"
+    assert_close(res[1][1], res[0][1], rtol=1e-6, what="dL/dA0")
+    for a, b, nm in zip(res[0][2], res[1][2], ("dW1", "db1", "dW2", "db2")):
+        assert_close(b, a, rtol=1e-6, what=nm)
+
+
+def test_rollout_node_loss_on_an_intermediate_state_only():
+    """A loss that reads only state 2 of 5: steps 3..5 carry no gradient and are skipped in the backward."""
+    K = 5
+    x, sections, h, dims, A0, params, masks, cfg = oracle_case(48, False, False, K, seed=8)
+    m = _rollout_model(False, h)
+    xd = x.to(DEV)
+    res = []
+    for fused_rollout in (False, True):
+        m.zero_grad()
+        grid, v = m.init_grid(xd, sections, h, dims)
+        A = A0.to(DEV).requires_grad_(True)
+        with forced_fire_masks(list(masks)):
+            if fused_rollout:
+                s2 = m.rollout(xd, v, A, h, grid, K)[2]
+            else:
+                cur = A
+                for k in range(K):
+                    if k == 2:
+                        s2 = cur
+                    _, cur = m(xd, v, cur, h, grid)
+        (s2[:, :6] ** 2).mean().backward()
+        res.append((A.grad.clone(), [p.grad.clone() for p in m.parameters()]))
+    assert_close(res[1][0], res[0][0], rtol=1e-6, what="dL/dA0")
+    for a, b, nm in zip(res[0][1], res[1][1], ("dW1", "db1", "dW2", "db2")):
+        assert_close(b, a, rtol=1e-6, what=nm)
+
+
+def test_rollout_node_inference_keeps_only_what_is_asked():
+    """No tape, keep_all=False: two states (first, last); same final state as the stepwise path; sequence protocol."""
+    import random
+    K = 4
+    x, sections, h, dims, A0, params, masks, cfg = oracle_case(48, False, True, K, seed=9)
+    m = _rollout_model(True, h)
+    xd = x.to(DEV)
+    grid, v = m.init_grid(xd, sections, h, dims)
+    with torch.no_grad(), forced_fire_masks(list(masks)):
+        cur = A0.to(DEV)
+        for _ in range(K):
+            _, cur = m(xd, v, cur, h, grid)
+    with torch.no_grad(), forced_fire_masks(list(masks)):
+        short = m.rollout(xd, v, A0.to(DEV), h, grid, K, keep_all=False)
+    with torch.no_grad(), forced_fire_masks(list(masks)):
+        full = m.rollout(xd, v, A0.to(DEV), h, grid, K)
+    assert len(short) == 2 and len(full) == K + 1
+    assert torch.equal(short[-1], cur) and torch.equal(full[-1], cur) and torch.equal(full[0], A0.to(DEV))
+    assert len(full[1:3]) == 2 and len(list(full)) == K + 1 and full[-1] is full[K]
+    assert len(random.choices(full, k=4)) == 4
+    with pytest.raises(IndexError):
+        full[K + 1]
