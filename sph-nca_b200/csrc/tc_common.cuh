@@ -111,6 +111,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
            "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
 // ---- mbarrier ------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
@@ -126,10 +135,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// ---- TMA bulk copy (1-D): global -> shared, completion counted in bytes on an mbarrier ------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 // Bounded wait: a protocol bug traps instead of hanging the GPU (try_wait itself sleeps in HW).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t it = 0; it < (1u << 24); ++it)
         if (mbar_try_wait(bar, parity)) return;
+    asm volatile("trap;");
+}
+
+// Same, with a short sleep between polls: a warp that spins on try_wait keeps issuing shared-memory
+// instructions and competes with the warps doing real LDS/STS/LDGSTS work for the SM's memory-instruction queue.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 32) {
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
+        if (mbar_try_wait(bar, parity)) return;
+        __nanosleep(ns);
+    }
     asm volatile("trap;");
 }
 
@@ -138,9 +166,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // fp32 remainder (itself fed to the tensor core, which reads its top 19 bits).  hi*hi + hi*lo + lo*hi
 // reproduces the fp32 product to ~2^-21 relative.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
+    // round-to-nearest (ties away) to 10 mantissa bits on the integer ALU: add half an ulp of the kept field to the
+    // magnitude and clear the 13 dropped bits -- the value `cvt.rna.tf32.f32` gives for finite inputs, in 2 full-rate
+    // instructions instead of the ~6-instruction sequence ptxas emits for the cvt (the epilogues are issue-bound)
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
     lo = x - hi;
 }
 

@@ -32,18 +32,24 @@ constexpr int LOADERS = LOAD_WARPS * 32;                     // 128
 constexpr int KO = 32;                                       // dO columns on the tensor core in the recompute
 constexpr int NY = 64;                                       // rows of yT: 48 inputs + ones + pad
 constexpr int NOUT = 48;                                     // rows of dOT: 36 outputs + pad
-constexpr int ROW = NF + 2 * NF + NO_PAD;                    // 84 floats = 21 float4 per particle
+constexpr int ROW = NF + 2 * NF + NO_PAD;                    // 84 floats per particle: A 16 | Y 32 | dO 36
+constexpr int KP = CH + 1;                                   // K-chunk pitch of the K-major chunk tiles in 16-byte units: one
+                                                             // pad piece makes the "lanes over k-chunks" writes conflict-free
 constexpr uint32_t COL_R1 = 0, COL_HLO = 64, COL_R3 = 128, COL_DHLO = 192, COL_ACC1 = 256, COL_ACC2 = 320, TMEM_COLS = 512;
-enum { K_FULL = 0, K_EMPTY, T_FULL, T_EMPTY, R_FULL, HT_FULL, ACC_FULL, NUM_BARS };
+enum { K_FULL = 0, K_EMPTY, T_FULL, T_EMPTY, R_FULL, HT_FULL, HT_FULL_B, HT_FULL_C, HT_FULL_D, ACC_FULL, STG_FULL0, STG_FULL1, NUM_BARS };
 
 struct Smem {
     float W1_hi[128 * NIN], W1_lo[128 * NIN];      // rows = h (this half), K = k
     float W2t_hi[128 * KO], W2t_lo[128 * KO];      // rows = h, K = o
-    float yK_hi[CH * NIN], yK_lo[CH * NIN];        // rows = p, K = k        (B of D1t)
-    float dOK_hi[CH * KO], dOK_lo[CH * KO];        // rows = p, K = o        (B of D3t)
+    float yK_hi[KP * NIN], yK_lo[KP * NIN];        // rows = p, K = k        (B of D1t), K-chunk pitch KP*16 B
+    float dOK_hi[KP * KO], dOK_lo[KP * KO];        // rows = p, K = o        (B of D3t), K-chunk pitch KP*16 B
     float yT_hi[NY * CH], yT_lo[NY * CH];          // rows = k (+ones), K = p (B of dW1)
     float dOT_hi[NOUT * CH], dOT_lo[NOUT * CH];    // rows = o, K = p        (B of dW2t)
-    float stage[2][CH][ROW];                       // raw fp32 rows [A 16 | Y 32 | dO 36] of a chunk, filled by cp.async (double buffered)
+    // raw fp32 rows of a chunk: three contiguous blocks of the cell-sorted arrays, each filled by ONE TMA bulk
+    // copy (double buffered; the 1344 16-byte LDGSTS this replaces took the loader warps ~3100 cycles per chunk)
+    float stA[2][CH][NF];
+    float stY[2][CH][2 * NF];
+    float stD[2][CH][NO_PAD];
     float dO32[2][CH];                             // scalar-gate column dO[:,32] for the epilogue (double buffered)
     float b1[128], w2_last[128];
     uint64_t bar[NUM_BARS];
@@ -95,8 +101,9 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
     if (tid == 0) {
         mbar_init(&s.bar[K_FULL], LOADERS); mbar_init(&s.bar[K_EMPTY], 1);
         mbar_init(&s.bar[T_FULL], LOADERS); mbar_init(&s.bar[T_EMPTY], 1);
-        mbar_init(&s.bar[R_FULL], 1);       mbar_init(&s.bar[HT_FULL], EPI_WARPS * 32);
+        mbar_init(&s.bar[R_FULL], 1);       for (int q = 0; q < 4; ++q) mbar_init(&s.bar[HT_FULL + q], EPI_WARPS * 16);
         mbar_init(&s.bar[ACC_FULL], 1);
+        mbar_init(&s.bar[STG_FULL0], 1);    mbar_init(&s.bar[STG_FULL1], 1);
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc(&s.tmem_base, TMEM_COLS);
@@ -112,90 +119,108 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
         float db2[NO_PAD];
 #pragma unroll
         for (int o = 0; o < NO_PAD; ++o) db2[o] = 0.f;
-        // cp.async staging: all 1344 16-byte pieces of a chunk (64 particles x 21 float4) are in flight at
-        // once and land in smem without passing through registers; they are issued one chunk ahead so the
-        // HBM/L2 latency overlaps the MMAs / epilogue of the current chunk.
+        // staging: one elected loader thread issues the three bulk copies of a chunk a full chunk ahead; rows past
+        // the end of the arrays (ragged last chunk) are zero-filled by plain stores
         auto issue_copy = [&](int64_t chn, int buf) {
-            for (int i = lt; i < CH * 21; i += LOADERS) {
-                const int pl = i / 21, q = i - pl * 21;
-                const int64_t p = chn * CH + pl;
-                float* dst = &s.stage[buf][pl][4 * q];
-                if (p < n_total) {
-                    const float* src = q < 4 ? A_s + p * NF + 4 * q : (q < 12 ? Y_s + p * 2 * NF + 4 * (q - 4) : dO_s + p * NO_PAD + 4 * (q - 12));
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
-                } else {
-                    *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int64_t p0 = chn * CH;
+            const int nv = (int)((n_total - p0) < CH ? (n_total - p0) : CH);
+            if (nv < CH) {
+                for (int i = lt; i < (CH - nv) * ROW; i += LOADERS) {
+                    const int pl = nv + i / ROW, c = i - (i / ROW) * ROW;
+                    if (c < NF) s.stA[buf][pl][c] = 0.f;
+                    else if (c < 3 * NF) s.stY[buf][pl][c - NF] = 0.f;
+                    else s.stD[buf][pl][c - 3 * NF] = 0.f;
                 }
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (lt == 0) {
+                uint64_t* bar = &s.bar[STG_FULL0 + buf];
+                mbar_arrive_expect_tx(bar, (uint32_t)nv * ROW * 4u);
+                bulk_g2s(&s.stA[buf][0][0], A_s + p0 * NF, (uint32_t)nv * NF * 4u, bar);
+                bulk_g2s(&s.stY[buf][0][0], Y_s + p0 * 2 * NF, (uint32_t)nv * 2 * NF * 4u, bar);
+                bulk_g2s(&s.stD[buf][0][0], dO_s + p0 * NO_PAD, (uint32_t)nv * NO_PAD * 4u, bar);
+            }
+        };
+        auto split4 = [](const float4 v, float4& hi, float4& lo) {
+            split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
         };
         if (c0 < c1) issue_copy(c0, 0);
         int it = 0;
         for (int64_t ch = c0; ch < c1; ++ch, ++it) {
             const int buf = it & 1;
-            float (*stg)[ROW] = s.stage[buf];
             // the other staging buffer was last read in phase 2 of the previous chunk (all loaders passed the
             // barrier at the end of that iteration): refill it now, a full chunk ahead
-            if (ch + 1 < c1) {
-                issue_copy(ch + 1, buf ^ 1);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");     // this chunk's group has landed
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
-            asm volatile("bar.sync 1, %0;" :: "r"(LOADERS) : "memory");  // ... for every loader thread
-            // phase 1 (K-major tiles).  Lanes vary over particles: stage rows are 336 B apart (8 lanes cover
-            // all 32 banks), tile chunks of consecutive particles are consecutive 16 B -> conflict-free
+            if (lt == 0) SPHNCA_TL(13);
+            if (ch + 1 < c1) issue_copy(ch + 1, buf ^ 1);
+            if (lt == 0) SPHNCA_TL(14);
+            mbar_wait(&s.bar[STG_FULL0 + buf], (it >> 1) & 1);           // this chunk's rows have landed
+            if (lt == 0) SPHNCA_TL(11);
+            if ((ch + 1) * CH > n_total)                                  // ragged last chunk: the zero-filled tail rows must be visible
+                asm volatile("bar.sync 1, %0;" :: "r"(LOADERS) : "memory");
+            if (lt == 0) SPHNCA_TL(12);
+            // phase 1 (K-major tiles): a piece = 4 consecutive k of one particle.  Lanes run over the pieces of a
+            // row (contiguous 16 B reads); the tile's K-chunk pitch is KP*16 B, so those lanes hit distinct banks.
             mbar_wait(&s.bar[K_EMPTY], (it & 1) ^ 1);         // recompute MMAs of the previous chunk are done
             if (lt == 0) SPHNCA_TL(0);
 #pragma unroll
-            for (int r = 0; r < CH * (NIN / 4) / LOADERS; ++r) {
-                const int i = lt + r * LOADERS;
-                const int q = i / CH, pl = i - q * CH;
-                const float4 v = *reinterpret_cast<const float4*>(&stg[pl][4 * q]);
-                float hi[4], lo[4];
-                split_tf32(v.x, hi[0], lo[0]); split_tf32(v.y, hi[1], lo[1]);
-                split_tf32(v.z, hi[2], lo[2]); split_tf32(v.w, hi[3], lo[3]);
-                const uint32_t o = chunk_off(CH, pl, q) / 4;
-                *reinterpret_cast<float4*>(&s.yK_hi[o]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(&s.yK_lo[o]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            for (int r = 0; r < CH * (NF / 4) / LOADERS; ++r) {           // A part: k chunks 0..3
+                const int i = lt + r * LOADERS, pl = i >> 2, q = i & 3;
+                float4 hi, lo; split4(*reinterpret_cast<const float4*>(&s.stA[buf][pl][4 * q]), hi, lo);
+                const uint32_t o = (q * KP + pl) * 4;
+                *reinterpret_cast<float4*>(&s.yK_hi[o]) = hi; *reinterpret_cast<float4*>(&s.yK_lo[o]) = lo;
             }
 #pragma unroll
-            for (int r = 0; r < CH * (KO / 4) / LOADERS; ++r) {
-                const int i = lt + r * LOADERS;
-                const int qo = i / CH, pl = i - qo * CH;
-                const float4 v = *reinterpret_cast<const float4*>(&stg[pl][3 * NF + 4 * qo]);
-                float hi[4], lo[4];
-                split_tf32(v.x, hi[0], lo[0]); split_tf32(v.y, hi[1], lo[1]);
-                split_tf32(v.z, hi[2], lo[2]); split_tf32(v.w, hi[3], lo[3]);
-                const uint32_t o = chunk_off(CH, pl, qo) / 4;
-                *reinterpret_cast<float4*>(&s.dOK_hi[o]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(&s.dOK_lo[o]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            for (int r = 0; r < CH * (2 * NF / 4) / LOADERS; ++r) {       // Y part: k chunks 4..11
+                const int i = lt + r * LOADERS, pl = i >> 3, q = i & 7;
+                float4 hi, lo; split4(*reinterpret_cast<const float4*>(&s.stY[buf][pl][4 * q]), hi, lo);
+                const uint32_t o = ((q + NF / 4) * KP + pl) * 4;
+                *reinterpret_cast<float4*>(&s.yK_hi[o]) = hi; *reinterpret_cast<float4*>(&s.yK_lo[o]) = lo;
             }
-            if (lt < CH) s.dO32[it & 1][lt] = stg[lt][3 * NF + KO];
+#pragma unroll
+            for (int r = 0; r < CH * (KO / 4) / LOADERS; ++r) {           // dO columns 0..31
+                const int i = lt + r * LOADERS, pl = i >> 3, q = i & 7;
+                float4 hi, lo; split4(*reinterpret_cast<const float4*>(&s.stD[buf][pl][4 * q]), hi, lo);
+                const uint32_t o = (q * KP + pl) * 4;
+                *reinterpret_cast<float4*>(&s.dOK_hi[o]) = hi; *reinterpret_cast<float4*>(&s.dOK_lo[o]) = lo;
+            }
+            if (lt < CH) s.dO32[it & 1][lt] = s.stD[buf][lt][KO];
             fence_proxy_async_smem();
             mbar_arrive(&s.bar[K_FULL]);
             if (lt == 0) SPHNCA_TL(1);
             if (hh == 0 && lt < CH) {                         // db2 partial sums (one CTA of the pair)
 #pragma unroll
-                for (int o = 0; o < NO_PAD; ++o) db2[o] += stg[lt][3 * NF + o];
+                for (int o = 0; o < NO_PAD; ++o) db2[o] += s.stD[buf][lt][o];
             }
             // phase 2 (transposed K-major tiles): one 16-byte piece = 4 consecutive particles of one row.
-            // Lanes vary over rows: consecutive words of a stage row, consecutive 16 B of the tile.
+            // Lanes vary over rows: consecutive words of a staged row, consecutive 16 B of the tile.
             mbar_wait(&s.bar[T_EMPTY], (it & 1) ^ 1);         // accumulate MMAs of the previous chunk are done
             if (lt == 0) SPHNCA_TL(2);
-            constexpr int ROWS2 = NIN + NO_PAD;               // 48 y rows + 36 dO rows = 84 = the stage row
-#pragma unroll 3
-            for (int i = lt; i < ROWS2 * (CH / 4); i += LOADERS) {
-                const int pg = i / ROWS2, row = i - pg * ROWS2;
-                float hi[4], lo[4];
+            // three convergent loops (one per staged block); in the A block a warp covers two particle groups whose
+            // rows are 64 words apart, so its upper half reads the 4 particles in the order 1,0,3,2 (distinct banks)
+            auto put = [&](float* th, float* tl, uint32_t o, const float4 v) {
+                float4 hi, lo; split4(v, hi, lo);
+                *reinterpret_cast<float4*>(&th[o]) = hi; *reinterpret_cast<float4*>(&tl[o]) = lo;
+            };
 #pragma unroll
-                for (int j = 0; j < 4; ++j) split_tf32(stg[4 * pg + j][row], hi[j], lo[j]);
-                const bool isy = row < NIN;
-                float* th = isy ? s.yT_hi : s.dOT_hi;
-                float* tl = isy ? s.yT_lo : s.dOT_lo;
-                const uint32_t o = (isy ? chunk_off(NY, row, pg) : chunk_off(NOUT, row - NIN, pg)) / 4;
-                *reinterpret_cast<float4*>(&th[o]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(&tl[o]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            for (int r = 0; r < NF * (CH / 4) / LOADERS; ++r) {           // A rows 0..15
+                const int i = lt + r * LOADERS, pg = i >> 4, row = i & 15, sw = (lane >> 4) & 1;
+                const float a = s.stA[buf][4 * pg + sw][row], b = s.stA[buf][4 * pg + (sw ^ 1)][row];
+                const float c = s.stA[buf][4 * pg + 2 + sw][row], d = s.stA[buf][4 * pg + 2 + (sw ^ 1)][row];
+                put(s.yT_hi, s.yT_lo, chunk_off(NY, row, pg) / 4, sw ? make_float4(b, a, d, c) : make_float4(a, b, c, d));
+            }
+#pragma unroll
+            for (int r = 0; r < 2 * NF * (CH / 4) / LOADERS; ++r) {       // Y rows 16..47
+                const int i = lt + r * LOADERS, pg = i >> 5, row = i & 31;
+                put(s.yT_hi, s.yT_lo, chunk_off(NY, NF + row, pg) / 4,
+                    make_float4(s.stY[buf][4 * pg][row], s.stY[buf][4 * pg + 1][row], s.stY[buf][4 * pg + 2][row], s.stY[buf][4 * pg + 3][row]));
+            }
+#pragma unroll
+            for (int r = 0; r < (NO_PAD * (CH / 4) + LOADERS - 1) / LOADERS; ++r) {   // dO rows 0..35
+                const int i = lt + r * LOADERS;
+                if (i < NO_PAD * (CH / 4)) {
+                    const int pg = i / NO_PAD, row = i - pg * NO_PAD;
+                    put(s.dOT_hi, s.dOT_lo, chunk_off(NOUT, row, pg) / 4,
+                        make_float4(s.stD[buf][4 * pg][row], s.stD[buf][4 * pg + 1][row], s.stD[buf][4 * pg + 2][row], s.stD[buf][4 * pg + 3][row]));
+                }
             }
             if (lt < CH / 4) {                                // ones row (-> db1): 1 for real particles
                 float one[4];
@@ -211,8 +236,8 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
         }
         // db2: fixed-order tree over the 64 row-owning loader threads, written by the hh == 0 CTA
         if (hh == 0) {
-            // scratch for the tree: the staging buffer (idle now; rows of 84 floats, 64 rows used)
-            float (*red)[ROW] = s.stage[0];
+            // scratch for the tree: the dO staging buffer (idle now)
+            float (*red)[NO_PAD] = s.stD[0];
             if (lt < CH) {
 #pragma unroll
                 for (int o = 0; o < NO_PAD; ++o) red[lt][o] = db2[o];
@@ -241,8 +266,8 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                 for (int ks = 0; ks < NIN / 8; ++ks) {
                     const uint64_t a_hi = make_smem_desc(smem_u32(s.W1_hi) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
                     const uint64_t a_lo = make_smem_desc(smem_u32(s.W1_lo) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                    const uint64_t b_hi = make_smem_desc(smem_u32(s.yK_hi) + chunk_off(CH, 0, 2 * ks), CH * 16, 128);
-                    const uint64_t b_lo = make_smem_desc(smem_u32(s.yK_lo) + chunk_off(CH, 0, 2 * ks), CH * 16, 128);
+                    const uint64_t b_hi = make_smem_desc(smem_u32(s.yK_hi) + 2 * ks * KP * 16, KP * 16, 128);
+                    const uint64_t b_lo = make_smem_desc(smem_u32(s.yK_lo) + 2 * ks * KP * 16, KP * 16, 128);
                     mma_tf32_ss_e(tbase + COL_R1, a_lo, b_hi, idR, ks > 0, go);
                     mma_tf32_ss_e(tbase + COL_R1, a_hi, b_lo, idR, true, go);
                     mma_tf32_ss_e(tbase + COL_R1, a_hi, b_hi, idR, true, go);
@@ -251,8 +276,8 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                 for (int ks = 0; ks < KO / 8; ++ks) {
                     const uint64_t a_hi = make_smem_desc(smem_u32(s.W2t_hi) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
                     const uint64_t a_lo = make_smem_desc(smem_u32(s.W2t_lo) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                    const uint64_t b_hi = make_smem_desc(smem_u32(s.dOK_hi) + chunk_off(CH, 0, 2 * ks), CH * 16, 128);
-                    const uint64_t b_lo = make_smem_desc(smem_u32(s.dOK_lo) + chunk_off(CH, 0, 2 * ks), CH * 16, 128);
+                    const uint64_t b_hi = make_smem_desc(smem_u32(s.dOK_hi) + 2 * ks * KP * 16, KP * 16, 128);
+                    const uint64_t b_lo = make_smem_desc(smem_u32(s.dOK_lo) + 2 * ks * KP * 16, KP * 16, 128);
                     mma_tf32_ss_e(tbase + COL_R3, a_lo, b_hi, idR, ks > 0, go);
                     mma_tf32_ss_e(tbase + COL_R3, a_hi, b_lo, idR, true, go);
                     mma_tf32_ss_e(tbase + COL_R3, a_hi, b_hi, idR, true, go);
@@ -267,6 +292,7 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                 SPHNCA_TL(7);
 #pragma unroll
                 for (int ks = 0; ks < CH / 8; ++ks) {
+                    if (ks > 0 && (ks & 1) == 0) { mbar_wait(&s.bar[HT_FULL + ks / 2], it & 1); fence_after_sync(); }   // next 16 columns converted
                     const uint64_t y_hi = make_smem_desc(smem_u32(s.yT_hi) + chunk_off(NY, 0, 2 * ks), NY * 16, 128);
                     const uint64_t y_lo = make_smem_desc(smem_u32(s.yT_lo) + chunk_off(NY, 0, 2 * ks), NY * 16, 128);
                     const uint64_t o_hi = make_smem_desc(smem_u32(s.dOT_hi) + chunk_off(NOUT, 0, 2 * ks), NOUT * 16, 128);
@@ -287,7 +313,7 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
     } else {
         // ============================ epilogue: thread = hidden unit ============================
         const int h = (warp & 3) * 32 + lane;                 // 0..127 within the half == TMEM lane
-        const int col0 = (warp >> 2) * (CH / 2);              // this warp's particle columns [col0, col0 + 32)
+        const int col0 = (warp >> 2) * (CH / 4);              // first of this warp's two 16-column quarters
         const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
         const float b1h = s.b1[h], w2l = s.w2_last[h];
         int it = 0;
@@ -295,18 +321,28 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
             mbar_wait(&s.bar[R_FULL], it & 1);
             fence_after_sync();
             if (tid == 0) SPHNCA_TL(9);
+            // 16 particle columns per quarter; warp group g = warp >> 2 converts quarters g and g + 2, so quarters 0|1 and
+            // 2|3 are produced in parallel and the accumulate MMAs over the first particles start while the later columns
+            // are still being converted; the second quarter's TMEM loads are in flight during the first one's arithmetic
+            uint32_t r1[2][16], r3[2][16];
+            tmem_ld16(lane_addr + COL_R1 + col0, r1[0]);
+            tmem_ld16(lane_addr + COL_R3 + col0, r3[0]);
 #pragma unroll
-            for (int cc = col0; cc < col0 + CH / 2; cc += 16) {
-                uint32_t r1[16], r3[16], hhi[16], hlo[16], dhi[16], dlo[16];
-                tmem_ld16(lane_addr + COL_R1 + cc, r1);
-                tmem_ld16(lane_addr + COL_R3 + cc, r3);
+            for (int ph = 0; ph < 2; ++ph) {
+                const int qt = 2 * ph + (warp >> 2);
+                const int cc = qt * (CH / 4);
+                uint32_t hhi[16], hlo[16], dhi[16], dlo[16];
                 wait_ld();
+                if (ph == 0) {
+                    tmem_ld16(lane_addr + COL_R1 + cc + CH / 2, r1[1]);
+                    tmem_ld16(lane_addr + COL_R3 + cc + CH / 2, r3[1]);
+                }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float pre = __uint_as_float(r1[j]) + b1h;
+                    const float pre = __uint_as_float(r1[ph][j]) + b1h;
                     const bool on = pre > 0.f;
                     const float hv = on ? pre : 0.f;
-                    const float dh = on ? fmaf(s.dO32[it & 1][cc + j], w2l, __uint_as_float(r3[j])) : 0.f;
+                    const float dh = on ? fmaf(s.dO32[it & 1][cc + j], w2l, __uint_as_float(r3[ph][j])) : 0.f;
                     float a, b;
                     split_tf32(hv, a, b); hhi[j] = __float_as_uint(a); hlo[j] = __float_as_uint(b);
                     split_tf32(dh, a, b); dhi[j] = __float_as_uint(a); dlo[j] = __float_as_uint(b);
@@ -315,10 +351,10 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                 tmem_st16(lane_addr + COL_HLO + cc, hlo);
                 tmem_st16(lane_addr + COL_R3 + cc, dhi);
                 tmem_st16(lane_addr + COL_DHLO + cc, dlo);
+                wait_st();
+                fence_before_sync();
+                mbar_arrive(&s.bar[HT_FULL + qt]);
             }
-            wait_st();
-            fence_before_sync();
-            mbar_arrive(&s.bar[HT_FULL]);
             if (tid == 0) SPHNCA_TL(10);
         }
         // the accumulators: dW1 row h (48) | db1 (column 48)   and   dW2[o][h] (column o of ACC2)

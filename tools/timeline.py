@@ -9,12 +9,13 @@ buf = (C.c_longlong * (64 * 16))()
 for fn in ("sphnca_debug_timeline_wgrad", "sphnca_debug_timeline_fwd"):
     getattr(_lib.lib, fn).argtypes = [C.POINTER(C.c_longlong), C.c_int32]
 print("rc", _lib.lib.sphnca_debug_timeline_wgrad(buf, 64 * 16))
-names = ["L K_EMPTY ok", "L K_FULL arr", "L T_EMPTY ok", "L T_FULL arr", "M K_FULL ok", "M recomp issued", "M HT_FULL ok", "M T_FULL ok", "M accum issued", "E R_FULL ok", "E HT arr"]
+names = ["L K_EMPTY ok", "L K_FULL arr", "L T_EMPTY ok", "L T_FULL arr", "M K_FULL ok", "M recomp issued", "M HT_FULL ok", "M T_FULL ok", "M accum issued", "E R_FULL ok", "E HT arr", "L cpasync landed", "L barsync", "L iter top", "L copy issued"]
 t0 = buf[4]
 for it in range(2, 8):
-    row = [buf[it * 16 + k] - t0 for k in range(11)]
+    row = [buf[it * 16 + k] - t0 for k in range(15)]
     print(f"chunk {it}: " + "  ".join(f"{n}={v}" for n, v in sorted(zip(names, row), key=lambda t: t[1])))
 
+sys.exit(0)
 print("---- step_fwd_tc timeline (cycles, CTA 0)")
 import runpy as _r
 g2 = _r.run_path(os.path.join(ROOT, "tools", "microbench_fwd.py"))
