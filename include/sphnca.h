@@ -147,6 +147,10 @@ int32_t sphnca_set_sweep_path(int32_t path);
  * place; flags_s bit1 = new_mask. */
 int32_t sphnca_step_mask(const sphnca_grid* g, const float* xv4, const uint8_t* alive_s,
                          float* A_new_s, uint8_t* flags_s, void* stream);
+/* The same update when use_alpha == 0 (reference nca.py:17-21: the activity field is all-ones, so the new life
+ * mask is the blur of the same constant field as the previous one, i.e. bit0 of flags_s as written by the perception
+ * sweep): flags_s bit1 = bit0, rows with bit0 == 0 are multiplied by 0.  Elementwise, no neighbour sweep. */
+int32_t sphnca_step_mask_static(int64_t N, float* A_new_s, uint8_t* flags_s, void* stream);
 
 /* One backward step = sphnca_step_bwd then sphnca_step_adjoint (one kernel each), gather-based,
  * no float atomics.

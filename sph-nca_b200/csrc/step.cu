@@ -15,6 +15,7 @@
 // All arrays are in cell-sorted order.  v1: the MLP runs on the fp32 CUDA-core pipe.
 #include "step_common.cuh"
 #include "sweep_tile.cuh"
+#include "sweep_stage.cuh"
 
 namespace sphnca {
 
@@ -493,8 +494,107 @@ static int g_sweep_path = 0;
 
 extern "C" {
 
+}  // extern "C"
+
+namespace sphnca {
+// ---- life mask without an alpha channel ------------------------------------------------------------------------
+// use_alpha == 0: cell_activity is all-ones (reference nca.py:17-21), so the new life mask is the blur of the same
+// constant field as the previous one -- the value the perception sweep already wrote into bit 0, bit for bit.  No sweep:
+// bit1 = bit0, dead rows are multiplied by 0 exactly like step_mask_kernel does.
+__global__ void __launch_bounds__(256) step_mask_static_kernel(int64_t n, float* __restrict__ An_s, uint8_t* __restrict__ flags_s) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint8_t fl = flags_s[p];
+    if (fl & 1) { flags_s[p] = fl | 2; return; }
+    float4* a4 = reinterpret_cast<float4*>(An_s + (size_t)p * NF);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { float4 t = a4[k]; a4[k] = make_float4(t.x * 0.f, t.y * 0.f, t.z * 0.f, t.w * 0.f); }
+}
+
+// ---- perception sweep with block-staged candidates (sweep_stage.cuh) --------------------------------------------
+// Opt-in (sphnca_set_sweep_path(2)).  Measured on B200, 524,288 particles: padded 2-D (BASELINE configs[1]) 0.266 ms
+// vs 0.300 ms for the gather kernel; 3-D clouds never fit the staging buffer (27 cells x 7.6 particles x 9 rows),
+// every tile falls back and pays the planning + the lower occupancy (0.475 vs 0.332 ms) -- hence not the default.
+// The two-pass variant (PERC_SLOTS > 0, padded rows, 256-particle tiles) executes 9 % fewer instructions at 25 instead
+// of 18 active lanes but issues on 31 % instead of 53 % of the cycles: 0.387 ms.
+constexpr int PERC_T = 128;        // particles per tile (~12 cells of a row in the padded 2-D configuration)
+constexpr int PERC_CAP = 552;      // candidates per tile: 552 x (16 + 64) B = 44 KB of shared memory -> 5 CTAs per SM
+constexpr int PERC_SLOTS = 0;      // 0 = single pass; > 0 = hit-list slots per thread of the two-pass variant
+template <int D>
+__global__ void __launch_bounds__(PERC_T, 5)
+step_perceive_staged_kernel(GridView g, const float4* __restrict__ xv4, const float* __restrict__ A_s, StepConsts c,
+                            float* __restrict__ Y_s, uint8_t* __restrict__ flags_s) {
+    extern __shared__ __align__(128) unsigned char stage_raw[];
+    using S = StageSmem<D, PERC_T, NF, PERC_CAP, PERC_SLOTS>;
+    S& sm = *reinterpret_cast<S*>(stage_raw);
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < g.n;
+    const int my_cell = valid ? g.sorted_cell[p] : 0;
+    int k = 0;
+    const bool staged = stage_tile(g, xv4, A_s, sm, p, valid, my_cell, k);
+    if (!valid) return;
+    const float4 xi = xv4[p];
+    float2 Ai[NF / 2], gx[NF / 2], gy[NF / 2];
+    {
+        const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)p * NF);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float4 t = __ldg(a4 + q); Ai[2*q] = make_float2(t.x, t.y); Ai[2*q+1] = make_float2(t.z, t.w); }
+    }
+#pragma unroll
+    for (int f = 0; f < NF / 2; ++f) { gx[f] = make_float2(0.f, 0.f); gy[f] = make_float2(0.f, 0.f); }
+    float blur = 0.f;
+    // the pair body of step_perceive_kernel, unchanged; `row4(q)` yields float4 q of the neighbour's 16 channels
+    auto pair = [&](const float4 xj, auto&& row4) {
+        float rx, ry;
+        const float d2 = pair_d2<D>(xi, xj, rx, ry);
+        if (d2 < c.h2) {
+            float2 Aj[NF / 2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float4 t = row4(q); Aj[2*q] = make_float2(t.x, t.y); Aj[2*q+1] = make_float2(t.z, t.w); }
+            const float t = c.h2 - d2;
+            const float alive = c.use_alpha ? (Aj[1].y > 0.1f ? 1.f : 0.f) : 1.f;
+            blur = fmaf(alive * xj.w, t * t * t, blur);
+            if (d2 > 0.f) {
+                const float inv = rsqrtf(d2);
+                const float hd = c.h - d2 * inv;
+                const float m = 3.f * hd * hd * inv * xj.w;
+                const float2 wx = make_float2(m * rx, m * rx), wy = make_float2(m * ry, m * ry);
+#pragma unroll
+                for (int f = 0; f < NF / 2; ++f) {
+                    const float2 dA = fsub2(Aj[f], Ai[f]);
+                    gx[f] = ffma2(dA, wx, gx[f]);
+                    gy[f] = ffma2(dA, wy, gy[f]);
+                }
+            }
+        }
+    };
+    if (staged) {
+        if (PERC_SLOTS > 0)
+            staged_two_pass(g, sm, my_cell, k,
+                [&](const float4 xj) { float rx, ry; return pair_d2<D>(xi, xj, rx, ry) < c.h2; },
+                [&](int j) { pair(sm.x[j], [&](int q) { return sm.row[j * S::RP4 + q]; }); });
+        else
+            for_each_staged(g, sm, my_cell, k, [&](int j) { pair(sm.x[j], [&](int q) { return sm.row[j * S::RP4 + q]; }); });
+    } else {
+        for_each_candidate<D>(g, my_cell, [&](int q_) {
+            const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)q_ * NF);
+            pair(__ldg(&xv4[q_]), [&](int q) { return __ldg(a4 + q); });
+        });
+    }
+    float4* y4 = reinterpret_cast<float4*>(Y_s + (size_t)p * 2 * NF);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) y4[q] = make_float4(gx[2*q].x * c.kg, gx[2*q].y * c.kg, gx[2*q+1].x * c.kg, gx[2*q+1].y * c.kg);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) y4[4 + q] = make_float4(gy[2*q].x * c.kg, gy[2*q].y * c.kg, gy[2*q+1].x * c.kg, gy[2*q+1].y * c.kg);
+    flags_s[p] = blur * c.cw > 0.1f ? 1 : 0;
+}
+}  // namespace sphnca
+
+extern "C" {
+using namespace sphnca;
+
 int32_t sphnca_set_sweep_path(int32_t path) {
-    if (path != 0 && path != 1) { set_error("sweep path must be 0 (per-thread gathers) or 1 (shared-memory tiles)"); return SPHNCA_ERR_INVALID; }
+    if (path < 0 || path > 2) { set_error("sweep path must be 0 (per-thread gathers), 1 (shared-memory tile engine) or 2 (TMA-staged tiles)"); return SPHNCA_ERR_INVALID; }
     g_sweep_path = path;
     return SPHNCA_OK;
 }
@@ -507,7 +607,14 @@ int32_t sphnca_step_perceive(const sphnca_grid* g, const float* xv4, const float
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(xv4 && A_s && Y_s && flags_s, "NULL argument");
     const int pblocks = (int)((gv.n + 127) / 128);
-    if (g_sweep_path == 1) {
+    if (g_sweep_path == 2) {
+        const size_t smem3 = sizeof(StageSmem<3, PERC_T, NF, PERC_CAP, PERC_SLOTS>), smem2 = sizeof(StageSmem<2, PERC_T, NF, PERC_CAP, PERC_SLOTS>);
+        const int sblocks = (int)((gv.n + PERC_T - 1) / PERC_T);
+        if (gv.dim == 3) SPHNCA_CUDA(cudaFuncSetAttribute(step_perceive_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        else SPHNCA_CUDA(cudaFuncSetAttribute(step_perceive_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        if (gv.dim == 3) SPHNCA_LAUNCH(step_perceive_staged_kernel<3>, sblocks, PERC_T, smem3, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+        else SPHNCA_LAUNCH(step_perceive_staged_kernel<2>, sblocks, PERC_T, smem2, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+    } else if (g_sweep_path == 1) {
         if (gv.dim == 3) SPHNCA_LAUNCH(step_perceive_tile_kernel<3>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
         else SPHNCA_LAUNCH(step_perceive_tile_kernel<2>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
     } else {
@@ -567,6 +674,15 @@ int32_t sphnca_step_mask(const sphnca_grid* g, const float* xv4, const uint8_t* 
     const int blocks = (int)((gv.n + 255) / 256);
     if (gv.dim == 3) SPHNCA_LAUNCH(step_mask_kernel<3>, blocks, 256, 0, stream, gv, (const float4*)xv4, alive_s, c, A_new_s, flags_s);
     else SPHNCA_LAUNCH(step_mask_kernel<2>, blocks, 256, 0, stream, gv, (const float4*)xv4, alive_s, c, A_new_s, flags_s);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_step_mask_static(int64_t N, float* A_new_s, uint8_t* flags_s, void* stream_) {
+    SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
+    if (N == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(A_new_s && flags_s, "NULL argument");
+    SPHNCA_LAUNCH(step_mask_static_kernel, (int)((N + 255) / 256), 256, 0, as_stream(stream_), N, A_new_s, flags_s);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

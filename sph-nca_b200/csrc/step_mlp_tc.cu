@@ -107,7 +107,9 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
 #pragma unroll
                 for (int k = 0; k < NIN / 4; ++k) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if (m == 0) SPHNCA_TL(12);
             mbar_wait(&s.bar[Y_EMPTY], (it & 1) ^ 1);
+            if (m == 0) SPHNCA_TL(13);
 #pragma unroll
             for (int ch = 0; ch < NIN / 4; ++ch) {
                 float hi[4], lo[4];
@@ -119,6 +121,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             }
             fence_proxy_async_smem();
             mbar_arrive(&s.bar[Y_FULL]);
+            if (m == 0) SPHNCA_TL(0);
         }
     } else if (warp == MMA_WARP) {
         {   // warp-uniform issue: every lane runs the loop, one elected lane issues (tc_common.cuh)
@@ -129,6 +132,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 mbar_wait(&s.bar[Y_FULL], it & 1);
                 fence_after_sync();
+                SPHNCA_TL(1);
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     if (half == 1) { mbar_wait(&s.bar[D1_EMPTY], 0); fence_after_sync(); }
@@ -145,6 +149,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                         mma_tf32_ss_e(tbase + COL_D1, a_hi, b_hi, idesc1, true, go);
                     }
                     mma_commit_e(&s.bar[D1_FULL], go);
+                    SPHNCA_TL(2 + half);
                 }
                 mma_commit_e(&s.bar[Y_EMPTY], go);
                 mbar_wait(&s.bar[D2_EMPTY], (it & 1) ^ 1);
@@ -162,6 +167,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                         mma_tf32_ts_e(tbase + COL_D2, tbase + COL_HHI + 8 * ks, b_hi, idesc2, true, go);
                     }
                     mma_commit_e(&s.bar[H_EMPTY], go);
+                    SPHNCA_TL(4 + half);
                 }
                 mma_commit_e(&s.bar[D2_FULL], go);
             }
@@ -195,6 +201,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 mbar_wait(&s.bar[D1_FULL], half);
                 mbar_wait(&s.bar[H_EMPTY], half ^ 1);
                 fence_after_sync();
+                if (tid == 0) SPHNCA_TL(6 + 2 * half);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const int cc = chalf * 64 + c4 * 16;
@@ -220,6 +227,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 fence_before_sync();
                 mbar_arrive(&s.bar[D1_EMPTY]);
                 mbar_arrive(&s.bar[H_FULL]);
+                if (tid == 0) SPHNCA_TL(7 + 2 * half);
             }
             const int slot = it & 1;
             if (chalf == 1) {
@@ -232,6 +240,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 mbar_wait(&s.bar[D2_FULL], it & 1);
                 fence_after_sync();
+                if (tid == 0) SPHNCA_TL(10);
                 float out[NO_PAD];
                 {
                     uint32_t r[16];
@@ -244,6 +253,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 }
                 fence_before_sync();
                 mbar_arrive(&s.bar[D2_EMPTY]);
+                if (tid == 0) SPHNCA_TL(14);
                 out[32] = o32 + s.o32[slot][m] + s.b2[32]; out[33] = 0.f; out[34] = 0.f; out[35] = 0.f;
                 if (c.rule != 0) {
 #pragma unroll
@@ -261,6 +271,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                     }
 #pragma unroll
                     for (int f = 0; f < NF; ++f) nA[f] = fire ? nA[f] : Ai[f];
+                    if (tid == 0) SPHNCA_TL(15);
                     float4* o4 = reinterpret_cast<float4*>(An_s + (size_t)p * NF);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) o4[k] = make_float4(nA[4 * k], nA[4 * k + 1], nA[4 * k + 2], nA[4 * k + 3]);
@@ -274,6 +285,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                     flags_s[p] = (uint8_t)(prevbit | (fire ? 4 : 0));
                     alive_s[p] = c.use_alpha ? (nA[3] > 0.1f ? 1 : 0) : 1;
                 }
+                if (tid == 0) SPHNCA_TL(11);
             }
         }
     }
@@ -302,3 +314,5 @@ int launch_step_mlp_tc(int64_t N, const StepConsts& c, const sphnca_step_params*
 }
 
 }  // namespace sphnca
+
+SPHNCA_TIMELINE_READER(sphnca_debug_timeline_mlp)

@@ -223,9 +223,13 @@ class SlabShardedNCA:
             check(lib.sphnca_step_perceive(g, ptr(self.xv4), ptr(A_s), C.byref(prm), ptr(Y_s), ptr(flags_s), st))
             check(lib.sphnca_step_mlp(N, ptr(A_s), ptr(Y_s), ptr(fire_s), C.byref(prm), ptr(An_s), ptr(alive_s), ptr(O_s),
                                       ptr(flags_s), ptr(relu_s), st))
-            nbytes += self._exchange_sorted(alive_s)
-            # the previous-mask bit of a halo particle is never used (its row is overwritten by the next exchange)
-            check(lib.sphnca_step_mask(g, ptr(self.xv4), ptr(alive_s), ptr(An_s), ptr(flags_s), st))
+            if m.use_alpha:
+                nbytes += self._exchange_sorted(alive_s)
+                # the previous-mask bit of a halo particle is never used (its row is overwritten by the next exchange)
+                check(lib.sphnca_step_mask(g, ptr(self.xv4), ptr(alive_s), ptr(An_s), ptr(flags_s), st))
+            else:
+                # no alpha channel: new life mask == previous one (include/sphnca.h), no sweep and no second halo round
+                check(lib.sphnca_step_mask_static(N, ptr(An_s), ptr(flags_s), st))
             A_s, An_s = An_s, A_s
         self.bytes_per_step = nbytes // max(steps, 1)
         return A_s[self.own_pos]

@@ -64,6 +64,7 @@ def _load():
         "sphnca_divergence_bwd": ([G, P, P, I32, P, P], I32),
         "sphnca_step_fwd": ([G, P, P, P, SP, P, P, P, P, P, P, P], I32),
         "sphnca_step_mask": ([G, P, P, P, P, P], I32),
+        "sphnca_step_mask_static": ([I64, P, P, P], I32),
         "sphnca_step_perceive": ([G, P, P, SP, P, P, P], I32),
         "sphnca_step_mlp": ([I64, P, P, P, SP, P, P, P, P, P, P], I32),
         "sphnca_step_bwd": ([I64, P, P, P, P, P, P, SP, P, P, P, P, P, P], I32),

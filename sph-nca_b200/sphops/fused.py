@@ -43,6 +43,15 @@ def _timed(name, fn, *args):
     PROFILE.setdefault(name, []).append((a, b))
 
 
+def _mask(use_alpha, g, N, xv4, alive_s, An_s, flags_s, st):
+    """Life-mask update of a step.  Without an alpha channel the new mask equals the previous one (both are the blur
+    of an all-ones field, reference nca.py:17-21,94-98), so no second neighbour sweep is needed."""
+    if use_alpha:
+        _timed("step_mask", lib.sphnca_step_mask, g, ptr(xv4), ptr(alive_s), ptr(An_s), ptr(flags_s), st)
+    else:
+        _timed("step_mask_static", lib.sphnca_step_mask_static, N, ptr(An_s), ptr(flags_s), st)
+
+
 class _NCAStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, v, A, update_mask, W1, b1, W2, b2, h, grid, update_rule, use_alpha, perception_scale, orig_rate):
@@ -73,7 +82,7 @@ class _NCAStep(torch.autograd.Function):
             else:
                 _timed("step_fwd", lib.sphnca_step_fwd, g, ptr(xv4), ptr(A_s), ptr(fire_s), C.byref(p), ptr(An_s),
                        ptr(alive_s), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
-            _timed("step_mask", lib.sphnca_step_mask, g, ptr(xv4), ptr(alive_s), ptr(An_s), ptr(flags_s), st)
+            _mask(use_alpha, g, N, xv4, alive_s, An_s, flags_s, st)
         out = grid.unpack_rows(An_s, 16)
         ctx.grid = grid
         ctx.cfg = (update_rule, use_alpha, perception_scale, orig_rate)
@@ -190,7 +199,7 @@ class _NCARollout(torch.autograd.Function):
                 else:
                     _timed("step_fwd", lib.sphnca_step_fwd, g, ptr(xv4), ptr(S), ptr(fire_s), C.byref(p), ptr(Sn),
                            ptr(alive_s), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
-                _timed("step_mask", lib.sphnca_step_mask, g, ptr(xv4), ptr(alive_s), ptr(Sn), ptr(flags_s), st)
+                _mask(use_alpha, g, N, xv4, alive_s, Sn, flags_s, st)
             if taped:
                 saved += [Y_s, O_s, flags_s, relu_s]
             if keep_all or taped:

@@ -401,7 +401,7 @@ def test_tile_sweeps_equal_gather_sweeps(kind):
     p = fused._step_params(*W, "gated", True, 1.7, 1.0)
     st = _lib.stream_ptr()
     res = []
-    for path in (0, 1):
+    for path in (0, 1, 2):
         _lib.check(_lib.lib.sphnca_set_sweep_path(path))
         Y = torch.zeros(N, 32, device=DEV); fl = torch.zeros(N, dtype=torch.uint8, device=DEV); dA = torch.zeros(N, 16, device=DEV)
         _lib.check(_lib.lib.sphnca_step_perceive(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), st))
@@ -412,6 +412,9 @@ def test_tile_sweeps_equal_gather_sweeps(kind):
     assert_close(res[1][0], res[0][0], rtol=2e-5 if kind != "one_cell_dense" else 2e-4, what="perception")
     assert int((res[1][1] != res[0][1]).sum()) <= max(1, N // 5000), "previous life mask"
     assert_close(res[1][2], res[0][2], rtol=2e-5 if kind != "one_cell_dense" else 2e-4, what="adjoint")
+    # TMA-staged tiles (path 2): same visiting order and arithmetic as the gathers -> bit-identical, including the
+    # tiles that fall back to global loads (more rows or candidates than the staging buffer holds)
+    assert torch.equal(res[2][0], res[0][0]) and torch.equal(res[2][1], res[0][1]) and torch.equal(res[2][2], res[0][2])
 
 
 def test_rollout_is_bit_reproducible_at_config_size():
@@ -547,3 +550,46 @@ def test_rollout_node_inference_keeps_only_what_is_asked():
     assert len(random.choices(full, k=4)) == 4
     with pytest.raises(IndexError):
         full[K + 1]
+
+
+def test_static_life_mask_equals_sweep_when_no_alpha():
+    """use_alpha=False: the elementwise sphnca_step_mask_static gives bit-identical flags / state to the neighbour-sweep
+    sphnca_step_mask fed with the all-ones activity, including particles whose life mask is 0 (sparse outliers)."""
+    import ctypes as C
+    import sphops
+    from sphops import _lib, fused
+    gen = torch.Generator().manual_seed(11)
+    x = torch.nn.functional.pad(jittered_lattice(90, 2, gen), (0, 1))
+    # a few isolated far-away particles in otherwise empty cells next to a dense blob: life mask may drop to 0 there
+    blob = torch.rand(4000, 3, generator=gen) * torch.tensor([0.05, 0.05, 0.0]) + torch.tensor([0.5, 0.5, 0.0])
+    x = torch.cat([x, blob])
+    N = x.shape[0]
+    h = 3.2 * 2 / 90
+    xd = x.to(DEV)
+    grid = sphops.initialize_hashgrid(xd, (N,), h, math.ceil(2 / h))
+    v = sphops.volume(xd, h, grid)
+    xv4 = grid.sorted_xv(xd, v)
+    A_s = grid.pack_rows(torch.rand(N, 16, generator=gen).to(DEV), 16)
+    w = load_golden("weights_zebra")
+    W = [torch.from_numpy(w[k]).to(DEV) for k in ("W1", "b1", "W2", "b2")]
+    p = fused._step_params(*W, "gated", False, 1.0 / h, 1.0)
+    st = _lib.stream_ptr()
+    fire_s = (torch.rand(N, generator=gen) <= 0.5).to(torch.uint8).to(DEV)
+    res = []
+    for static in (False, True):
+        An = torch.empty(N, 16, device=DEV); Y = torch.empty(N, 32, device=DEV); O = torch.empty(N, 36, device=DEV)
+        fl = torch.empty(N, dtype=torch.uint8, device=DEV); al = torch.empty(N, dtype=torch.uint8, device=DEV)
+        rl = torch.empty(N, 8, dtype=torch.int32, device=DEV)
+        _lib.check(_lib.lib.sphnca_step_perceive(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), st))
+        _lib.check(_lib.lib.sphnca_step_mlp(N, _lib.ptr(A_s), _lib.ptr(Y), _lib.ptr(fire_s), C.byref(p), _lib.ptr(An), _lib.ptr(al),
+                                            _lib.ptr(O), _lib.ptr(fl), _lib.ptr(rl), st))
+        if static:
+            _lib.check(_lib.lib.sphnca_step_mask_static(N, _lib.ptr(An), _lib.ptr(fl), st))
+        else:
+            assert bool((al == 1).all())
+            _lib.check(_lib.lib.sphnca_step_mask(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(al), _lib.ptr(An), _lib.ptr(fl), st))
+        torch.cuda.synchronize()
+        res.append((An, fl))
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][0], res[1][0])
+    dead = int(((res[0][1] & 1) == 0).sum())
+    print("particles with life mask 0:", dead)

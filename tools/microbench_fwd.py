@@ -33,3 +33,16 @@ for path, name in ((0, "simt fused"), (2, "tcgen05 fused"), (1, "tcgen05 split (
     ms = a.elapsed_time(b) / 10
     print(f"step_fwd [{name}]: {ms:.4f} ms  ({N/ms/1e6:.2f} G particles/s, {ms*1e-3*1.965e9*148/N:.0f} clk*SM/particle)")
 _lib.check(_lib.lib.sphnca_set_mlp_path(1))
+# perception sweep alone, per sweep path (0 gathers, 1 smem tile engine, 2 TMA-staged tiles)
+for sp in (0, 1, 2):
+    _lib.check(_lib.lib.sphnca_set_sweep_path(sp))
+    def perc():
+        _lib.check(_lib.lib.sphnca_step_perceive(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), _lib.stream_ptr()))
+    for _ in range(3): perc()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10): perc()
+    b.record(); torch.cuda.synchronize()
+    print(f"step_perceive [sweep path {sp}]: {a.elapsed_time(b) / 10:.4f} ms")
+_lib.check(_lib.lib.sphnca_set_sweep_path(0))
