@@ -141,8 +141,17 @@ int32_t sphnca_step_mlp(int64_t N, const float* A_s, const float* Y_s, const uin
 int32_t sphnca_set_mlp_path(int32_t path);
 /* Implementation switch of the two hot sweeps (sphnca_step_perceive, sphnca_step_adjoint): 0 (default) =
  * one-thread-per-particle gathers out of L1/L2 with packed-pair FMAs, 1 = shared-memory tile engine with
- * in-radius compaction (csrc/sweep_tile.cuh; measured slower on B200, kept for A/B). */
+ * in-radius compaction (csrc/sweep_tile.cuh; measured slower on B200, kept for A/B), 2 = sphnca_step_perceive
+ * runs the TMA-staged kernel below. */
 int32_t sphnca_set_sweep_path(int32_t path);
+/* sphnca_step_perceive with the candidates of every 128-particle tile staged in shared memory by TMA bulk copies
+ * (csrc/sweep_stage.cuh).  Same arguments, bit-identical results.  Faster when (nearly) all tiles fit the 44 KB staging
+ * buffer -- planar / padded-2-D clouds, ~0.27 vs 0.30 ms on BASELINE configs[1] -- and slower when they do not (3-D
+ * clouds: every tile plans, gives up and gathers at a lower occupancy).  sphnca_stage_fit counts both:
+ * counts[0] = tiles, counts[1] = tiles that do not fit (device int32[2], asynchronous on `stream`). */
+int32_t sphnca_step_perceive_staged(const sphnca_grid* g, const float* xv4, const float* A_s, const sphnca_step_params* p,
+                                    float* Y_s, uint8_t* flags_s, void* stream);
+int32_t sphnca_stage_fit(const sphnca_grid* g, int32_t* counts, void* stream);
 /* sphnca_step_mask: new life mask = blur(alive_s) > 0.1 (nca.py:112); A_new_s *= prev & new in
  * place; flags_s bit1 = new_mask. */
 int32_t sphnca_step_mask(const sphnca_grid* g, const float* xv4, const uint8_t* alive_s,

@@ -588,6 +588,20 @@ step_perceive_staged_kernel(GridView g, const float4* __restrict__ xv4, const fl
     for (int q = 0; q < 4; ++q) y4[4 + q] = make_float4(gy[2*q].x * c.kg, gy[2*q].y * c.kg, gy[2*q+1].x * c.kg, gy[2*q+1].y * c.kg);
     flags_s[p] = blur * c.cw > 0.1f ? 1 : 0;
 }
+
+// counts[0] += 1 per tile, counts[1] += 1 per tile that does not fit the staging buffer of step_perceive_staged_kernel
+template <int D>
+__global__ void __launch_bounds__(PERC_T) stage_fit_kernel(GridView g, int32_t* __restrict__ counts) {
+    extern __shared__ __align__(128) unsigned char stage_raw[];
+    using S = StageSmem<D, PERC_T, NF, PERC_CAP, PERC_SLOTS>;
+    S& sm = *reinterpret_cast<S*>(stage_raw);
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < g.n;
+    const int my_cell = valid ? g.sorted_cell[p] : 0;
+    int k = 0, nseg = 0;
+    const bool fits = plan_tile<D, PERC_T, NF, PERC_CAP, PERC_SLOTS, 4>(g, nullptr, nullptr, sm, p, valid, my_cell, k, nseg);
+    if (threadIdx.x == 0) { atomicAdd(&counts[0], 1); if (!fits) atomicAdd(&counts[1], 1); }
+}
 }  // namespace sphnca
 
 extern "C" {
@@ -596,6 +610,51 @@ using namespace sphnca;
 int32_t sphnca_set_sweep_path(int32_t path) {
     if (path < 0 || path > 2) { set_error("sweep path must be 0 (per-thread gathers), 1 (shared-memory tile engine) or 2 (TMA-staged tiles)"); return SPHNCA_ERR_INVALID; }
     g_sweep_path = path;
+    return SPHNCA_OK;
+}
+
+static int launch_perceive_staged(const GridView& gv, const StepConsts& c, const float* xv4, const float* A_s, float* Y_s,
+                                  uint8_t* flags_s, cudaStream_t stream) {
+    const int sblocks = (int)((gv.n + PERC_T - 1) / PERC_T);
+    if (gv.dim == 3) {
+        const size_t smem = sizeof(StageSmem<3, PERC_T, NF, PERC_CAP, PERC_SLOTS>);
+        SPHNCA_CUDA(cudaFuncSetAttribute(step_perceive_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SPHNCA_LAUNCH(step_perceive_staged_kernel<3>, sblocks, PERC_T, smem, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+    } else {
+        const size_t smem = sizeof(StageSmem<2, PERC_T, NF, PERC_CAP, PERC_SLOTS>);
+        SPHNCA_CUDA(cudaFuncSetAttribute(step_perceive_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SPHNCA_LAUNCH(step_perceive_staged_kernel<2>, sblocks, PERC_T, smem, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+    }
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_step_perceive_staged(const sphnca_grid* g, const float* xv4, const float* A_s, const sphnca_step_params* p,
+                                    float* Y_s, uint8_t* flags_s, void* stream_) {
+    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
+    if (gv.n == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(xv4 && A_s && Y_s && flags_s, "NULL argument");
+    return launch_perceive_staged(gv, c, xv4, A_s, Y_s, flags_s, as_stream(stream_));
+}
+
+int32_t sphnca_stage_fit(const sphnca_grid* g, int32_t* counts, void* stream_) {
+    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    SPHNCA_CHECK_ARG(counts, "NULL argument");
+    cudaStream_t stream = as_stream(stream_);
+    SPHNCA_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), stream));
+    if (gv.n == 0) return SPHNCA_OK;
+    const int sblocks = (int)((gv.n + PERC_T - 1) / PERC_T);
+    if (gv.dim == 3) {
+        const size_t smem = sizeof(StageSmem<3, PERC_T, NF, PERC_CAP, PERC_SLOTS>);
+        SPHNCA_CUDA(cudaFuncSetAttribute(stage_fit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SPHNCA_LAUNCH(stage_fit_kernel<3>, sblocks, PERC_T, smem, stream, gv, counts);
+    } else {
+        const size_t smem = sizeof(StageSmem<2, PERC_T, NF, PERC_CAP, PERC_SLOTS>);
+        SPHNCA_CUDA(cudaFuncSetAttribute(stage_fit_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SPHNCA_LAUNCH(stage_fit_kernel<2>, sblocks, PERC_T, smem, stream, gv, counts);
+    }
+    SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }
 
@@ -608,12 +667,7 @@ int32_t sphnca_step_perceive(const sphnca_grid* g, const float* xv4, const float
     SPHNCA_CHECK_ARG(xv4 && A_s && Y_s && flags_s, "NULL argument");
     const int pblocks = (int)((gv.n + 127) / 128);
     if (g_sweep_path == 2) {
-        const size_t smem3 = sizeof(StageSmem<3, PERC_T, NF, PERC_CAP, PERC_SLOTS>), smem2 = sizeof(StageSmem<2, PERC_T, NF, PERC_CAP, PERC_SLOTS>);
-        const int sblocks = (int)((gv.n + PERC_T - 1) / PERC_T);
-        if (gv.dim == 3) SPHNCA_CUDA(cudaFuncSetAttribute(step_perceive_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        else SPHNCA_CUDA(cudaFuncSetAttribute(step_perceive_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        if (gv.dim == 3) SPHNCA_LAUNCH(step_perceive_staged_kernel<3>, sblocks, PERC_T, smem3, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
-        else SPHNCA_LAUNCH(step_perceive_staged_kernel<2>, sblocks, PERC_T, smem2, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
+        return launch_perceive_staged(gv, c, xv4, A_s, Y_s, flags_s, stream);
     } else if (g_sweep_path == 1) {
         if (gv.dim == 3) SPHNCA_LAUNCH(step_perceive_tile_kernel<3>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);
         else SPHNCA_LAUNCH(step_perceive_tile_kernel<2>, pblocks, 128, 0, stream, gv, (const float4*)xv4, A_s, c, Y_s, flags_s);

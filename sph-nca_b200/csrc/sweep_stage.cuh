@@ -41,11 +41,12 @@ struct StageSmem {                                        // SLOTS == 0: no hit 
     uint64_t bar;                                         // completion of the bulk copies (single-pass variant)
 };
 
-// Returns true when the tile is staged (uniform over the CTA); k = index of this thread's block row.
-// Must be called by all T threads of the CTA; `valid` threads own the particle at sorted position p in cell `my_cell`.
+// Plan the tile: rows, segments, shared-memory offsets.  Returns true when it fits (uniform over the CTA); k = index of
+// this thread's block row, nseg = number of plan entries.  Must be called by all T threads of the CTA; `valid` threads
+// own the particle at sorted position p in cell `my_cell`.
 template <int D, int T, int ROWF, int CAP, int SLOTS, int MAXROWS>
-__device__ __forceinline__ bool stage_tile(const GridView& g, const float4* __restrict__ xv4, const float* __restrict__ payload,
-                                           StageSmem<D, T, ROWF, CAP, SLOTS, MAXROWS>& sm, int64_t p, bool valid, int my_cell, int& k) {
+__device__ __forceinline__ bool plan_tile(const GridView& g, const float4* __restrict__ xv4, const float* __restrict__ payload,
+                                          StageSmem<D, T, ROWF, CAP, SLOTS, MAXROWS>& sm, int64_t p, bool valid, int my_cell, int& k, int& nseg) {
     using S = StageSmem<D, T, ROWF, CAP, SLOTS, MAXROWS>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int dx = g.dims[0], dy = g.dims[1], dz = D == 3 ? g.dims[2] : 1;
@@ -69,7 +70,7 @@ __device__ __forceinline__ bool stage_tile(const GridView& g, const float4* __re
     __syncthreads();
     // plan: one thread per (block row, neighbouring row)
     constexpr int NB = S::NB;
-    const int nseg = nrows * NB;
+    nseg = nrows * NB;
     if (tid < nseg) {
         typename S::Seg sg{};
         const int kr = tid / NB, o = tid - kr * NB;
@@ -93,7 +94,17 @@ __device__ __forceinline__ bool stage_tile(const GridView& g, const float4* __re
         sm.seg[tid] = sg;
     }
     __syncthreads();
-    if (sm.total > CAP) return false;
+    return sm.total <= CAP;
+}
+
+// Plan and fetch.  Returns true when the tile is staged (uniform over the CTA).
+template <int D, int T, int ROWF, int CAP, int SLOTS, int MAXROWS>
+__device__ __forceinline__ bool stage_tile(const GridView& g, const float4* __restrict__ xv4, const float* __restrict__ payload,
+                                           StageSmem<D, T, ROWF, CAP, SLOTS, MAXROWS>& sm, int64_t p, bool valid, int my_cell, int& k) {
+    using S = StageSmem<D, T, ROWF, CAP, SLOTS, MAXROWS>;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int nseg = 0;
+    if (!plan_tile(g, xv4, payload, sm, p, valid, my_cell, k, nseg)) return false;
     if (SLOTS == 0) {
         // single-pass variant (unpadded rows): every segment is two TMA bulk copies (positions, payload rows) that
         // complete on one mbarrier -- no copy instructions in the threads at all (measured: 0.266 ms vs 0.293 ms with

@@ -214,13 +214,14 @@ class SlabShardedNCA:
         prm = fused._step_params(lin1.weight.detach(), lin1.bias.detach(), lin2.weight.detach(), lin2.bias.detach(),
                                  m.update_rule, m.use_alpha, m.perception_scale(self.h), m.fire_rate / fr)
         g, st = self.grid.c_grid(), _lib.stream_ptr()
+        perceive = fused._perceive_entry(self.grid)      # staged sweep when the slab's tiles fit its buffer
         nbytes = 0
         for k in range(steps):
             nbytes += self._exchange_sorted(A_s)
             fire = torch.zeros((N,), dtype=torch.uint8, device=dev)
             fire[:p.n_own] = (fire_masks[k] if fire_masks is not None else (torch.rand(p.n_own, device=dev) <= fr)).to(torch.uint8)
             fire_s = self.grid.pack_bytes(fire)
-            check(lib.sphnca_step_perceive(g, ptr(self.xv4), ptr(A_s), C.byref(prm), ptr(Y_s), ptr(flags_s), st))
+            check(perceive(g, ptr(self.xv4), ptr(A_s), C.byref(prm), ptr(Y_s), ptr(flags_s), st))
             check(lib.sphnca_step_mlp(N, ptr(A_s), ptr(Y_s), ptr(fire_s), C.byref(prm), ptr(An_s), ptr(alive_s), ptr(O_s),
                                       ptr(flags_s), ptr(relu_s), st))
             if m.use_alpha:

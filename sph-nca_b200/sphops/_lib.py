@@ -63,6 +63,8 @@ def _load():
         "sphnca_divergence_fwd": ([G, P, P, I32, P, P], I32),
         "sphnca_divergence_bwd": ([G, P, P, I32, P, P], I32),
         "sphnca_step_fwd": ([G, P, P, P, SP, P, P, P, P, P, P, P], I32),
+        "sphnca_step_perceive_staged": ([G, P, P, SP, P, P, P], I32),
+        "sphnca_stage_fit": ([G, P, P], I32),
         "sphnca_step_mask": ([G, P, P, P, P, P], I32),
         "sphnca_step_mask_static": ([I64, P, P, P], I32),
         "sphnca_step_perceive": ([G, P, P, SP, P, P, P], I32),
@@ -90,6 +92,8 @@ def _load():
 lib, DECLARED_SYMBOLS, MISSING_SYMBOLS = _load()
 
 # optional implementation switches for A/B runs (see include/sphnca.h)
+# SPHNCA_SWEEP_PATH set: the fused step always calls sphnca_step_perceive (no per-grid choice of the staged kernel)
+FORCE_SWEEP_PATH = os.environ.get("SPHNCA_SWEEP_PATH")
 for _env, _fn in (("SPHNCA_MLP_PATH", "sphnca_set_mlp_path"), ("SPHNCA_SWEEP_PATH", "sphnca_set_sweep_path")):
     if os.environ.get(_env) is not None and _fn not in MISSING_SYMBOLS:
         getattr(lib, _fn)(int(os.environ[_env]))

@@ -43,6 +43,11 @@ def _timed(name, fn, *args):
     PROFILE.setdefault(name, []).append((a, b))
 
 
+def _perceive_entry(grid):
+    """The TMA-staged perception sweep when the grid's tiles fit its staging buffer, else the gather sweep."""
+    return lib.sphnca_step_perceive_staged if grid.staged_sweep_ok() else lib.sphnca_step_perceive
+
+
 def _mask(use_alpha, g, N, xv4, alive_s, An_s, flags_s, st):
     """Life-mask update of a step.  Without an alpha channel the new mask equals the previous one (both are the blur
     of an all-ones field, reference nca.py:17-21,94-98), so no second neighbour sweep is needed."""
@@ -76,7 +81,7 @@ class _NCAStep(torch.autograd.Function):
         if N:
             g, st = grid.c_grid(), stream_ptr()
             if SPLIT_FORWARD:
-                _timed("step_perceive", lib.sphnca_step_perceive, g, ptr(xv4), ptr(A_s), C.byref(p), ptr(Y_s), ptr(flags_s), st)
+                _timed("step_perceive", _perceive_entry(grid), g, ptr(xv4), ptr(A_s), C.byref(p), ptr(Y_s), ptr(flags_s), st)
                 _timed("step_mlp", lib.sphnca_step_mlp, N, ptr(A_s), ptr(Y_s), ptr(fire_s), C.byref(p), ptr(An_s),
                        ptr(alive_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
             else:
@@ -193,7 +198,7 @@ class _NCARollout(torch.autograd.Function):
             Sn = torch.empty((N, 16), **f32)
             if N:
                 if SPLIT_FORWARD:
-                    _timed("step_perceive", lib.sphnca_step_perceive, g, ptr(xv4), ptr(S), C.byref(p), ptr(Y_s), ptr(flags_s), st)
+                    _timed("step_perceive", _perceive_entry(grid), g, ptr(xv4), ptr(S), C.byref(p), ptr(Y_s), ptr(flags_s), st)
                     _timed("step_mlp", lib.sphnca_step_mlp, N, ptr(S), ptr(Y_s), ptr(fire_s), C.byref(p), ptr(Sn),
                            ptr(alive_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
                 else:

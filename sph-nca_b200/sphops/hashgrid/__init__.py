@@ -34,6 +34,7 @@ class Hashgrid:
         self._xv4 = None
         self._xyz_key = None
         self._xyz4 = None
+        self._staged_ok = None
 
     # -- reference API -------------------------------------------------------------------
     def get_num_blocks(self, block_size):
@@ -106,6 +107,20 @@ class Hashgrid:
 
     def remember_xv(self, x, v, xv4):
         self._xv_key, self._xv4, self._xv_ref = (self._key(x), self._key(v)), xv4, (x, v)
+
+    def staged_sweep_ok(self):
+        """True when (nearly) every 128-particle tile of this grid fits the shared-memory staging buffer of
+        sphnca_step_perceive_staged (planar / padded-2-D clouds).  Evaluated once per grid: one small kernel and
+        ONE device->host read of two integers (the only synchronisation the fused step ever does)."""
+        if self._staged_ok is None:
+            if self.num_particles == 0 or "sphnca_stage_fit" in _lib.MISSING_SYMBOLS or _lib.FORCE_SWEEP_PATH is not None:
+                self._staged_ok = False
+            else:
+                counts = torch.empty((2,), dtype=torch.int32, device=self.cell_off.device)
+                _lib.check(_lib.lib.sphnca_stage_fit(self.c_grid(), _lib.ptr(counts), _lib.stream_ptr()))
+                tiles, unfit = counts.tolist()
+                self._staged_ok = unfit * 10 <= tiles
+        return self._staged_ok
 
     def pack_rows(self, t, row):
         out = torch.empty((self.num_particles, row), dtype=torch.float32, device=t.device)

@@ -593,3 +593,19 @@ def test_static_life_mask_equals_sweep_when_no_alpha():
     assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][0], res[1][0])
     dead = int(((res[0][1] & 1) == 0).sum())
     print("particles with life mask 0:", dead)
+
+
+def test_staged_sweep_is_chosen_per_grid():
+    """sphnca_stage_fit: planar clouds fit the staging buffer of the TMA-staged perception sweep, 3-D clouds do not;
+    the fused step picks its kernel from that (results are bit-identical either way, see the sweep test above)."""
+    import sphops
+    gen = torch.Generator().manual_seed(2)
+    x2 = torch.nn.functional.pad(jittered_lattice(160, 2, gen), (0, 1)).to(DEV)
+    g2 = sphops.initialize_hashgrid(x2, (160 * 160,), 3.2 * 2 / 160, 50)
+    x3 = jittered_lattice(30, 3, gen).to(DEV)
+    g3 = sphops.initialize_hashgrid(x3, (27000,), 1.97 * 2 / 30, 31)
+    from sphops import _lib
+    if _lib.FORCE_SWEEP_PATH is None:
+        assert g2.staged_sweep_ok() is True and g3.staged_sweep_ok() is False
+    else:
+        assert g2.staged_sweep_ok() is False
