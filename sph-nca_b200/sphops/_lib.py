@@ -65,6 +65,10 @@ def _load():
         "sphnca_step_fwd": ([G, P, P, P, SP, P, P, P, P, P, P, P], I32),
         "sphnca_step_perceive_staged": ([G, P, P, SP, P, P, P], I32),
         "sphnca_stage_fit": ([G, P, P], I32),
+        "sphnca_pairs_count": ([G, P, P, P], I32),
+        "sphnca_pairs_fill": ([G, P, P, P, P, P, P, P, P, P], I32),
+        "sphnca_step_perceive_pairs": ([G, P, P, P, P, P, P, SP, P, P, P], I32),
+        "sphnca_step_adjoint_pairs": ([G, P, P, P, P, P, P, P, P, SP, P, P], I32),
         "sphnca_step_mask": ([G, P, P, P, P, P], I32),
         "sphnca_step_mask_static": ([I64, P, P, P], I32),
         "sphnca_step_perceive": ([G, P, P, SP, P, P, P], I32),
@@ -94,6 +98,8 @@ lib, DECLARED_SYMBOLS, MISSING_SYMBOLS = _load()
 # optional implementation switches for A/B runs (see include/sphnca.h)
 # SPHNCA_SWEEP_PATH set: the fused step always calls sphnca_step_perceive (no per-grid choice of the staged kernel)
 FORCE_SWEEP_PATH = os.environ.get("SPHNCA_SWEEP_PATH")
+# SPHNCA_PAIRS=0: never build pair lists (the fused step then sweeps the cells every step)
+USE_PAIR_LISTS = os.environ.get("SPHNCA_PAIRS", "1") != "0"
 for _env, _fn in (("SPHNCA_MLP_PATH", "sphnca_set_mlp_path"), ("SPHNCA_SWEEP_PATH", "sphnca_set_sweep_path")):
     if os.environ.get(_env) is not None and _fn not in MISSING_SYMBOLS:
         getattr(lib, _fn)(int(os.environ[_env]))

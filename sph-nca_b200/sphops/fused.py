@@ -48,6 +48,25 @@ def _perceive_entry(grid):
     return lib.sphnca_step_perceive_staged if grid.staged_sweep_ok() else lib.sphnca_step_perceive
 
 
+def _perceive(grid, x, v, g, xv4, A_s, p, Y_s, flags_s, st):
+    """Perception sweep: from the grid's pair lists when they exist, else by sweeping the cells."""
+    pl = grid.pair_lists(x, v)
+    if pl is not None:
+        _timed("step_perceive", lib.sphnca_step_perceive_pairs, g, ptr(pl["slots"]), ptr(pl["base"]), ptr(pl["J"]), ptr(pl["WP"]),
+               ptr(pl["WB"]), ptr(A_s), C.byref(p), ptr(Y_s), ptr(flags_s), st)
+    else:
+        _timed("step_perceive", _perceive_entry(grid), g, ptr(xv4), ptr(A_s), C.byref(p), ptr(Y_s), ptr(flags_s), st)
+    return pl
+
+
+def _adjoint(grid, pl, xv4, dY_s, dAdir_s, p, dA_s, st):
+    if pl is not None:
+        _timed("step_adjoint", lib.sphnca_step_adjoint_pairs, grid.c_grid(), ptr(pl["slots"]), ptr(pl["base"]), ptr(pl["J"]),
+               ptr(pl["WA"]), ptr(pl["SXY"]), ptr(xv4), ptr(dY_s), ptr(dAdir_s), C.byref(p), ptr(dA_s), st)
+    else:
+        _timed("step_adjoint", lib.sphnca_step_adjoint, grid.c_grid(), ptr(xv4), ptr(dY_s), ptr(dAdir_s), C.byref(p), ptr(dA_s), st)
+
+
 def _mask(use_alpha, g, N, xv4, alive_s, An_s, flags_s, st):
     """Life-mask update of a step.  Without an alpha channel the new mask equals the previous one (both are the blur
     of an all-ones field, reference nca.py:17-21,94-98), so no second neighbour sweep is needed."""
@@ -81,7 +100,7 @@ class _NCAStep(torch.autograd.Function):
         if N:
             g, st = grid.c_grid(), stream_ptr()
             if SPLIT_FORWARD:
-                _timed("step_perceive", _perceive_entry(grid), g, ptr(xv4), ptr(A_s), C.byref(p), ptr(Y_s), ptr(flags_s), st)
+                _perceive(grid, x, v, g, xv4, A_s, p, Y_s, flags_s, st)
                 _timed("step_mlp", lib.sphnca_step_mlp, N, ptr(A_s), ptr(Y_s), ptr(fire_s), C.byref(p), ptr(An_s),
                        ptr(alive_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
             else:
@@ -90,6 +109,7 @@ class _NCAStep(torch.autograd.Function):
             _mask(use_alpha, g, N, xv4, alive_s, An_s, flags_s, st)
         out = grid.unpack_rows(An_s, 16)
         ctx.grid = grid
+        ctx.pairs = grid.pair_lists(x, v) if N else None          # cached by the grid; the adjoint sweep reads the same lists
         ctx.cfg = (update_rule, use_alpha, perception_scale, orig_rate)
         ctx.save_for_backward(xv4, A_s, Y_s, O_s, flags_s, relu_s, W1c, b1c, W2c, b2c)
         return out
@@ -138,8 +158,7 @@ class _NCAStep(torch.autograd.Function):
                 if want_w:
                     _timed("mlp_wgrad", lib.sphnca_mlp_wgrad, n, ptr(A_s[lo:]), ptr(Y_s[lo:]), ptr(dO_s[lo:]), ptr(Hc), ptr(dHc),
                            C.byref(p), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value, st)
-            _timed("step_adjoint", lib.sphnca_step_adjoint, grid.c_grid(), ptr(xv4), ptr(dY_s), ptr(dAdir_s),
-                   C.byref(p), ptr(dA_s), st)
+            _adjoint(grid, ctx.pairs, xv4, dY_s, dAdir_s, p, dA_s, st)
         dA = grid.unpack_rows(dA_s, 16) if g[2] else None
         return (None, None, dA, None, dW1 if g[4] else None, db1 if g[5] else None,
                 dW2 if g[6] else None, db2 if g[7] else None, None, None, None, None, None, None)
@@ -198,7 +217,7 @@ class _NCARollout(torch.autograd.Function):
             Sn = torch.empty((N, 16), **f32)
             if N:
                 if SPLIT_FORWARD:
-                    _timed("step_perceive", _perceive_entry(grid), g, ptr(xv4), ptr(S), C.byref(p), ptr(Y_s), ptr(flags_s), st)
+                    _perceive(grid, x, v, g, xv4, S, p, Y_s, flags_s, st)
                     _timed("step_mlp", lib.sphnca_step_mlp, N, ptr(S), ptr(Y_s), ptr(fire_s), C.byref(p), ptr(Sn),
                            ptr(alive_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
                 else:
@@ -213,6 +232,7 @@ class _NCARollout(torch.autograd.Function):
                 states = [states[0], Sn] if len(states) else [Sn]
             S = Sn
         ctx.grid, ctx.cfg, ctx.steps = grid, cfg, steps
+        ctx.pairs = grid.pair_lists(x, v) if (N and taped) else None
         if taped:
             ctx.save_for_backward(xv4, W1c, b1c, W2c, b2c, *states, *saved)
         return tuple(states)
@@ -254,8 +274,7 @@ class _NCARollout(torch.autograd.Function):
                     _timed("mlp_wgrad", lib.sphnca_mlp_wgrad, N, ptr(states[k]), ptr(Y_s), ptr(dO_s), None, None,
                            C.byref(p), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value, st)
                 out = own[k & 1]
-                _timed("step_adjoint", lib.sphnca_step_adjoint, grid.c_grid(), ptr(xv4), ptr(dY_s), ptr(dAdir_s),
-                       C.byref(p), ptr(out), st)
+                _adjoint(grid, ctx.pairs, xv4, dY_s, dAdir_s, p, out, st)
                 gcur = out
             if dstates[k] is not None:
                 dk = require_cuda_f32(dstates[k], "dS")

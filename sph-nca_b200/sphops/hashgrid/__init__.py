@@ -35,6 +35,8 @@ class Hashgrid:
         self._xyz_key = None
         self._xyz4 = None
         self._staged_ok = None
+        self._pairs_key = None
+        self._pairs = None
 
     # -- reference API -------------------------------------------------------------------
     def get_num_blocks(self, block_size):
@@ -107,6 +109,40 @@ class Hashgrid:
 
     def remember_xv(self, x, v, xv4):
         self._xv_key, self._xv4, self._xv_ref = (self._key(x), self._key(v)), xv4, (x, v)
+
+    # fraction of the free device memory the pair lists of one grid may take (about 1.3 KB per particle)
+    PAIR_LIST_MEMORY_FRACTION = 0.4
+
+    def pair_lists(self, x, v):
+        """Per-pair neighbour lists and kernel weights of this grid (csrc/pairs.cu), cached per (x, v) pair; None when
+        disabled or when they would not fit the memory budget.  Building them reads back ONE integer (the total number
+        of list entries) -- the only host synchronisation besides `staged_sweep_ok`."""
+        if not _lib.USE_PAIR_LISTS or _lib.FORCE_SWEEP_PATH is not None or "sphnca_pairs_fill" in _lib.MISSING_SYMBOLS:
+            return None
+        key = (self._key(x), self._key(v))
+        if self._pairs_key != key:
+            self._pairs_key, self._pairs, self._pairs_ref = key, None, (x, v)
+            N = self.num_particles
+            if N:
+                dev = x.device
+                xv4 = self.sorted_xv(x, v)
+                nw = (N + 31) // 32
+                slots = torch.empty((nw,), dtype=torch.int32, device=dev)
+                st = _lib.stream_ptr()
+                _lib.check(_lib.lib.sphnca_pairs_count(self.c_grid(), _lib.ptr(xv4), _lib.ptr(slots), st))
+                cum = torch.cumsum(slots, 0, dtype=torch.int64)
+                base = ((cum - slots) * 32).contiguous()
+                total = int(cum[-1].item()) * 32
+                free, _ = torch.cuda.mem_get_info(dev)
+                if 0 < total and total * 28 <= self.PAIR_LIST_MEMORY_FRACTION * free:
+                    f32 = dict(dtype=torch.float32, device=dev)
+                    J = torch.empty((total,), dtype=torch.int32, device=dev)
+                    WP, WB, WA = (torch.empty((total, 2), **f32) for _ in range(3))
+                    SXY = torch.empty((N, 2), **f32)
+                    _lib.check(_lib.lib.sphnca_pairs_fill(self.c_grid(), _lib.ptr(xv4), _lib.ptr(slots), _lib.ptr(base), _lib.ptr(J),
+                                                          _lib.ptr(WP), _lib.ptr(WB), _lib.ptr(WA), _lib.ptr(SXY), st))
+                    self._pairs = dict(slots=slots, base=base, J=J, WP=WP, WB=WB, WA=WA, SXY=SXY, entries=total)
+        return self._pairs
 
     def staged_sweep_ok(self):
         """True when (nearly) every 128-particle tile of this grid fits the shared-memory staging buffer of

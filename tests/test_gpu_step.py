@@ -415,6 +415,21 @@ def test_tile_sweeps_equal_gather_sweeps(kind):
     # TMA-staged tiles (path 2): same visiting order and arithmetic as the gathers -> bit-identical, including the
     # tiles that fall back to global loads (more rows or candidates than the staging buffer holds)
     assert torch.equal(res[2][0], res[0][0]) and torch.equal(res[2][1], res[0][1]) and torch.equal(res[2][2], res[0][2])
+    # pair lists (csrc/pairs.cu): geometry, in-radius test and weights precomputed once per grid; same visiting order and
+    # the same floats -> bit-identical perception, life mask and adjoint
+    pl = grid.pair_lists(xd, v)
+    if _lib.USE_PAIR_LISTS and _lib.FORCE_SWEEP_PATH is None:
+        assert pl is not None and pl["entries"] % 32 == 0
+        Y = torch.zeros(N, 32, device=DEV); fl = torch.zeros(N, dtype=torch.uint8, device=DEV); dA = torch.zeros(N, 16, device=DEV)
+        _lib.check(_lib.lib.sphnca_step_perceive_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]),
+                                                       _lib.ptr(pl["WP"]), _lib.ptr(pl["WB"]), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), st))
+        _lib.check(_lib.lib.sphnca_step_adjoint_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]),
+                                                      _lib.ptr(pl["WA"]), _lib.ptr(pl["SXY"]), _lib.ptr(xv4), _lib.ptr(dY_s), _lib.ptr(dAd_s),
+                                                      C.byref(p), _lib.ptr(dA), st))
+        torch.cuda.synchronize()
+        assert torch.equal(Y, res[0][0]), "perception from pair lists"
+        assert torch.equal(fl, res[0][1]), "life mask from pair lists"
+        assert torch.equal(dA, res[0][2]), "adjoint from pair lists"
 
 
 def test_rollout_is_bit_reproducible_at_config_size():

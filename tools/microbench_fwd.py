@@ -46,3 +46,25 @@ for sp in (0, 1, 2):
     b.record(); torch.cuda.synchronize()
     print(f"step_perceive [sweep path {sp}]: {a.elapsed_time(b) / 10:.4f} ms")
 _lib.check(_lib.lib.sphnca_set_sweep_path(0))
+# pair-list sweeps
+import time
+torch.cuda.synchronize(); t0 = time.time()
+pl = grid.pair_lists(x, v)
+torch.cuda.synchronize(); print(f"pair lists: {pl['entries']} entries ({pl['entries'] * 28 / 1e6:.0f} MB, {pl['entries'] / N:.1f} slots/particle), built in {(time.time() - t0) * 1e3:.1f} ms")
+dY = torch.randn(N, 32, device=dev); dAd = torch.randn(N, 16, device=dev); dA = torch.zeros(N, 16, device=dev)
+def percp():
+    _lib.check(_lib.lib.sphnca_step_perceive_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]), _lib.ptr(pl["WP"]),
+               _lib.ptr(pl["WB"]), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), _lib.stream_ptr()))
+def adjp():
+    _lib.check(_lib.lib.sphnca_step_adjoint_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]), _lib.ptr(pl["WA"]),
+               _lib.ptr(pl["SXY"]), _lib.ptr(xv4), _lib.ptr(dY), _lib.ptr(dAd), C.byref(p), _lib.ptr(dA), _lib.stream_ptr()))
+def adjg():
+    _lib.check(_lib.lib.sphnca_step_adjoint(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(dY), _lib.ptr(dAd), C.byref(p), _lib.ptr(dA), _lib.stream_ptr()))
+for name, fn in (("perceive from pair lists", percp), ("adjoint from pair lists", adjp), ("adjoint gather", adjg)):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10): fn()
+    b.record(); torch.cuda.synchronize()
+    print(f"{name}: {a.elapsed_time(b) / 10:.4f} ms")
