@@ -39,7 +39,8 @@ template <int D>
 __global__ void __launch_bounds__(128)
 pairs_fill_kernel(GridView g, const float4* __restrict__ xv4, float h, float h2, const int32_t* __restrict__ warp_slots,
                   const int64_t* __restrict__ warp_base, int32_t* __restrict__ J, float2* __restrict__ WP,
-                  float2* __restrict__ WB, float2* __restrict__ WA, float2* __restrict__ SXY) {
+                  float2* __restrict__ WB, float2* __restrict__ WA, float2* __restrict__ SXY, float cw,
+                  uint8_t* __restrict__ FLG) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t w = p >> 5;
     if (w * 32 >= g.n) return;
@@ -50,13 +51,14 @@ pairs_fill_kernel(GridView g, const float4* __restrict__ xv4, float h, float h2,
     const int64_t self = p < g.n ? p : g.n - 1;
     if (p < g.n) {
         const float4 xi = xv4[p];
-        float sx = 0.f, sy = 0.f;
+        float sx = 0.f, sy = 0.f, blur1 = 0.f;
         for_each_candidate<D>(g, g.sorted_cell[p], [&](int q) {
             float rx, ry;
             const float4 xj = __ldg(&xv4[q]);
             const float d2 = pair_d2<D>(xi, xj, rx, ry);
             if (d2 < h2) {
                 const float t = h2 - d2;
+                blur1 = fmaf(1.f * xj.w, t * t * t, blur1);           // the life-mask blur of an all-alive field (no alpha channel)
                 float2 wp = make_float2(0.f, 0.f), wa = make_float2(0.f, 0.f);
                 if (d2 > 0.f) {
                     // the expressions of step_perceive_kernel / step_adjoint_kernel, operation for operation
@@ -73,6 +75,7 @@ pairs_fill_kernel(GridView g, const float4* __restrict__ xv4, float h, float h2,
             }
         });
         SXY[p] = make_float2(sx, sy);
+        FLG[p] = blur1 * cw > 0.1f ? 1 : 0;
     }
     for (; cnt < slots; ++cnt, e += 32) {                 // zero-weight self pairs up to the warp's slot count
         J[e] = (int32_t)self; WP[e] = make_float2(0.f, 0.f); WB[e] = make_float2(0.f, 0.f); WA[e] = make_float2(0.f, 0.f);
@@ -83,10 +86,14 @@ pairs_fill_kernel(GridView g, const float4* __restrict__ xv4, float h, float h2,
 // One lane per particle: the three list arrays are read fully coalesced (128/256 bytes per warp and slot); the 64-byte
 // neighbour row is gathered with four 16-byte loads per lane.  (Four lanes per particle, as in the adjoint below, and a
 // shuffle-distributed hybrid were measured at 0.24 / 0.23 ms against 0.21 ms for this form.)
+// ALPHA = false (no alpha channel): the life mask does not depend on the state; it was evaluated once by the fill kernel
+// (FLG) and the blur weights WB are not read at all.
+template <bool ALPHA>
 __global__ void __launch_bounds__(128)
 step_perceive_pairs_kernel(int64_t n, const int32_t* __restrict__ warp_slots, const int64_t* __restrict__ warp_base,
                            const int32_t* __restrict__ J, const float2* __restrict__ WP, const float2* __restrict__ WB,
-                           const float* __restrict__ A_s, StepConsts c, float* __restrict__ Y_s, uint8_t* __restrict__ flags_s) {
+                           const uint8_t* __restrict__ FLG, const float* __restrict__ A_s, StepConsts c,
+                           float* __restrict__ Y_s, uint8_t* __restrict__ flags_s) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t w = p >> 5;
     if (w * 32 >= n) return;
@@ -104,7 +111,7 @@ step_perceive_pairs_kernel(int64_t n, const int32_t* __restrict__ warp_slots, co
     float blur = 0.f;
     // list entries one slot ahead of the arithmetic (streaming loads: read once per sweep)
     int j = 0; float2 wp = make_float2(0.f, 0.f), wb = make_float2(0.f, 0.f);
-    if (slots > 0) { j = __ldcs(J + e0); wp = __ldcs(WP + e0); wb = __ldcs(WB + e0); }
+    if (slots > 0) { j = __ldcs(J + e0); wp = __ldcs(WP + e0); if (ALPHA) wb = __ldcs(WB + e0); }
 #pragma unroll 1
     for (int s = 0; s < slots; ++s) {
         const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)j * NF);
@@ -112,9 +119,11 @@ step_perceive_pairs_kernel(int64_t n, const int32_t* __restrict__ warp_slots, co
 #pragma unroll
         for (int k = 0; k < 4; ++k) { const float4 t = __ldg(a4 + k); Aj[2*k] = make_float2(t.x, t.y); Aj[2*k+1] = make_float2(t.z, t.w); }
         const float2 wpc = wp, wbc = wb;
-        if (s + 1 < slots) { const int64_t e = e0 + (int64_t)(s + 1) * 32; j = __ldcs(J + e); wp = __ldcs(WP + e); wb = __ldcs(WB + e); }
-        const float alive = c.use_alpha ? (Aj[1].y > 0.1f ? 1.f : 0.f) : 1.f;      // channel 3
-        blur = fmaf(alive * wbc.x, wbc.y, blur);
+        if (s + 1 < slots) { const int64_t e = e0 + (int64_t)(s + 1) * 32; j = __ldcs(J + e); wp = __ldcs(WP + e); if (ALPHA) wb = __ldcs(WB + e); }
+        if (ALPHA) {
+            const float alive = Aj[1].y > 0.1f ? 1.f : 0.f;                         // channel 3
+            blur = fmaf(alive * wbc.x, wbc.y, blur);
+        }
         const float2 wx = make_float2(wpc.x, wpc.x), wy = make_float2(wpc.y, wpc.y);
 #pragma unroll
         for (int f = 0; f < NF / 2; ++f) {
@@ -129,7 +138,7 @@ step_perceive_pairs_kernel(int64_t n, const int32_t* __restrict__ warp_slots, co
     for (int q = 0; q < 4; ++q) y4[q] = make_float4(gx[2*q].x * c.kg, gx[2*q].y * c.kg, gx[2*q+1].x * c.kg, gx[2*q+1].y * c.kg);
 #pragma unroll
     for (int q = 0; q < 4; ++q) y4[4 + q] = make_float4(gy[2*q].x * c.kg, gy[2*q].y * c.kg, gy[2*q+1].x * c.kg, gy[2*q+1].y * c.kg);
-    flags_s[p] = blur * c.cw > 0.1f ? 1 : 0;
+    flags_s[p] = ALPHA ? (blur * c.cw > 0.1f ? 1 : 0) : FLG[p];
 }
 
 // Gather adjoint of the perception sweep from the pair lists (same output as step_adjoint_kernel).
@@ -205,30 +214,33 @@ int32_t sphnca_pairs_count(const sphnca_grid* g, const float* xv4, int32_t* warp
 }
 
 int32_t sphnca_pairs_fill(const sphnca_grid* g, const float* xv4, const int32_t* warp_slots, const int64_t* warp_base,
-                          int32_t* J, float* WP, float* WB, float* WA, float* SXY, void* stream_) {
+                          int32_t* J, float* WP, float* WB, float* WA, float* SXY, uint8_t* FLG, void* stream_) {
     GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
     if (gv.n == 0) return SPHNCA_OK;
-    SPHNCA_CHECK_ARG(xv4 && warp_slots && warp_base && J && WP && WB && WA && SXY, "NULL argument");
+    SPHNCA_CHECK_ARG(xv4 && warp_slots && warp_base && J && WP && WB && WA && SXY && FLG, "NULL argument");
+    const float cw = (float)poly6_norm(g->dim, g->h);
     const int blocks = (int)((gv.n + 127) / 128);
     const float h = (float)g->h, h2 = (float)(g->h * g->h);
     if (gv.dim == 3) SPHNCA_LAUNCH(pairs_fill_kernel<3>, blocks, 128, 0, as_stream(stream_), gv, (const float4*)xv4, h, h2, warp_slots, warp_base,
-                                   J, (float2*)WP, (float2*)WB, (float2*)WA, (float2*)SXY);
+                                   J, (float2*)WP, (float2*)WB, (float2*)WA, (float2*)SXY, cw, FLG);
     else SPHNCA_LAUNCH(pairs_fill_kernel<2>, blocks, 128, 0, as_stream(stream_), gv, (const float4*)xv4, h, h2, warp_slots, warp_base,
-                       J, (float2*)WP, (float2*)WB, (float2*)WA, (float2*)SXY);
+                       J, (float2*)WP, (float2*)WB, (float2*)WA, (float2*)SXY, cw, FLG);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }
 
 int32_t sphnca_step_perceive_pairs(const sphnca_grid* g, const int32_t* warp_slots, const int64_t* warp_base, const int32_t* J,
-                                   const float* WP, const float* WB, const float* A_s, const sphnca_step_params* p,
-                                   float* Y_s, uint8_t* flags_s, void* stream_) {
+                                   const float* WP, const float* WB, const uint8_t* FLG, const float* A_s,
+                                   const sphnca_step_params* p, float* Y_s, uint8_t* flags_s, void* stream_) {
     GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
     StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
     if (gv.n == 0) return SPHNCA_OK;
-    SPHNCA_CHECK_ARG(warp_slots && warp_base && J && WP && WB && A_s && Y_s && flags_s, "NULL argument");
+    SPHNCA_CHECK_ARG(warp_slots && warp_base && J && WP && WB && FLG && A_s && Y_s && flags_s, "NULL argument");
     const int blocks = (int)((gv.n + 127) / 128);
-    SPHNCA_LAUNCH(step_perceive_pairs_kernel, blocks, 128, 0, as_stream(stream_), gv.n, warp_slots, warp_base, J, (const float2*)WP,
-                  (const float2*)WB, A_s, c, Y_s, flags_s);
+    if (c.use_alpha) SPHNCA_LAUNCH(step_perceive_pairs_kernel<true>, blocks, 128, 0, as_stream(stream_), gv.n, warp_slots, warp_base, J,
+                                   (const float2*)WP, (const float2*)WB, FLG, A_s, c, Y_s, flags_s);
+    else SPHNCA_LAUNCH(step_perceive_pairs_kernel<false>, blocks, 128, 0, as_stream(stream_), gv.n, warp_slots, warp_base, J,
+                       (const float2*)WP, (const float2*)WB, FLG, A_s, c, Y_s, flags_s);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

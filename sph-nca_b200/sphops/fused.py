@@ -53,7 +53,7 @@ def _perceive(grid, x, v, g, xv4, A_s, p, Y_s, flags_s, st):
     pl = grid.pair_lists(x, v)
     if pl is not None:
         _timed("step_perceive", lib.sphnca_step_perceive_pairs, g, ptr(pl["slots"]), ptr(pl["base"]), ptr(pl["J"]), ptr(pl["WP"]),
-               ptr(pl["WB"]), ptr(A_s), C.byref(p), ptr(Y_s), ptr(flags_s), st)
+               ptr(pl["WB"]), ptr(pl["FLG"]), ptr(A_s), C.byref(p), ptr(Y_s), ptr(flags_s), st)
     else:
         _timed("step_perceive", _perceive_entry(grid), g, ptr(xv4), ptr(A_s), C.byref(p), ptr(Y_s), ptr(flags_s), st)
     return pl

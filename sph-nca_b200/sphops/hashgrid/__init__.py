@@ -139,9 +139,10 @@ class Hashgrid:
                     J = torch.empty((total,), dtype=torch.int32, device=dev)
                     WP, WB, WA = (torch.empty((total, 2), **f32) for _ in range(3))
                     SXY = torch.empty((N, 2), **f32)
+                    FLG = torch.empty((N,), dtype=torch.uint8, device=dev)
                     _lib.check(_lib.lib.sphnca_pairs_fill(self.c_grid(), _lib.ptr(xv4), _lib.ptr(slots), _lib.ptr(base), _lib.ptr(J),
-                                                          _lib.ptr(WP), _lib.ptr(WB), _lib.ptr(WA), _lib.ptr(SXY), st))
-                    self._pairs = dict(slots=slots, base=base, J=J, WP=WP, WB=WB, WA=WA, SXY=SXY, entries=total)
+                                                          _lib.ptr(WP), _lib.ptr(WB), _lib.ptr(WA), _lib.ptr(SXY), _lib.ptr(FLG), st))
+                    self._pairs = dict(slots=slots, base=base, J=J, WP=WP, WB=WB, WA=WA, SXY=SXY, FLG=FLG, entries=total)
         return self._pairs
 
     def staged_sweep_ok(self):

@@ -422,7 +422,7 @@ def test_tile_sweeps_equal_gather_sweeps(kind):
         assert pl is not None and pl["entries"] % 32 == 0
         Y = torch.zeros(N, 32, device=DEV); fl = torch.zeros(N, dtype=torch.uint8, device=DEV); dA = torch.zeros(N, 16, device=DEV)
         _lib.check(_lib.lib.sphnca_step_perceive_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]),
-                                                       _lib.ptr(pl["WP"]), _lib.ptr(pl["WB"]), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), st))
+                                                       _lib.ptr(pl["WP"]), _lib.ptr(pl["WB"]), _lib.ptr(pl["FLG"]), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), st))
         _lib.check(_lib.lib.sphnca_step_adjoint_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]),
                                                       _lib.ptr(pl["WA"]), _lib.ptr(pl["SXY"]), _lib.ptr(xv4), _lib.ptr(dY_s), _lib.ptr(dAd_s),
                                                       C.byref(p), _lib.ptr(dA), st))
@@ -430,6 +430,20 @@ def test_tile_sweeps_equal_gather_sweeps(kind):
         assert torch.equal(Y, res[0][0]), "perception from pair lists"
         assert torch.equal(fl, res[0][1]), "life mask from pair lists"
         assert torch.equal(dA, res[0][2]), "adjoint from pair lists"
+        # no alpha channel: the life mask comes from the flag the fill kernel evaluated once (the blur weights are not read)
+        p0 = fused._step_params(*W, "gated", False, 1.7, 1.0)
+        outs = []
+        for use_lists in (False, True):
+            Y = torch.zeros(N, 32, device=DEV); fl = torch.zeros(N, dtype=torch.uint8, device=DEV)
+            if use_lists:
+                _lib.check(_lib.lib.sphnca_step_perceive_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]),
+                                                               _lib.ptr(pl["WP"]), _lib.ptr(pl["WB"]), _lib.ptr(pl["FLG"]), _lib.ptr(A_s), C.byref(p0),
+                                                               _lib.ptr(Y), _lib.ptr(fl), st))
+            else:
+                _lib.check(_lib.lib.sphnca_step_perceive(grid.c_grid(), _lib.ptr(xv4), _lib.ptr(A_s), C.byref(p0), _lib.ptr(Y), _lib.ptr(fl), st))
+            torch.cuda.synchronize()
+            outs.append((Y, fl))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), "no-alpha perception from pair lists"
 
 
 def test_rollout_is_bit_reproducible_at_config_size():

@@ -54,7 +54,7 @@ torch.cuda.synchronize(); print(f"pair lists: {pl['entries']} entries ({pl['entr
 dY = torch.randn(N, 32, device=dev); dAd = torch.randn(N, 16, device=dev); dA = torch.zeros(N, 16, device=dev)
 def percp():
     _lib.check(_lib.lib.sphnca_step_perceive_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]), _lib.ptr(pl["WP"]),
-               _lib.ptr(pl["WB"]), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), _lib.stream_ptr()))
+               _lib.ptr(pl["WB"]), _lib.ptr(pl["FLG"]), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), _lib.stream_ptr()))
 def adjp():
     _lib.check(_lib.lib.sphnca_step_adjoint_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]), _lib.ptr(pl["WA"]),
                _lib.ptr(pl["SXY"]), _lib.ptr(xv4), _lib.ptr(dY), _lib.ptr(dAd), C.byref(p), _lib.ptr(dA), _lib.stream_ptr()))

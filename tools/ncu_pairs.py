@@ -19,7 +19,7 @@ p = fused._step_params(*W, "gated", False, 1.0 / h, 1.0)
 pl = grid.pair_lists(x, v)
 for _ in range(3):
     _lib.check(_lib.lib.sphnca_step_perceive_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]), _lib.ptr(pl["WP"]),
-               _lib.ptr(pl["WB"]), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), _lib.stream_ptr()))
+               _lib.ptr(pl["WB"]), _lib.ptr(pl["FLG"]), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), _lib.stream_ptr()))
     _lib.check(_lib.lib.sphnca_step_adjoint_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]), _lib.ptr(pl["WA"]),
                _lib.ptr(pl["SXY"]), _lib.ptr(xv4), _lib.ptr(dY), _lib.ptr(dAd), C.byref(p), _lib.ptr(dA), _lib.stream_ptr()))
 torch.cuda.synchronize()
