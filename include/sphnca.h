@@ -155,21 +155,21 @@ int32_t sphnca_stage_fit(const sphnca_grid* g, int32_t* counts, void* stream);
 
 /* Pair lists (csrc/pairs.cu).  Positions and volumes are fixed over the K steps of a rollout (nca.py:141-145), so the
  * 3^D-cell walk, the in-radius test and the kernel weights of the two hot sweeps are computed once per grid and
- * stored per in-radius pair, [slot][lane] per warp of 32 consecutive sorted particles (a warp's slot count = the
- * largest neighbour count of its lanes; shorter lists are padded with zero-weight self pairs):
- *   sphnca_pairs_count   warp_slots int32 [ceil(N/32)]
- *   caller               warp_base int64 [ceil(N/32)] = 32 * exclusive prefix sum of warp_slots; E = 32 * sum
+ * stored per in-radius pair, [slot][8] per group of 8 consecutive sorted particles (a group's slot count = the largest
+ * neighbour count of its particles rounded up to a multiple of 4; shorter lists are padded with zero-weight self pairs):
+ *   sphnca_pairs_count   group_slots int32 [ceil(N/8)]
+ *   caller               group_base int64 [ceil(N/8)] = 8 * exclusive prefix sum of group_slots; E = 8 * sum
  *   sphnca_pairs_fill    J int32 [E], WP / WB / WA float [E,2], SXY float [N,2], FLG uint8 [N] (the life mask of an
  *                        all-alive field: what the perception sweep reports when use_alpha == 0)
  *   sphnca_step_perceive_pairs / sphnca_step_adjoint_pairs: same outputs, bit for bit, as sphnca_step_perceive /
  *   sphnca_step_adjoint (same visiting order, same floats), from the lists. */
-int32_t sphnca_pairs_count(const sphnca_grid* g, const float* xv4, int32_t* warp_slots, void* stream);
-int32_t sphnca_pairs_fill(const sphnca_grid* g, const float* xv4, const int32_t* warp_slots, const int64_t* warp_base,
+int32_t sphnca_pairs_count(const sphnca_grid* g, const float* xv4, int32_t* group_slots, void* stream);
+int32_t sphnca_pairs_fill(const sphnca_grid* g, const float* xv4, const int32_t* group_slots, const int64_t* group_base,
                           int32_t* J, float* WP, float* WB, float* WA, float* SXY, uint8_t* FLG, void* stream);
-int32_t sphnca_step_perceive_pairs(const sphnca_grid* g, const int32_t* warp_slots, const int64_t* warp_base, const int32_t* J,
+int32_t sphnca_step_perceive_pairs(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
                                    const float* WP, const float* WB, const uint8_t* FLG, const float* A_s,
                                    const sphnca_step_params* p, float* Y_s, uint8_t* flags_s, void* stream);
-int32_t sphnca_step_adjoint_pairs(const sphnca_grid* g, const int32_t* warp_slots, const int64_t* warp_base, const int32_t* J,
+int32_t sphnca_step_adjoint_pairs(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
                                   const float* WA, const float* SXY, const float* xv4, const float* dY_s, const float* dAdir_s,
                                   const sphnca_step_params* p, float* dA_s, void* stream);
 /* sphnca_step_mask: new life mask = blur(alive_s) > 0.1 (nca.py:112); A_new_s *= prev & new in

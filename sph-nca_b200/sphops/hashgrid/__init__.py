@@ -126,13 +126,13 @@ class Hashgrid:
             if N:
                 dev = x.device
                 xv4 = self.sorted_xv(x, v)
-                nw = (N + 31) // 32
-                slots = torch.empty((nw,), dtype=torch.int32, device=dev)
+                ng = (N + 7) // 8                                   # list groups of 8 particles (csrc/pairs.cu)
+                slots = torch.empty((ng,), dtype=torch.int32, device=dev)
                 st = _lib.stream_ptr()
                 _lib.check(_lib.lib.sphnca_pairs_count(self.c_grid(), _lib.ptr(xv4), _lib.ptr(slots), st))
                 cum = torch.cumsum(slots, 0, dtype=torch.int64)
-                base = ((cum - slots) * 32).contiguous()
-                total = int(cum[-1].item()) * 32
+                base = ((cum - slots) * 8).contiguous()
+                total = int(cum[-1].item()) * 8
                 free, _ = torch.cuda.mem_get_info(dev)
                 if 0 < total and total * 28 <= self.PAIR_LIST_MEMORY_FRACTION * free:
                     f32 = dict(dtype=torch.float32, device=dev)

@@ -419,7 +419,7 @@ def test_tile_sweeps_equal_gather_sweeps(kind):
     # the same floats -> bit-identical perception, life mask and adjoint
     pl = grid.pair_lists(xd, v)
     if _lib.USE_PAIR_LISTS and _lib.FORCE_SWEEP_PATH is None:
-        assert pl is not None and pl["entries"] % 32 == 0
+        assert pl is not None and pl["entries"] % 32 == 0      # groups of 8 particles, slot counts in multiples of 4
         Y = torch.zeros(N, 32, device=DEV); fl = torch.zeros(N, dtype=torch.uint8, device=DEV); dA = torch.zeros(N, 16, device=DEV)
         _lib.check(_lib.lib.sphnca_step_perceive_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]),
                                                        _lib.ptr(pl["WP"]), _lib.ptr(pl["WB"]), _lib.ptr(pl["FLG"]), _lib.ptr(A_s), C.byref(p), _lib.ptr(Y), _lib.ptr(fl), st))
