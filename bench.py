@@ -62,18 +62,20 @@ UNIT = "particle-steps/s"
 # (compulsory traffic of that kernel's interface), flops = algorithmic FLOPs per particle (FMA = 2),
 # bound = which roof applies: "hbm" (sweeps: memory/latency side) or "tensor" (tcgen05 MLP kernels).
 KERNELS = {
-    # sweep: read x,v,A (80) + write scaled dA/dx|dA/dy (128) + 1 flag byte; ~12 FLOP/candidate + ~137 FLOP/neighbour
-    "step_perceive": dict(bytes=209.0, flops=5500.0, bound="hbm"),
+    # perception from the pair lists (csrc/pairs.cu): ~36 list slots x 12 B (J, WP; +8 B WB with an alpha channel) + A row (64)
+    # + write dA/dx|dA/dy (128) + flag; 24 packed FMA/ADD pairs per slot
+    "step_perceive": dict(bytes=626.0, flops=36 * 64.0, bound="hbm"),
     # MLP + update: read A,Y (192) + fire (1) ; write A' (64), O (144), relu bits (32), flags/alive (2); 2*(48*256+256*33) FLOP
     "step_mlp": dict(bytes=435.0, flops=41472.0, bound="tensor"),
     "step_fwd": dict(bytes=152.0, flops=41472.0 + 5500.0, bound="tensor"),   # fused forward (A/B path)
-    "step_mask": dict(bytes=24.0, flops=1300.0, bound="hbm"),
+    "step_mask": dict(bytes=24.0, flops=1300.0, bound="hbm"),               # neighbour-sweep life mask (alpha channel only)
+    "step_mask_static": dict(bytes=2.0, flops=0.0, bound="hbm"),            # no alpha channel: elementwise
     # data gradient: read A,O,dA',relu,flags (64+144+64+32+1) ; write dO (144), dY (128), dAdir (64); 2*(33*256+256*48) FLOP
     "step_bwd": dict(bytes=641.0, flops=41472.0, bound="tensor"),
     # weight gradient with transposed recompute: read A,Y,dO (336); recompute 2*(48*256+33*256) + accumulate the same
     "mlp_wgrad": dict(bytes=336.0, flops=82944.0, bound="tensor"),
-    # gather adjoint: read x,v (16), dY (128), dAdir (64) ; write dA (64)
-    "step_adjoint": dict(bytes=272.0, flops=5000.0, bound="hbm"),
+    # adjoint from the pair lists: ~36 slots x 12 B (J, WA) + x,v (16) + SXY (8) + dY (128) + dAdir (64) ; write dA (64)
+    "step_adjoint": dict(bytes=712.0, flops=36 * 64.0, bound="hbm"),
 }
 
 
@@ -419,8 +421,8 @@ def main():
             roofline = {"kernel": dominant, "bound": "hbm", "achieved": k["hbm_gbs"], "peak": hbm, "unit": "GB/s",
                         "frac": k["hbm_frac"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
                         "algorithmic_bytes_per_particle": info["bytes"], "particles_per_launch": N, "avg_launch_ms": k["avg_ms"],
-                        "note": "neighbour sweep: ~32 gathered 64-byte rows per particle out of L1/L2; latency/issue bound, "
-                                "not HBM bound (DESIGN.md 4)"}
+                        "note": "pair-list sweep: list stream from HBM + ~36 gathered rows per particle out of L1/L2; bound by the L1 "
+                                "data pipe (DESIGN.md 4)"}
 
     if roofline is not None:
         roofline["traffic"] = traffic
