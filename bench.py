@@ -270,6 +270,9 @@ def main():
     ap.add_argument("--nca-steps", type=int, default=0, help="override the workload's NCA steps per rollout (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="operator-by-operator path (sphops ops + torch MLP)")
+    ap.add_argument("--checkpoint", choices=["auto", "on", "off"], default="auto",
+                    help="activation checkpointing inside the rollout node: keep states + fire bytes only (65 B per "
+                         "particle-step) and recompute each step's forward in the backward; auto = by free HBM")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.nca_steps > 0:
@@ -308,6 +311,7 @@ def main():
         wl["batch"] = wl["batch_total"] // world
     nca.USE_3D = True
     nca.USE_FUSED_STEP = not args.no_fused
+    fused.CHECKPOINT = {"auto": "auto", "on": True, "off": False}[args.checkpoint]
     torch.manual_seed(1234 + rank)
     x_cpu, A_cpu, sections, h, dims = make_inputs(wl, seed=rank)
     N, K_nca = x_cpu.shape[0], wl["k_nca"]
@@ -321,6 +325,8 @@ def main():
     x_pin, A_pin = x_cpu.pin_memory(), A_cpu.pin_memory()
     out_pin = torch.empty_like(A_pin).pin_memory()
     x_dev, A_dev = x_pin.to(dev), A_pin.to(dev)
+    tape_mode = {1: "full tape", 2: "checkpointed (states + fire bytes kept, forward recomputed in backward)"}[
+        fused._tape_mode(N, K_nca, dev, None)]
 
     def one_step(x0, A0):
         return nca.sample_plane(model, x0, A0, sections, h, dims, iter_n=K_nca, loss_fn=bench_loss, img=None, optimizer=opt)
@@ -433,7 +439,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "description": wl["desc"], "particles_per_gpu": N, "nca_steps": K_nca,
                    "h": h, "dims": dims, "weights": "zebra (trained, tests/golden/weights_zebra.npz)", "optimizer": "Adam lr=1e-5",
-                   "path": "fused" if nca.USE_FUSED_STEP else "ops", "parallelism": f"dp{world}",
+                   "path": "fused" if nca.USE_FUSED_STEP else "ops", "parallelism": f"dp{world}", "rollout_tape": tape_mode,
                    "l2": "no flush needed: ~340 B/particle/NCA-step of saved state => working set "
                          f"{340 * N * K_nca / 1e9:.1f} GB per step >> 126 MB L2"},
         "clocks": clocks, "gpu_launches": launches,

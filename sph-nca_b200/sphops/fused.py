@@ -51,12 +51,17 @@ def _perceive_entry(grid):
 def _perceive(grid, x, v, g, xv4, A_s, p, Y_s, flags_s, st):
     """Perception sweep: from the grid's pair lists when they exist, else by sweeping the cells."""
     pl = grid.pair_lists(x, v)
+    _perceive_pl(grid, pl, g, xv4, A_s, p, Y_s, flags_s, st)
+    return pl
+
+
+def _perceive_pl(grid, pl, g, xv4, A_s, p, Y_s, flags_s, st):
+    """Perception sweep with the pair lists (or their absence) already looked up."""
     if pl is not None:
         _timed("step_perceive", lib.sphnca_step_perceive_pairs, g, ptr(pl["slots"]), ptr(pl["base"]), ptr(pl["J"]), ptr(pl["WP"]),
                ptr(pl["WB"]), ptr(pl["FLG"]), ptr(A_s), C.byref(p), ptr(Y_s), ptr(flags_s), st)
     else:
         _timed("step_perceive", _perceive_entry(grid), g, ptr(xv4), ptr(A_s), C.byref(p), ptr(Y_s), ptr(flags_s), st)
-    return pl
 
 
 def _adjoint(grid, pl, xv4, dY_s, dAdir_s, p, dA_s, st):
@@ -185,6 +190,10 @@ class _NCARollout(torch.autograd.Function):
     sweep adjoint, with the parameter gradients accumulated in place over all steps (fixed order:
     deterministic).  Outputs: the K+1 states S_0..S_K in SORTED order (unpack lazily, `RolloutStates`);
     a loss may read any subset of them -- missing output gradients are skipped, not materialised.
+    `taped`: 0 = no tape (inference), 1 = keep every step's perception / MLP output / ReLU bits / flags
+    (~305 B per particle-step besides the states), 2 = activation checkpointing: keep only the states and the
+    packed fire bytes (65 B per particle-step) and re-run perceive -> MLP -> mask of a step right before its
+    backward; the kernels are deterministic, so both modes give bit-identical gradients.
     The fire mask of step k is drawn here by `torch.rand(N) <= fire_rate`, the same call, in the same
     order, as the reference's `SPHNCA.forward` (nca.py:100)."""
 
@@ -211,7 +220,7 @@ class _NCARollout(torch.autograd.Function):
         for _ in range(steps):
             fire = torch.rand(N, device=dev) <= fire_rate
             fire_s = grid.pack_bytes(fire.view(torch.uint8))
-            if taped or Y_s is None:
+            if taped == 1 or Y_s is None:
                 Y_s = torch.empty((N, 32), **f32); O_s = torch.empty((N, 36), **f32)
                 flags_s = torch.empty((N,), **u8); relu_s = torch.empty((N, 8), dtype=torch.int32, device=dev)
             Sn = torch.empty((N, 16), **f32)
@@ -224,14 +233,16 @@ class _NCARollout(torch.autograd.Function):
                     _timed("step_fwd", lib.sphnca_step_fwd, g, ptr(xv4), ptr(S), ptr(fire_s), C.byref(p), ptr(Sn),
                            ptr(alive_s), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
                 _mask(use_alpha, g, N, xv4, alive_s, Sn, flags_s, st)
-            if taped:
+            if taped == 1:
                 saved += [Y_s, O_s, flags_s, relu_s]
+            elif taped == 2:
+                saved.append(fire_s)
             if keep_all or taped:
                 states.append(Sn)
             else:
                 states = [states[0], Sn] if len(states) else [Sn]
             S = Sn
-        ctx.grid, ctx.cfg, ctx.steps = grid, cfg, steps
+        ctx.grid, ctx.cfg, ctx.steps, ctx.taped = grid, cfg, steps, taped
         ctx.pairs = grid.pair_lists(x, v) if (N and taped) else None
         if taped:
             ctx.save_for_backward(xv4, W1c, b1c, W2c, b2c, *states, *saved)
@@ -262,12 +273,25 @@ class _NCARollout(torch.autograd.Function):
         dAdir_s = torch.empty((N, 16), **f32)
         own = [torch.empty((N, 16), **f32), torch.empty((N, 16), **f32)]   # gradient ping-pong (never write autograd's buffers)
         st = stream_ptr()
+        recompute = ctx.taped == 2
+        if recompute and N:
+            u8 = dict(dtype=torch.uint8, device=dev)
+            Y_s = torch.empty((N, 32), **f32); O_s = torch.empty((N, 36), **f32)
+            flags_s = torch.empty((N,), **u8); relu_s = torch.empty((N, 8), dtype=torch.int32, device=dev)
+            Sn_scr, alive_s = torch.empty((N, 16), **f32), torch.empty((N,), **u8)
+            g = grid.c_grid()
         gcur = dstates[K]
         if gcur is not None:
             gcur = require_cuda_f32(gcur, "dS")
         for k in range(K - 1, -1, -1):
             if gcur is not None and N:          # steps after the last state a loss reads carry no gradient
-                Y_s, O_s, flags_s, relu_s = saved[4 * k:4 * k + 4]
+                if recompute:                   # the forward of step k again, from the saved state and fire bytes
+                    _perceive_pl(grid, ctx.pairs, g, xv4, states[k], p, Y_s, flags_s, st)
+                    _timed("step_mlp", lib.sphnca_step_mlp, N, ptr(states[k]), ptr(Y_s), ptr(saved[k]), C.byref(p),
+                           ptr(Sn_scr), ptr(alive_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
+                    _mask(ctx.cfg[1], g, N, xv4, alive_s, Sn_scr, flags_s, st)
+                else:
+                    Y_s, O_s, flags_s, relu_s = saved[4 * k:4 * k + 4]
                 _timed("step_bwd", lib.sphnca_step_bwd, N, ptr(states[k]), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(relu_s),
                        ptr(gcur), C.byref(p), ptr(dO_s), ptr(dY_s), ptr(dAdir_s), None, None, st)
                 if want_w:
@@ -312,16 +336,35 @@ class RolloutStates:
         return (self[k] for k in range(len(self._s)))
 
 
+# Activation checkpointing inside the rollout node: True / False, or "auto" = checkpoint when
+# the full tape (TAPE_BYTES per particle-step) would take more than AUTO_CHECKPOINT_FRACTION of the free HBM.
+CHECKPOINT = "auto"
+TAPE_BYTES = 4 * (32 + 36 + 8) + 1
+AUTO_CHECKPOINT_FRACTION = 0.5
+
+
+def _tape_mode(N, steps, device, checkpoint):
+    if checkpoint is None:
+        checkpoint = CHECKPOINT
+    if checkpoint == "auto":
+        free, _ = torch.cuda.mem_get_info(device)
+        free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)   # torch's cached blocks are reusable
+        checkpoint = N * steps * TAPE_BYTES > AUTO_CHECKPOINT_FRACTION * free
+    return 2 if checkpoint else 1
+
+
 def nca_rollout(x, v, A, W1, b1, W2, b2, h, grid, steps, fire_rate, update_rule="gated", use_alpha=True,
-                perception_scale=1.0, orig_rate=1.0, keep_all=True):
+                perception_scale=1.0, orig_rate=1.0, keep_all=True, checkpoint=None):
     """`steps` NCA steps from state A [N,16] as one autograd node -> RolloutStates (K+1 states if `keep_all`
-    or anything requires grad, else [first, last])."""
+    or anything requires grad, else [first, last]).  `checkpoint`: None = module default `CHECKPOINT`."""
     if "sphnca_step_fwd" in _lib.MISSING_SYMBOLS:
         raise RuntimeError("libsphnca.so was built without the fused step (step.cu)")
     hval = h.item() if isinstance(h, torch.Tensor) else float(h)
     if abs(hval - grid.h) > 1e-9 * abs(grid.h):
         raise ValueError(f"h={hval} differs from the grid's cell size {grid.h}")
-    taped = torch.is_grad_enabled() and any(t.requires_grad for t in (A, W1, b1, W2, b2))
+    taped = int(torch.is_grad_enabled() and any(t.requires_grad for t in (A, W1, b1, W2, b2)))
+    if taped:
+        taped = _tape_mode(x.shape[0], int(steps), x.device, checkpoint)
     states = _NCARollout.apply(x, v, A, W1, b1, W2, b2, grid, (update_rule, use_alpha, perception_scale, orig_rate),
                                int(steps), fire_rate, keep_all, taped)
     return RolloutStates(states, grid)

@@ -557,6 +557,49 @@ def test_rollout_node_loss_on_an_intermediate_state_only():
         assert_close(b, a, rtol=1e-6, what=nm)
 
 
+@pytest.mark.parametrize("use_alpha", [False, True], ids=["noalpha", "alpha"])
+@pytest.mark.parametrize("pairs", [True, False], ids=["pairlists", "cellsweep"])
+def test_rollout_node_checkpointing_is_bit_identical(use_alpha, pairs, monkeypatch):
+    """Activation checkpointing: keeping only the states + fire bytes and re-running each step's
+    forward in the backward gives the SAME bits as the full tape (deterministic kernels), for a multi-state loss and
+    with steps past the last read state skipped; and it holds ~4.7x less memory per particle-step."""
+    from sphops import _lib, fused
+    if not pairs:
+        monkeypatch.setattr(_lib, "USE_PAIR_LISTS", False)
+    K = 6
+    x, sections, h, dims, A0, params, masks, cfg = oracle_case(72, False, use_alpha, K, seed=11)
+    m = _rollout_model(use_alpha, h)
+    xd = x.to(DEV)
+    res, held = [], []
+    for ckpt in (False, True):
+        m.zero_grad()
+        grid, v = m.init_grid(xd, sections, h, dims)
+        A = A0.to(DEV).requires_grad_(True)
+        torch.cuda.synchronize()
+        before = torch.cuda.memory_allocated()
+        with forced_fire_masks(list(masks)):
+            out = m.rollout(xd, v, A, h, grid, K, checkpoint=ckpt)
+        held.append(torch.cuda.memory_allocated() - before)
+        loss = (out[4][:, :4] ** 2).mean() + 0.1 * (out[2][:, :4] - 0.25).abs().mean()     # steps 5, 6 carry no gradient
+        loss.backward()
+        res.append([o.detach().clone() for o in out] + [A.grad.clone()] + [p.grad.clone() for p in m.parameters()])
+    for k, (a, b) in enumerate(zip(*res)):
+        assert torch.equal(a, b), f"tensor {k} differs between full tape and checkpointed rollout"
+    N = x.shape[0]
+    assert held[0] - held[1] >= 0.9 * N * (K - 1) * fused.TAPE_BYTES, held     # the tape that is not kept
+
+
+def test_rollout_node_auto_checkpoint_follows_free_memory(monkeypatch):
+    from sphops import fused
+    free, _ = torch.cuda.mem_get_info()
+    n_small, n_huge = 1000, int(free / fused.TAPE_BYTES)
+    assert fused._tape_mode(n_small, 8, torch.device(DEV), None) == 1
+    assert fused._tape_mode(n_huge, 8, torch.device(DEV), None) == 2
+    assert fused._tape_mode(n_small, 8, torch.device(DEV), True) == 2 and fused._tape_mode(n_huge, 8, torch.device(DEV), False) == 1
+    monkeypatch.setattr(fused, "CHECKPOINT", True)
+    assert fused._tape_mode(n_small, 8, torch.device(DEV), None) == 2
+
+
 def test_rollout_node_inference_keeps_only_what_is_asked():
     """No tape, keep_all=False: two states (first, last); same final state as the stepwise path; sequence protocol."""
     import random
