@@ -12,7 +12,11 @@
 //
 // (MN-major tf32 operands need the SW128_32B layout, so instead of re-viewing the forward's W1/W2 tiles
 //  the kernel stages transposed K-major copies: W2^T 64 KB + W1^T 96 KB, hi/lo.)
-// TMEM: D3/dH_hi 128 + dH_lo 128 + Dy 48 = 304 columns.  MMAs execute in issue order, so GEMM3 of the
+// GEMM4 has only 48 output columns, where an MMA costs ~32 cycles + N/4 whatever N is (probes/tc_timing4: A from
+// TMEM, N=48 59 cycles, N=128 71), so the hi and lo copies of W1^T are STACKED along N (96 rows): dH_hi . [W_hi ; W_lo]
+// is one MMA into Dy columns 0..47 | 48..95 and dH_lo . W_hi adds to columns 0..47 -- 2 MMAs per k-step instead of 3;
+// the final epilogue adds the two column groups.
+// TMEM: D3/dH_hi 128 + dH_lo 128 + Dy 96 = 352 columns.  MMAs execute in issue order, so GEMM3 of the
 // next half may be issued right behind GEMM4 of the previous one on the same columns.
 #include "step_common.cuh"
 #include "tc_common.cuh"
@@ -32,7 +36,7 @@ enum { DO_FULL = 0, DO_EMPTY, D3_FULL, DH_FULL, DY_FULL, DY_EMPTY, NUM_BARS };
 
 struct Smem {
     float W2t_hi[2][128 * KO], W2t_lo[2][128 * KO];       // [hidden half] rows = h (128), K = o (32)
-    float W1t_hi[2][NIN * 128], W1t_lo[2][NIN * 128];     // [hidden half] rows = k (48),  K = h (128)
+    float W1t[2][2 * NIN * 128];                          // [hidden half] rows 0..47 = k hi, 48..95 = k lo ; K = h (128)
     float dO_hi[TILE * KO], dO_lo[TILE * KO];             // rows = particle, K = o
     float dAdir[2][TILE][NF];
     float dO32[2][TILE];
@@ -64,8 +68,7 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     for (int i = tid; i < NH * NIN; i += THREADS) {           // W1 [h][k] -> W1t[half] (rows k, K = h)
         const int h = i / NIN, k = i - h * NIN;
         float hi, lo; split_tf32(__ldg(prm.W1 + i), hi, lo);
-        const uint32_t o = fidx(NIN, k, h & 127);
-        s.W1t_hi[h >> 7][o] = hi; s.W1t_lo[h >> 7][o] = lo;
+        s.W1t[h >> 7][fidx(2 * NIN, k, h & 127)] = hi; s.W1t[h >> 7][fidx(2 * NIN, NIN + k, h & 127)] = lo;
     }
     for (int i = tid; i < NH; i += THREADS) s.w2_last[i] = c.n_out > KO ? __ldg(prm.W2 + (size_t)KO * NH + i) : 0.f;
     if (tid == 0) {
@@ -163,7 +166,7 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     } else if (warp == MMA_WARP) {
         {   // warp-uniform issue: every lane runs the loop, one elected lane issues (tc_common.cuh)
             const uint32_t go = elect_one();
-            const uint32_t idesc3 = make_idesc_tf32(TILE, 128), idesc4 = make_idesc_tf32(TILE, NIN);
+            const uint32_t idesc3 = make_idesc_tf32(TILE, 128), idesc4 = make_idesc_tf32(TILE, NIN), idesc4c = make_idesc_tf32(TILE, 2 * NIN);
             const uint32_t ah = smem_u32(s.dO_hi), al = smem_u32(s.dO_lo);
             auto gemm3 = [&](int half) {
                 const uint32_t wh = smem_u32(s.W2t_hi[half]), wl = smem_u32(s.W2t_lo[half]);
@@ -179,14 +182,13 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 }
             };
             auto gemm4 = [&](int half) {
-                const uint32_t wh = smem_u32(s.W1t_hi[half]), wl = smem_u32(s.W1t_lo[half]);
+                const uint32_t w = smem_u32(s.W1t[half]);
 #pragma unroll
                 for (int ks = 0; ks < 128 / 8; ++ks) {
-                    const uint64_t b_hi = make_smem_desc(wh + chunk_off(NIN, 0, 2 * ks), NIN * 16, 128);
-                    const uint64_t b_lo = make_smem_desc(wl + chunk_off(NIN, 0, 2 * ks), NIN * 16, 128);
-                    mma_tf32_ts_e(tbase + COL_DY, tbase + COL_DHLO + 8 * ks, b_hi, idesc4, (half | ks) > 0, go);
-                    mma_tf32_ts_e(tbase + COL_DY, tbase + COL_D3 + 8 * ks, b_lo, idesc4, true, go);
-                    mma_tf32_ts_e(tbase + COL_DY, tbase + COL_D3 + 8 * ks, b_hi, idesc4, true, go);
+                    // rows 0..47 of this tile = W1^T hi, all 96 rows = the stacked [hi ; lo] tile
+                    const uint64_t b = make_smem_desc(w + chunk_off(2 * NIN, 0, 2 * ks), 2 * NIN * 16, 128);
+                    mma_tf32_ts_e(tbase + COL_DY, tbase + COL_D3 + 8 * ks, b, idesc4c, (half | ks) > 0, go);   // dH_hi . [W_hi ; W_lo]
+                    mma_tf32_ts_e(tbase + COL_DY, tbase + COL_DHLO + 8 * ks, b, idesc4, true, go);             // dH_lo . W_hi
                 }
             };
             int it = 0;
@@ -251,10 +253,10 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             float dy[NIN];
 #pragma unroll
             for (int cc = 0; cc < NIN; cc += 16) {
-                uint32_t r[16];
-                tmem_ld16(lane_addr + COL_DY + cc, r); wait_ld();
+                uint32_t r[16], r2[16];
+                tmem_ld16(lane_addr + COL_DY + cc, r); tmem_ld16(lane_addr + COL_DY + NIN + cc, r2); wait_ld();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) dy[cc + j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 16; ++j) dy[cc + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
             }
             fence_before_sync();
             mbar_arrive(&s.bar[DY_EMPTY]);

@@ -6,7 +6,12 @@
 //   step_mlp_tc_kernel (this file)   loader warps pull rows [A | Y] (192 B / particle) one tile ahead into
 //                                    registers and write the tf32 hi/lo MMA A tile; MMA warp and TMEM
 //                                    pipeline as in step_tc.cu; 8 epilogue warps (two per TMEM lane
-//                                    quarter, half of the hidden columns each).
+//                                    quarter, half of the hidden columns each) for the hidden layer and
+//                                    4 finalizer warps (gates, update, row stores) one tile behind them.
+//
+// GEMM2 has 32 output columns, where an MMA costs ~32 cycles + N/4 (probes/tc_timing4: A from TMEM, N=32 40 cycles,
+// N=64 57): W2 hi and lo are STACKED along N (64 rows), H_hi . [W_hi ; W_lo] is one MMA into D2 columns 0..31 | 32..63,
+// H_lo . W_hi adds to columns 0..31 -- 2 MMAs per k-step instead of 3; the final epilogue adds the column groups.
 //
 // Why split: the fused kernel (step_tc.cu) needs 215 KB of shared memory, which leaves ~13 KB of L1 per SM,
 // so its neighbour gathers all go to L2 and the sweep (41-58 k cycles per 128-particle tile, measured with
@@ -21,25 +26,35 @@ using namespace tc;
 
 namespace mt {
 constexpr int TILE = 128;
-constexpr int EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP0 = 9, LOAD_WARPS = 4;
-constexpr int THREADS = (LOAD_WARP0 + LOAD_WARPS) * 32;        // 416
+constexpr int EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP0 = 9, LOAD_WARPS = 4, FIN_WARP0 = 13, FIN_WARPS = 4;
+constexpr int THREADS = (FIN_WARP0 + FIN_WARPS) * 32;          // 544
 constexpr int N2 = 32;
-constexpr uint32_t COL_D1 = 0, COL_HHI = 128, COL_HLO = 256, COL_D2 = 384, TMEM_COLS = 512;
-enum { Y_FULL = 0, Y_EMPTY, D1_FULL, D1_EMPTY, H_FULL, H_EMPTY, D2_FULL, D2_EMPTY, NUM_BARS };
+constexpr uint32_t COL_D1 = 0, COL_HHI = 128, COL_HLO = 256, COL_D2 = 384, TMEM_COLS = 512;   // D2: 2 slots x 64 columns
+enum { Y_FULL = 0, Y_EMPTY, D1_FULL, D1_EMPTY, H_FULL, H_EMPTY, D2_FULL, D2_FULL1, D2_EMPTY, D2_EMPTY1, FIN_FULL, FIN_FULL1, NUM_BARS };
 
 struct Smem {
     float W1_hi[2][128 * NIN], W1_lo[2][128 * NIN];
-    float W2_hi[2][N2 * 128], W2_lo[2][N2 * 128];
+    float W2[2][2 * N2 * 128];          // [hidden half] rows 0..31 = outputs hi, 32..63 = lo ; K = h (128)
     float Y_hi[TILE * NIN], Y_lo[TILE * NIN];
     float b1[NH], w2_last[NH], b2[NO_PAD];
-    float o32[2][TILE];                 // partial scalar-gate sums of the second column-half warps
-    uint32_t relu[2][TILE][NH / 64];    // ReLU words of the second column-half warps (4 of the 8 words)
+    float o32[2][2][TILE];              // [slot][column-half group] partial scalar-gate sums
     uint64_t bar[NUM_BARS];
     uint32_t tmem_base;
 };
 __device__ __forceinline__ uint32_t fidx(uint32_t rows, uint32_t m, uint32_t k) { return chunk_off(rows, m, k >> 2) / 4 + (k & 3); }
 // gates: fast exponential (2 ulp) -> |error| ~1e-7 on sigmoid / tanh, far inside the 1e-5 parity bar
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// loads whose results must not be touched before they are needed (see the epilogue's prefetch)
+__device__ __forceinline__ uint32_t ldg_u8_raw(const uint8_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_f4_raw(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ float fast_tanh(float x) {
     const float e = __expf(-2.f * fabsf(x));
     const float t = __fdividef(1.f - e, 1.f + e);
@@ -67,8 +82,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     for (int i = tid; i < N2 * NH; i += THREADS) {
         const int o_ = i / NH, k = i - o_ * NH;
         float hi, lo; split_tf32(o_ < n_mma ? __ldg(prm.W2 + (size_t)o_ * NH + k) : 0.f, hi, lo);
-        const uint32_t o = fidx(N2, o_, k & 127);
-        s.W2_hi[k >> 7][o] = hi; s.W2_lo[k >> 7][o] = lo;
+        s.W2[k >> 7][fidx(2 * N2, o_, k & 127)] = hi; s.W2[k >> 7][fidx(2 * N2, N2 + o_, k & 127)] = lo;
     }
     for (int i = tid; i < NH; i += THREADS) {
         s.b1[i] = __ldg(prm.b1 + i);
@@ -79,7 +93,9 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
         mbar_init(&s.bar[Y_FULL], LOAD_WARPS * 32); mbar_init(&s.bar[Y_EMPTY], 1);
         mbar_init(&s.bar[D1_FULL], 1);              mbar_init(&s.bar[D1_EMPTY], EPI_WARPS * 32);
         mbar_init(&s.bar[H_FULL], EPI_WARPS * 32);  mbar_init(&s.bar[H_EMPTY], 1);
-        mbar_init(&s.bar[D2_FULL], 1);              mbar_init(&s.bar[D2_EMPTY], 4 * 32);
+        for (int q = 0; q < 2; ++q) {
+            mbar_init(&s.bar[D2_FULL + q], 1); mbar_init(&s.bar[D2_EMPTY + q], FIN_WARPS * 32); mbar_init(&s.bar[FIN_FULL + q], EPI_WARPS * 32);
+        }
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc(&s.tmem_base, TMEM_COLS);
@@ -89,7 +105,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     fence_after_sync();
     const uint32_t tbase = s.tmem_base;
 
-    if (warp >= LOAD_WARP0) {
+    if (warp >= LOAD_WARP0 && warp < FIN_WARP0) {
         // ===================== loader: rows [A | Y] -> tf32 hi/lo A tile, one tile ahead =====================
         const int m = tid - LOAD_WARP0 * 32;
         int it = 0;
@@ -126,7 +142,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     } else if (warp == MMA_WARP) {
         {   // warp-uniform issue: every lane runs the loop, one elected lane issues (tc_common.cuh)
             const uint32_t go = elect_one();
-            const uint32_t idesc1 = make_idesc_tf32(TILE, 128), idesc2 = make_idesc_tf32(TILE, N2);
+            const uint32_t idesc1 = make_idesc_tf32(TILE, 128), idesc2 = make_idesc_tf32(TILE, N2), idesc2c = make_idesc_tf32(TILE, 2 * N2);
             const uint32_t yh = smem_u32(s.Y_hi), yl = smem_u32(s.Y_lo);
             int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -152,46 +168,113 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                     SPHNCA_TL(2 + half);
                 }
                 mma_commit_e(&s.bar[Y_EMPTY], go);
-                mbar_wait(&s.bar[D2_EMPTY], (it & 1) ^ 1);
+                const int slot = it & 1;                      // D2 is double buffered: the finalizer warps drain tile it-1 meanwhile
+                mbar_wait(&s.bar[D2_EMPTY + slot], ((it >> 1) & 1) ^ 1);
+                fence_after_sync();
+                const uint32_t d2 = tbase + COL_D2 + 2 * N2 * slot;
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     mbar_wait(&s.bar[H_FULL], half);
                     fence_after_sync();
-                    const uint32_t wh = smem_u32(s.W2_hi[half]), wl = smem_u32(s.W2_lo[half]);
+                    const uint32_t w = smem_u32(s.W2[half]);
 #pragma unroll
                     for (int ks = 0; ks < 128 / 8; ++ks) {
-                        const uint64_t b_hi = make_smem_desc(wh + chunk_off(N2, 0, 2 * ks), N2 * 16, 128);
-                        const uint64_t b_lo = make_smem_desc(wl + chunk_off(N2, 0, 2 * ks), N2 * 16, 128);
-                        mma_tf32_ts_e(tbase + COL_D2, tbase + COL_HLO + 8 * ks, b_hi, idesc2, (half | ks) > 0, go);
-                        mma_tf32_ts_e(tbase + COL_D2, tbase + COL_HHI + 8 * ks, b_lo, idesc2, true, go);
-                        mma_tf32_ts_e(tbase + COL_D2, tbase + COL_HHI + 8 * ks, b_hi, idesc2, true, go);
+                        // rows 0..31 of this tile = W2 hi, all 64 rows = the stacked [hi ; lo] tile
+                        const uint64_t b = make_smem_desc(w + chunk_off(2 * N2, 0, 2 * ks), 2 * N2 * 16, 128);
+                        mma_tf32_ts_e(d2, tbase + COL_HHI + 8 * ks, b, idesc2c, (half | ks) > 0, go);   // H_hi . [W_hi ; W_lo]
+                        mma_tf32_ts_e(d2, tbase + COL_HLO + 8 * ks, b, idesc2, true, go);               // H_lo . W_hi
                     }
                     mma_commit_e(&s.bar[H_EMPTY], go);
                     SPHNCA_TL(4 + half);
                 }
-                mma_commit_e(&s.bar[D2_FULL], go);
+                mma_commit_e(&s.bar[D2_FULL + slot], go);
             }
         }
-    } else {
-        // ===================== epilogue: 8 warps; warp & 3 = TMEM lane quarter, warp >> 2 = column half =====================
-        const int m = (warp & 3) * 32 + lane;                 // tile row == TMEM lane
-        const int chalf = warp >> 2;                          // hidden columns [64*chalf, 64*chalf+64) of each 128 half
+    } else if (warp >= FIN_WARP0) {
+        // ===================== finalizer: 4 warps, thread = tile row; gates + update + the row stores =====================
+        // Its own warps, so that the update of tile i (~3 k cycles, bound by the 17 row-strided 16-byte stores per row) runs
+        // beside the MMAs and the hidden-layer epilogue of tile i+1 instead of in front of them (D2 has two slots).
+        const int m = (warp & 3) * 32 + lane;                 // a warp may only touch TMEM lanes 32*(warp % 4)..+31
         const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int p = tile * TILE + m;
             const bool valid = p < n_total;
-            // operands of the final update, fetched early (L2) so their latency hides behind the MMAs
-            float Ai[NF];
-            bool fire = false;
-            uint8_t prevbit = 0;
-            if (chalf == 0) {
-                if (valid) { load16(A_s + (size_t)p * NF, Ai); fire = fire_s[p] != 0; prevbit = flags_s[p] & 1; }
-                else {
+            const int slot = it & 1;
+            // fetched before the waits (raw asm loads: nothing consumes them until the update below)
+            float4 Ai4[4];
 #pragma unroll
-                    for (int f = 0; f < NF; ++f) Ai[f] = 0.f;
-                }
+            for (int k = 0; k < 4; ++k) Ai4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t fire_raw = 0, flag_raw = 0;
+            if (valid) {
+                const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)p * NF);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) Ai4[k] = ldg_f4_raw(a4 + k);
+                fire_raw = ldg_u8_raw(fire_s + p);
+                flag_raw = ldg_u8_raw(flags_s + p);
             }
+            mbar_wait(&s.bar[FIN_FULL + slot], (it >> 1) & 1);
+            const float o32sum = s.o32[slot][0][m] + s.o32[slot][1][m];      // fixed order: group 0 + group 1
+            mbar_wait(&s.bar[D2_FULL + slot], (it >> 1) & 1);
+            fence_after_sync();
+            if (tid == (FIN_WARP0 + 3) * 32) SPHNCA_TL(10);
+            const uint32_t d2 = lane_addr + COL_D2 + 2 * N2 * slot;
+            float out[NO_PAD];
+            {
+                uint32_t r[16], r2[16];                       // hi.(hi+lo of H) group and hi.lo group of the stacked GEMM2
+                tmem_ld16(d2, r); tmem_ld16(d2 + N2, r2); wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) out[j] = (__uint_as_float(r[j]) + __uint_as_float(r2[j])) + s.b2[j];
+                tmem_ld16(d2 + 16, r); tmem_ld16(d2 + N2 + 16, r2); wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) out[16 + j] = (__uint_as_float(r[j]) + __uint_as_float(r2[j])) + s.b2[16 + j];
+            }
+            fence_before_sync();
+            mbar_arrive(&s.bar[D2_EMPTY + slot]);
+            if (tid == (FIN_WARP0 + 3) * 32) SPHNCA_TL(14);
+            out[32] = o32sum + s.b2[32]; out[33] = 0.f; out[34] = 0.f; out[35] = 0.f;
+            if (c.rule != 0) {
+#pragma unroll
+                for (int o = NF; o < NO_PAD; ++o) out[o] = 0.f;
+            }
+            if (valid) {
+                float Ai[NF], nA[NF];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { Ai[4 * k] = Ai4[k].x; Ai[4 * k + 1] = Ai4[k].y; Ai[4 * k + 2] = Ai4[k].z; Ai[4 * k + 3] = Ai4[k].w; }
+                const bool fire = fire_raw != 0;
+                if (c.rule == 0) {
+                    const float mult = fast_sigmoid(out[2 * NF]);
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) nA[f] = fmaf(Ai[f], fast_sigmoid(out[f]), fast_tanh(out[NF + f]) * mult);
+                } else {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) nA[f] = fmaf(out[f], c.orig_rate, Ai[f]);
+                }
+#pragma unroll
+                for (int f = 0; f < NF; ++f) nA[f] = fire ? nA[f] : Ai[f];
+                if (tid == (FIN_WARP0 + 3) * 32) SPHNCA_TL(15);
+                float4* o4 = reinterpret_cast<float4*>(An_s + (size_t)p * NF);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o4[k] = make_float4(nA[4 * k], nA[4 * k + 1], nA[4 * k + 2], nA[4 * k + 3]);
+                float4* oo4 = reinterpret_cast<float4*>(O_s + (size_t)p * NO_PAD);
+#pragma unroll
+                for (int k = 0; k < NO_PAD / 4; ++k) oo4[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+                flags_s[p] = (uint8_t)((flag_raw & 1u) | (fire ? 4u : 0u));
+                alive_s[p] = c.use_alpha ? (nA[3] > 0.1f ? 1 : 0) : 1;
+            }
+            if (tid == (FIN_WARP0 + 3) * 32) SPHNCA_TL(11);
+        }
+    } else {
+        // ===================== epilogue: 8 warps; warp & 3 = TMEM lane quarter, warp >> 2 = column half =====================
+        // group chalf converts hidden columns [64*chalf, 64*chalf+64) of each 128 half: bias + ReLU, the ReLU bits, the partial
+        // scalar-gate dot product, H as tf32 hi/lo back to TMEM (the A operand of GEMM2)
+        const int m = (warp & 3) * 32 + lane;                 // tile row == TMEM lane
+        const int chalf = warp >> 2;
+        const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int p = tile * TILE + m;
+            const bool valid = p < n_total;
             float o32 = 0.f;
             uint32_t rmask[NH / 64];                          // this warp's 4 ReLU words: (half, chalf) -> word 4*half + 2*chalf + {0,1}
 #pragma unroll
@@ -199,20 +282,24 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 mbar_wait(&s.bar[D1_FULL], half);
+                fence_after_sync();
+                // the next 16 columns are in flight while the current ones are converted (two register sets)
+                uint32_t r[2][16];
+                tmem_ld16(lane_addr + COL_D1 + chalf * 64, r[0]);
                 mbar_wait(&s.bar[H_EMPTY], half ^ 1);
                 fence_after_sync();
                 if (tid == 0) SPHNCA_TL(6 + 2 * half);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const int cc = chalf * 64 + c4 * 16;
-                    uint32_t r[16], hi[16], lo[16];
-                    tmem_ld16(lane_addr + COL_D1 + cc, r);
+                    uint32_t hi[16], lo[16];
                     wait_ld();
+                    if (c4 < 3) tmem_ld16(lane_addr + COL_D1 + cc + 16, r[(c4 + 1) & 1]);
                     uint32_t bits = 0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int n = half * 128 + cc + j;
-                        const float pre = __uint_as_float(r[j]) + s.b1[n];
+                        const float pre = __uint_as_float(r[c4 & 1][j]) + s.b1[n];
                         bits |= (pre > 0.f ? 1u : 0u) << j;
                         const float hv = fmaxf(pre, 0.f);
                         o32 = fmaf(hv, s.w2_last[n], o32);
@@ -229,63 +316,16 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 mbar_arrive(&s.bar[H_FULL]);
                 if (tid == 0) SPHNCA_TL(7 + 2 * half);
             }
+            // hand the partial scalar-gate sum to the row's finalizer thread.  The slot was last read by the finalizer of tile
+            // it-2, before it released D2's slot; GEMM2 of this tile waited for that release and this epilogue for GEMM2.
             const int slot = it & 1;
-            if (chalf == 1) {
-                // hand the partial scalar-gate sum and ReLU words to the row's first-half warp
-                s.o32[slot][m] = o32;
-#pragma unroll
-                for (int wd = 0; wd < NH / 64; ++wd) s.relu[slot][m][wd] = rmask[wd];
-                asm volatile("bar.sync 2, 256;" ::: "memory");   // epilogue-only barrier (8 warps)
-            } else {
-                asm volatile("bar.sync 2, 256;" ::: "memory");
-                mbar_wait(&s.bar[D2_FULL], it & 1);
-                fence_after_sync();
-                if (tid == 0) SPHNCA_TL(10);
-                float out[NO_PAD];
-                {
-                    uint32_t r[16];
-                    tmem_ld16(lane_addr + COL_D2, r); wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) out[j] = __uint_as_float(r[j]) + s.b2[j];
-                    tmem_ld16(lane_addr + COL_D2 + 16, r); wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) out[16 + j] = __uint_as_float(r[j]) + s.b2[16 + j];
-                }
-                fence_before_sync();
-                mbar_arrive(&s.bar[D2_EMPTY]);
-                if (tid == 0) SPHNCA_TL(14);
-                out[32] = o32 + s.o32[slot][m] + s.b2[32]; out[33] = 0.f; out[34] = 0.f; out[35] = 0.f;
-                if (c.rule != 0) {
-#pragma unroll
-                    for (int o = NF; o < NO_PAD; ++o) out[o] = 0.f;
-                }
-                if (valid) {
-                    float nA[NF];
-                    if (c.rule == 0) {
-                        const float mult = fast_sigmoid(out[2 * NF]);
-#pragma unroll
-                        for (int f = 0; f < NF; ++f) nA[f] = fmaf(Ai[f], fast_sigmoid(out[f]), fast_tanh(out[NF + f]) * mult);
-                    } else {
-#pragma unroll
-                        for (int f = 0; f < NF; ++f) nA[f] = fmaf(out[f], c.orig_rate, Ai[f]);
-                    }
-#pragma unroll
-                    for (int f = 0; f < NF; ++f) nA[f] = fire ? nA[f] : Ai[f];
-                    if (tid == 0) SPHNCA_TL(15);
-                    float4* o4 = reinterpret_cast<float4*>(An_s + (size_t)p * NF);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) o4[k] = make_float4(nA[4 * k], nA[4 * k + 1], nA[4 * k + 2], nA[4 * k + 3]);
-                    float4* oo4 = reinterpret_cast<float4*>(O_s + (size_t)p * NO_PAD);
-#pragma unroll
-                    for (int k = 0; k < NO_PAD / 4; ++k) oo4[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
-                    // relu words: hidden 0..63 -> words 0,1 (mine) ; 64..127 -> 2,3 (partner) ; 128..191 -> 4,5 (mine) ; 192..255 -> 6,7 (partner)
-                    uint4* rm4 = reinterpret_cast<uint4*>(relu_s + (size_t)p * (NH / 32));
-                    rm4[0] = make_uint4(rmask[0], rmask[1], s.relu[slot][m][0], s.relu[slot][m][1]);
-                    rm4[1] = make_uint4(rmask[2], rmask[3], s.relu[slot][m][2], s.relu[slot][m][3]);
-                    flags_s[p] = (uint8_t)(prevbit | (fire ? 4 : 0));
-                    alive_s[p] = c.use_alpha ? (nA[3] > 0.1f ? 1 : 0) : 1;
-                }
-                if (tid == 0) SPHNCA_TL(11);
+            s.o32[slot][chalf][m] = o32;
+            mbar_arrive(&s.bar[FIN_FULL + slot]);
+            if (valid) {
+                // ReLU words: hidden 0..63 -> words 0,1 (group 0); 64..127 -> 2,3 (group 1); 128..191 -> 4,5 (group 0); 192..255 -> 6,7 (group 1)
+                uint2* rm2 = reinterpret_cast<uint2*>(relu_s + (size_t)p * (NH / 32));
+                rm2[chalf] = make_uint2(rmask[0], rmask[1]);
+                rm2[2 + chalf] = make_uint2(rmask[2], rmask[3]);
             }
         }
     }

@@ -8,8 +8,13 @@
 //               tf32 hi/lo, written back IN PLACE as TMEM A operands [lanes = h][columns = p]
 //   accumulate  dW1_half[128h x 64] += dH^T . [y | 1 | 0]   (column 48 of the result = db1)
 //               dW2t_half[128h x 48] += H^T . dO            (B operands = K-major TRANSPOSED copies yT, dOT)
-//   the two accumulators (112 TMEM columns) live in TMEM for the whole CTA; one partial per CTA pair
-//   is written at the end and reduced in fixed order by mlp_wgrad_reduce_kernel (wgrad.cu).
+//               The hi and lo B tiles are stacked along N ([y_hi ; y_lo] = 128 rows, [dO_hi ; dO_lo] = 96 rows), so the
+//               two passes that share the A operand are ONE MMA: dH_hi . [y_hi ; y_lo] lands in columns 0..63 | 64..127
+//               of the accumulator and dH_lo . y_hi adds to columns 0..63 -- 4 MMAs per k-step instead of 6.  An MMA
+//               with A from TMEM costs ~32 cycles + N/4 (probes/tc_timing4: N=64 57, N=128 71), so the stacked form
+//               takes 71 + 57 + 64 + 59 = 251 cycles per k-step instead of 3*57 + 3*59 = 348.
+//   the two accumulators (224 TMEM columns) live in TMEM for the whole CTA; the final dump adds the column groups,
+//   one partial per CTA pair is written and reduced in fixed order by mlp_wgrad_reduce_kernel (wgrad.cu).
 //
 // A CTA owns ONE hidden half (blockIdx.x & 1) and a contiguous range of 64-particle chunks, so the
 // weights it stages are halves: W1 48 KB + W2^T 32 KB (hi/lo); chunk operand tiles 96 KB.
@@ -35,7 +40,8 @@ constexpr int NOUT = 48;                                     // rows of dOT: 36 
 constexpr int ROW = NF + 2 * NF + NO_PAD;                    // 84 floats per particle: A 16 | Y 32 | dO 36
 constexpr int KP = CH + 1;                                   // K-chunk pitch of the K-major chunk tiles in 16-byte units: one
                                                              // pad piece makes the "lanes over k-chunks" writes conflict-free
-constexpr uint32_t COL_R1 = 0, COL_HLO = 64, COL_R3 = 128, COL_DHLO = 192, COL_ACC1 = 256, COL_ACC2 = 320, TMEM_COLS = 512;
+constexpr uint32_t COL_R1 = 0, COL_HLO = 64, COL_R3 = 128, COL_DHLO = 192, COL_ACC1 = 256, COL_ACC2 = 384, TMEM_COLS = 512;
+static_assert(COL_ACC1 + 2 * NY <= COL_ACC2 && COL_ACC2 + 2 * NOUT <= TMEM_COLS, "accumulator columns");
 enum { K_FULL = 0, K_EMPTY, T_FULL, T_EMPTY, R_FULL, HT_FULL, HT_FULL_B, HT_FULL_C, HT_FULL_D, ACC_FULL, STG_FULL0, STG_FULL1, NUM_BARS };
 
 struct Smem {
@@ -43,8 +49,8 @@ struct Smem {
     float W2t_hi[128 * KO], W2t_lo[128 * KO];      // rows = h, K = o
     float yK_hi[KP * NIN], yK_lo[KP * NIN];        // rows = p, K = k        (B of D1t), K-chunk pitch KP*16 B
     float dOK_hi[KP * KO], dOK_lo[KP * KO];        // rows = p, K = o        (B of D3t), K-chunk pitch KP*16 B
-    float yT_hi[NY * CH], yT_lo[NY * CH];          // rows = k (+ones), K = p (B of dW1)
-    float dOT_hi[NOUT * CH], dOT_lo[NOUT * CH];    // rows = o, K = p        (B of dW2t)
+    float yT[2 * NY * CH];                         // rows 0..63 = k (+ones) hi, 64..127 = lo ; K = p (B of dW1)
+    float dOT[2 * NOUT * CH];                      // rows 0..47 = o hi, 48..95 = lo ;          K = p (B of dW2t)
     // raw fp32 rows of a chunk: three contiguous blocks of the cell-sorted arrays, each filled by ONE TMA bulk
     // copy (double buffered; the 1344 16-byte LDGSTS this replaces took the loader warps ~3100 cycles per chunk)
     float stA[2][CH][NF];
@@ -92,11 +98,11 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
     // the ones column that yields db1, is rewritten per chunk because of the ragged last chunk)
     for (int i = tid; i < (NY - NIN) * CH; i += THREADS) {
         const int row = NIN + i / CH, pl = i - (i / CH) * CH;
-        s.yT_hi[fidx(NY, row, pl)] = 0.f; s.yT_lo[fidx(NY, row, pl)] = 0.f;
+        s.yT[fidx(2 * NY, row, pl)] = 0.f; s.yT[fidx(2 * NY, NY + row, pl)] = 0.f;
     }
     for (int i = tid; i < (NOUT - NO_PAD) * CH; i += THREADS) {
         const int row = NO_PAD + i / CH, pl = i - (i / CH) * CH;
-        s.dOT_hi[fidx(NOUT, row, pl)] = 0.f; s.dOT_lo[fidx(NOUT, row, pl)] = 0.f;
+        s.dOT[fidx(2 * NOUT, row, pl)] = 0.f; s.dOT[fidx(2 * NOUT, NOUT + row, pl)] = 0.f;
     }
     if (tid == 0) {
         mbar_init(&s.bar[K_FULL], LOADERS); mbar_init(&s.bar[K_EMPTY], 1);
@@ -196,21 +202,21 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
             if (lt == 0) SPHNCA_TL(2);
             // three convergent loops (one per staged block); in the A block a warp covers two particle groups whose
             // rows are 64 words apart, so its upper half reads the 4 particles in the order 1,0,3,2 (distinct banks)
-            auto put = [&](float* th, float* tl, uint32_t o, const float4 v) {
+            auto put = [&](float* t, uint32_t o, uint32_t lo_rows, const float4 v) {     // hi piece at o, lo piece lo_rows below
                 float4 hi, lo; split4(v, hi, lo);
-                *reinterpret_cast<float4*>(&th[o]) = hi; *reinterpret_cast<float4*>(&tl[o]) = lo;
+                *reinterpret_cast<float4*>(&t[o]) = hi; *reinterpret_cast<float4*>(&t[o + 4 * lo_rows]) = lo;
             };
 #pragma unroll
             for (int r = 0; r < NF * (CH / 4) / LOADERS; ++r) {           // A rows 0..15
                 const int i = lt + r * LOADERS, pg = i >> 4, row = i & 15, sw = (lane >> 4) & 1;
                 const float a = s.stA[buf][4 * pg + sw][row], b = s.stA[buf][4 * pg + (sw ^ 1)][row];
                 const float c = s.stA[buf][4 * pg + 2 + sw][row], d = s.stA[buf][4 * pg + 2 + (sw ^ 1)][row];
-                put(s.yT_hi, s.yT_lo, chunk_off(NY, row, pg) / 4, sw ? make_float4(b, a, d, c) : make_float4(a, b, c, d));
+                put(s.yT, chunk_off(2 * NY, row, pg) / 4, NY, sw ? make_float4(b, a, d, c) : make_float4(a, b, c, d));
             }
 #pragma unroll
             for (int r = 0; r < 2 * NF * (CH / 4) / LOADERS; ++r) {       // Y rows 16..47
                 const int i = lt + r * LOADERS, pg = i >> 5, row = i & 31;
-                put(s.yT_hi, s.yT_lo, chunk_off(NY, NF + row, pg) / 4,
+                put(s.yT, chunk_off(2 * NY, NF + row, pg) / 4, NY,
                     make_float4(s.stY[buf][4 * pg][row], s.stY[buf][4 * pg + 1][row], s.stY[buf][4 * pg + 2][row], s.stY[buf][4 * pg + 3][row]));
             }
 #pragma unroll
@@ -218,7 +224,7 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                 const int i = lt + r * LOADERS;
                 if (i < NO_PAD * (CH / 4)) {
                     const int pg = i / NO_PAD, row = i - pg * NO_PAD;
-                    put(s.dOT_hi, s.dOT_lo, chunk_off(NOUT, row, pg) / 4,
+                    put(s.dOT, chunk_off(2 * NOUT, row, pg) / 4, NOUT,
                         make_float4(s.stD[buf][4 * pg][row], s.stD[buf][4 * pg + 1][row], s.stD[buf][4 * pg + 2][row], s.stD[buf][4 * pg + 3][row]));
                 }
             }
@@ -226,7 +232,7 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                 float one[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) one[j] = (ch * CH + 4 * lt + j < n_total) ? 1.f : 0.f;
-                *reinterpret_cast<float4*>(&s.yT_hi[chunk_off(NY, NIN, lt) / 4]) = make_float4(one[0], one[1], one[2], one[3]);
+                *reinterpret_cast<float4*>(&s.yT[chunk_off(2 * NY, NIN, lt) / 4]) = make_float4(one[0], one[1], one[2], one[3]);
             }
             fence_proxy_async_smem();
             mbar_arrive(&s.bar[T_FULL]);
@@ -256,6 +262,7 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
         {   // warp-uniform issue: every lane runs the loop, one elected lane issues (tc_common.cuh)
             const uint32_t go = elect_one();
             const uint32_t idR = make_idesc_tf32(128, CH), idA1 = make_idesc_tf32(128, NY), idA2 = make_idesc_tf32(128, NOUT);
+            const uint32_t idA1c = make_idesc_tf32(128, 2 * NY), idA2c = make_idesc_tf32(128, 2 * NOUT);   // stacked [hi ; lo] B tiles
             int it = 0;
             for (int64_t ch = c0; ch < c1; ++ch, ++it) {
                 mbar_wait(&s.bar[K_FULL], it & 1);
@@ -293,17 +300,14 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
 #pragma unroll
                 for (int ks = 0; ks < CH / 8; ++ks) {
                     if (ks > 0 && (ks & 1) == 0) { mbar_wait(&s.bar[HT_FULL + ks / 2], it & 1); fence_after_sync(); }   // next 16 columns converted
-                    const uint64_t y_hi = make_smem_desc(smem_u32(s.yT_hi) + chunk_off(NY, 0, 2 * ks), NY * 16, 128);
-                    const uint64_t y_lo = make_smem_desc(smem_u32(s.yT_lo) + chunk_off(NY, 0, 2 * ks), NY * 16, 128);
-                    const uint64_t o_hi = make_smem_desc(smem_u32(s.dOT_hi) + chunk_off(NOUT, 0, 2 * ks), NOUT * 16, 128);
-                    const uint64_t o_lo = make_smem_desc(smem_u32(s.dOT_lo) + chunk_off(NOUT, 0, 2 * ks), NOUT * 16, 128);
+                    // one descriptor per tile: rows 0..N-1 of it are the hi tile, all 2N rows the stacked [hi ; lo] tile
+                    const uint64_t y_t = make_smem_desc(smem_u32(s.yT) + chunk_off(2 * NY, 0, 2 * ks), 2 * NY * 16, 128);
+                    const uint64_t o_t = make_smem_desc(smem_u32(s.dOT) + chunk_off(2 * NOUT, 0, 2 * ks), 2 * NOUT * 16, 128);
                     const bool acc = (it | ks) > 0;
-                    mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_DHLO + 8 * ks, y_hi, idA1, acc, go);
-                    mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_R3 + 8 * ks, y_lo, idA1, true, go);
-                    mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_R3 + 8 * ks, y_hi, idA1, true, go);
-                    mma_tf32_ts_e(tbase + COL_ACC2, tbase + COL_HLO + 8 * ks, o_hi, idA2, acc, go);
-                    mma_tf32_ts_e(tbase + COL_ACC2, tbase + COL_R1 + 8 * ks, o_lo, idA2, true, go);
-                    mma_tf32_ts_e(tbase + COL_ACC2, tbase + COL_R1 + 8 * ks, o_hi, idA2, true, go);
+                    mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_R3 + 8 * ks, y_t, idA1c, acc, go);      // dH_hi . [y_hi ; y_lo]
+                    mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_DHLO + 8 * ks, y_t, idA1, true, go);    // dH_lo . y_hi
+                    mma_tf32_ts_e(tbase + COL_ACC2, tbase + COL_R1 + 8 * ks, o_t, idA2c, acc, go);      // H_hi . [dO_hi ; dO_lo]
+                    mma_tf32_ts_e(tbase + COL_ACC2, tbase + COL_HLO + 8 * ks, o_t, idA2, true, go);     // H_lo . dO_hi
                 }
                 mma_commit_e(&s.bar[T_EMPTY], go);
                 SPHNCA_TL(8);
@@ -367,23 +371,24 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
             fence_after_sync();
 #pragma unroll
             for (int cc = 0; cc < NY; cc += 16) {
-                uint32_t r[16];
-                tmem_ld16(lane_addr + COL_ACC1 + cc, r); wait_ld();
+                uint32_t r[16], r2[16];                      // columns of the hi.(hi + lo of A) group and of the hi.lo group
+                tmem_ld16(lane_addr + COL_ACC1 + cc, r); tmem_ld16(lane_addr + COL_ACC1 + NY + cc, r2); wait_ld();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int k = cc + j;
-                    if (k < NIN) out[hg * NIN + k] = __uint_as_float(r[j]);
-                    else if (k == NIN) out[NH * NIN + hg] = __uint_as_float(r[j]);
+                    const float val = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                    if (k < NIN) out[hg * NIN + k] = val;
+                    else if (k == NIN) out[NH * NIN + hg] = val;
                 }
             }
 #pragma unroll
             for (int cc = 0; cc < NOUT; cc += 16) {
-                uint32_t r[16];
-                tmem_ld16(lane_addr + COL_ACC2 + cc, r); wait_ld();
+                uint32_t r[16], r2[16];
+                tmem_ld16(lane_addr + COL_ACC2 + cc, r); tmem_ld16(lane_addr + COL_ACC2 + NOUT + cc, r2); wait_ld();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int o = cc + j;
-                    if (o < NO_PAD) out[NH * NIN + NH + o * NH + hg] = __uint_as_float(r[j]);
+                    if (o < NO_PAD) out[NH * NIN + NH + o * NH + hg] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
                 }
             }
         } else {
