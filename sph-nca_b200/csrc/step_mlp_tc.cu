@@ -17,6 +17,7 @@
 // so its neighbour gathers all go to L2 and the sweep (41-58 k cycles per 128-particle tile, measured with
 // the in-kernel timeline) hides the whole MLP chain.  The extra HBM traffic of the split is one 192-byte
 // row read per particle.  Both paths are kept (sphnca_set_mlp_path) and produce identical tensors.
+#include <type_traits>
 #include "step_common.cuh"
 #include "tc_common.cuh"
 
@@ -29,8 +30,10 @@ constexpr int TILE = 128;
 constexpr int EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP0 = 9, LOAD_WARPS = 4, FIN_WARP0 = 13, FIN_WARPS = 4;
 constexpr int THREADS = (FIN_WARP0 + FIN_WARPS) * 32;          // 544
 constexpr int N2 = 32;
-constexpr uint32_t COL_D1 = 0, COL_HHI = 128, COL_HLO = 256, COL_D2 = 384, TMEM_COLS = 512;   // D2: 2 slots x 64 columns
-enum { Y_FULL = 0, Y_EMPTY, D1_FULL, D1_EMPTY, H_FULL, H_EMPTY, D2_FULL, D2_FULL1, D2_EMPTY, D2_EMPTY1, FIN_FULL, FIN_FULL1, NUM_BARS };
+// TMEM: one 128-column region per hidden half (GEMM1 writes the pre-activations there, the epilogue converts them IN PLACE to
+// H_hi), one shared H_lo region, D2 in two slots of 64 columns
+constexpr uint32_t COL_DA = 0, COL_DB = 128, COL_HLO = 256, COL_D2 = 384, TMEM_COLS = 512;
+enum { Y_FULL = 0, Y_EMPTY, D1_FULL, D1_FULL1, H_FULL, H_FULL1, H_EMPTY, D2_FULL, D2_FULL1, D2_EMPTY, D2_EMPTY1, FIN_FULL, FIN_FULL1, NUM_BARS };
 
 struct Smem {
     float W1_hi[2][128 * NIN], W1_lo[2][128 * NIN];
@@ -91,8 +94,8 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     if (tid < NO_PAD) s.b2[tid] = tid < c.n_out ? __ldg(prm.b2 + tid) : 0.f;
     if (tid == 0) {
         mbar_init(&s.bar[Y_FULL], LOAD_WARPS * 32); mbar_init(&s.bar[Y_EMPTY], 1);
-        mbar_init(&s.bar[D1_FULL], 1);              mbar_init(&s.bar[D1_EMPTY], EPI_WARPS * 32);
-        mbar_init(&s.bar[H_FULL], EPI_WARPS * 32);  mbar_init(&s.bar[H_EMPTY], 1);
+        mbar_init(&s.bar[D1_FULL], 1);              mbar_init(&s.bar[D1_FULL1], 1);
+        mbar_init(&s.bar[H_FULL], EPI_WARPS * 32);  mbar_init(&s.bar[H_FULL1], EPI_WARPS * 32);  mbar_init(&s.bar[H_EMPTY], 1);
         for (int q = 0; q < 2; ++q) {
             mbar_init(&s.bar[D2_FULL + q], 1); mbar_init(&s.bar[D2_EMPTY + q], FIN_WARPS * 32); mbar_init(&s.bar[FIN_FULL + q], EPI_WARPS * 32);
         }
@@ -141,53 +144,81 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
         }
     } else if (warp == MMA_WARP) {
         {   // warp-uniform issue: every lane runs the loop, one elected lane issues (tc_common.cuh)
+            // Software pipeline over tiles.  MMAs execute in issue order, so a GEMM1 may be issued into a hidden half's region
+            // right behind the GEMM2 MMAs that read it as H_hi:
+            //   G2a(i) | G1a(i+1) | G2b(i) | G1b(i+1) | G2a(i+1) ...
+            // GEMM1 of the next tile runs while the epilogue warps convert the other half, and each GEMM2 half issues its
+            // H_lo MMAs first and releases the shared H_lo region (H_EMPTY) before its H_hi MMAs.
             const uint32_t go = elect_one();
             const uint32_t idesc1 = make_idesc_tf32(TILE, 128), idesc2 = make_idesc_tf32(TILE, N2), idesc2c = make_idesc_tf32(TILE, 2 * N2);
             const uint32_t yh = smem_u32(s.Y_hi), yl = smem_u32(s.Y_lo);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                mbar_wait(&s.bar[Y_FULL], it & 1);
-                fence_after_sync();
-                SPHNCA_TL(1);
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    if (half == 1) { mbar_wait(&s.bar[D1_EMPTY], 0); fence_after_sync(); }
-                    else if (it > 0) { mbar_wait(&s.bar[D1_EMPTY], 1); fence_after_sync(); }
-                    const uint32_t wh = smem_u32(s.W1_hi[half]), wl = smem_u32(s.W1_lo[half]);
+            auto gemm1 = [&](const int half) {
+                const uint32_t wh = smem_u32(s.W1_hi[half]), wl = smem_u32(s.W1_lo[half]);
+                const uint32_t d1 = tbase + (half ? COL_DB : COL_DA);
 #pragma unroll
-                    for (int ks = 0; ks < NIN / 8; ++ks) {
-                        const uint64_t a_hi = make_smem_desc(yh + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
-                        const uint64_t a_lo = make_smem_desc(yl + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
-                        const uint64_t b_hi = make_smem_desc(wh + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                        const uint64_t b_lo = make_smem_desc(wl + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                        mma_tf32_ss_e(tbase + COL_D1, a_lo, b_hi, idesc1, ks > 0, go);
-                        mma_tf32_ss_e(tbase + COL_D1, a_hi, b_lo, idesc1, true, go);
-                        mma_tf32_ss_e(tbase + COL_D1, a_hi, b_hi, idesc1, true, go);
-                    }
-                    mma_commit_e(&s.bar[D1_FULL], go);
-                    SPHNCA_TL(2 + half);
+                for (int ks = 0; ks < NIN / 8; ++ks) {
+                    const uint64_t a_hi = make_smem_desc(yh + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
+                    const uint64_t a_lo = make_smem_desc(yl + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
+                    const uint64_t b_hi = make_smem_desc(wh + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
+                    const uint64_t b_lo = make_smem_desc(wl + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
+                    mma_tf32_ss_e(d1, a_lo, b_hi, idesc1, ks > 0, go);
+                    mma_tf32_ss_e(d1, a_hi, b_lo, idesc1, true, go);
+                    mma_tf32_ss_e(d1, a_hi, b_hi, idesc1, true, go);
                 }
+                mma_commit_e(&s.bar[D1_FULL + half], go);
+            };
+            auto gemm2 = [&](const int half, const uint32_t d2) {
+                const uint32_t w = smem_u32(s.W2[half]);
+                const uint32_t hhi = tbase + (half ? COL_DB : COL_DA);
+                // rows 0..31 of a W2 tile = hi, all 64 rows = the stacked [hi ; lo] tile.  H_lo part first; the very first MMA of
+                // a tile initialises all 64 columns of the slot (its extra H_lo . W_lo block is the term the split drops anyway)
+#pragma unroll
+                for (int ks = 0; ks < 128 / 8; ++ks) {
+                    const uint64_t b = make_smem_desc(w + chunk_off(2 * N2, 0, 2 * ks), 2 * N2 * 16, 128);
+                    if (half == 0 && ks == 0) mma_tf32_ts_e(d2, tbase + COL_HLO, b, idesc2c, false, go);
+                    else mma_tf32_ts_e(d2, tbase + COL_HLO + 8 * ks, b, idesc2, true, go);              // H_lo . W_hi
+                }
+                mma_commit_e(&s.bar[H_EMPTY], go);                                                      // H_lo region free again
+#pragma unroll
+                for (int ks = 0; ks < 128 / 8; ++ks) {
+                    const uint64_t b = make_smem_desc(w + chunk_off(2 * N2, 0, 2 * ks), 2 * N2 * 16, 128);
+                    mma_tf32_ts_e(d2, hhi + 8 * ks, b, idesc2c, true, go);                              // H_hi . [W_hi ; W_lo]
+                }
+            };
+            int it = 0;
+            if (blockIdx.x < num_tiles) {
+                mbar_wait(&s.bar[Y_FULL], 0);
+                fence_after_sync();
+                gemm1(0); gemm1(1);
                 mma_commit_e(&s.bar[Y_EMPTY], go);
+            }
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const bool next = tile + (int)gridDim.x < num_tiles;
                 const int slot = it & 1;                      // D2 is double buffered: the finalizer warps drain tile it-1 meanwhile
                 mbar_wait(&s.bar[D2_EMPTY + slot], ((it >> 1) & 1) ^ 1);
                 fence_after_sync();
                 const uint32_t d2 = tbase + COL_D2 + 2 * N2 * slot;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    mbar_wait(&s.bar[H_FULL], half);
+                mbar_wait(&s.bar[H_FULL], it & 1);
+                fence_after_sync();
+                SPHNCA_TL(1);
+                gemm2(0, d2);
+                SPHNCA_TL(4);
+                if (next) {
+                    mbar_wait(&s.bar[Y_FULL], (it + 1) & 1);
                     fence_after_sync();
-                    const uint32_t w = smem_u32(s.W2[half]);
-#pragma unroll
-                    for (int ks = 0; ks < 128 / 8; ++ks) {
-                        // rows 0..31 of this tile = W2 hi, all 64 rows = the stacked [hi ; lo] tile
-                        const uint64_t b = make_smem_desc(w + chunk_off(2 * N2, 0, 2 * ks), 2 * N2 * 16, 128);
-                        mma_tf32_ts_e(d2, tbase + COL_HHI + 8 * ks, b, idesc2c, (half | ks) > 0, go);   // H_hi . [W_hi ; W_lo]
-                        mma_tf32_ts_e(d2, tbase + COL_HLO + 8 * ks, b, idesc2, true, go);               // H_lo . W_hi
-                    }
-                    mma_commit_e(&s.bar[H_EMPTY], go);
-                    SPHNCA_TL(4 + half);
+                    gemm1(0);
+                    SPHNCA_TL(2);
                 }
+                mbar_wait(&s.bar[H_FULL1], it & 1);
+                fence_after_sync();
+                gemm2(1, d2);
                 mma_commit_e(&s.bar[D2_FULL + slot], go);
+                SPHNCA_TL(5);
+                if (next) {
+                    gemm1(1);
+                    mma_commit_e(&s.bar[Y_EMPTY], go);
+                    SPHNCA_TL(3);
+                }
             }
         }
     } else if (warp >= FIN_WARP0) {
@@ -275,51 +306,63 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int p = tile * TILE + m;
             const bool valid = p < n_total;
-            float o32 = 0.f;
+            float2 o32p = make_float2(0.f, 0.f);              // even / odd hidden units of the scalar-gate dot product
             uint32_t rmask[NH / 64];                          // this warp's 4 ReLU words: (half, chalf) -> word 4*half + 2*chalf + {0,1}
 #pragma unroll
             for (int wd = 0; wd < NH / 64; ++wd) rmask[wd] = 0u;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                mbar_wait(&s.bar[D1_FULL], half);
-                fence_after_sync();
-                // the next 16 columns are in flight while the current ones are converted (two register sets)
-                uint32_t r[2][16];
-                tmem_ld16(lane_addr + COL_D1 + chalf * 64, r[0]);
-                mbar_wait(&s.bar[H_EMPTY], half ^ 1);
+                const uint32_t d1 = lane_addr + (half ? COL_DB : COL_DA);
+                mbar_wait(&s.bar[D1_FULL + half], it & 1);
                 fence_after_sync();
                 if (tid == 0) SPHNCA_TL(6 + 2 * half);
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
+                // the next 16 columns are in flight while the current ones are converted (two register sets)
+                uint32_t r[2][16];
+                tmem_ld16(d1 + chalf * 64, r[0]);
+                // (a generic lambda per 16-column block: the block index must be a compile-time constant for the register sets)
+                auto block = [&](auto C4) {
+                    constexpr int c4 = decltype(C4)::value;
                     const int cc = chalf * 64 + c4 * 16;
                     uint32_t hi[16], lo[16];
                     wait_ld();
-                    if (c4 < 3) tmem_ld16(lane_addr + COL_D1 + cc + 16, r[(c4 + 1) & 1]);
+                    if (c4 < 3) tmem_ld16(d1 + cc + 16, r[(c4 + 1) & 1]);
                     uint32_t bits = 0;
+                    // packed fp32 pairs (FADD2 / FFMA2) for the bias add, the scalar-gate dot product and the lo remainder:
+                    // the 8 epilogue warps are issue-bound, every instruction saved per element counts
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 16; j += 2) {
                         const int n = half * 128 + cc + j;
-                        const float pre = __uint_as_float(r[c4 & 1][j]) + s.b1[n];
-                        bits |= (pre > 0.f ? 1u : 0u) << j;
-                        const float hv = fmaxf(pre, 0.f);
-                        o32 = fmaf(hv, s.w2_last[n], o32);
-                        float h_, l_; split_tf32(hv, h_, l_);
-                        hi[j] = __float_as_uint(h_); lo[j] = __float_as_uint(l_);
+                        const float2 pre = fadd2(make_float2(__uint_as_float(r[c4 & 1][j]), __uint_as_float(r[c4 & 1][j + 1])),
+                                                 *reinterpret_cast<const float2*>(&s.b1[n]));
+                        bits |= (pre.x > 0.f ? 1u : 0u) << j;
+                        bits |= (pre.y > 0.f ? 1u : 0u) << (j + 1);
+                        const float2 hv = make_float2(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f));
+                        o32p = ffma2(hv, *reinterpret_cast<const float2*>(&s.w2_last[n]), o32p);
+                        const float2 h_ = make_float2(__uint_as_float((__float_as_uint(hv.x) + 0x1000u) & 0xffffe000u),
+                                                      __uint_as_float((__float_as_uint(hv.y) + 0x1000u) & 0xffffe000u));   // split_tf32
+                        const float2 l_ = fsub2(hv, h_);
+                        hi[j] = __float_as_uint(h_.x); hi[j + 1] = __float_as_uint(h_.y);
+                        lo[j] = __float_as_uint(l_.x); lo[j + 1] = __float_as_uint(l_.y);
                     }
                     rmask[2 * half + (c4 >> 1)] |= bits << ((c4 & 1) * 16);
-                    tmem_st16(lane_addr + COL_HHI + cc, hi);
+                    tmem_st16(d1 + cc, hi);                   // in place: pre-activations -> H_hi
+                    if (c4 == 0) {                            // the shared H_lo region: free once the previous GEMM2 half's H_lo MMAs are done
+                        mbar_wait(&s.bar[H_EMPTY], half ^ 1);
+                        fence_after_sync();
+                    }
                     tmem_st16(lane_addr + COL_HLO + cc, lo);
-                }
+                };
+                block(std::integral_constant<int, 0>{}); block(std::integral_constant<int, 1>{});
+                block(std::integral_constant<int, 2>{}); block(std::integral_constant<int, 3>{});
                 wait_st();
                 fence_before_sync();
-                mbar_arrive(&s.bar[D1_EMPTY]);
-                mbar_arrive(&s.bar[H_FULL]);
+                mbar_arrive(&s.bar[H_FULL + half]);
                 if (tid == 0) SPHNCA_TL(7 + 2 * half);
             }
             // hand the partial scalar-gate sum to the row's finalizer thread.  The slot was last read by the finalizer of tile
             // it-2, before it released D2's slot; GEMM2 of this tile waited for that release and this epilogue for GEMM2.
             const int slot = it & 1;
-            s.o32[slot][chalf][m] = o32;
+            s.o32[slot][chalf][m] = o32p.x + o32p.y;
             mbar_arrive(&s.bar[FIN_FULL + slot]);
             if (valid) {
                 // ReLU words: hidden 0..63 -> words 0,1 (group 0); 64..127 -> 2,3 (group 1); 128..191 -> 4,5 (group 0); 192..255 -> 6,7 (group 1)

@@ -337,7 +337,7 @@ class RolloutStates:
 
 
 # Activation checkpointing inside the rollout node: True / False, or "auto" = checkpoint when
-# the full tape (TAPE_BYTES per particle-step) would take more than AUTO_CHECKPOINT_FRACTION of the free HBM.
+# the full tape (TAPE_BYTES per particle-step) would take more than AUTO_CHECKPOINT_FRACTION of the HBM torch does not hold.
 CHECKPOINT = "auto"
 TAPE_BYTES = 4 * (32 + 36 + 8) + 1
 AUTO_CHECKPOINT_FRACTION = 0.5
@@ -347,8 +347,9 @@ def _tape_mode(N, steps, device, checkpoint):
     if checkpoint is None:
         checkpoint = CHECKPOINT
     if checkpoint == "auto":
-        free, _ = torch.cuda.mem_get_info(device)
-        free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)   # torch's cached blocks are reusable
+        # the device's capacity minus what torch holds live (host-side counters: cudaMemGetInfo costs ~25 ms per call
+        # on a busy device and this runs once per rollout; torch's cached-but-free blocks are reusable)
+        free = torch.cuda.get_device_properties(device).total_memory - torch.cuda.memory_allocated(device)
         checkpoint = N * steps * TAPE_BYTES > AUTO_CHECKPOINT_FRACTION * free
     return 2 if checkpoint else 1
 

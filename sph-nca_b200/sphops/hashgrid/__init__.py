@@ -133,7 +133,8 @@ class Hashgrid:
                 cum = torch.cumsum(slots, 0, dtype=torch.int64)
                 base = ((cum - slots) * 8).contiguous()
                 total = int(cum[-1].item()) * 8
-                free, _ = torch.cuda.mem_get_info(dev)
+                # capacity minus torch's live tensors (host-side counters; cudaMemGetInfo stalls ~25 ms on a busy device)
+                free = torch.cuda.get_device_properties(dev).total_memory - torch.cuda.memory_allocated(dev)
                 if 0 < total and total * 28 <= self.PAIR_LIST_MEMORY_FRACTION * free:
                     f32 = dict(dtype=torch.float32, device=dev)
                     J = torch.empty((total,), dtype=torch.int32, device=dev)
