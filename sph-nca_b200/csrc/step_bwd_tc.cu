@@ -7,8 +7,14 @@
 //                      the direct part of dL/dA, the scalar-gate column dO[32], the ReLU bits -> smem.
 //   MMA warp (1 lane)  GEMM3  D3[128p x 128h] = dO[128 x 32] . W2t_half^T      (B = W2^T stored K-major)
 //                      GEMM4  Dy[128p x 48]  += dH[128 x 128](TMEM) . W1t_half^T (B = W1^T stored K-major)
-//   epilogue warps (4) tcgen05.ld D3 -> (+ dO[32]*W2[32][h]) -> ReLU bits -> tf32 hi/lo -> tcgen05.st dH
-//                      IN PLACE over D3; final: tcgen05.ld Dy -> dL/dY (32) and dL/dA direct part (16).
+//   epilogue warps (8) tcgen05.ld D3 -> (+ dO[32]*W2[32][h]) -> ReLU bits -> tf32 hi/lo -> tcgen05.st dH
+//                      IN PLACE over D3 (hi) and into the shared dH_lo region.
+//   finalizer warps (4) tcgen05.ld Dy -> dL/dY (32) and dL/dA direct part (16): the row stores of tile i run
+//                      beside the MMAs and the dH epilogue of tile i+1.
+//   The MMA warp runs a software pipeline over tiles (MMAs execute in issue order):
+//       G4a(i) | G3a(i+1) | G4b(i) | G3b(i+1) | G4a(i+1) ...
+//   each hidden half has its own D3/dH_hi region, GEMM3 of the next tile is issued right behind the GEMM4 MMAs that
+//   read the region, and each GEMM4 half issues its dH_lo MMAs first and then releases the dH_lo region.
 //
 // (MN-major tf32 operands need the SW128_32B layout, so instead of re-viewing the forward's W1/W2 tiles
 //  the kernel stages transposed K-major copies: W2^T 64 KB + W1^T 96 KB, hi/lo.)
@@ -16,8 +22,8 @@
 // TMEM, N=48 59 cycles, N=128 71), so the hi and lo copies of W1^T are STACKED along N (96 rows): dH_hi . [W_hi ; W_lo]
 // is one MMA into Dy columns 0..47 | 48..95 and dH_lo . W_hi adds to columns 0..47 -- 2 MMAs per k-step instead of 3;
 // the final epilogue adds the two column groups.
-// TMEM: D3/dH_hi 128 + dH_lo 128 + Dy 96 = 352 columns.  MMAs execute in issue order, so GEMM3 of the
-// next half may be issued right behind GEMM4 of the previous one on the same columns.
+// TMEM: D3/dH_hi 2 x 128 + dH_lo 128 + Dy 96 = 480 columns.
+#include <type_traits>
 #include "step_common.cuh"
 #include "tc_common.cuh"
 
@@ -28,11 +34,11 @@ using namespace tc;
 namespace bw {
 constexpr int TILE = 128;
 // epilogue warps 0..7: warp & 3 = TMEM lane quarter, warp >> 2 = which 64 of a half's 128 hidden columns
-constexpr int EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP0 = 9, LOAD_WARPS = 4;
-constexpr int THREADS = (LOAD_WARP0 + LOAD_WARPS) * 32;      // 416
+constexpr int EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP0 = 9, LOAD_WARPS = 4, FIN_WARP0 = 13, FIN_WARPS = 4;
+constexpr int THREADS = (FIN_WARP0 + FIN_WARPS) * 32;        // 544
 constexpr int KO = 32;                                       // outputs handled by the tensor core
-constexpr uint32_t COL_D3 = 0, COL_DHLO = 128, COL_DY = 256, TMEM_COLS = 512;
-enum { DO_FULL = 0, DO_EMPTY, D3_FULL, DH_FULL, DY_FULL, DY_EMPTY, NUM_BARS };
+constexpr uint32_t COL_DA = 0, COL_DB = 128, COL_DHLO = 256, COL_DY = 384, TMEM_COLS = 512;
+enum { DO_FULL = 0, DO_EMPTY, D3_FULL, D3_FULL1, DH_FULL, DH_FULL1, DH_EMPTY, DY_FULL, DY_EMPTY, NUM_BARS };
 
 struct Smem {
     float W2t_hi[2][128 * KO], W2t_lo[2][128 * KO];       // [hidden half] rows = h (128), K = o (32)
@@ -73,8 +79,9 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     for (int i = tid; i < NH; i += THREADS) s.w2_last[i] = c.n_out > KO ? __ldg(prm.W2 + (size_t)KO * NH + i) : 0.f;
     if (tid == 0) {
         mbar_init(&s.bar[DO_FULL], LOAD_WARPS * 32); mbar_init(&s.bar[DO_EMPTY], 1);
-        mbar_init(&s.bar[D3_FULL], 1);               mbar_init(&s.bar[DH_FULL], EPI_WARPS * 32);
-        mbar_init(&s.bar[DY_FULL], 1);               mbar_init(&s.bar[DY_EMPTY], 4 * 32);
+        mbar_init(&s.bar[D3_FULL], 1);               mbar_init(&s.bar[D3_FULL1], 1);
+        mbar_init(&s.bar[DH_FULL], EPI_WARPS * 32);  mbar_init(&s.bar[DH_FULL1], EPI_WARPS * 32);  mbar_init(&s.bar[DH_EMPTY], 1);
+        mbar_init(&s.bar[DY_FULL], 1);               mbar_init(&s.bar[DY_EMPTY], FIN_WARPS * 32);
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc(&s.tmem_base, TMEM_COLS);
@@ -84,7 +91,7 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     fence_after_sync();
     const uint32_t tbase = s.tmem_base;
 
-    if (warp >= LOAD_WARP0) {
+    if (warp >= LOAD_WARP0 && warp < FIN_WARP0) {
         // ======================= prologue: dL/d(MLP output) and the direct dL/dA part =======================
         const int m = tid - LOAD_WARP0 * 32;
         int it = 0;
@@ -143,7 +150,8 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
 #pragma unroll
                 for (int k = 0; k < NO_PAD / 4; ++k) do4[k] = make_float4(dO[4*k], dO[4*k+1], dO[4*k+2], dO[4*k+3]);
             }
-            mbar_wait(&s.bar[DO_EMPTY], (it & 1) ^ 1);        // GEMM3 of the previous tile consumed the dO tile
+            // GEMM3 of the previous tile consumed the dO tile and the finalizer of tile it-2 this slot's dAdir rows
+            mbar_wait(&s.bar[DO_EMPTY], (it & 1) ^ 1);
 #pragma unroll
             for (int ch = 0; ch < KO / 4; ++ch) {
                 float hi[4], lo[4];
@@ -168,108 +176,144 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             const uint32_t go = elect_one();
             const uint32_t idesc3 = make_idesc_tf32(TILE, 128), idesc4 = make_idesc_tf32(TILE, NIN), idesc4c = make_idesc_tf32(TILE, 2 * NIN);
             const uint32_t ah = smem_u32(s.dO_hi), al = smem_u32(s.dO_lo);
-            auto gemm3 = [&](int half) {
+            auto gemm3 = [&](const int half) {
                 const uint32_t wh = smem_u32(s.W2t_hi[half]), wl = smem_u32(s.W2t_lo[half]);
+                const uint32_t d3 = tbase + (half ? COL_DB : COL_DA);
 #pragma unroll
                 for (int ks = 0; ks < KO / 8; ++ks) {
                     const uint64_t a_hi = make_smem_desc(ah + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
                     const uint64_t a_lo = make_smem_desc(al + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
                     const uint64_t b_hi = make_smem_desc(wh + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
                     const uint64_t b_lo = make_smem_desc(wl + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                    mma_tf32_ss_e(tbase + COL_D3, a_lo, b_hi, idesc3, ks > 0, go);
-                    mma_tf32_ss_e(tbase + COL_D3, a_hi, b_lo, idesc3, true, go);
-                    mma_tf32_ss_e(tbase + COL_D3, a_hi, b_hi, idesc3, true, go);
+                    mma_tf32_ss_e(d3, a_lo, b_hi, idesc3, ks > 0, go);
+                    mma_tf32_ss_e(d3, a_hi, b_lo, idesc3, true, go);
+                    mma_tf32_ss_e(d3, a_hi, b_hi, idesc3, true, go);
                 }
+                mma_commit_e(&s.bar[D3_FULL + half], go);
             };
-            auto gemm4 = [&](int half) {
+            auto gemm4 = [&](const int half) {
                 const uint32_t w = smem_u32(s.W1t[half]);
+                const uint32_t dhhi = tbase + (half ? COL_DB : COL_DA);
+                // rows 0..47 of a W1^T tile = hi, all 96 rows = the stacked [hi ; lo] tile.  dH_lo part first; the very first
+                // MMA of a tile initialises all 96 Dy columns (its extra dH_lo . W_lo block is the term the split drops anyway)
 #pragma unroll
                 for (int ks = 0; ks < 128 / 8; ++ks) {
-                    // rows 0..47 of this tile = W1^T hi, all 96 rows = the stacked [hi ; lo] tile
                     const uint64_t b = make_smem_desc(w + chunk_off(2 * NIN, 0, 2 * ks), 2 * NIN * 16, 128);
-                    mma_tf32_ts_e(tbase + COL_DY, tbase + COL_D3 + 8 * ks, b, idesc4c, (half | ks) > 0, go);   // dH_hi . [W_hi ; W_lo]
-                    mma_tf32_ts_e(tbase + COL_DY, tbase + COL_DHLO + 8 * ks, b, idesc4, true, go);             // dH_lo . W_hi
+                    if (half == 0 && ks == 0) mma_tf32_ts_e(tbase + COL_DY, tbase + COL_DHLO, b, idesc4c, false, go);
+                    else mma_tf32_ts_e(tbase + COL_DY, tbase + COL_DHLO + 8 * ks, b, idesc4, true, go);         // dH_lo . W_hi
+                }
+                mma_commit_e(&s.bar[DH_EMPTY], go);                                                             // dH_lo region free again
+#pragma unroll
+                for (int ks = 0; ks < 128 / 8; ++ks) {
+                    const uint64_t b = make_smem_desc(w + chunk_off(2 * NIN, 0, 2 * ks), 2 * NIN * 16, 128);
+                    mma_tf32_ts_e(tbase + COL_DY, dhhi + 8 * ks, b, idesc4c, true, go);                         // dH_hi . [W_hi ; W_lo]
                 }
             };
             int it = 0;
+            if (blockIdx.x < num_tiles) {
+                mbar_wait(&s.bar[DO_FULL], 0);
+                fence_after_sync();
+                gemm3(0); gemm3(1);
+            }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                mbar_wait(&s.bar[DO_FULL], it & 1);
+                const bool next = tile + (int)gridDim.x < num_tiles;
+                mbar_wait(&s.bar[DH_FULL], it & 1);
                 fence_after_sync();
-                gemm3(0);
-                mma_commit_e(&s.bar[D3_FULL], go);
-                mbar_wait(&s.bar[DH_FULL], 0);
+                mbar_wait(&s.bar[DY_EMPTY], (it & 1) ^ 1);    // the finalizer drained Dy (and its dAdir rows) of the previous tile
                 fence_after_sync();
-                mbar_wait(&s.bar[DY_EMPTY], (it & 1) ^ 1);    // epilogue drained Dy of the previous tile
-                fence_after_sync();
-                gemm4(0);
-                gemm3(1);                                     // in issue order behind GEMM4(0) on the same columns
-                mma_commit_e(&s.bar[D3_FULL], go);
+                // loader release: GEMM3 of THIS tile (issued one iteration ago) has read the dO tile, and -- by the wait above --
+                // the finalizer of tile it-1 is done with its smem slot, the one the loader of tile it+1 writes
                 mma_commit_e(&s.bar[DO_EMPTY], go);
-                mbar_wait(&s.bar[DH_FULL], 1);
+                gemm4(0);
+                if (next) {
+                    mbar_wait(&s.bar[DO_FULL], (it + 1) & 1);
+                    fence_after_sync();
+                    gemm3(0);
+                }
+                mbar_wait(&s.bar[DH_FULL1], it & 1);
                 fence_after_sync();
                 gemm4(1);
                 mma_commit_e(&s.bar[DY_FULL], go);
+                if (next) gemm3(1);
             }
         }
-    } else {
-        // ======================= epilogue =======================
-        const int m = (warp & 3) * 32 + lane;
-        const int chalf = warp >> 2;
+    } else if (warp >= FIN_WARP0) {
+        // ======================= finalizer: thread = tile row; Dy -> dL/dY and the direct dL/dA part =======================
+        const int m = (warp & 3) * 32 + lane;                 // a warp may only touch TMEM lanes 32*(warp % 4)..+31
         const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int p = tile * TILE + m;
             const bool valid = p < n_total;
             const int slot = it & 1;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                mbar_wait(&s.bar[D3_FULL], half);
-                fence_after_sync();
-                const float d32 = s.dO32[slot][m];
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const int cc = chalf * 64 + c4 * 16;
-                    uint32_t r[16], hi[16], lo[16];
-                    tmem_ld16(lane_addr + COL_D3 + cc, r);
-                    wait_ld();
-                    const uint32_t bits = s.relu[slot][m][(half * 128 + cc) >> 5] >> (cc & 16);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = half * 128 + cc + j;
-                        const float dh = ((bits >> j) & 1u) ? fmaf(d32, s.w2_last[n], __uint_as_float(r[j])) : 0.f;
-                        float h_, l_; split_tf32(dh, h_, l_);
-                        hi[j] = __float_as_uint(h_); lo[j] = __float_as_uint(l_);
-                    }
-                    tmem_st16(lane_addr + COL_D3 + cc, hi);       // in place: D3 -> dH_hi
-                    tmem_st16(lane_addr + COL_DHLO + cc, lo);
-                }
-                wait_st();
-                fence_before_sync();
-                mbar_arrive(&s.bar[DH_FULL]);
-            }
-            if (chalf != 0) continue;                         // the final part belongs to the first column-half warps
             mbar_wait(&s.bar[DY_FULL], it & 1);
             fence_after_sync();
             float dy[NIN];
 #pragma unroll
             for (int cc = 0; cc < NIN; cc += 16) {
-                uint32_t r[16], r2[16];
+                uint32_t r[16], r2[16];                       // hi.(hi+lo of dH) group and hi.lo group of the stacked GEMM4
                 tmem_ld16(lane_addr + COL_DY + cc, r); tmem_ld16(lane_addr + COL_DY + NIN + cc, r2); wait_ld();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) dy[cc + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
             }
+            float4 dir[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dir[k] = *reinterpret_cast<const float4*>(&s.dAdir[slot][m][4 * k]);
             fence_before_sync();
-            mbar_arrive(&s.bar[DY_EMPTY]);
+            mbar_arrive(&s.bar[DY_EMPTY]);                    // Dy and this slot's dAdir rows are in registers
             if (valid) {
                 float4* d4 = reinterpret_cast<float4*>(dAdir_s + (size_t)p * NF);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 a = *reinterpret_cast<const float4*>(&s.dAdir[slot][m][4 * k]);
-                    d4[k] = make_float4(a.x + dy[4*k], a.y + dy[4*k+1], a.z + dy[4*k+2], a.w + dy[4*k+3]);
-                }
+                for (int k = 0; k < 4; ++k)
+                    d4[k] = make_float4(dir[k].x + dy[4*k], dir[k].y + dy[4*k+1], dir[k].z + dy[4*k+2], dir[k].w + dy[4*k+3]);
                 float4* g4 = reinterpret_cast<float4*>(dY_s + (size_t)p * 2 * NF);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) g4[k] = make_float4(dy[NF+4*k], dy[NF+4*k+1], dy[NF+4*k+2], dy[NF+4*k+3]);
+            }
+        }
+    } else {
+        // ======================= epilogue: dH = (D3 + dO[32] W2[32][h]) * ReLU bits, tf32 hi (in place) / lo =======================
+        const int m = (warp & 3) * 32 + lane;
+        const int chalf = warp >> 2;
+        const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int slot = it & 1;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t d3 = lane_addr + (half ? COL_DB : COL_DA);
+                mbar_wait(&s.bar[D3_FULL + half], it & 1);
+                fence_after_sync();
+                const float d32 = s.dO32[slot][m];
+                // the next 16 columns are in flight while the current ones are converted (two register sets)
+                uint32_t r[2][16];
+                tmem_ld16(d3 + chalf * 64, r[0]);
+                auto block = [&](auto C4) {
+                    constexpr int c4 = decltype(C4)::value;
+                    const int cc = chalf * 64 + c4 * 16;
+                    uint32_t hi[16], lo[16];
+                    wait_ld();
+                    if (c4 < 3) tmem_ld16(d3 + cc + 16, r[(c4 + 1) & 1]);
+                    const uint32_t bits = s.relu[slot][m][(half * 128 + cc) >> 5] >> (cc & 16);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = half * 128 + cc + j;
+                        const float dh = ((bits >> j) & 1u) ? fmaf(d32, s.w2_last[n], __uint_as_float(r[c4 & 1][j])) : 0.f;
+                        float h_, l_; split_tf32(dh, h_, l_);
+                        hi[j] = __float_as_uint(h_); lo[j] = __float_as_uint(l_);
+                    }
+                    tmem_st16(d3 + cc, hi);                   // in place: D3 -> dH_hi
+                    if (c4 == 0) {                            // the shared dH_lo region: free once the previous GEMM4 half's dH_lo MMAs are done
+                        mbar_wait(&s.bar[DH_EMPTY], half ^ 1);
+                        fence_after_sync();
+                    }
+                    tmem_st16(lane_addr + COL_DHLO + cc, lo);
+                };
+                block(std::integral_constant<int, 0>{}); block(std::integral_constant<int, 1>{});
+                block(std::integral_constant<int, 2>{}); block(std::integral_constant<int, 3>{});
+                wait_st();
+                fence_before_sync();
+                mbar_arrive(&s.bar[DH_FULL + half]);
             }
         }
     }
