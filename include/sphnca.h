@@ -139,6 +139,7 @@ int32_t sphnca_step_mlp(int64_t N, const float* A_s, const float* Y_s, const uin
  *   2           same, forward fused into one persistent kernel (csrc/step_tc.cu);
  *   0           fp32 CUDA-core MLP (csrc/step.cu). */
 int32_t sphnca_set_mlp_path(int32_t path);
+int32_t sphnca_get_mlp_path(void);
 /* Implementation switch of the two hot sweeps (sphnca_step_perceive, sphnca_step_adjoint): 0 (default) =
  * one-thread-per-particle gathers out of L1/L2 with packed-pair FMAs, 1 = shared-memory tile engine with
  * in-radius compaction (csrc/sweep_tile.cuh; measured slower on B200, kept for A/B), 2 = sphnca_step_perceive
@@ -207,6 +208,35 @@ int32_t sphnca_mlp_wgrad(int64_t N, const float* A_s, const float* Y_s, const fl
 /* sphnca_step_adjoint: dA_s = dAdir_s + (adjoint of the perception sweep applied to dY_s). */
 int32_t sphnca_step_adjoint(const sphnca_grid* g, const float* xv4, const float* dY_s, const float* dAdir_s,
                             const sphnca_step_params* p, float* dA_s, void* stream);
+
+/* ---- fire lists: the MLP half of a step only for the particles whose fire-mask draw came up ------------------------
+ * Reference code/nca.py:100-107 evaluates the MLP for every particle and keeps the old state where the stochastic
+ * update mask is off (`torch.where(update_mask, nA, A)`): for those particles the MLP output is discarded and no
+ * gradient reaches the MLP, so skipping them changes no result.  With fire rate 0.5 it halves the tensor-core work.
+ *   sphnca_fire_list        rows[0..*count) = sorted positions of the fired particles in increasing order (deterministic
+ *                           ordered compaction); not-fired rows: A_new_s = A_s, alive byte.  count is a DEVICE int32 that
+ *                           the _list kernels read themselves: no host synchronisation.
+ *   sphnca_step_mlp_list    sphnca_step_mlp over the listed rows.  O_c [N,36], relu_c [N,8] and the optional compact
+ *                           copies A_c [N,16], Y_c [N,32] (contiguous input of sphnca_mlp_wgrad_list) are indexed by
+ *                           list position; A_new_s, alive_s, flags_s by particle.
+ *   sphnca_step_bwd_list    sphnca_step_bwd over the listed rows (dO_c by list position, dY_s / dAdir_s by particle);
+ *   sphnca_step_bwd_unfired the not-fired rows of the same step: dY_s = 0, dAdir_s = living ? dA_next_s : 0.
+ *   sphnca_mlp_wgrad_list   sphnca_mlp_wgrad over the first *count rows of the compact arrays (workspace sized for N). */
+int32_t sphnca_fire_list_workspace_bytes(int64_t N, size_t* bytes);
+int32_t sphnca_fire_list(int64_t N, const uint8_t* fire_s, const float* A_s, int32_t use_alpha, int32_t* rows,
+                         int32_t* count, float* A_new_s, uint8_t* alive_s, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int32_t sphnca_step_mlp_list(int64_t N, const int32_t* rows, const int32_t* count, const float* A_s, const float* Y_s,
+                             const sphnca_step_params* p, float* A_new_s, uint8_t* alive_s, float* O_c, uint8_t* flags_s,
+                             uint32_t* relu_c, float* A_c, float* Y_c, void* stream);
+int32_t sphnca_step_bwd_list(int64_t N, const int32_t* rows, const int32_t* count, const float* A_c, const float* O_c,
+                             const uint8_t* flags_s, const uint32_t* relu_c, const float* dA_next_s,
+                             const sphnca_step_params* p, float* dO_c, float* dY_s, float* dAdir_s, void* stream);
+int32_t sphnca_step_bwd_unfired(int64_t N, const uint8_t* flags_s, const float* dA_next_s, float* dY_s, float* dAdir_s,
+                                void* stream);
+int32_t sphnca_mlp_wgrad_list(int64_t N, const int32_t* count, const float* A_c, const float* Y_c, const float* dO_c,
+                              const sphnca_step_params* p, float* dW1, float* db1, float* dW2, float* db2,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

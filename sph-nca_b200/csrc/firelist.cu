@@ -1,0 +1,174 @@
+// Fire lists: the MLP half of an NCA step only matters for the particles whose fire-mask draw came up.
+//
+// Reference code/nca.py:100-107 evaluates the MLP for EVERY particle and then keeps the old state where the
+// stochastic update mask is off (`torch.where(update_mask, nA, A)`): for those particles the MLP output is
+// discarded in the forward, and in the backward no gradient reaches the MLP (dL/dO == 0, so they add exactly 0
+// to dW1, db1, dW2, db2 and to dL/dY).  With the default fire rate 0.5 that is half of all tensor-core work.
+//
+//   fire_list        rows[0..count) = sorted positions of the fired particles, in increasing order (ordered
+//                    compaction: block counts -> single-block scan -> in-block ranks; no atomics, deterministic);
+//                    the not-fired rows get their new state right here: A_new = A, alive byte from A.
+//   bwd_unfired      the backward of those rows: dL/dY = 0, direct dL/dA = (living ? dL/dA_new : 0).
+//
+// The tensor-core kernels (step_mlp_tc.cu, step_bwd_tc.cu, wgrad_tc.cu) then run over the `count` listed rows only;
+// `count` stays on the device (they read it from memory), so there is no host synchronisation.
+#include "step_common.cuh"
+
+namespace sphnca {
+
+namespace fl {
+constexpr int THREADS = 256, PER_THREAD = 4, BLOCK_ROWS = THREADS * PER_THREAD;   // 1024 rows per block
+}
+
+__global__ void __launch_bounds__(fl::THREADS)
+fire_count_kernel(int64_t n, const uint8_t* __restrict__ fire_s, int32_t* __restrict__ block_count) {
+    using namespace fl;
+    const int64_t base = (int64_t)blockIdx.x * BLOCK_ROWS + (int64_t)threadIdx.x * PER_THREAD;
+    int c = 0;
+    if (base + PER_THREAD <= n) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(fire_s + base);      // 4 bytes, 4-aligned (base % 4 == 0)
+        c = ((w & 0xffu) != 0) + ((w & 0xff00u) != 0) + ((w & 0xff0000u) != 0) + ((w & 0xff000000u) != 0);
+    } else {
+        for (int k = 0; k < PER_THREAD; ++k) c += (base + k < n && fire_s[base + k] != 0) ? 1 : 0;
+    }
+    __shared__ int wsum[THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) t += wsum[w];
+        block_count[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the block counts in place (one block; fixed order), total -> count[0]
+__global__ void __launch_bounds__(1024)
+fire_scan_kernel(int nb, int32_t* __restrict__ block_count, int32_t* __restrict__ count) {
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += 1024) {
+        const int i = b0 + threadIdx.x;
+        const int v = i < nb ? block_count[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = wsum[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += y; }
+            wsum[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int incl = x + (threadIdx.x >= 32 ? wsum[(threadIdx.x >> 5) - 1] : 0);
+        if (i < nb) block_count[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count[0] = carry_s;
+}
+
+__global__ void __launch_bounds__(fl::THREADS)
+fire_fill_kernel(int64_t n, const uint8_t* __restrict__ fire_s, const int32_t* __restrict__ block_off,
+                 const float* __restrict__ A_s, int use_alpha, int32_t* __restrict__ rows,
+                 float* __restrict__ A_new_s, uint8_t* __restrict__ alive_s) {
+    using namespace fl;
+    const int64_t base = (int64_t)blockIdx.x * BLOCK_ROWS + (int64_t)threadIdx.x * PER_THREAD;
+    bool f[PER_THREAD];
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) { f[k] = base + k < n && fire_s[base + k] != 0; c += f[k] ? 1 : 0; }
+    // exclusive rank of this thread's first row among the block's fired rows
+    __shared__ int wsum[THREADS / 32];
+    int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    int before = x - c;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += wsum[w];
+    int slot = block_off[blockIdx.x] + before;
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+        const int64_t p = base + k;
+        if (p >= n) break;
+        if (f[k]) { rows[slot++] = (int32_t)p; continue; }
+        // not fired: the state is carried over unchanged (reference nca.py:107); fire bit of the flags stays 0
+        const float4* a4 = reinterpret_cast<const float4*>(A_s + p * NF);
+        float4* o4 = reinterpret_cast<float4*>(A_new_s + p * NF);
+        const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), a2 = __ldg(a4 + 2), a3 = __ldg(a4 + 3);
+        o4[0] = a0; o4[1] = a1; o4[2] = a2; o4[3] = a3;
+        alive_s[p] = use_alpha ? (a0.w > 0.1f ? 1 : 0) : 1;
+    }
+}
+
+// backward of the not-fired rows: thread = one 16-byte piece of a row's (dAdir 4 | dY 8) pieces, coalesced
+__global__ void __launch_bounds__(256)
+step_bwd_unfired_kernel(int64_t n, const uint8_t* __restrict__ flags_s, const float* __restrict__ dAn_s,
+                        float* __restrict__ dY_s, float* __restrict__ dAdir_s) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = t / 12;
+    const int piece = (int)(t - p * 12);
+    if (p >= n) return;
+    const uint8_t fl_ = flags_s[p];
+    if (fl_ & 4) return;                                      // fired rows belong to the tensor-core kernel
+    if (piece < 4) {
+        const bool living = (fl_ & 1) && (fl_ & 2);
+        const float4 g = living ? __ldg(reinterpret_cast<const float4*>(dAn_s + p * NF) + piece) : make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(dAdir_s + p * NF)[piece] = g;
+    } else {
+        reinterpret_cast<float4*>(dY_s + p * 2 * NF)[piece - 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+}  // namespace sphnca
+
+using namespace sphnca;
+
+extern "C" {
+
+int32_t sphnca_fire_list_workspace_bytes(int64_t N, size_t* bytes) {
+    SPHNCA_CHECK_ARG(N >= 0 && bytes, "bad argument");
+    *bytes = (size_t)((N + fl::BLOCK_ROWS - 1) / fl::BLOCK_ROWS + 1) * sizeof(int32_t);
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_fire_list(int64_t N, const uint8_t* fire_s, const float* A_s, int32_t use_alpha, int32_t* rows,
+                         int32_t* count, float* A_new_s, uint8_t* alive_s, void* workspace, size_t workspace_bytes,
+                         void* stream_) {
+    SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
+    SPHNCA_CHECK_ARG(count, "NULL argument");
+    cudaStream_t stream = as_stream(stream_);
+    if (N == 0) { SPHNCA_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), stream)); return SPHNCA_OK; }
+    SPHNCA_CHECK_ARG(fire_s && A_s && rows && A_new_s && alive_s, "NULL argument");
+    SPHNCA_CHECK_ARG(((uintptr_t)fire_s & 3) == 0, "fire_s must be 4-byte aligned");
+    const int nb = (int)((N + fl::BLOCK_ROWS - 1) / fl::BLOCK_ROWS);
+    if (!workspace || workspace_bytes < (size_t)(nb + 1) * sizeof(int32_t)) { set_error("fire-list workspace too small"); return SPHNCA_ERR_WORKSPACE; }
+    int32_t* bc = reinterpret_cast<int32_t*>(workspace);
+    SPHNCA_LAUNCH(fire_count_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc);
+    SPHNCA_LAUNCH(fire_scan_kernel, 1, 1024, 0, stream, nb, bc, count);
+    SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_step_bwd_unfired(int64_t N, const uint8_t* flags_s, const float* dA_next_s, float* dY_s, float* dAdir_s,
+                                void* stream_) {
+    SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
+    if (N == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(flags_s && dA_next_s && dY_s && dAdir_s, "NULL argument");
+    const int64_t threads = N * 12;
+    SPHNCA_LAUNCH(step_bwd_unfired_kernel, (unsigned)((threads + 255) / 256), 256, 0, as_stream(stream_), N, flags_s, dA_next_s, dY_s, dAdir_s);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+}  // extern "C"

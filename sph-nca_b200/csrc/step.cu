@@ -607,6 +607,8 @@ __global__ void __launch_bounds__(PERC_T) stage_fit_kernel(GridView g, int32_t* 
 extern "C" {
 using namespace sphnca;
 
+int32_t sphnca_get_mlp_path(void) { return mlp_path(); }
+
 int32_t sphnca_set_sweep_path(int32_t path) {
     if (path < 0 || path > 2) { set_error("sweep path must be 0 (per-thread gathers), 1 (shared-memory tile engine) or 2 (TMA-staged tiles)"); return SPHNCA_ERR_INVALID; }
     g_sweep_path = path;
@@ -689,6 +691,18 @@ int32_t sphnca_step_mlp(int64_t N, const float* A_s, const float* Y_s, const uin
     return launch_step_mlp_tc(N, c, p, A_s, Y_s, fire_s, A_new_s, alive_s, O_s, flags_s, relu_s, as_stream(stream_));
 }
 
+int32_t sphnca_step_mlp_list(int64_t N, const int32_t* rows, const int32_t* count, const float* A_s, const float* Y_s,
+                             const sphnca_step_params* p, float* A_new_s, uint8_t* alive_s, float* O_c, uint8_t* flags_s,
+                             uint32_t* relu_c, float* A_c, float* Y_c, void* stream_) {
+    SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
+    sphnca_grid fake{}; fake.dim = 3; fake.h = 1.0;      // geometry constants are unused by the MLP half
+    StepConsts c; { int rc = make_consts(&fake, p, &c); if (rc) return rc; }
+    if (N == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(rows && count && A_s && Y_s && A_new_s && alive_s && O_c && flags_s && relu_c, "NULL argument");
+    SPHNCA_CHECK_ARG((A_c == nullptr) == (Y_c == nullptr), "A_c and Y_c must be given together");
+    return launch_step_mlp_tc(N, c, p, A_s, Y_s, nullptr, A_new_s, alive_s, O_c, flags_s, relu_c, as_stream(stream_), rows, count, A_c, Y_c);
+}
+
 int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s, const uint8_t* fire_s,
                         const sphnca_step_params* p, float* A_new_s, uint8_t* alive_s, float* Y_s, float* O_s,
                         uint8_t* flags_s, uint32_t* relu_s, void* stream_) {
@@ -761,6 +775,17 @@ int32_t sphnca_step_bwd(int64_t N, const float* A_s, const float* Y_s, const flo
                   (int)N, A_s, Y_s, O_s, flags_s, dA_next_s, *p, c, dO_s, dY_s, dAdir_s, Ht, dHt);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
+}
+
+int32_t sphnca_step_bwd_list(int64_t N, const int32_t* rows, const int32_t* count, const float* A_c, const float* O_c,
+                             const uint8_t* flags_s, const uint32_t* relu_c, const float* dA_next_s,
+                             const sphnca_step_params* p, float* dO_c, float* dY_s, float* dAdir_s, void* stream_) {
+    SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
+    sphnca_grid fake{}; fake.dim = 3; fake.h = 1.0;
+    StepConsts c; { int rc = make_consts(&fake, p, &c); if (rc) return rc; }
+    if (N == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(rows && count && A_c && O_c && flags_s && relu_c && dA_next_s && dO_c && dY_s && dAdir_s, "NULL argument");
+    return launch_step_bwd_tc(N, c, p, A_c, O_c, flags_s, relu_c, dA_next_s, dO_c, dY_s, dAdir_s, as_stream(stream_), rows, count);
 }
 
 int32_t sphnca_step_adjoint(const sphnca_grid* g, const float* xv4, const float* dY_s, const float* dAdir_s,

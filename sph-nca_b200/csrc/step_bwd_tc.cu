@@ -58,8 +58,15 @@ __global__ void __launch_bounds__(bw::THREADS, 1)
 step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __restrict__ O_s,
                    const uint8_t* __restrict__ flags_s, const uint32_t* __restrict__ relu_s,
                    const float* __restrict__ dAn_s, sphnca_step_params prm, StepConsts c,
-                   float* __restrict__ dO_s, float* __restrict__ dY_s, float* __restrict__ dAdir_s, int num_tiles) {
+                   float* __restrict__ dO_s, float* __restrict__ dY_s, float* __restrict__ dAdir_s, int num_tiles,
+                   const int32_t* __restrict__ rows, const int32_t* __restrict__ count_ptr) {
     using namespace bw;
+    // Fire-list mode (rows != NULL, firelist.cu): tile row j stands for sorted particle rows[j], j < *count.  A_s (the compact
+    // copy A_c), O_s, relu_s and dO_s are indexed by j; flags, dL/dA_new, dL/dY and the direct dL/dA part by the particle.
+    if (count_ptr != nullptr) {
+        n_total = __ldg(count_ptr);
+        num_tiles = (n_total + TILE - 1) / TILE;
+    }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -96,8 +103,9 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
         const int m = tid - LOAD_WARP0 * 32;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int p = tile * TILE + m;
-            const bool valid = p < n_total;
+            const int j = tile * TILE + m;
+            const bool valid = j < n_total;
+            const int p = (valid && rows) ? __ldg(rows + j) : j;
             float dO[NO_PAD], dAdir[NF];
             uint32_t rbits[NH / 32];
 #pragma unroll
@@ -108,14 +116,14 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             for (int w = 0; w < NH / 32; ++w) rbits[w] = 0u;
             if (valid) {
                 float Ai[NF], dnA[NF];
-                load16(A_s + (size_t)p * NF, Ai);
+                load16(A_s + (size_t)j * NF, Ai);
                 load16(dAn_s + (size_t)p * NF, dnA);
                 const uint8_t fl = flags_s[p];
                 const bool living = (fl & 1) && (fl & 2), fire = fl & 4;
 #pragma unroll
                 for (int f = 0; f < NF; ++f) dnA[f] = living ? dnA[f] : 0.f;
                 if (fire) {
-                    const float4* o4 = reinterpret_cast<const float4*>(O_s + (size_t)p * NO_PAD);
+                    const float4* o4 = reinterpret_cast<const float4*>(O_s + (size_t)j * NO_PAD);
                     float out[NO_PAD];
 #pragma unroll
                     for (int k = 0; k < NO_PAD / 4; ++k) { float4 t = __ldg(o4 + k); out[4*k] = t.x; out[4*k+1] = t.y; out[4*k+2] = t.z; out[4*k+3] = t.w; }
@@ -138,7 +146,7 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
 #pragma unroll
                         for (int f = 0; f < NF; ++f) { dO[f] = dnA[f] * c.orig_rate; dAdir[f] = dnA[f]; }
                     }
-                    const uint4* r4 = reinterpret_cast<const uint4*>(relu_s + (size_t)p * (NH / 32));
+                    const uint4* r4 = reinterpret_cast<const uint4*>(relu_s + (size_t)j * (NH / 32));
                     const uint4 r0 = __ldg(r4), r1 = __ldg(r4 + 1);
                     rbits[0] = r0.x; rbits[1] = r0.y; rbits[2] = r0.z; rbits[3] = r0.w;
                     rbits[4] = r1.x; rbits[5] = r1.y; rbits[6] = r1.z; rbits[7] = r1.w;
@@ -146,7 +154,7 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
 #pragma unroll
                     for (int f = 0; f < NF; ++f) dAdir[f] = dnA[f];
                 }
-                float4* do4 = reinterpret_cast<float4*>(dO_s + (size_t)p * NO_PAD);
+                float4* do4 = reinterpret_cast<float4*>(dO_s + (size_t)j * NO_PAD);
 #pragma unroll
                 for (int k = 0; k < NO_PAD / 4; ++k) do4[k] = make_float4(dO[4*k], dO[4*k+1], dO[4*k+2], dO[4*k+3]);
             }
@@ -243,8 +251,9 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
         const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int p = tile * TILE + m;
-            const bool valid = p < n_total;
+            const int j = tile * TILE + m;
+            const bool valid = j < n_total;
+            const int p = (valid && rows) ? __ldg(rows + j) : j;
             const int slot = it & 1;
             mbar_wait(&s.bar[DY_FULL], it & 1);
             fence_after_sync();
@@ -324,7 +333,7 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
 
 int launch_step_bwd_tc(int64_t N, const StepConsts& c, const sphnca_step_params* p, const float* A_s, const float* O_s,
                        const uint8_t* flags_s, const uint32_t* relu_s, const float* dA_next_s, float* dO_s, float* dY_s,
-                       float* dAdir_s, cudaStream_t stream) {
+                       float* dAdir_s, cudaStream_t stream, const int32_t* rows, const int32_t* count) {
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -336,7 +345,7 @@ int launch_step_bwd_tc(int64_t N, const StepConsts& c, const sphnca_step_params*
     const size_t smem = sizeof(bw::Smem);
     SPHNCA_CUDA(cudaFuncSetAttribute(step_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPHNCA_LAUNCH(step_bwd_tc_kernel, blocks, bw::THREADS, smem, stream, (int)N, A_s, O_s, flags_s, relu_s, dA_next_s, *p, c,
-                  dO_s, dY_s, dAdir_s, num_tiles);
+                  dO_s, dY_s, dAdir_s, num_tiles, rows, count);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

@@ -54,14 +54,18 @@ int launch_step_fwd_tc(const GridView& gv, const StepConsts& c, const sphnca_ste
                        const float* A_s, const uint8_t* fire_s, float* A_new_s, uint8_t* alive_s, float* Y_s,
                        float* O_s, uint8_t* flags_s, uint32_t* relu_s, cudaStream_t stream);
 
+// rows / count (fire-list mode, firelist.cu): NULL = all N rows in order; else the kernels run over rows[0..*count) and
+// N is only the upper bound the grid is sized for
 int launch_step_mlp_tc(int64_t N, const StepConsts& c, const sphnca_step_params* p, const float* A_s, const float* Y_s,
                        const uint8_t* fire_s, float* A_new_s, uint8_t* alive_s, float* O_s, uint8_t* flags_s,
-                       uint32_t* relu_s, cudaStream_t stream);
+                       uint32_t* relu_s, cudaStream_t stream, const int32_t* rows = nullptr, const int32_t* count = nullptr,
+                       float* A_c = nullptr, float* Y_c = nullptr);
 int launch_step_bwd_tc(int64_t N, const StepConsts& c, const sphnca_step_params* p, const float* A_s, const float* O_s,
                        const uint8_t* flags_s, const uint32_t* relu_s, const float* dA_next_s, float* dO_s, float* dY_s,
-                       float* dAdir_s, cudaStream_t stream);
+                       float* dAdir_s, cudaStream_t stream, const int32_t* rows = nullptr, const int32_t* count = nullptr);
 int wgrad_tc_streams(int64_t N);
 int launch_mlp_wgrad_tc(int64_t N, const float* A_s, const float* Y_s, const float* dO_s, const sphnca_step_params* p,
-                        int n_out, float* partial, int part_floats, int streams, cudaStream_t stream);
+                        int n_out, float* partial, int part_floats, int streams, cudaStream_t stream,
+                        const int32_t* count = nullptr);
 
 }  // namespace sphnca

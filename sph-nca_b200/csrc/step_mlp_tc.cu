@@ -69,8 +69,17 @@ __global__ void __launch_bounds__(mt::THREADS, 1)
 step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __restrict__ Y_s,
                    const uint8_t* __restrict__ fire_s, sphnca_step_params prm, StepConsts c,
                    float* __restrict__ An_s, float* __restrict__ O_s, uint8_t* __restrict__ flags_s,
-                   uint8_t* __restrict__ alive_s, uint32_t* __restrict__ relu_s, int num_tiles) {
+                   uint8_t* __restrict__ alive_s, uint32_t* __restrict__ relu_s, int num_tiles,
+                   const int32_t* __restrict__ rows, const int32_t* __restrict__ count_ptr,
+                   float* __restrict__ A_c, float* __restrict__ Y_c) {
     using namespace mt;
+    // Fire-list mode (rows != NULL, firelist.cu): tile row j stands for sorted particle rows[j], j < *count (the count is
+    // read from device memory: no host synchronisation); every listed particle fired.  O_s, relu_s and the compact copies
+    // A_c, Y_c (the weight-gradient kernel's contiguous input) are indexed by j, the state / flag arrays by the particle.
+    if (count_ptr != nullptr) {
+        n_total = __ldg(count_ptr);
+        num_tiles = (n_total + TILE - 1) / TILE;
+    }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -113,15 +122,24 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
         const int m = tid - LOAD_WARP0 * 32;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int p = tile * TILE + m;
+            const int j = tile * TILE + m;
             float4 v[NIN / 4];
-            if (p < n_total) {
+            if (j < n_total) {
+                const int p = rows ? __ldg(rows + j) : j;
                 const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)p * NF);
                 const float4* y4 = reinterpret_cast<const float4*>(Y_s + (size_t)p * 2 * NF);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) v[k] = __ldg(a4 + k);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[4 + k] = __ldg(y4 + k);
+                if (A_c != nullptr) {                         // compact copies for the backward
+                    float4* ac = reinterpret_cast<float4*>(A_c + (size_t)j * NF);
+                    float4* yc = reinterpret_cast<float4*>(Y_c + (size_t)j * 2 * NF);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ac[k] = v[k];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) yc[k] = v[4 + k];
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < NIN / 4; ++k) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -229,8 +247,9 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
         const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int p = tile * TILE + m;
-            const bool valid = p < n_total;
+            const int j = tile * TILE + m;
+            const bool valid = j < n_total;
+            const int p = (valid && rows) ? __ldg(rows + j) : j;
             const int slot = it & 1;
             // fetched before the waits (raw asm loads: nothing consumes them until the update below)
             float4 Ai4[4];
@@ -241,7 +260,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)p * NF);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) Ai4[k] = ldg_f4_raw(a4 + k);
-                fire_raw = ldg_u8_raw(fire_s + p);
+                fire_raw = rows ? 1u : ldg_u8_raw(fire_s + p);
                 flag_raw = ldg_u8_raw(flags_s + p);
             }
             mbar_wait(&s.bar[FIN_FULL + slot], (it >> 1) & 1);
@@ -287,7 +306,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 float4* o4 = reinterpret_cast<float4*>(An_s + (size_t)p * NF);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) o4[k] = make_float4(nA[4 * k], nA[4 * k + 1], nA[4 * k + 2], nA[4 * k + 3]);
-                float4* oo4 = reinterpret_cast<float4*>(O_s + (size_t)p * NO_PAD);
+                float4* oo4 = reinterpret_cast<float4*>(O_s + (size_t)j * NO_PAD);
 #pragma unroll
                 for (int k = 0; k < NO_PAD / 4; ++k) oo4[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
                 flags_s[p] = (uint8_t)((flag_raw & 1u) | (fire ? 4u : 0u));
@@ -304,8 +323,8 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
         const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int p = tile * TILE + m;
-            const bool valid = p < n_total;
+            const int j = tile * TILE + m;
+            const bool valid = j < n_total;
             float2 o32p = make_float2(0.f, 0.f);              // even / odd hidden units of the scalar-gate dot product
             uint32_t rmask[NH / 64];                          // this warp's 4 ReLU words: (half, chalf) -> word 4*half + 2*chalf + {0,1}
 #pragma unroll
@@ -366,7 +385,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             mbar_arrive(&s.bar[FIN_FULL + slot]);
             if (valid) {
                 // ReLU words: hidden 0..63 -> words 0,1 (group 0); 64..127 -> 2,3 (group 1); 128..191 -> 4,5 (group 0); 192..255 -> 6,7 (group 1)
-                uint2* rm2 = reinterpret_cast<uint2*>(relu_s + (size_t)p * (NH / 32));
+                uint2* rm2 = reinterpret_cast<uint2*>(relu_s + (size_t)j * (NH / 32));
                 rm2[chalf] = make_uint2(rmask[0], rmask[1]);
                 rm2[2 + chalf] = make_uint2(rmask[2], rmask[3]);
             }
@@ -379,7 +398,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
 
 int launch_step_mlp_tc(int64_t N, const StepConsts& c, const sphnca_step_params* p, const float* A_s, const float* Y_s,
                        const uint8_t* fire_s, float* A_new_s, uint8_t* alive_s, float* O_s, uint8_t* flags_s,
-                       uint32_t* relu_s, cudaStream_t stream) {
+                       uint32_t* relu_s, cudaStream_t stream, const int32_t* rows, const int32_t* count, float* A_c, float* Y_c) {
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -391,7 +410,7 @@ int launch_step_mlp_tc(int64_t N, const StepConsts& c, const sphnca_step_params*
     const size_t smem = sizeof(mt::Smem);
     SPHNCA_CUDA(cudaFuncSetAttribute(step_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPHNCA_LAUNCH(step_mlp_tc_kernel, blocks, mt::THREADS, smem, stream, (int)N, A_s, Y_s, fire_s, *p, c, A_new_s, O_s, flags_s,
-                  alive_s, relu_s, num_tiles);
+                  alive_s, relu_s, num_tiles, rows, count, A_c, Y_c);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

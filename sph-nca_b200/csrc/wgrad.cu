@@ -190,4 +190,22 @@ int32_t sphnca_mlp_wgrad(int64_t N, const float* A_s, const float* Y_s, const fl
     return SPHNCA_OK;
 }
 
+int32_t sphnca_mlp_wgrad_list(int64_t N, const int32_t* count, const float* A_c, const float* Y_c, const float* dO_c,
+                              const sphnca_step_params* p, float* dW1, float* db1, float* dW2, float* db2,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
+    SPHNCA_CHECK_ARG(N >= 0 && p && (p->update_rule == 0 || p->update_rule == 1), "bad N / params");
+    const int n_out = p->update_rule == 0 ? 2 * NF + 1 : NF;
+    if (N == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(count && A_c && Y_c && dO_c && dW1 && db1 && dW2 && db2, "NULL argument");
+    SPHNCA_CHECK_ARG(p->W1 && p->b1 && p->W2, "weights are required by the recompute path");
+    const int streams = wgrad_tc_streams(N);
+    if (!workspace || workspace_bytes < (size_t)streams * WG_PART * sizeof(float)) { set_error("wgrad workspace too small"); return SPHNCA_ERR_WORKSPACE; }
+    float* partial = reinterpret_cast<float*>(workspace);
+    int rc = launch_mlp_wgrad_tc(N, A_c, Y_c, dO_c, p, n_out, partial, WG_PART, streams, as_stream(stream_), count);
+    if (rc) return rc;
+    SPHNCA_LAUNCH(mlp_wgrad_reduce_kernel, (WG_PART + 255) / 256, 256, 0, as_stream(stream_), partial, streams, n_out, dW1, db1, dW2, db2);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
 }  // extern "C"

@@ -67,8 +67,9 @@ __device__ __forceinline__ uint32_t fidx(uint32_t rows, uint32_t m, uint32_t k) 
 __global__ void __launch_bounds__(wg::THREADS, 1)
 mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float* __restrict__ Y_s,
                     const float* __restrict__ dO_s, sphnca_step_params prm, int n_out, float* __restrict__ partial,
-                    int part_floats) {
+                    int part_floats, const int32_t* __restrict__ count_ptr) {
     using namespace wg;
+    if (count_ptr != nullptr) n_total = __ldg(count_ptr);     // fire-list mode: the first *count rows of the compact arrays
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -415,10 +416,10 @@ int wgrad_tc_streams(int64_t N) {
 }
 
 int launch_mlp_wgrad_tc(int64_t N, const float* A_s, const float* Y_s, const float* dO_s, const sphnca_step_params* p,
-                        int n_out, float* partial, int part_floats, int streams, cudaStream_t stream) {
+                        int n_out, float* partial, int part_floats, int streams, cudaStream_t stream, const int32_t* count) {
     const size_t smem = sizeof(wg::Smem);
     SPHNCA_CUDA(cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SPHNCA_LAUNCH(mlp_wgrad_tc_kernel, 2 * streams, wg::THREADS, smem, stream, N, A_s, Y_s, dO_s, *p, n_out, partial, part_floats);
+    SPHNCA_LAUNCH(mlp_wgrad_tc_kernel, 2 * streams, wg::THREADS, smem, stream, N, A_s, Y_s, dO_s, *p, n_out, partial, part_floats, count);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

@@ -169,6 +169,62 @@ class _NCAStep(torch.autograd.Function):
                 dW2 if g[6] else None, db2 if g[7] else None, None, None, None, None, None, None)
 
 
+# The MLP half of a rollout step runs over the fired rows only (csrc/firelist.cu) when the tensor-core kernels are the
+# active path; False = every row goes through the MLP kernels like in the single-step node.
+FIRE_LISTS = True
+
+
+def _fire_lists_on():
+    return (FIRE_LISTS and SPLIT_FORWARD and not SIMT_BACKWARD and "sphnca_fire_list" not in _lib.MISSING_SYMBOLS
+            and lib.sphnca_get_mlp_path() >= 1)
+
+
+def _fire_list_workspace(N, dev):
+    nb = C.c_size_t(0)
+    check(lib.sphnca_fire_list_workspace_bytes(N, C.byref(nb)))
+    return torch.empty((nb.value,), dtype=torch.uint8, device=dev)
+
+
+class _FireBuffers:
+    """Per-step tensors of the fire-list path: the list (rows, device-side count), the saved MLP output / ReLU bits and
+    the compact copies of the MLP input rows, all indexed by list position, plus the per-particle flag bytes.  Sized for
+    N rows: the count stays on the device, so the host never learns how many particles fired."""
+    PER_STEP = 7
+
+    def __init__(self, N, dev, compact_inputs=True):
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.rows = torch.empty((N,), dtype=torch.int32, device=dev)
+        self.count = torch.empty((1,), dtype=torch.int32, device=dev)
+        self.O_c = torch.empty((N, 36), **f32)
+        self.relu_c = torch.empty((N, 8), dtype=torch.int32, device=dev)
+        self.flags = torch.empty((N,), dtype=torch.uint8, device=dev)
+        self.A_c = torch.empty((N, 16), **f32) if compact_inputs else None
+        self.Y_c = torch.empty((N, 32), **f32) if compact_inputs else None
+
+    def tensors(self):
+        return [self.rows, self.count, self.A_c, self.Y_c, self.O_c, self.flags, self.relu_c]
+
+    @classmethod
+    def from_tensors(cls, t):
+        self = cls.__new__(cls)
+        self.rows, self.count, self.A_c, self.Y_c, self.O_c, self.flags, self.relu_c = t
+        return self
+
+
+def _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, alive_s, fb, ws_fl, st, pl=False):
+    """One forward step on the fire-list path: list + carried-over rows, perception sweep, MLP over the list, life mask."""
+    N = S.shape[0]
+    _timed("fire_list", lib.sphnca_fire_list, N, ptr(fire_s), ptr(S), int(bool(use_alpha)), ptr(fb.rows), ptr(fb.count), ptr(Sn),
+           ptr(alive_s), ptr(ws_fl), ws_fl.numel(), st)
+    if pl is False:
+        _perceive(grid, x, v, g, xv4, S, p, Y_s, fb.flags, st)
+    else:
+        _perceive_pl(grid, pl, g, xv4, S, p, Y_s, fb.flags, st)
+    _timed("step_mlp", lib.sphnca_step_mlp_list, N, ptr(fb.rows), ptr(fb.count), ptr(S), ptr(Y_s), C.byref(p), ptr(Sn), ptr(alive_s),
+           ptr(fb.O_c), ptr(fb.flags), ptr(fb.relu_c), ptr(fb.A_c), ptr(fb.Y_c), st)
+    _mask(use_alpha, g, N, xv4, alive_s, Sn, fb.flags, st)
+
+
 class _UnpackRows(torch.autograd.Function):
     """cell-sorted rows -> the caller's particle order (adjoint: the inverse permutation)."""
 
@@ -217,13 +273,33 @@ class _NCARollout(torch.autograd.Function):
         states, saved = [S], []
         alive_s = torch.empty((N,), **u8)
         Y_s = O_s = flags_s = relu_s = None
+        fl = _fire_lists_on() and N > 0
+        fbuf = ws_fl = None
+        if fl:
+            ws_fl = _fire_list_workspace(N, dev)
+            Y_s = torch.empty((N, 32), **f32)                 # perception of the current step: scratch, the tape keeps Y_c
         for _ in range(steps):
             fire = torch.rand(N, device=dev) <= fire_rate
             fire_s = grid.pack_bytes(fire.view(torch.uint8))
+            Sn = torch.empty((N, 16), **f32)
+            if fl:
+                # MLP half over the fired rows only (firelist.cu); not-fired rows are carried over by the list kernel
+                if taped == 1 or fbuf is None:
+                    fbuf = _FireBuffers(N, dev, compact_inputs=taped == 1)
+                _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, alive_s, fbuf, ws_fl, st)
+                if taped == 1:
+                    saved += fbuf.tensors()
+                elif taped == 2:
+                    saved.append(fire_s)
+                if keep_all or taped:
+                    states.append(Sn)
+                else:
+                    states = [states[0], Sn]
+                S = Sn
+                continue
             if taped == 1 or Y_s is None:
                 Y_s = torch.empty((N, 32), **f32); O_s = torch.empty((N, 36), **f32)
                 flags_s = torch.empty((N,), **u8); relu_s = torch.empty((N, 8), dtype=torch.int32, device=dev)
-            Sn = torch.empty((N, 16), **f32)
             if N:
                 if SPLIT_FORWARD:
                     _perceive(grid, x, v, g, xv4, S, p, Y_s, flags_s, st)
@@ -242,7 +318,7 @@ class _NCARollout(torch.autograd.Function):
             else:
                 states = [states[0], Sn] if len(states) else [Sn]
             S = Sn
-        ctx.grid, ctx.cfg, ctx.steps, ctx.taped = grid, cfg, steps, taped
+        ctx.grid, ctx.cfg, ctx.steps, ctx.taped, ctx.fire_lists = grid, cfg, steps, taped, fl
         ctx.pairs = grid.pair_lists(x, v) if (N and taped) else None
         if taped:
             ctx.save_for_backward(xv4, W1c, b1c, W2c, b2c, *states, *saved)
@@ -274,7 +350,16 @@ class _NCARollout(torch.autograd.Function):
         own = [torch.empty((N, 16), **f32), torch.empty((N, 16), **f32)]   # gradient ping-pong (never write autograd's buffers)
         st = stream_ptr()
         recompute = ctx.taped == 2
-        if recompute and N:
+        fl = ctx.fire_lists
+        if fl:
+            g = grid.c_grid()
+            dO_c = dO_s                                       # dL/d(MLP output) of the listed rows, by list position
+            if recompute:
+                fbuf = _FireBuffers(N, dev, compact_inputs=True)
+                Y_s = torch.empty((N, 32), **f32)
+                Sn_scr, alive_s = torch.empty((N, 16), **f32), torch.empty((N,), dtype=torch.uint8, device=dev)
+                ws_fl = _fire_list_workspace(N, dev)
+        elif recompute and N:
             u8 = dict(dtype=torch.uint8, device=dev)
             Y_s = torch.empty((N, 32), **f32); O_s = torch.empty((N, 36), **f32)
             flags_s = torch.empty((N,), **u8); relu_s = torch.empty((N, 8), dtype=torch.int32, device=dev)
@@ -284,7 +369,23 @@ class _NCARollout(torch.autograd.Function):
         if gcur is not None:
             gcur = require_cuda_f32(gcur, "dS")
         for k in range(K - 1, -1, -1):
-            if gcur is not None and N:          # steps after the last state a loss reads carry no gradient
+            if gcur is not None and N and fl:
+                if recompute:                   # the forward of step k again, from the saved state and fire bytes
+                    _step_forward_lists(grid, None, None, g, xv4, states[k], saved[k], p, ctx.cfg[1], Y_s, Sn_scr, alive_s, fbuf,
+                                        ws_fl, st, pl=ctx.pairs)
+                    fb = fbuf
+                else:
+                    fb = _FireBuffers.from_tensors(saved[_FireBuffers.PER_STEP * k:_FireBuffers.PER_STEP * (k + 1)])
+                _timed("step_bwd_unfired", lib.sphnca_step_bwd_unfired, N, ptr(fb.flags), ptr(gcur), ptr(dY_s), ptr(dAdir_s), st)
+                _timed("step_bwd", lib.sphnca_step_bwd_list, N, ptr(fb.rows), ptr(fb.count), ptr(fb.A_c), ptr(fb.O_c), ptr(fb.flags),
+                       ptr(fb.relu_c), ptr(gcur), C.byref(p), ptr(dO_c), ptr(dY_s), ptr(dAdir_s), st)
+                if want_w:
+                    _timed("mlp_wgrad", lib.sphnca_mlp_wgrad_list, N, ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), ptr(dO_c), C.byref(p),
+                           ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value, st)
+                out = own[k & 1]
+                _adjoint(grid, ctx.pairs, xv4, dY_s, dAdir_s, p, out, st)
+                gcur = out
+            elif gcur is not None and N:        # steps after the last state a loss reads carry no gradient
                 if recompute:                   # the forward of step k again, from the saved state and fire bytes
                     _perceive_pl(grid, ctx.pairs, g, xv4, states[k], p, Y_s, flags_s, st)
                     _timed("step_mlp", lib.sphnca_step_mlp, N, ptr(states[k]), ptr(Y_s), ptr(saved[k]), C.byref(p),
@@ -339,7 +440,7 @@ class RolloutStates:
 # Activation checkpointing inside the rollout node: True / False, or "auto" = checkpoint when
 # the full tape (TAPE_BYTES per particle-step) would take more than AUTO_CHECKPOINT_FRACTION of the HBM torch does not hold.
 CHECKPOINT = "auto"
-TAPE_BYTES = 4 * (32 + 36 + 8) + 1
+TAPE_BYTES = 4 * (32 + 36 + 8) + 1 + 4 * (16 + 1)       # + compact state rows and the list on the fire-list path
 AUTO_CHECKPOINT_FRACTION = 0.5
 
 

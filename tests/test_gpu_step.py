@@ -600,6 +600,65 @@ def test_rollout_node_auto_checkpoint_follows_free_memory(monkeypatch):
     assert fused._tape_mode(n_small, 8, torch.device(DEV), None) == 2
 
 
+@pytest.mark.parametrize("n,rate", [(1, 1.0), (5, 0.0), (1023, 0.5), (1024, 0.5), (1025, 0.3), (300_000, 0.5), (2_100_000, 0.9)])
+def test_fire_list_is_the_ordered_compaction(n, rate):
+    """sphnca_fire_list: rows[0..count) == nonzero(fire) in increasing order, count on the device; not-fired rows carry
+    their state over and get their alive byte; fired rows of A_new are left to the MLP kernel."""
+    import ctypes as C
+    from sphops import _lib
+    gen = torch.Generator().manual_seed(n)
+    fire = (torch.rand(n, generator=gen) < rate).to(torch.uint8).to(DEV)
+    A = torch.rand(n, 16, generator=gen).to(DEV)
+    rows = torch.full((n,), -1, dtype=torch.int32, device=DEV)
+    count = torch.full((1,), -7, dtype=torch.int32, device=DEV)
+    An = torch.full((n, 16), -5.0, device=DEV)
+    alive = torch.full((n,), 9, dtype=torch.uint8, device=DEV)
+    nb = C.c_size_t(0)
+    _lib.check(_lib.lib.sphnca_fire_list_workspace_bytes(n, C.byref(nb)))
+    ws = torch.empty((nb.value,), dtype=torch.uint8, device=DEV)
+    _lib.check(_lib.lib.sphnca_fire_list(n, _lib.ptr(fire), _lib.ptr(A), 1, _lib.ptr(rows), _lib.ptr(count), _lib.ptr(An), _lib.ptr(alive),
+                                         _lib.ptr(ws), nb.value, _lib.stream_ptr()))
+    want = torch.nonzero(fire)[:, 0].to(torch.int32)
+    assert int(count.item()) == want.numel()
+    assert torch.equal(rows[:want.numel()], want)
+    off = fire == 0
+    assert torch.equal(An[off], A[off]) and bool((An[~off] == -5.0).all())
+    assert torch.equal(alive[off], (A[off][:, 3] > 0.1).to(torch.uint8)) and bool((alive[~off] == 9).all())
+
+
+@pytest.mark.parametrize("use_alpha", [False, True], ids=["noalpha", "alpha"])
+@pytest.mark.parametrize("rate", [0.5, 1.0, 0.0], ids=["half", "all_fire", "none_fire"])
+def test_rollout_fire_lists_equal_full_mlp(use_alpha, rate, monkeypatch):
+    """The MLP half over the fired rows only (csrc/firelist.cu) == the MLP over every row followed by the reference's
+    `where(update_mask, nA, A)`: states bit-identical (row-independent arithmetic), gradients to fp32 summation order
+    (the weight gradient sums the same per-particle terms in another chunking)."""
+    from sphops import fused
+    K = 4
+    x, sections, h, dims, A0, params, masks, cfg = oracle_case(72, False, use_alpha, K, seed=21)
+    gen = torch.Generator().manual_seed(3)
+    masks = torch.rand(K, x.shape[0], generator=gen) < rate
+    m = _rollout_model(use_alpha, h)
+    xd = x.to(DEV)
+    res = []
+    for lists in (False, True):
+        monkeypatch.setattr(fused, "FIRE_LISTS", lists)
+        m.zero_grad()
+        grid, v = m.init_grid(xd, sections, h, dims)
+        A = A0.to(DEV).requires_grad_(True)
+        with forced_fire_masks(list(masks)):
+            out = m.rollout(xd, v, A, h, grid, K, checkpoint=False)
+        _multi_state_loss(out, (1, 2)).backward()
+        res.append(([o.detach().clone() for o in out], A.grad.clone(), [p.grad.clone() for p in m.parameters()]))
+    for k, (a, b) in enumerate(zip(res[0][0], res[1][0])):
+        assert torch.equal(a, b), f"state {k}"
+    assert_close(res[1][1], res[0][1], rtol=1e-6, what="dL/dA0")
+    for a, b, nm in zip(res[0][2], res[1][2], ("dW1", "db1", "dW2", "db2")):
+        if float(a.abs().max()) == 0.0:
+            assert float(b.abs().max()) == 0.0, nm
+        else:
+            assert_close(b, a, rtol=2e-6, what=nm)
+
+
 def test_rollout_node_inference_keeps_only_what_is_asked():
     """No tape, keep_all=False: two states (first, last); same final state as the stepwise path; sequence protocol."""
     import random
