@@ -65,15 +65,23 @@ KERNELS = {
     # perception from the pair lists (csrc/pairs.cu): ~36 list slots x 12 B (J, WP; +8 B WB with an alpha channel) + A row (64)
     # + write dA/dx|dA/dy (128) + flag; 24 packed FMA/ADD pairs per slot
     "step_perceive": dict(bytes=626.0, flops=36 * 64.0, bound="hbm"),
-    # MLP + update: read A,Y (192) + fire (1) ; write A' (64), O (144), relu bits (32), flags/alive (2); 2*(48*256+256*33) FLOP
-    "step_mlp": dict(bytes=435.0, flops=41472.0, bound="tensor"),
+    # ordered compaction of the fire mask + carry-over of the not-fired rows: fire bytes twice (2), list entry (4 x 0.5),
+    # not-fired row copy (129 x 0.5)
+    "fire_list": dict(bytes=68.5, flops=0.0, bound="hbm"),
+    # The three MLP kernels run over the FIRED rows only (csrc/firelist.cu); their figures are per fired row and are scaled
+    # by the fire rate (0.5) below ("rows": "fired").
+    # MLP + update: read A,Y (192) + list entry, flag (5) ; write A' (64), O (144), relu bits (32), flags/alive (2), compact A,Y
+    # copies for the backward (192); 2*(48*256+256*33) FLOP
+    "step_mlp": dict(bytes=631.0, flops=41472.0, bound="tensor", rows="fired"),
     "step_fwd": dict(bytes=152.0, flops=41472.0 + 5500.0, bound="tensor"),   # fused forward (A/B path)
     "step_mask": dict(bytes=24.0, flops=1300.0, bound="hbm"),               # neighbour-sweep life mask (alpha channel only)
     "step_mask_static": dict(bytes=2.0, flops=0.0, bound="hbm"),            # no alpha channel: elementwise
-    # data gradient: read A,O,dA',relu,flags (64+144+64+32+1) ; write dO (144), dY (128), dAdir (64); 2*(33*256+256*48) FLOP
-    "step_bwd": dict(bytes=641.0, flops=41472.0, bound="tensor"),
+    # data gradient: read A,O,dA',relu,flags,list entry (64+144+64+32+1+4) ; write dO (144), dY (128), dAdir (64); 2*(33*256+256*48) FLOP
+    "step_bwd": dict(bytes=645.0, flops=41472.0, bound="tensor", rows="fired"),
+    # backward of the not-fired rows: flag (1) + (read dA' 64 + write dAdir 64, dY 128) x 0.5
+    "step_bwd_unfired": dict(bytes=129.0, flops=0.0, bound="hbm"),
     # weight gradient with transposed recompute: read A,Y,dO (336); recompute 2*(48*256+33*256) + accumulate the same
-    "mlp_wgrad": dict(bytes=336.0, flops=82944.0, bound="tensor"),
+    "mlp_wgrad": dict(bytes=336.0, flops=82944.0, bound="tensor", rows="fired"),
     # adjoint from the pair lists: ~36 slots x 12 B (J, WA) + x,v (16) + SXY (8) + dY (128) + dAdir (64) ; write dA (64)
     "step_adjoint": dict(bytes=712.0, flops=36 * 64.0, bound="hbm"),
 }
@@ -387,6 +395,8 @@ def main():
         return
 
     hbm, bf16_burst, bf16_sust, which = peaks()
+    # rows the MLP kernels process per launch: the fired ones when the rollout runs on fire lists (model fire rate 0.5)
+    fire_fraction = model.fire_rate if (nca.USE_FUSED_STEP and fused._fire_lists_on()) else 1.0
     kernels, dominant = {}, None
     for name, evs in prof.items():
         tot = sum(a.elapsed_time(b) for a, b in evs)
@@ -394,9 +404,11 @@ def main():
         info = KERNELS.get(name)
         if info:
             sec = k["avg_ms"] * 1e-3
-            k["hbm_gbs"] = info["bytes"] * N / sec / 1e9
+            rows = N * (fire_fraction if info.get("rows") == "fired" else 1.0)     # rows one launch processes
+            k["rows_per_launch"] = rows
+            k["hbm_gbs"] = info["bytes"] * rows / sec / 1e9
             k["hbm_frac"] = k["hbm_gbs"] / hbm
-            k["tflops"] = info["flops"] * N / sec / 1e12
+            k["tflops"] = info["flops"] * rows / sec / 1e12
             k["bound"] = info["bound"]
         kernels[name] = k
         if dominant is None or tot > kernels[dominant]["avg_ms"] * kernels[dominant]["launches"]:
@@ -418,11 +430,11 @@ def main():
             roofline = {"kernel": dominant, "bound": "tensor", "achieved": k["tflops"], "peak": bf16_sust, "unit": "TFLOP/s",
                         "frac": k["tflops"] / bf16_sust, "traffic": None,
                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({which})",
-                        "algorithmic_flops_per_particle": info["flops"], "particles_per_launch": N, "avg_launch_ms": k["avg_ms"],
+                        "algorithmic_flops_per_row": info["flops"], "rows_per_launch": k["rows_per_launch"], "avg_launch_ms": k["avg_ms"],
                         "note": "fp32-accurate MLP on tcgen05 kind::tf32 with the 3xTF32 split: ceiling = peak/6 "
                                 f"= {bf16_sust / 6:.0f} TFLOP/s of algorithmic FLOPs; frac_of_3xtf32_ceiling below",
                         "frac_of_3xtf32_ceiling": k["tflops"] / (bf16_sust / 6),
-                        "algorithmic_bytes_per_launch": info["bytes"] * N}
+                        "algorithmic_bytes_per_launch": info["bytes"] * k["rows_per_launch"]}
         else:
             roofline = {"kernel": dominant, "bound": "hbm", "achieved": k["hbm_gbs"], "peak": hbm, "unit": "GB/s",
                         "frac": k["hbm_frac"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
@@ -440,8 +452,9 @@ def main():
         "config": {"workload": args.workload, "description": wl["desc"], "particles_per_gpu": N, "nca_steps": K_nca,
                    "h": h, "dims": dims, "weights": "zebra (trained, tests/golden/weights_zebra.npz)", "optimizer": "Adam lr=1e-5",
                    "path": "fused" if nca.USE_FUSED_STEP else "ops", "parallelism": f"dp{world}", "rollout_tape": tape_mode,
-                   "l2": "no flush needed: ~340 B/particle/NCA-step of saved state => working set "
-                         f"{340 * N * K_nca / 1e9:.1f} GB per step >> 126 MB L2"},
+                   "mlp_rows": "fired particles only (fire lists)" if fire_fraction < 1.0 else "all particles",
+                   "l2": f"no flush needed: ~{fused.TAPE_BYTES + 64} B/particle/NCA-step of saved state => working set "
+                         f"{(fused.TAPE_BYTES + 64) * N * K_nca / 1e9:.1f} GB per step >> 126 MB L2"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": x_pin.numel() * 4 + A_pin.numel() * 4, "d2h_bytes_per_step": out_pin.numel() * 4 + 4},

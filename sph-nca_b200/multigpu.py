@@ -150,7 +150,8 @@ class SlabShardedNCA:
 
     Per rank and step, in the cell-sorted domain of the LOCAL particle set (interior + halo):
       1. halo exchange of the state rows (64 B / halo particle)
-      2. perception sweep + tcgen05 MLP/update for every local particle (halo results are discarded)
+      2. perception sweep for every local particle (from the slab's pair lists when they fit) + tcgen05 MLP/update
+         for the fired ones (halo results are discarded)
       3. halo exchange of the alive bytes of the updated state (1 B / halo particle)
       4. life-mask sweep, masking of the new state
     Volume: computed locally (interior exact), halo values fetched once from their owners.
@@ -214,16 +215,30 @@ class SlabShardedNCA:
         prm = fused._step_params(lin1.weight.detach(), lin1.bias.detach(), lin2.weight.detach(), lin2.bias.detach(),
                                  m.update_rule, m.use_alpha, m.perception_scale(self.h), m.fire_rate / fr)
         g, st = self.grid.c_grid(), _lib.stream_ptr()
-        perceive = fused._perceive_entry(self.grid)      # staged sweep when the slab's tiles fit its buffer
+        # the slab's own pair lists (built once per partition) and, per step, the list of the fired rows: the MLP runs
+        # over those only (halo rows never fire: their results are overwritten by the next exchange anyway)
+        pl = self.grid.pair_lists(self.x_loc, self.v)
+        lists = fused._fire_lists_on() and N > 0
+        if lists:
+            rows = torch.empty((N,), dtype=torch.int32, device=dev)
+            count = torch.empty((1,), dtype=torch.int32, device=dev)
+            ws_fl = fused._fire_list_workspace(N, dev)
         nbytes = 0
         for k in range(steps):
             nbytes += self._exchange_sorted(A_s)
             fire = torch.zeros((N,), dtype=torch.uint8, device=dev)
             fire[:p.n_own] = (fire_masks[k] if fire_masks is not None else (torch.rand(p.n_own, device=dev) <= fr)).to(torch.uint8)
             fire_s = self.grid.pack_bytes(fire)
-            check(perceive(g, ptr(self.xv4), ptr(A_s), C.byref(prm), ptr(Y_s), ptr(flags_s), st))
-            check(lib.sphnca_step_mlp(N, ptr(A_s), ptr(Y_s), ptr(fire_s), C.byref(prm), ptr(An_s), ptr(alive_s), ptr(O_s),
-                                      ptr(flags_s), ptr(relu_s), st))
+            if lists:
+                check(lib.sphnca_fire_list(N, ptr(fire_s), ptr(A_s), int(bool(m.use_alpha)), ptr(rows), ptr(count), ptr(An_s),
+                                           ptr(alive_s), ptr(ws_fl), ws_fl.numel(), st))
+            fused._perceive_pl(self.grid, pl, g, self.xv4, A_s, prm, Y_s, flags_s, st)
+            if lists:
+                check(lib.sphnca_step_mlp_list(N, ptr(rows), ptr(count), ptr(A_s), ptr(Y_s), C.byref(prm), ptr(An_s), ptr(alive_s),
+                                               ptr(O_s), ptr(flags_s), ptr(relu_s), None, None, st))
+            else:
+                check(lib.sphnca_step_mlp(N, ptr(A_s), ptr(Y_s), ptr(fire_s), C.byref(prm), ptr(An_s), ptr(alive_s), ptr(O_s),
+                                          ptr(flags_s), ptr(relu_s), st))
             if m.use_alpha:
                 nbytes += self._exchange_sorted(alive_s)
                 # the previous-mask bit of a halo particle is never used (its row is overwritten by the next exchange)

@@ -26,14 +26,16 @@ def launches(src, dst, cmd):
         for k, v in sorted(tot.items(), key=lambda t: -t[1]):
             f.write(f"\"{k}\",{cnt[k]},{v:.3f},{v / total:.3f}\n")
 
-WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+WANT = ["sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_uniform.sum", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 KEYS = {"step_perceive_pairs_kernel": "step_perceive", "step_mlp_tc_kernel": "step_mlp", "step_bwd_tc_kernel": "step_bwd",
-        "mlp_wgrad_tc_kernel": "mlp_wgrad", "step_adjoint_pairs_kernel": "step_adjoint"}
+        "mlp_wgrad_tc_kernel": "mlp_wgrad", "step_adjoint_pairs_kernel": "step_adjoint", "fire_fill_kernel": "fire_list",
+        "step_bwd_unfired_kernel": "step_bwd_unfired"}
 
 def full(src, txt, js, particles):
     rows = list(csv.reader(open(src)))
