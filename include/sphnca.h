@@ -234,6 +234,13 @@ int32_t sphnca_step_bwd_list(int64_t N, const int32_t* rows, const int32_t* coun
                              const sphnca_step_params* p, float* dO_c, float* dY_s, float* dAdir_s, void* stream);
 int32_t sphnca_step_bwd_unfired(int64_t N, const uint8_t* flags_s, const float* dA_next_s, float* dY_s, float* dAdir_s,
                                 void* stream);
+/* sphnca_step_adjoint_pairs for a fire-list step: rows of dY_s / dAdir_s are read only for the particles whose flag byte has the
+ * fire bit (4); for the others dL/dY is zero and the direct part is (living ? dA_next_s : 0), taken from flags_s / dA_next_s --
+ * no sphnca_step_bwd_unfired pass is needed and the row gathers of not-fired neighbours are skipped. */
+int32_t sphnca_step_adjoint_pairs_fired(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
+                                        const float* WA, const float* SXY, const float* xv4, const float* dY_s, const float* dAdir_s,
+                                        const uint8_t* flags_s, const float* dA_next_s, const sphnca_step_params* p, float* dA_s,
+                                        void* stream);
 int32_t sphnca_mlp_wgrad_list(int64_t N, const int32_t* count, const float* A_c, const float* Y_c, const float* dO_c,
                               const sphnca_step_params* p, float* dW1, float* db1, float* dW2, float* db2,
                               void* workspace, size_t workspace_bytes, void* stream);

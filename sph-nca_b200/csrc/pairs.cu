@@ -152,11 +152,17 @@ step_perceive_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, c
 }
 
 // Gather adjoint of the perception sweep from the pair lists (same output as step_adjoint_kernel).
+// FIRED (fire-list rollouts, firelist.cu): dL/dY of a particle that did not fire is exactly zero and its direct dL/dA part is
+// (living ? dL/dA_new : 0), so both are taken from the flag byte instead of from memory: the 128-byte row gather of a not-fired
+// neighbour (half of them at fire rate 0.5 -- this kernel is bound by the L1 data pipe) is skipped, and nobody has to write
+// those rows of dY_s / dAdir_s first.
+template <bool FIRED>
 __global__ void __launch_bounds__(128)
 step_adjoint_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, const int64_t* __restrict__ group_base,
                           const int32_t* __restrict__ J, const float2* __restrict__ WA, const float2* __restrict__ SXY,
                           const float4* __restrict__ xv4, const float* __restrict__ dY_s, const float* __restrict__ dAdir_s,
-                          StepConsts c, float* __restrict__ dA_s) {
+                          StepConsts c, float* __restrict__ dA_s, const uint8_t* __restrict__ flags_s,
+                          const float* __restrict__ dAn_s) {
     const int64_t grp = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (grp * PG >= n) return;
     const int lane = threadIdx.x & 31, part = lane & 3, q = lane >> 2;
@@ -172,8 +178,13 @@ step_adjoint_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, co
         float4 a[4], bb[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const size_t row = (size_t)__shfl_sync(0xffffffffu, jv, u * PG + q) * 8;
-            a[u] = __ldg(G4 + row + part); bb[u] = __ldg(G4 + row + 4 + part);
+            const int j = __shfl_sync(0xffffffffu, jv, u * PG + q);
+            const size_t row = (size_t)j * 8;
+            if (FIRED && !(__ldg(flags_s + j) & 4)) {
+                a[u] = make_float4(0.f, 0.f, 0.f, 0.f); bb[u] = a[u];
+            } else {
+                a[u] = __ldg(G4 + row + part); bb[u] = __ldg(G4 + row + 4 + part);
+            }
         }
         const float2 wac = wa;
         if (b + 1 < batches) { const int64_t e = e0 + (int64_t)(b + 1) * 32; jv = __ldcs(J + e); wa = __ldcs(WA + e); }
@@ -189,8 +200,15 @@ step_adjoint_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, co
     if (p >= n) return;
     const float vi = xv4[p].w;
     const float2 sxy = SXY[p];
-    const float4 Gx = __ldg(G4 + (size_t)p * 8 + part), Gy = __ldg(G4 + (size_t)p * 8 + 4 + part);
-    const float4 dir = __ldg(reinterpret_cast<const float4*>(dAdir_s) + (size_t)p * 4 + part);
+    float4 Gx, Gy, dir;
+    const uint8_t fl_ = FIRED ? flags_s[p] : (uint8_t)4;
+    if (fl_ & 4) {
+        Gx = __ldg(G4 + (size_t)p * 8 + part); Gy = __ldg(G4 + (size_t)p * 8 + 4 + part);
+        dir = __ldg(reinterpret_cast<const float4*>(dAdir_s) + (size_t)p * 4 + part);
+    } else {
+        Gx = make_float4(0.f, 0.f, 0.f, 0.f); Gy = Gx;
+        dir = ((fl_ & 1) && (fl_ & 2)) ? __ldg(reinterpret_cast<const float4*>(dAn_s) + (size_t)p * 4 + part) : Gx;
+    }
     float4 r;
     r.x = dir.x - c.kg * fmaf(vi, acc.x, fmaf(Gx.x, sxy.x, Gy.x * sxy.y));
     r.y = dir.y - c.kg * fmaf(vi, acc.y, fmaf(Gx.y, sxy.x, Gy.y * sxy.y));
@@ -248,18 +266,36 @@ int32_t sphnca_step_perceive_pairs(const sphnca_grid* g, const int32_t* group_sl
     return SPHNCA_OK;
 }
 
-int32_t sphnca_step_adjoint_pairs(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
-                                  const float* WA, const float* SXY, const float* xv4, const float* dY_s, const float* dAdir_s,
-                                  const sphnca_step_params* p, float* dA_s, void* stream_) {
+static int launch_adjoint_pairs(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
+                                const float* WA, const float* SXY, const float* xv4, const float* dY_s, const float* dAdir_s,
+                                const sphnca_step_params* p, float* dA_s, const uint8_t* flags_s, const float* dAn_s, void* stream_) {
     GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
     StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(group_slots && group_base && J && WA && SXY && xv4 && dY_s && dAdir_s && dA_s, "NULL argument");
     const int blocks = (int)((gv.n + 31) / 32);           // one warp per group of 8 particles, 4 groups per CTA
-    SPHNCA_LAUNCH(step_adjoint_pairs_kernel, blocks, 128, 0, as_stream(stream_), gv.n, group_slots, group_base, J, (const float2*)WA,
-                  (const float2*)SXY, (const float4*)xv4, dY_s, dAdir_s, c, dA_s);
+    if (flags_s != nullptr)
+        SPHNCA_LAUNCH(step_adjoint_pairs_kernel<true>, blocks, 128, 0, as_stream(stream_), gv.n, group_slots, group_base, J, (const float2*)WA,
+                      (const float2*)SXY, (const float4*)xv4, dY_s, dAdir_s, c, dA_s, flags_s, dAn_s);
+    else
+        SPHNCA_LAUNCH(step_adjoint_pairs_kernel<false>, blocks, 128, 0, as_stream(stream_), gv.n, group_slots, group_base, J, (const float2*)WA,
+                      (const float2*)SXY, (const float4*)xv4, dY_s, dAdir_s, c, dA_s, flags_s, dAn_s);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
+}
+
+int32_t sphnca_step_adjoint_pairs(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
+                                  const float* WA, const float* SXY, const float* xv4, const float* dY_s, const float* dAdir_s,
+                                  const sphnca_step_params* p, float* dA_s, void* stream_) {
+    return launch_adjoint_pairs(g, group_slots, group_base, J, WA, SXY, xv4, dY_s, dAdir_s, p, dA_s, nullptr, nullptr, stream_);
+}
+
+int32_t sphnca_step_adjoint_pairs_fired(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
+                                        const float* WA, const float* SXY, const float* xv4, const float* dY_s, const float* dAdir_s,
+                                        const uint8_t* flags_s, const float* dA_next_s, const sphnca_step_params* p, float* dA_s,
+                                        void* stream_) {
+    SPHNCA_CHECK_ARG(flags_s && dA_next_s, "NULL argument");
+    return launch_adjoint_pairs(g, group_slots, group_base, J, WA, SXY, xv4, dY_s, dAdir_s, p, dA_s, flags_s, dA_next_s, stream_);
 }
 
 }  // extern "C"

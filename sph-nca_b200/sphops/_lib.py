@@ -69,6 +69,7 @@ def _load():
         "sphnca_pairs_fill": ([G, P, P, P, P, P, P, P, P, P, P], I32),
         "sphnca_step_perceive_pairs": ([G, P, P, P, P, P, P, P, SP, P, P, P], I32),
         "sphnca_step_adjoint_pairs": ([G, P, P, P, P, P, P, P, P, SP, P, P], I32),
+        "sphnca_step_adjoint_pairs_fired": ([G, P, P, P, P, P, P, P, P, P, P, SP, P, P], I32),
         "sphnca_step_mask": ([G, P, P, P, P, P], I32),
         "sphnca_step_mask_static": ([I64, P, P, P], I32),
         "sphnca_step_perceive": ([G, P, P, SP, P, P, P], I32),

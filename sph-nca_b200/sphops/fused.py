@@ -376,14 +376,20 @@ class _NCARollout(torch.autograd.Function):
                     fb = fbuf
                 else:
                     fb = _FireBuffers.from_tensors(saved[_FireBuffers.PER_STEP * k:_FireBuffers.PER_STEP * (k + 1)])
-                _timed("step_bwd_unfired", lib.sphnca_step_bwd_unfired, N, ptr(fb.flags), ptr(gcur), ptr(dY_s), ptr(dAdir_s), st)
+                pl = ctx.pairs
+                if pl is None:      # the cell-sweep adjoint reads every row: the not-fired ones are written first
+                    _timed("step_bwd_unfired", lib.sphnca_step_bwd_unfired, N, ptr(fb.flags), ptr(gcur), ptr(dY_s), ptr(dAdir_s), st)
                 _timed("step_bwd", lib.sphnca_step_bwd_list, N, ptr(fb.rows), ptr(fb.count), ptr(fb.A_c), ptr(fb.O_c), ptr(fb.flags),
                        ptr(fb.relu_c), ptr(gcur), C.byref(p), ptr(dO_c), ptr(dY_s), ptr(dAdir_s), st)
                 if want_w:
                     _timed("mlp_wgrad", lib.sphnca_mlp_wgrad_list, N, ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), ptr(dO_c), C.byref(p),
                            ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value, st)
                 out = own[k & 1]
-                _adjoint(grid, ctx.pairs, xv4, dY_s, dAdir_s, p, out, st)
+                if pl is not None:  # fire-aware list adjoint: rows of not-fired particles come from their flag byte
+                    _timed("step_adjoint", lib.sphnca_step_adjoint_pairs_fired, grid.c_grid(), ptr(pl["slots"]), ptr(pl["base"]), ptr(pl["J"]),
+                           ptr(pl["WA"]), ptr(pl["SXY"]), ptr(xv4), ptr(dY_s), ptr(dAdir_s), ptr(fb.flags), ptr(gcur), C.byref(p), ptr(out), st)
+                else:
+                    _adjoint(grid, None, xv4, dY_s, dAdir_s, p, out, st)
                 gcur = out
             elif gcur is not None and N:        # steps after the last state a loss reads carry no gradient
                 if recompute:                   # the forward of step k again, from the saved state and fire bytes
