@@ -72,17 +72,19 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     const int n_mma = c.n_out < KO ? c.n_out : KO;
-    for (int i = tid; i < KO * NH; i += THREADS) {            // W2 [o][h] -> W2t[half] (rows h, K = o)
+    // W2 [o][h] -> W2t[half] (rows h, K = o)
+    stage_batched<8>(KO * NH, tid, THREADS, [&](int i) { return i / NH < n_mma ? __ldg(prm.W2 + i) : 0.f; }, [&](int i, float w) {
         const int o_ = i / NH, h = i - o_ * NH;
-        float hi, lo; split_tf32(o_ < n_mma ? __ldg(prm.W2 + (size_t)o_ * NH + h) : 0.f, hi, lo);
+        float hi, lo; split_tf32(w, hi, lo);
         const uint32_t o = fidx(128, h & 127, o_);
         s.W2t_hi[h >> 7][o] = hi; s.W2t_lo[h >> 7][o] = lo;
-    }
-    for (int i = tid; i < NH * NIN; i += THREADS) {           // W1 [h][k] -> W1t[half] (rows k, K = h)
+    });
+    // W1 [h][k] -> W1t[half] (rows k, K = h)
+    stage_batched<8>(NH * NIN, tid, THREADS, [&](int i) { return __ldg(prm.W1 + i); }, [&](int i, float w) {
         const int h = i / NIN, k = i - h * NIN;
-        float hi, lo; split_tf32(__ldg(prm.W1 + i), hi, lo);
+        float hi, lo; split_tf32(w, hi, lo);
         s.W1t[h >> 7][fidx(2 * NIN, k, h & 127)] = hi; s.W1t[h >> 7][fidx(2 * NIN, NIN + k, h & 127)] = lo;
-    }
+    });
     for (int i = tid; i < NH; i += THREADS) s.w2_last[i] = c.n_out > KO ? __ldg(prm.W2 + (size_t)KO * NH + i) : 0.f;
     if (tid == 0) {
         mbar_init(&s.bar[DO_FULL], LOAD_WARPS * 32); mbar_init(&s.bar[DO_EMPTY], 1);

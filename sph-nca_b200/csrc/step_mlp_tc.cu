@@ -84,18 +84,18 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int i = tid; i < NH * NIN; i += THREADS) {
+    stage_batched<8>(NH * NIN, tid, THREADS, [&](int i) { return __ldg(prm.W1 + i); }, [&](int i, float w) {
         const int n = i / NIN, k = i - n * NIN;
-        float hi, lo; split_tf32(__ldg(prm.W1 + i), hi, lo);
+        float hi, lo; split_tf32(w, hi, lo);
         const uint32_t o = fidx(128, n & 127, k);
         s.W1_hi[n >> 7][o] = hi; s.W1_lo[n >> 7][o] = lo;
-    }
+    });
     const int n_mma = c.n_out < N2 ? c.n_out : N2;
-    for (int i = tid; i < N2 * NH; i += THREADS) {
+    stage_batched<8>(N2 * NH, tid, THREADS, [&](int i) { return i / NH < n_mma ? __ldg(prm.W2 + i) : 0.f; }, [&](int i, float w) {
         const int o_ = i / NH, k = i - o_ * NH;
-        float hi, lo; split_tf32(o_ < n_mma ? __ldg(prm.W2 + (size_t)o_ * NH + k) : 0.f, hi, lo);
+        float hi, lo; split_tf32(w, hi, lo);
         s.W2[k >> 7][fidx(2 * N2, o_, k & 127)] = hi; s.W2[k >> 7][fidx(2 * N2, N2 + o_, k & 127)] = lo;
-    }
+    });
     for (int i = tid; i < NH; i += THREADS) {
         s.b1[i] = __ldg(prm.b1 + i);
         s.w2_last[i] = c.n_out > N2 ? __ldg(prm.W2 + (size_t)N2 * NH + i) : 0.f;

@@ -175,6 +175,20 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = x - hi;
 }
 
+// Weight staging at kernel start: U independent global loads per thread are issued before the first of them is used, so a
+// CTA pays the L2 latency total/(threads*U) times instead of total/threads times (the plain loop cost ~13 us per launch for
+// the 84 KB of weights -- visible now that a launch of the MLP kernels is only ~100 us).
+template <int U, typename L, typename S>
+__device__ __forceinline__ void stage_batched(int total, int tid, int threads, L load, S store) {
+    for (int i0 = tid; i0 < total; i0 += threads * U) {
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int i = i0 + u * threads; w[u] = i < total ? load(i) : 0.f; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int i = i0 + u * threads; if (i < total) store(i, w[u]); }
+    }
+}
+
 }  // namespace tc
 
 // development aid: per-role clock64 timestamps of CTA 0, 16 slots per tile/chunk iteration.  One buffer

@@ -79,18 +79,19 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
     const int64_t c0 = chunks_total * stream_id / num_streams, c1 = chunks_total * (stream_id + 1) / num_streams;
     const int n_mma = n_out < KO ? n_out : KO;
 
-    for (int i = tid; i < 128 * NIN; i += THREADS) {
+    stage_batched<8>(128 * NIN, tid, THREADS, [&](int i) { return __ldg(prm.W1 + (size_t)hh * 128 * NIN + i); }, [&](int i, float w) {
         const int h = i / NIN, k = i - h * NIN;
-        float hi, lo; split_tf32(__ldg(prm.W1 + (size_t)(hh * 128 + h) * NIN + k), hi, lo);
+        float hi, lo; split_tf32(w, hi, lo);
         const uint32_t o = fidx(128, h, k);
         s.W1_hi[o] = hi; s.W1_lo[o] = lo;
-    }
-    for (int i = tid; i < KO * 128; i += THREADS) {
+    });
+    stage_batched<8>(KO * 128, tid, THREADS, [&](int i) { return (i >> 7) < n_mma ? __ldg(prm.W2 + (size_t)(i >> 7) * NH + hh * 128 + (i & 127)) : 0.f; },
+                     [&](int i, float w) {
         const int o_ = i / 128, h = i - o_ * 128;
-        float hi, lo; split_tf32(o_ < n_mma ? __ldg(prm.W2 + (size_t)o_ * NH + hh * 128 + h) : 0.f, hi, lo);
+        float hi, lo; split_tf32(w, hi, lo);
         const uint32_t o = fidx(128, h, o_);
         s.W2t_hi[o] = hi; s.W2t_lo[o] = lo;
-    }
+    });
     for (int i = tid; i < 128; i += THREADS) {
         s.b1[i] = __ldg(prm.b1 + hh * 128 + i);
         s.w2_last[i] = n_out > KO ? __ldg(prm.W2 + (size_t)KO * NH + hh * 128 + i) : 0.f;
