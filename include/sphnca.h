@@ -218,17 +218,25 @@ int32_t sphnca_step_adjoint(const sphnca_grid* g, const float* xv4, const float*
  *                           the _list kernels read themselves: no host synchronisation.
  *   sphnca_step_mlp_list    sphnca_step_mlp over the listed rows.  O_c [N,36], relu_c [N,8] and the optional compact
  *                           copies A_c [N,16], Y_c [N,32] (contiguous input of sphnca_mlp_wgrad_list) are indexed by
- *                           list position; A_new_s, alive_s, flags_s by particle.
+ *                           list position; A_new_s, alive_s, flags_s by particle.  inputs_by_list != 0: A_s / Y_s are
+ *                           such compact arrays already (written by sphnca_step_perceive_pairs_fired), A_c = Y_c = NULL.
+ *   sphnca_step_perceive_pairs_fired  the perception sweep for the listed particles only (no alpha channel: the
+ *                           perception vector feeds nothing but the MLP); writes Y_c and the compact state rows A_c by
+ *                           list position, bit-identical to the rows of the full sweep.  sphnca_fire_list's FLG / flags_s
+ *                           pair (optional, both or neither) copies the static life-mask bit of every row meanwhile.
  *   sphnca_step_bwd_list    sphnca_step_bwd over the listed rows (dO_c by list position, dY_s / dAdir_s by particle);
  *   sphnca_step_bwd_unfired the not-fired rows of the same step: dY_s = 0, dAdir_s = living ? dA_next_s : 0.
  *   sphnca_mlp_wgrad_list   sphnca_mlp_wgrad over the first *count rows of the compact arrays (workspace sized for N). */
 int32_t sphnca_fire_list_workspace_bytes(int64_t N, size_t* bytes);
 int32_t sphnca_fire_list(int64_t N, const uint8_t* fire_s, const float* A_s, int32_t use_alpha, int32_t* rows,
-                         int32_t* count, float* A_new_s, uint8_t* alive_s, void* workspace, size_t workspace_bytes,
-                         void* stream);
+                         int32_t* count, float* A_new_s, uint8_t* alive_s, const uint8_t* FLG, uint8_t* flags_s,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int32_t sphnca_step_perceive_pairs_fired(const sphnca_grid* g, const int32_t* rows, const int32_t* count, const int32_t* group_slots,
+                                         const int64_t* group_base, const int32_t* J, const float* WP, const float* A_s,
+                                         const sphnca_step_params* p, float* Y_c, float* A_c, void* stream);
 int32_t sphnca_step_mlp_list(int64_t N, const int32_t* rows, const int32_t* count, const float* A_s, const float* Y_s,
                              const sphnca_step_params* p, float* A_new_s, uint8_t* alive_s, float* O_c, uint8_t* flags_s,
-                             uint32_t* relu_c, float* A_c, float* Y_c, void* stream);
+                             uint32_t* relu_c, float* A_c, float* Y_c, int32_t inputs_by_list, void* stream);
 int32_t sphnca_step_bwd_list(int64_t N, const int32_t* rows, const int32_t* count, const float* A_c, const float* O_c,
                              const uint8_t* flags_s, const uint32_t* relu_c, const float* dA_next_s,
                              const sphnca_step_params* p, float* dO_c, float* dY_s, float* dAdir_s, void* stream);

@@ -7,7 +7,8 @@
 //
 //   fire_list        rows[0..count) = sorted positions of the fired particles, in increasing order (ordered
 //                    compaction: block counts -> single-block scan -> in-block ranks; no atomics, deterministic);
-//                    the not-fired rows get their new state right here: A_new = A, alive byte from A.
+//                    the not-fired rows get their new state right here: A_new = A, alive byte from A; optionally the
+//                    static life-mask bit of every row (no alpha channel: pairs.cu FLG) is copied into the flag bytes.
 //   bwd_unfired      the backward of those rows: dL/dY = 0, direct dL/dA = (living ? dL/dA_new : 0).
 //
 // The tensor-core kernels (step_mlp_tc.cu, step_bwd_tc.cu, wgrad_tc.cu) then run over the `count` listed rows only;
@@ -79,7 +80,8 @@ fire_scan_kernel(int nb, int32_t* __restrict__ block_count, int32_t* __restrict_
 __global__ void __launch_bounds__(fl::THREADS)
 fire_fill_kernel(int64_t n, const uint8_t* __restrict__ fire_s, const int32_t* __restrict__ block_off,
                  const float* __restrict__ A_s, int use_alpha, int32_t* __restrict__ rows,
-                 float* __restrict__ A_new_s, uint8_t* __restrict__ alive_s) {
+                 float* __restrict__ A_new_s, uint8_t* __restrict__ alive_s, const uint8_t* __restrict__ FLG,
+                 uint8_t* __restrict__ flags_s) {
     using namespace fl;
     const int64_t base = (int64_t)blockIdx.x * BLOCK_ROWS + (int64_t)threadIdx.x * PER_THREAD;
     bool f[PER_THREAD];
@@ -100,6 +102,7 @@ fire_fill_kernel(int64_t n, const uint8_t* __restrict__ fire_s, const int32_t* _
     for (int k = 0; k < PER_THREAD; ++k) {
         const int64_t p = base + k;
         if (p >= n) break;
+        if (FLG != nullptr) flags_s[p] = FLG[p];            // static life mask (no alpha channel): the previous-mask bit of every row
         if (f[k]) { rows[slot++] = (int32_t)p; continue; }
         // not fired: the state is carried over unchanged (reference nca.py:107); fire bit of the flags stays 0
         const float4* a4 = reinterpret_cast<const float4*>(A_s + p * NF);
@@ -142,20 +145,21 @@ int32_t sphnca_fire_list_workspace_bytes(int64_t N, size_t* bytes) {
 }
 
 int32_t sphnca_fire_list(int64_t N, const uint8_t* fire_s, const float* A_s, int32_t use_alpha, int32_t* rows,
-                         int32_t* count, float* A_new_s, uint8_t* alive_s, void* workspace, size_t workspace_bytes,
-                         void* stream_) {
+                         int32_t* count, float* A_new_s, uint8_t* alive_s, const uint8_t* FLG, uint8_t* flags_s,
+                         void* workspace, size_t workspace_bytes, void* stream_) {
     SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
     SPHNCA_CHECK_ARG(count, "NULL argument");
     cudaStream_t stream = as_stream(stream_);
     if (N == 0) { SPHNCA_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), stream)); return SPHNCA_OK; }
     SPHNCA_CHECK_ARG(fire_s && A_s && rows && A_new_s && alive_s, "NULL argument");
+    SPHNCA_CHECK_ARG(FLG == nullptr || flags_s != nullptr, "flags_s is required with FLG");
     SPHNCA_CHECK_ARG(((uintptr_t)fire_s & 3) == 0, "fire_s must be 4-byte aligned");
     const int nb = (int)((N + fl::BLOCK_ROWS - 1) / fl::BLOCK_ROWS);
     if (!workspace || workspace_bytes < (size_t)(nb + 1) * sizeof(int32_t)) { set_error("fire-list workspace too small"); return SPHNCA_ERR_WORKSPACE; }
     int32_t* bc = reinterpret_cast<int32_t*>(workspace);
     SPHNCA_LAUNCH(fire_count_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc);
     SPHNCA_LAUNCH(fire_scan_kernel, 1, 1024, 0, stream, nb, bc, count);
-    SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s);
+    SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s, FLG, flags_s);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

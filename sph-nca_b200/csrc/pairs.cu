@@ -151,6 +151,64 @@ step_perceive_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, c
     if (part == 0) flags_s[p] = ALPHA ? (blur * c.cw > 0.1f ? 1 : 0) : FLG[p];
 }
 
+// Perception for the FIRED particles only (fire-list rollouts without an alpha channel, firelist.cu): the perception vector
+// feeds nothing but the MLP, and the MLP runs over the fired rows only, so the sweep of a not-fired particle is dead work.
+// One warp takes 8 consecutive list positions (4 lanes per particle as above); the 4 lanes of a particle fetch 4 slots of its
+// own list column (particles of one group share the 32-byte sectors of a slot), entries travel inside the quad by shuffle.
+// Same slot order and arithmetic as the full sweep: Y_c[j] is bit-identical to Y_s[rows[j]].  Also writes the compact copy of
+// the state row, so the MLP kernel reads [A_c | Y_c] rows contiguously by list position.
+__global__ void __launch_bounds__(128)
+step_perceive_pairs_fired_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ count_ptr,
+                                 const int32_t* __restrict__ group_slots, const int64_t* __restrict__ group_base,
+                                 const int32_t* __restrict__ J, const float2* __restrict__ WP, const float* __restrict__ A_s,
+                                 StepConsts c, float* __restrict__ Y_c, float* __restrict__ A_c) {
+    const int cnt = __ldg(count_ptr);
+    const int64_t j0 = ((int64_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * PG;
+    if (j0 >= cnt) return;
+    const int lane = threadIdx.x & 31, part = lane & 3, q = lane >> 2, quad0 = lane & ~3;
+    const int64_t j = j0 + q;
+    const bool valid = j < cnt;
+    const int64_t p = __ldg(rows + (valid ? j : (int64_t)cnt - 1));
+    const int64_t grp = p >> 3;
+    const int nb = group_slots[grp] >> 2;                 // batches of 4 slots of this particle's group
+    int maxb = nb;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) maxb = max(maxb, __shfl_xor_sync(0xffffffffu, maxb, o));
+    const int64_t e0 = group_base[grp] + (p & 7) + (int64_t)part * PG;      // slot `part` of batch 0, this particle's column
+    const float4* __restrict__ A4 = reinterpret_cast<const float4*>(A_s);
+    const float4 Ai = __ldg(A4 + (size_t)p * 4 + part);
+    float4 gx = make_float4(0.f, 0.f, 0.f, 0.f), gy = make_float4(0.f, 0.f, 0.f, 0.f);
+    // past the end of a shorter list: zero-weight self pairs (adding 0 * (A_i - A_i) leaves the sums bit-identical)
+    int jv = (int)p; float2 wp = make_float2(0.f, 0.f);
+    if (nb > 0) { jv = __ldcs(J + e0); wp = __ldcs(WP + e0); }
+#pragma unroll 1
+    for (int b = 0; b < maxb; ++b) {
+        float4 Aj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) Aj[u] = __ldg(A4 + (size_t)__shfl_sync(0xffffffffu, jv, quad0 + u) * 4 + part);
+        const float2 wpc = wp;
+        if (b + 1 < nb) { const int64_t e = e0 + (int64_t)(b + 1) * 32; jv = __ldcs(J + e); wp = __ldcs(WP + e); }
+        else { jv = (int)p; wp = make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float wxs = __shfl_sync(0xffffffffu, wpc.x, quad0 + u), wys = __shfl_sync(0xffffffffu, wpc.y, quad0 + u);
+            const float2 wx = make_float2(wxs, wxs), wy = make_float2(wys, wys);
+            const float2 d0 = fsub2(make_float2(Aj[u].x, Aj[u].y), make_float2(Ai.x, Ai.y));
+            const float2 d1 = fsub2(make_float2(Aj[u].z, Aj[u].w), make_float2(Ai.z, Ai.w));
+            float2 t;
+            t = ffma2(d0, wx, make_float2(gx.x, gx.y)); gx.x = t.x; gx.y = t.y;
+            t = ffma2(d1, wx, make_float2(gx.z, gx.w)); gx.z = t.x; gx.w = t.y;
+            t = ffma2(d0, wy, make_float2(gy.x, gy.y)); gy.x = t.x; gy.y = t.y;
+            t = ffma2(d1, wy, make_float2(gy.z, gy.w)); gy.z = t.x; gy.w = t.y;
+        }
+    }
+    if (!valid) return;
+    float4* y4 = reinterpret_cast<float4*>(Y_c + (size_t)j * 2 * NF);
+    y4[part] = make_float4(gx.x * c.kg, gx.y * c.kg, gx.z * c.kg, gx.w * c.kg);
+    y4[4 + part] = make_float4(gy.x * c.kg, gy.y * c.kg, gy.z * c.kg, gy.w * c.kg);
+    reinterpret_cast<float4*>(A_c + (size_t)j * NF)[part] = Ai;
+}
+
 // Gather adjoint of the perception sweep from the pair lists (same output as step_adjoint_kernel).
 // FIRED (fire-list rollouts, firelist.cu): dL/dY of a particle that did not fire is exactly zero and its direct dL/dA part is
 // (living ? dL/dA_new : 0), so both are taken from the flag byte instead of from memory: the 128-byte row gather of a not-fired
@@ -262,6 +320,21 @@ int32_t sphnca_step_perceive_pairs(const sphnca_grid* g, const int32_t* group_sl
                                    (const float2*)WP, (const float2*)WB, FLG, A_s, c, Y_s, flags_s);
     else SPHNCA_LAUNCH(step_perceive_pairs_kernel<false>, blocks, 128, 0, as_stream(stream_), gv.n, group_slots, group_base, J,
                        (const float2*)WP, (const float2*)WB, FLG, A_s, c, Y_s, flags_s);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_step_perceive_pairs_fired(const sphnca_grid* g, const int32_t* rows, const int32_t* count, const int32_t* group_slots,
+                                         const int64_t* group_base, const int32_t* J, const float* WP, const float* A_s,
+                                         const sphnca_step_params* p, float* Y_c, float* A_c, void* stream_) {
+    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
+    if (gv.n == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(rows && count && group_slots && group_base && J && WP && A_s && Y_c && A_c, "NULL argument");
+    SPHNCA_CHECK_ARG(!p->use_alpha, "the fired-rows sweep has no life-mask part: use sphnca_step_perceive_pairs with an alpha channel");
+    const int blocks = (int)((gv.n + 31) / 32);           // sized for all N particles; warps past *count exit at once
+    SPHNCA_LAUNCH(step_perceive_pairs_fired_kernel, blocks, 128, 0, as_stream(stream_), rows, count, group_slots, group_base, J,
+                  (const float2*)WP, A_s, c, Y_c, A_c);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

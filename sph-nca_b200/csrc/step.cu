@@ -693,14 +693,16 @@ int32_t sphnca_step_mlp(int64_t N, const float* A_s, const float* Y_s, const uin
 
 int32_t sphnca_step_mlp_list(int64_t N, const int32_t* rows, const int32_t* count, const float* A_s, const float* Y_s,
                              const sphnca_step_params* p, float* A_new_s, uint8_t* alive_s, float* O_c, uint8_t* flags_s,
-                             uint32_t* relu_c, float* A_c, float* Y_c, void* stream_) {
+                             uint32_t* relu_c, float* A_c, float* Y_c, int32_t inputs_by_list, void* stream_) {
     SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
     sphnca_grid fake{}; fake.dim = 3; fake.h = 1.0;      // geometry constants are unused by the MLP half
     StepConsts c; { int rc = make_consts(&fake, p, &c); if (rc) return rc; }
     if (N == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(rows && count && A_s && Y_s && A_new_s && alive_s && O_c && flags_s && relu_c, "NULL argument");
     SPHNCA_CHECK_ARG((A_c == nullptr) == (Y_c == nullptr), "A_c and Y_c must be given together");
-    return launch_step_mlp_tc(N, c, p, A_s, Y_s, nullptr, A_new_s, alive_s, O_c, flags_s, relu_c, as_stream(stream_), rows, count, A_c, Y_c);
+    SPHNCA_CHECK_ARG(!(inputs_by_list && A_c), "inputs_by_list: A_s / Y_s are the compact arrays already, no copies are made");
+    return launch_step_mlp_tc(N, c, p, A_s, Y_s, nullptr, A_new_s, alive_s, O_c, flags_s, relu_c, as_stream(stream_), rows, count, A_c, Y_c,
+                              inputs_by_list ? 1 : 0);
 }
 
 int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s, const uint8_t* fire_s,

@@ -71,11 +71,12 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                    float* __restrict__ An_s, float* __restrict__ O_s, uint8_t* __restrict__ flags_s,
                    uint8_t* __restrict__ alive_s, uint32_t* __restrict__ relu_s, int num_tiles,
                    const int32_t* __restrict__ rows, const int32_t* __restrict__ count_ptr,
-                   float* __restrict__ A_c, float* __restrict__ Y_c) {
+                   float* __restrict__ A_c, float* __restrict__ Y_c, int in_by_list) {
     using namespace mt;
     // Fire-list mode (rows != NULL, firelist.cu): tile row j stands for sorted particle rows[j], j < *count (the count is
     // read from device memory: no host synchronisation); every listed particle fired.  O_s, relu_s and the compact copies
     // A_c, Y_c (the weight-gradient kernel's contiguous input) are indexed by j, the state / flag arrays by the particle.
+    // in_by_list: A_s and Y_s ARE such compact arrays already (the fired-rows perception sweep wrote them): rows are read by j.
     if (count_ptr != nullptr) {
         n_total = __ldg(count_ptr);
         num_tiles = (n_total + TILE - 1) / TILE;
@@ -125,7 +126,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             const int j = tile * TILE + m;
             float4 v[NIN / 4];
             if (j < n_total) {
-                const int p = rows ? __ldg(rows + j) : j;
+                const int p = (rows && !in_by_list) ? __ldg(rows + j) : j;
                 const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)p * NF);
                 const float4* y4 = reinterpret_cast<const float4*>(Y_s + (size_t)p * 2 * NF);
 #pragma unroll
@@ -257,7 +258,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             for (int k = 0; k < 4; ++k) Ai4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             uint32_t fire_raw = 0, flag_raw = 0;
             if (valid) {
-                const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)p * NF);
+                const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)(in_by_list ? j : p) * NF);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) Ai4[k] = ldg_f4_raw(a4 + k);
                 fire_raw = rows ? 1u : ldg_u8_raw(fire_s + p);
@@ -398,7 +399,8 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
 
 int launch_step_mlp_tc(int64_t N, const StepConsts& c, const sphnca_step_params* p, const float* A_s, const float* Y_s,
                        const uint8_t* fire_s, float* A_new_s, uint8_t* alive_s, float* O_s, uint8_t* flags_s,
-                       uint32_t* relu_s, cudaStream_t stream, const int32_t* rows, const int32_t* count, float* A_c, float* Y_c) {
+                       uint32_t* relu_s, cudaStream_t stream, const int32_t* rows, const int32_t* count, float* A_c, float* Y_c,
+                       int in_by_list) {
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -410,7 +412,7 @@ int launch_step_mlp_tc(int64_t N, const StepConsts& c, const sphnca_step_params*
     const size_t smem = sizeof(mt::Smem);
     SPHNCA_CUDA(cudaFuncSetAttribute(step_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPHNCA_LAUNCH(step_mlp_tc_kernel, blocks, mt::THREADS, smem, stream, (int)N, A_s, Y_s, fire_s, *p, c, A_new_s, O_s, flags_s,
-                  alive_s, relu_s, num_tiles, rows, count, A_c, Y_c);
+                  alive_s, relu_s, num_tiles, rows, count, A_c, Y_c, in_by_list);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

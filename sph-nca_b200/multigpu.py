@@ -231,11 +231,11 @@ class SlabShardedNCA:
             fire_s = self.grid.pack_bytes(fire)
             if lists:
                 check(lib.sphnca_fire_list(N, ptr(fire_s), ptr(A_s), int(bool(m.use_alpha)), ptr(rows), ptr(count), ptr(An_s),
-                                           ptr(alive_s), ptr(ws_fl), ws_fl.numel(), st))
+                                           ptr(alive_s), None, None, ptr(ws_fl), ws_fl.numel(), st))
             fused._perceive_pl(self.grid, pl, g, self.xv4, A_s, prm, Y_s, flags_s, st)
             if lists:
                 check(lib.sphnca_step_mlp_list(N, ptr(rows), ptr(count), ptr(A_s), ptr(Y_s), C.byref(prm), ptr(An_s), ptr(alive_s),
-                                               ptr(O_s), ptr(flags_s), ptr(relu_s), None, None, st))
+                                               ptr(O_s), ptr(flags_s), ptr(relu_s), None, None, 0, st))
             else:
                 check(lib.sphnca_step_mlp(N, ptr(A_s), ptr(Y_s), ptr(fire_s), C.byref(prm), ptr(An_s), ptr(alive_s), ptr(O_s),
                                           ptr(flags_s), ptr(relu_s), st))

@@ -212,16 +212,24 @@ class _FireBuffers:
 
 
 def _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, alive_s, fb, ws_fl, st, pl=False):
-    """One forward step on the fire-list path: list + carried-over rows, perception sweep, MLP over the list, life mask."""
+    """One forward step on the fire-list path: list + carried-over rows, perception sweep, MLP over the list, life mask.
+    Without an alpha channel and with pair lists the perception sweep itself runs over the fired particles only and writes the
+    compact [A_c | Y_c] rows the MLP kernel reads (needs fb.A_c / fb.Y_c); otherwise the full sweep fills Y_s."""
     N = S.shape[0]
-    _timed("fire_list", lib.sphnca_fire_list, N, ptr(fire_s), ptr(S), int(bool(use_alpha)), ptr(fb.rows), ptr(fb.count), ptr(Sn),
-           ptr(alive_s), ptr(ws_fl), ws_fl.numel(), st)
     if pl is False:
-        _perceive(grid, x, v, g, xv4, S, p, Y_s, fb.flags, st)
+        pl = grid.pair_lists(x, v)
+    fired_sweep = pl is not None and not use_alpha and fb.A_c is not None
+    _timed("fire_list", lib.sphnca_fire_list, N, ptr(fire_s), ptr(S), int(bool(use_alpha)), ptr(fb.rows), ptr(fb.count), ptr(Sn),
+           ptr(alive_s), ptr(pl["FLG"]) if fired_sweep else None, ptr(fb.flags) if fired_sweep else None, ptr(ws_fl), ws_fl.numel(), st)
+    if fired_sweep:
+        _timed("step_perceive", lib.sphnca_step_perceive_pairs_fired, g, ptr(fb.rows), ptr(fb.count), ptr(pl["slots"]), ptr(pl["base"]),
+               ptr(pl["J"]), ptr(pl["WP"]), ptr(S), C.byref(p), ptr(fb.Y_c), ptr(fb.A_c), st)
+        _timed("step_mlp", lib.sphnca_step_mlp_list, N, ptr(fb.rows), ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), C.byref(p), ptr(Sn),
+               ptr(alive_s), ptr(fb.O_c), ptr(fb.flags), ptr(fb.relu_c), None, None, 1, st)
     else:
         _perceive_pl(grid, pl, g, xv4, S, p, Y_s, fb.flags, st)
-    _timed("step_mlp", lib.sphnca_step_mlp_list, N, ptr(fb.rows), ptr(fb.count), ptr(S), ptr(Y_s), C.byref(p), ptr(Sn), ptr(alive_s),
-           ptr(fb.O_c), ptr(fb.flags), ptr(fb.relu_c), ptr(fb.A_c), ptr(fb.Y_c), st)
+        _timed("step_mlp", lib.sphnca_step_mlp_list, N, ptr(fb.rows), ptr(fb.count), ptr(S), ptr(Y_s), C.byref(p), ptr(Sn), ptr(alive_s),
+               ptr(fb.O_c), ptr(fb.flags), ptr(fb.relu_c), ptr(fb.A_c), ptr(fb.Y_c), 0, st)
     _mask(use_alpha, g, N, xv4, alive_s, Sn, fb.flags, st)
 
 
@@ -285,7 +293,7 @@ class _NCARollout(torch.autograd.Function):
             if fl:
                 # MLP half over the fired rows only (firelist.cu); not-fired rows are carried over by the list kernel
                 if taped == 1 or fbuf is None:
-                    fbuf = _FireBuffers(N, dev, compact_inputs=taped == 1)
+                    fbuf = _FireBuffers(N, dev, compact_inputs=True)
                 _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, alive_s, fbuf, ws_fl, st)
                 if taped == 1:
                     saved += fbuf.tensors()

@@ -617,7 +617,7 @@ def test_fire_list_is_the_ordered_compaction(n, rate):
     _lib.check(_lib.lib.sphnca_fire_list_workspace_bytes(n, C.byref(nb)))
     ws = torch.empty((nb.value,), dtype=torch.uint8, device=DEV)
     _lib.check(_lib.lib.sphnca_fire_list(n, _lib.ptr(fire), _lib.ptr(A), 1, _lib.ptr(rows), _lib.ptr(count), _lib.ptr(An), _lib.ptr(alive),
-                                         _lib.ptr(ws), nb.value, _lib.stream_ptr()))
+                                         None, None, _lib.ptr(ws), nb.value, _lib.stream_ptr()))
     want = torch.nonzero(fire)[:, 0].to(torch.int32)
     assert int(count.item()) == want.numel()
     assert torch.equal(rows[:want.numel()], want)
