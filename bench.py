@@ -28,6 +28,9 @@ import sys
 import threading
 import time
 
+# NCCL writes its version / debug lines to stdout by default; stdout carries exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "sph-nca_b200"))
