@@ -34,6 +34,38 @@ def test_pool_api():
     assert torch.allclose(pool.A[idx[1]], As.view(4, 50, 16)[1] + 1)
 
 
+def _pool_run(device):
+    import nca
+    torch.manual_seed(7)
+    x = torch.rand(40, 2); A = torch.rand(40, 16)
+    pool = nca.Pool((x, A), 6, randomized_feat=False, device=device)
+    out = []
+    for it in range(3):
+        xs, As, sections, idx = pool.sample(3, pool.device if device else "cpu", replace_worst=True,
+                                            loss_fn=lambda x, A, img: [float(a.sum()) for a in A], degrade_prob=0.0)
+        pool.update(xs, As * 0.5 + it, idx)
+        out.append((xs.cpu(), As.cpu(), idx.clone()))
+    return out, pool.A.cpu()
+
+
+def test_pool_resident_on_a_device_equals_cpu_pool():
+    """`device=` keeps the pool on that device; the samples, the order and the stored states equal the CPU pool's."""
+    a, Aa = _pool_run(None)
+    b, Ab = _pool_run("cpu")
+    for (x0, A0, i0), (x1, A1, i1) in zip(a, b):
+        assert torch.equal(x0, x1) and torch.equal(A0, A1) and torch.equal(i0, i1)
+    assert torch.equal(Aa, Ab)
+
+
+@pytest.mark.gpu
+def test_pool_resident_on_the_gpu_equals_cpu_pool():
+    a, Aa = _pool_run(None)
+    b, Ab = _pool_run(DEV)
+    for (x0, A0, i0), (x1, A1, i1) in zip(a, b):
+        assert torch.equal(x0, x1) and torch.equal(A0, A1) and torch.equal(i0, i1)
+    assert torch.equal(Aa, Ab)
+
+
 def _model(g, **kw):
     import nca
     m = nca.SPHNCA(16, 0.5, **kw).to(DEV)

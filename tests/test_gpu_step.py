@@ -659,6 +659,34 @@ def test_rollout_fire_lists_equal_full_mlp(use_alpha, rate, monkeypatch):
             assert_close(b, a, rtol=2e-6, what=nm)
 
 
+def test_rollout_fire_lists_orig_rule_and_call_fire_rate(monkeypatch):
+    """Same equality for the `orig` update rule (16 MLP outputs, rate-scaled residual) with a per-call fire rate."""
+    import nca
+    from sphops import fused
+    K = 3
+    x, sections, h, dims, A0, params, masks, cfg = oracle_case(56, False, False, K, seed=31)
+    nca.USE_3D, nca.USE_FUSED_STEP = True, True
+    torch.manual_seed(5)
+    m = nca.SPHNCA(16, 0.5, update_rule="orig", use_alpha=False, normalize_perception=1.0 / h).to(DEV)
+    with torch.no_grad():
+        m.model[2].weight.copy_(0.05 * torch.randn_like(m.model[2].weight))
+    xd = x.to(DEV)
+    res = []
+    for lists in (False, True):
+        monkeypatch.setattr(fused, "FIRE_LISTS", lists)
+        m.zero_grad()
+        grid, v = m.init_grid(xd, sections, h, dims)
+        A = A0.to(DEV).requires_grad_(True)
+        with forced_fire_masks(list(masks)):
+            out = m.rollout(xd, v, A, h, grid, K, fire_rate=0.25, checkpoint=False)
+        (out[-1][:, :5] ** 2).mean().backward()
+        res.append((out[-1].detach().clone(), A.grad.clone(), [p.grad.clone() for p in m.parameters()]))
+    assert torch.equal(res[0][0], res[1][0])
+    assert_close(res[1][1], res[0][1], rtol=1e-6, what="dL/dA0")
+    for a, b, nm in zip(res[0][2], res[1][2], ("dW1", "db1", "dW2", "db2")):
+        assert_close(b, a, rtol=2e-6, what=nm)
+
+
 def test_rollout_node_inference_keeps_only_what_is_asked():
     """No tape, keep_all=False: two states (first, last); same final state as the stepwise path; sequence protocol."""
     import random
