@@ -65,9 +65,9 @@ UNIT = "particle-steps/s"
 # (compulsory traffic of that kernel's interface), flops = algorithmic FLOPs per particle (FMA = 2),
 # bound = which roof applies: "hbm" (sweeps: memory/latency side) or "tensor" (tcgen05 MLP kernels).
 KERNELS = {
-    # perception from the pair lists (csrc/pairs.cu): ~36 list slots x 12 B (J, WP; +8 B WB with an alpha channel) + A row (64)
-    # + write dA/dx|dA/dy (128) + flag; 24 packed FMA/ADD pairs per slot
-    "step_perceive": dict(bytes=626.0, flops=36 * 64.0, bound="hbm"),
+    # perception from the pair lists (csrc/pairs.cu), over the FIRED rows only (no alpha channel): ~36 list slots x 12 B (J, WP)
+    # + A row (64) + list entry (4) + write compact Y_c (128) and A_c (64); 24 packed FMA/ADD pairs per slot
+    "step_perceive": dict(bytes=692.0, flops=36 * 64.0, bound="hbm", rows="fired"),
     # ordered compaction of the fire mask + carry-over of the not-fired rows: fire bytes twice (2), list entry (4 x 0.5),
     # not-fired row copy (129 x 0.5)
     "fire_list": dict(bytes=68.5, flops=0.0, bound="hbm"),

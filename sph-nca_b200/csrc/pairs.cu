@@ -209,6 +209,8 @@ step_perceive_pairs_fired_kernel(const int32_t* __restrict__ rows, const int32_t
     reinterpret_cast<float4*>(A_c + (size_t)j * NF)[part] = Ai;
 }
 
+__device__ float4 g_zero_row[8];      // 128 bytes of zeros: the dL/dY row of every particle that did not fire
+
 // Gather adjoint of the perception sweep from the pair lists (same output as step_adjoint_kernel).
 // FIRED (fire-list rollouts, firelist.cu): dL/dY of a particle that did not fire is exactly zero and its direct dL/dA part is
 // (living ? dL/dA_new : 0), so both are taken from the flag byte instead of from memory: the 128-byte row gather of a not-fired
@@ -238,11 +240,9 @@ step_adjoint_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, co
         for (int u = 0; u < 4; ++u) {
             const int j = __shfl_sync(0xffffffffu, jv, u * PG + q);
             const size_t row = (size_t)j * 8;
-            if (FIRED && !(__ldg(flags_s + j) & 4)) {
-                a[u] = make_float4(0.f, 0.f, 0.f, 0.f); bb[u] = a[u];
-            } else {
-                a[u] = __ldg(G4 + row + part); bb[u] = __ldg(G4 + row + 4 + part);
-            }
+            // not fired: read a row of zeros instead (one shared, always-cached line) -- a select on the pointer, no divergent branch
+            const float4* src = (FIRED && !(__ldg(flags_s + j) & 4)) ? g_zero_row : G4 + row;
+            a[u] = __ldg(src + part); bb[u] = __ldg(src + 4 + part);
         }
         const float2 wac = wa;
         if (b + 1 < batches) { const int64_t e = e0 + (int64_t)(b + 1) * 32; jv = __ldcs(J + e); wa = __ldcs(WA + e); }
