@@ -224,11 +224,21 @@ class SlabShardedNCA:
             count = torch.empty((1,), dtype=torch.int32, device=dev)
             ws_fl = fused._fire_list_workspace(N, dev)
         nbytes = 0
+        fb = None
         for k in range(steps):
             nbytes += self._exchange_sorted(A_s)
             fire = torch.zeros((N,), dtype=torch.uint8, device=dev)
             fire[:p.n_own] = (fire_masks[k] if fire_masks is not None else (torch.rand(p.n_own, device=dev) <= fr)).to(torch.uint8)
             fire_s = self.grid.pack_bytes(fire)
+            if lists and not m.use_alpha:
+                # no alpha channel: list, perception sweep over the fired rows, MLP over compact rows, static life mask --
+                # the rollout node's forward step; halo rows never fire, so nothing at all is computed for them
+                if fb is None:
+                    fb = fused._FireBuffers(N, dev, compact_inputs=True)
+                fb.flags = flags_s
+                fused._step_forward_lists(self.grid, None, None, g, self.xv4, A_s, fire_s, prm, False, Y_s, An_s, alive_s, fb, ws_fl, st, pl=pl)
+                A_s, An_s = An_s, A_s
+                continue
             if lists:
                 check(lib.sphnca_fire_list(N, ptr(fire_s), ptr(A_s), int(bool(m.use_alpha)), ptr(rows), ptr(count), ptr(An_s),
                                            ptr(alive_s), None, None, ptr(ws_fl), ws_fl.numel(), st))
