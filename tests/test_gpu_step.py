@@ -97,6 +97,82 @@ def test_step_matches_reference(name, path):
         assert_close(P[pn].grad, g[key], rtol=GRAD_RTOL, what=key)
 
 
+@pytest.mark.parametrize("checkpoint", [False, True], ids=["tape", "checkpointed"])
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_rollout_node_matches_reference(name, checkpoint):
+    """The DEFAULT product path -- `SPHNCA.rollout`: one autograd node, fire lists, fired-rows perception, tcgen05 kernels,
+    with and without activation checkpointing -- against the reference's golden vectors: every state, the loss,
+    dL/dA0 and the four parameter gradients (same loss as run_case: final state + 0.1 x state 1)."""
+    import nca
+    g = load_golden(name)
+    nca.USE_FUSED_STEP = True
+    model = build_model(g)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    h, dims = float(g["h"]), int(g["dims"])
+    fr = float(g["fire_rate_call"])
+    fr = None if fr < 0 else fr
+    grid, v = model.init_grid(x, tuple(g["sections"]), h, dims)
+    A0 = torch.from_numpy(g["states"][0]).to(DEV).requires_grad_(True)
+    K = g["masks"].shape[0]
+    with forced_fire_masks(g["masks"]):
+        out = model.rollout(x, v, A0, h, grid, K, fire_rate=fr, checkpoint=checkpoint)
+    assert out is not None and len(out) == K + 1
+    loss = (out[-1][:, :4] ** 2).mean()
+    if K > 1:
+        loss = loss + 0.1 * (out[1][:, :4] ** 2).mean()
+    loss.backward()
+    for k in range(1, K + 1):
+        ref = g["states"][k]
+        diff = np.abs(out[k].detach().cpu().numpy().astype(np.float64) - ref)
+        bad = (diff.max(-1) > RTOL * np.abs(ref).max()).mean()
+        assert bad == 0.0, f"step {k}: {bad:.3%} of particles differ (max rel {diff.max()/np.abs(ref).max():.2e})"
+    assert abs(float(loss.detach()) - float(g["loss"])) <= RTOL * abs(float(g["loss"]))
+    assert_close(A0.grad, g["dA0"], rtol=GRAD_RTOL, what="dL/dA0")
+    P = dict(model.named_parameters())
+    for key, pn in (("dW1", "model.0.weight"), ("db1", "model.0.bias"), ("dW2", "model.2.weight"), ("db2", "model.2.bias")):
+        assert_close(P[pn].grad, g[key], rtol=GRAD_RTOL, what=key)
+
+
+def test_rollout_node_matches_oracle_midsize_and_is_reproducible():
+    """The default rollout node vs the fp64 oracle at 14 k 3-D particles with the BASELINE neighbour count (K=4, fwd+bwd), and
+    a second run of it: bit-identical states and gradients (ordered fire lists, fixed-order reductions, gather adjoints)."""
+    import nca
+    from oracle import sphnca_oracle as O
+    K = 4
+    x, sections, h, dims, A0, params, masks, cfg = oracle_case(24, True, False, K, seed=21)
+    A_ref, loss_ref, dA0_ref, dP_ref = O.rollout_fwd_bwd(x, sections, h, dims, A0, params, masks, cfg)
+    nca.USE_FUSED_STEP = True
+    m = nca.SPHNCA(16, 0.5, use_alpha=False, normalize_perception=cfg.normalize_perception).to(DEV)
+    with torch.no_grad():
+        for t, src in zip((m.model[0].weight, m.model[0].bias, m.model[2].weight, m.model[2].bias), params):
+            t.copy_(src)
+    xd = x.to(DEV)
+    runs = []
+    for _ in range(2):
+        m.zero_grad()
+        grid, v = m.init_grid(xd, sections, h, dims)
+        A = A0.to(DEV).requires_grad_(True)
+        with forced_fire_masks(list(masks)):
+            out = m.rollout(xd, v, A, h, grid, K)
+        loss = (out[-1][:, :4] ** 2).mean()
+        loss.backward()
+        runs.append([out[-1].detach().clone(), A.grad.clone()] + [p.grad.clone() for p in m.parameters()])
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)
+    A_K, dA0 = runs[0][0], runs[0][1]
+    ref = A_ref.numpy()
+    diff = np.abs(A_K.cpu().numpy().astype(np.float64) - ref).max(-1)
+    assert (diff > 1e-4 * np.abs(ref).max()).mean() == 0.0
+    assert_close(A_K, A_ref, rtol=2e-5, what="A_K")
+    assert abs(float(loss.detach()) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+    gref = dA0_ref.numpy()
+    gerr = np.abs(dA0.cpu().numpy().astype(np.float64) - gref).max(-1) / np.abs(gref).max()
+    frac = (gerr > 5e-5).mean()         # ReLU-kink flips, see test_fused_rollout_matches_oracle_midsize
+    assert frac <= 2e-2 and gerr.max() <= 2e-2, f"dL/dA0: {frac:.3%} rows > 5e-5, worst {gerr.max():.2e}"
+    for t, r, nm in zip(runs[0][2:], dP_ref, ("dW1", "db1", "dW2", "db2")):
+        assert_close(t, r, rtol=5e-4, what=nm)
+
+
 def test_sample_plane_driver_matches_reference_call_pattern():
     """nca.sample_plane on the fused path: pads 2-D to 3-D, K steps, returns x in 2-D; masks forced to the
     reference run's draws (the reference drew them on the CPU generator)."""
