@@ -161,7 +161,9 @@ int32_t sphnca_stage_fit(const sphnca_grid* g, int32_t* counts, void* stream);
  *   sphnca_pairs_count   group_slots int32 [ceil(N/8)]
  *   caller               group_base int64 [ceil(N/8)] = 8 * exclusive prefix sum of group_slots; E = 8 * sum
  *   sphnca_pairs_fill    J int32 [E], WP / WB / WA float [E,2], SXY float [N,2], FLG uint8 [N] (the life mask of an
- *                        all-alive field: what the perception sweep reports when use_alpha == 0)
+ *                        all-alive field: what the perception sweep reports when use_alpha == 0); WB (the life-mask blur
+ *                        weights, 8 of the 28 bytes per pair) may be NULL when no model with an alpha channel will use the
+ *                        lists -- sphnca_step_perceive_pairs then requires use_alpha == 0
  *   sphnca_step_perceive_pairs / sphnca_step_adjoint_pairs: same outputs, bit for bit, as sphnca_step_perceive /
  *   sphnca_step_adjoint (same visiting order, same floats), from the lists. */
 int32_t sphnca_pairs_count(const sphnca_grid* g, const float* xv4, int32_t* group_slots, void* stream);

@@ -83,7 +83,8 @@ pairs_fill_kernel(GridView g, const float4* __restrict__ xv4, float h, float h2,
                     wa = make_float2(ma * rx, ma * ry);
                     sx = fmaf(wa.x, xj.w, sx); sy = fmaf(wa.y, xj.w, sy);
                 }
-                J[e] = q; WP[e] = wp; WB[e] = make_float2(xj.w, t * t * t); WA[e] = wa;
+                J[e] = q; WP[e] = wp; WA[e] = wa;
+                if (WB != nullptr) WB[e] = make_float2(xj.w, t * t * t);
                 e += PG; ++cnt;
             }
         });
@@ -91,7 +92,8 @@ pairs_fill_kernel(GridView g, const float4* __restrict__ xv4, float h, float h2,
         FLG[p] = blur1 * cw > 0.1f ? 1 : 0;
     }
     for (; cnt < slots; ++cnt, e += PG) {                 // zero-weight self pairs up to the group's slot count
-        J[e] = (int32_t)self; WP[e] = make_float2(0.f, 0.f); WB[e] = make_float2(0.f, 0.f); WA[e] = make_float2(0.f, 0.f);
+        J[e] = (int32_t)self; WP[e] = make_float2(0.f, 0.f); WA[e] = make_float2(0.f, 0.f);
+        if (WB != nullptr) WB[e] = make_float2(0.f, 0.f);
     }
 }
 
@@ -296,7 +298,7 @@ int32_t sphnca_pairs_fill(const sphnca_grid* g, const float* xv4, const int32_t*
                           int32_t* J, float* WP, float* WB, float* WA, float* SXY, uint8_t* FLG, void* stream_) {
     GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
     if (gv.n == 0) return SPHNCA_OK;
-    SPHNCA_CHECK_ARG(xv4 && group_slots && group_base && J && WP && WB && WA && SXY && FLG, "NULL argument");
+    SPHNCA_CHECK_ARG(xv4 && group_slots && group_base && J && WP && WA && SXY && FLG, "NULL argument");   // WB may be NULL
     const float cw = (float)poly6_norm(g->dim, g->h);
     const int blocks = (int)((gv.n + 127) / 128);
     const float h = (float)g->h, h2 = (float)(g->h * g->h);
@@ -314,7 +316,8 @@ int32_t sphnca_step_perceive_pairs(const sphnca_grid* g, const int32_t* group_sl
     GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
     StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
     if (gv.n == 0) return SPHNCA_OK;
-    SPHNCA_CHECK_ARG(group_slots && group_base && J && WP && WB && FLG && A_s && Y_s && flags_s, "NULL argument");
+    SPHNCA_CHECK_ARG(group_slots && group_base && J && WP && FLG && A_s && Y_s && flags_s, "NULL argument");
+    SPHNCA_CHECK_ARG(WB != nullptr || !p->use_alpha, "the blur weights WB are required with an alpha channel");
     const int blocks = (int)((gv.n + 31) / 32);           // one warp per group of 8 particles, 4 groups per CTA
     if (c.use_alpha) SPHNCA_LAUNCH(step_perceive_pairs_kernel<true>, blocks, 128, 0, as_stream(stream_), gv.n, group_slots, group_base, J,
                                    (const float2*)WP, (const float2*)WB, FLG, A_s, c, Y_s, flags_s);

@@ -217,7 +217,7 @@ class SlabShardedNCA:
         g, st = self.grid.c_grid(), _lib.stream_ptr()
         # the slab's own pair lists (built once per partition) and, per step, the list of the fired rows: the MLP runs
         # over those only (halo rows never fire: their results are overwritten by the next exchange anyway)
-        pl = self.grid.pair_lists(self.x_loc, self.v)
+        pl = self.grid.pair_lists(self.x_loc, self.v, blur=bool(m.use_alpha))
         lists = fused._fire_lists_on() and N > 0
         if lists:
             rows = torch.empty((N,), dtype=torch.int32, device=dev)

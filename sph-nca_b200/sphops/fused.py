@@ -50,7 +50,7 @@ def _perceive_entry(grid):
 
 def _perceive(grid, x, v, g, xv4, A_s, p, Y_s, flags_s, st):
     """Perception sweep: from the grid's pair lists when they exist, else by sweeping the cells."""
-    pl = grid.pair_lists(x, v)
+    pl = grid.pair_lists(x, v, blur=bool(p.use_alpha))
     _perceive_pl(grid, pl, g, xv4, A_s, p, Y_s, flags_s, st)
     return pl
 
@@ -114,7 +114,7 @@ class _NCAStep(torch.autograd.Function):
             _mask(use_alpha, g, N, xv4, alive_s, An_s, flags_s, st)
         out = grid.unpack_rows(An_s, 16)
         ctx.grid = grid
-        ctx.pairs = grid.pair_lists(x, v) if N else None          # cached by the grid; the adjoint sweep reads the same lists
+        ctx.pairs = grid.pair_lists(x, v, blur=bool(use_alpha)) if N else None     # cached by the grid; the adjoint sweep reads the same lists
         ctx.cfg = (update_rule, use_alpha, perception_scale, orig_rate)
         ctx.save_for_backward(xv4, A_s, Y_s, O_s, flags_s, relu_s, W1c, b1c, W2c, b2c)
         return out
@@ -217,7 +217,7 @@ def _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, al
     compact [A_c | Y_c] rows the MLP kernel reads (needs fb.A_c / fb.Y_c); otherwise the full sweep fills Y_s."""
     N = S.shape[0]
     if pl is False:
-        pl = grid.pair_lists(x, v)
+        pl = grid.pair_lists(x, v, blur=bool(use_alpha))
     fired_sweep = pl is not None and not use_alpha and fb.A_c is not None
     _timed("fire_list", lib.sphnca_fire_list, N, ptr(fire_s), ptr(S), int(bool(use_alpha)), ptr(fb.rows), ptr(fb.count), ptr(Sn),
            ptr(alive_s), ptr(pl["FLG"]) if fired_sweep else None, ptr(fb.flags) if fired_sweep else None, ptr(ws_fl), ws_fl.numel(), st)
@@ -327,7 +327,7 @@ class _NCARollout(torch.autograd.Function):
                 states = [states[0], Sn] if len(states) else [Sn]
             S = Sn
         ctx.grid, ctx.cfg, ctx.steps, ctx.taped, ctx.fire_lists = grid, cfg, steps, taped, fl
-        ctx.pairs = grid.pair_lists(x, v) if (N and taped) else None
+        ctx.pairs = grid.pair_lists(x, v, blur=bool(use_alpha)) if (N and taped) else None
         if taped:
             ctx.save_for_backward(xv4, W1c, b1c, W2c, b2c, *states, *saved)
         return tuple(states)

@@ -113,13 +113,17 @@ class Hashgrid:
     # fraction of the free device memory the pair lists of one grid may take (about 1.3 KB per particle)
     PAIR_LIST_MEMORY_FRACTION = 0.4
 
-    def pair_lists(self, x, v):
+    def pair_lists(self, x, v, blur=True):
         """Per-pair neighbour lists and kernel weights of this grid (csrc/pairs.cu), cached per (x, v) pair; None when
         disabled or when they would not fit the memory budget.  Building them reads back ONE integer (the total number
-        of list entries) -- the only host synchronisation besides `staged_sweep_ok`."""
+        of list entries) -- the only host synchronisation besides `staged_sweep_ok`.  blur=False leaves out the life-mask
+        blur weights WB (8 of the 28 bytes per pair; only models with an alpha channel read them); lists built without
+        them are rebuilt when a later caller needs them."""
         if not _lib.USE_PAIR_LISTS or _lib.FORCE_SWEEP_PATH is not None or "sphnca_pairs_fill" in _lib.MISSING_SYMBOLS:
             return None
         key = (self._key(x), self._key(v))
+        if self._pairs_key == key and self._pairs is not None and blur and self._pairs["WB"] is None:
+            self._pairs_key = None                                  # built without the blur weights: build again with them
         if self._pairs_key != key:
             self._pairs_key, self._pairs, self._pairs_ref = key, None, (x, v)
             N = self.num_particles
@@ -135,10 +139,11 @@ class Hashgrid:
                 total = int(cum[-1].item()) * 8
                 # capacity minus torch's live tensors (host-side counters; cudaMemGetInfo stalls ~25 ms on a busy device)
                 free = torch.cuda.get_device_properties(dev).total_memory - torch.cuda.memory_allocated(dev)
-                if 0 < total and total * 28 <= self.PAIR_LIST_MEMORY_FRACTION * free:
+                if 0 < total and total * (28 if blur else 20) <= self.PAIR_LIST_MEMORY_FRACTION * free:
                     f32 = dict(dtype=torch.float32, device=dev)
                     J = torch.empty((total,), dtype=torch.int32, device=dev)
-                    WP, WB, WA = (torch.empty((total, 2), **f32) for _ in range(3))
+                    WP, WA = (torch.empty((total, 2), **f32) for _ in range(2))
+                    WB = torch.empty((total, 2), **f32) if blur else None
                     SXY = torch.empty((N, 2), **f32)
                     FLG = torch.empty((N,), dtype=torch.uint8, device=dev)
                     _lib.check(_lib.lib.sphnca_pairs_fill(self.c_grid(), _lib.ptr(xv4), _lib.ptr(slots), _lib.ptr(base), _lib.ptr(J),
