@@ -233,6 +233,15 @@ int32_t sphnca_fire_list_workspace_bytes(int64_t N, size_t* bytes);
 int32_t sphnca_fire_list(int64_t N, const uint8_t* fire_s, const float* A_s, int32_t use_alpha, int32_t* rows,
                          int32_t* count, float* A_new_s, uint8_t* alive_s, const uint8_t* FLG, uint8_t* flags_s,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* sphnca_fire_list with the draw fused in: fire byte of sorted row p = (u[sorted_id[p]] <= rate), u = the reference's
+ * `torch.rand(N)` in particle order (nca.py:100); fire_s [N] receives the bytes (kept for activation checkpointing).
+ * fold_static_mask != 0 (no alpha channel, FLG given): the life mask of the step is applied right here and by
+ * sphnca_step_mlp_list(inputs_by_list | 2) -- flag bits 0|1 set for living rows, dead rows multiplied by 0 -- so that
+ * no sphnca_step_mask_static pass is needed. */
+int32_t sphnca_fire_list_draw(const sphnca_grid* g, const float* u, float rate, uint8_t* fire_s, const float* A_s,
+                              int32_t use_alpha, int32_t* rows, int32_t* count, float* A_new_s, uint8_t* alive_s,
+                              const uint8_t* FLG, uint8_t* flags_s, int32_t fold_static_mask, void* workspace,
+                              size_t workspace_bytes, void* stream);
 int32_t sphnca_step_perceive_pairs_fired(const sphnca_grid* g, const int32_t* rows, const int32_t* count, const int32_t* group_slots,
                                          const int64_t* group_base, const int32_t* J, const float* WP, const float* A_s,
                                          const sphnca_step_params* p, float* Y_c, float* A_c, void* stream);

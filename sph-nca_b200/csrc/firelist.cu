@@ -45,6 +45,36 @@ fire_count_kernel(int64_t n, const uint8_t* __restrict__ fire_s, int32_t* __rest
     }
 }
 
+// The draw itself, fused with the count: fire byte of sorted row p = (u[sorted_id[p]] <= rate), u = the reference's
+// `torch.rand(N)` in particle order (nca.py:100) -- replaces torch's compare, the byte permutation and fire_count_kernel.
+__global__ void __launch_bounds__(fl::THREADS)
+fire_draw_count_kernel(int64_t n, const float* __restrict__ u, float rate, const int32_t* __restrict__ sorted_id,
+                       uint8_t* __restrict__ fire_s, int32_t* __restrict__ block_count) {
+    using namespace fl;
+    const int64_t base = (int64_t)blockIdx.x * BLOCK_ROWS + (int64_t)threadIdx.x * PER_THREAD;
+    int c = 0;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+        const int64_t p = base + k;
+        const uint32_t f = (p < n && __ldg(u + __ldg(sorted_id + p)) <= rate) ? 1u : 0u;
+        packed |= f << (8 * k); c += (int)f;
+    }
+    if (base + PER_THREAD <= n) *reinterpret_cast<uint32_t*>(fire_s + base) = packed;
+    else for (int k = 0; k < PER_THREAD; ++k) if (base + k < n) fire_s[base + k] = (uint8_t)((packed >> (8 * k)) & 1u);
+    __shared__ int wsum[THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) t += wsum[w];
+        block_count[blockIdx.x] = t;
+    }
+}
+
 // exclusive scan of the block counts in place (one block; fixed order), total -> count[0]
 __global__ void __launch_bounds__(1024)
 fire_scan_kernel(int nb, int32_t* __restrict__ block_count, int32_t* __restrict__ count) {
@@ -81,7 +111,7 @@ __global__ void __launch_bounds__(fl::THREADS)
 fire_fill_kernel(int64_t n, const uint8_t* __restrict__ fire_s, const int32_t* __restrict__ block_off,
                  const float* __restrict__ A_s, int use_alpha, int32_t* __restrict__ rows,
                  float* __restrict__ A_new_s, uint8_t* __restrict__ alive_s, const uint8_t* __restrict__ FLG,
-                 uint8_t* __restrict__ flags_s) {
+                 uint8_t* __restrict__ flags_s, int fold_mask) {
     using namespace fl;
     const int64_t base = (int64_t)blockIdx.x * BLOCK_ROWS + (int64_t)threadIdx.x * PER_THREAD;
     bool f[PER_THREAD];
@@ -102,13 +132,19 @@ fire_fill_kernel(int64_t n, const uint8_t* __restrict__ fire_s, const int32_t* _
     for (int k = 0; k < PER_THREAD; ++k) {
         const int64_t p = base + k;
         if (p >= n) break;
-        if (FLG != nullptr) flags_s[p] = FLG[p];            // static life mask (no alpha channel): the previous-mask bit of every row
+        // static life mask (no alpha channel): the previous-mask bit of every row; fold_mask: the new mask is the same bit
+        // (step_mask_static_kernel), so bit 1 is set here too and dead rows are zeroed below / by the MLP kernel
+        const bool live = FLG == nullptr || FLG[p] != 0;
+        if (FLG != nullptr) flags_s[p] = live ? (fold_mask ? 3 : 1) : 0;
         if (f[k]) { rows[slot++] = (int32_t)p; continue; }
         // not fired: the state is carried over unchanged (reference nca.py:107); fire bit of the flags stays 0
         const float4* a4 = reinterpret_cast<const float4*>(A_s + p * NF);
         float4* o4 = reinterpret_cast<float4*>(A_new_s + p * NF);
         const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), a2 = __ldg(a4 + 2), a3 = __ldg(a4 + 3);
-        o4[0] = a0; o4[1] = a1; o4[2] = a2; o4[3] = a3;
+        if (fold_mask && !live) {                           // the product with 0 of step_mask_static_kernel, bit for bit
+            o4[0] = make_float4(a0.x * 0.f, a0.y * 0.f, a0.z * 0.f, a0.w * 0.f); o4[1] = make_float4(a1.x * 0.f, a1.y * 0.f, a1.z * 0.f, a1.w * 0.f);
+            o4[2] = make_float4(a2.x * 0.f, a2.y * 0.f, a2.z * 0.f, a2.w * 0.f); o4[3] = make_float4(a3.x * 0.f, a3.y * 0.f, a3.z * 0.f, a3.w * 0.f);
+        } else { o4[0] = a0; o4[1] = a1; o4[2] = a2; o4[3] = a3; }
         alive_s[p] = use_alpha ? (a0.w > 0.1f ? 1 : 0) : 1;
     }
 }
@@ -159,7 +195,31 @@ int32_t sphnca_fire_list(int64_t N, const uint8_t* fire_s, const float* A_s, int
     int32_t* bc = reinterpret_cast<int32_t*>(workspace);
     SPHNCA_LAUNCH(fire_count_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc);
     SPHNCA_LAUNCH(fire_scan_kernel, 1, 1024, 0, stream, nb, bc, count);
-    SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s, FLG, flags_s);
+    SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s, FLG, flags_s, 0);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_fire_list_draw(const sphnca_grid* g, const float* u, float rate, uint8_t* fire_s, const float* A_s,
+                              int32_t use_alpha, int32_t* rows, int32_t* count, float* A_new_s, uint8_t* alive_s,
+                              const uint8_t* FLG, uint8_t* flags_s, int32_t fold_static_mask, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
+    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    const int64_t N = gv.n;
+    SPHNCA_CHECK_ARG(count, "NULL argument");
+    cudaStream_t stream = as_stream(stream_);
+    if (N == 0) { SPHNCA_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), stream)); return SPHNCA_OK; }
+    SPHNCA_CHECK_ARG(u && fire_s && A_s && rows && A_new_s && alive_s, "NULL argument");
+    SPHNCA_CHECK_ARG(((uintptr_t)fire_s & 3) == 0, "fire_s must be 4-byte aligned");
+    SPHNCA_CHECK_ARG(FLG == nullptr || flags_s != nullptr, "flags_s is required with FLG");
+    SPHNCA_CHECK_ARG(!fold_static_mask || (FLG != nullptr && !use_alpha), "the static life mask needs FLG and no alpha channel");
+    const int nb = (int)((N + fl::BLOCK_ROWS - 1) / fl::BLOCK_ROWS);
+    if (!workspace || workspace_bytes < (size_t)(nb + 1) * sizeof(int32_t)) { set_error("fire-list workspace too small"); return SPHNCA_ERR_WORKSPACE; }
+    int32_t* bc = reinterpret_cast<int32_t*>(workspace);
+    SPHNCA_LAUNCH(fire_draw_count_kernel, nb, fl::THREADS, 0, stream, N, u, rate, gv.sorted_id, fire_s, bc);
+    SPHNCA_LAUNCH(fire_scan_kernel, 1, 1024, 0, stream, nb, bc, count);
+    SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s, FLG, flags_s,
+                  fold_static_mask ? 1 : 0);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

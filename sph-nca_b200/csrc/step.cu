@@ -700,9 +700,11 @@ int32_t sphnca_step_mlp_list(int64_t N, const int32_t* rows, const int32_t* coun
     if (N == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(rows && count && A_s && Y_s && A_new_s && alive_s && O_c && flags_s && relu_c, "NULL argument");
     SPHNCA_CHECK_ARG((A_c == nullptr) == (Y_c == nullptr), "A_c and Y_c must be given together");
-    SPHNCA_CHECK_ARG(!(inputs_by_list && A_c), "inputs_by_list: A_s / Y_s are the compact arrays already, no copies are made");
+    SPHNCA_CHECK_ARG(!((inputs_by_list & 1) && A_c), "inputs_by_list: A_s / Y_s are the compact arrays already, no copies are made");
+    // inputs_by_list bit 0: A_s / Y_s are compact arrays; bit 1: apply the static life mask here (flags from sphnca_fire_list_draw)
+    SPHNCA_CHECK_ARG(!(inputs_by_list & 2) || !p->use_alpha, "the static life mask exists without an alpha channel only");
     return launch_step_mlp_tc(N, c, p, A_s, Y_s, nullptr, A_new_s, alive_s, O_c, flags_s, relu_c, as_stream(stream_), rows, count, A_c, Y_c,
-                              inputs_by_list ? 1 : 0);
+                              inputs_by_list & 1, (inputs_by_list >> 1) & 1);
 }
 
 int32_t sphnca_step_fwd(const sphnca_grid* g, const float* xv4, const float* A_s, const uint8_t* fire_s,

@@ -59,7 +59,7 @@ int launch_step_fwd_tc(const GridView& gv, const StepConsts& c, const sphnca_ste
 int launch_step_mlp_tc(int64_t N, const StepConsts& c, const sphnca_step_params* p, const float* A_s, const float* Y_s,
                        const uint8_t* fire_s, float* A_new_s, uint8_t* alive_s, float* O_s, uint8_t* flags_s,
                        uint32_t* relu_s, cudaStream_t stream, const int32_t* rows = nullptr, const int32_t* count = nullptr,
-                       float* A_c = nullptr, float* Y_c = nullptr, int in_by_list = 0);
+                       float* A_c = nullptr, float* Y_c = nullptr, int in_by_list = 0, int fold_mask = 0);
 int launch_step_bwd_tc(int64_t N, const StepConsts& c, const sphnca_step_params* p, const float* A_s, const float* O_s,
                        const uint8_t* flags_s, const uint32_t* relu_s, const float* dA_next_s, float* dO_s, float* dY_s,
                        float* dAdir_s, cudaStream_t stream, const int32_t* rows = nullptr, const int32_t* count = nullptr);

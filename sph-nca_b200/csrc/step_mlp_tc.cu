@@ -71,7 +71,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                    float* __restrict__ An_s, float* __restrict__ O_s, uint8_t* __restrict__ flags_s,
                    uint8_t* __restrict__ alive_s, uint32_t* __restrict__ relu_s, int num_tiles,
                    const int32_t* __restrict__ rows, const int32_t* __restrict__ count_ptr,
-                   float* __restrict__ A_c, float* __restrict__ Y_c, int in_by_list) {
+                   float* __restrict__ A_c, float* __restrict__ Y_c, int in_by_list, int fold_mask) {
     using namespace mt;
     // Fire-list mode (rows != NULL, firelist.cu): tile row j stands for sorted particle rows[j], j < *count (the count is
     // read from device memory: no host synchronisation); every listed particle fired.  O_s, relu_s and the compact copies
@@ -304,13 +304,19 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
 #pragma unroll
                 for (int f = 0; f < NF; ++f) nA[f] = fire ? nA[f] : Ai[f];
                 if (tid == (FIN_WARP0 + 3) * 32) SPHNCA_TL(15);
+                if (fold_mask && !(flag_raw & 1u)) {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) nA[f] *= 0.f;
+                }
                 float4* o4 = reinterpret_cast<float4*>(An_s + (size_t)p * NF);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) o4[k] = make_float4(nA[4 * k], nA[4 * k + 1], nA[4 * k + 2], nA[4 * k + 3]);
                 float4* oo4 = reinterpret_cast<float4*>(O_s + (size_t)j * NO_PAD);
 #pragma unroll
                 for (int k = 0; k < NO_PAD / 4; ++k) oo4[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
-                flags_s[p] = (uint8_t)((flag_raw & 1u) | (fire ? 4u : 0u));
+                // fold_mask (no alpha channel, sphnca_fire_list_draw set bits 0|1 of the living rows): the static life mask is applied
+                // here instead of by step_mask_static_kernel -- dead rows are multiplied by 0 exactly like there
+                flags_s[p] = (uint8_t)((flag_raw & (fold_mask ? 3u : 1u)) | (fire ? 4u : 0u));
                 alive_s[p] = c.use_alpha ? (nA[3] > 0.1f ? 1 : 0) : 1;
             }
             if (tid == (FIN_WARP0 + 3) * 32) SPHNCA_TL(11);
@@ -400,7 +406,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
 int launch_step_mlp_tc(int64_t N, const StepConsts& c, const sphnca_step_params* p, const float* A_s, const float* Y_s,
                        const uint8_t* fire_s, float* A_new_s, uint8_t* alive_s, float* O_s, uint8_t* flags_s,
                        uint32_t* relu_s, cudaStream_t stream, const int32_t* rows, const int32_t* count, float* A_c, float* Y_c,
-                       int in_by_list) {
+                       int in_by_list, int fold_mask) {
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -412,7 +418,7 @@ int launch_step_mlp_tc(int64_t N, const StepConsts& c, const sphnca_step_params*
     const size_t smem = sizeof(mt::Smem);
     SPHNCA_CUDA(cudaFuncSetAttribute(step_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPHNCA_LAUNCH(step_mlp_tc_kernel, blocks, mt::THREADS, smem, stream, (int)N, A_s, Y_s, fire_s, *p, c, A_new_s, O_s, flags_s,
-                  alive_s, relu_s, num_tiles, rows, count, A_c, Y_c, in_by_list);
+                  alive_s, relu_s, num_tiles, rows, count, A_c, Y_c, in_by_list, fold_mask);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

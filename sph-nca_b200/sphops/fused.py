@@ -211,21 +211,32 @@ class _FireBuffers:
         return self
 
 
-def _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, alive_s, fb, ws_fl, st, pl=False):
+def _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, alive_s, fb, ws_fl, st, pl=False, draw=None):
     """One forward step on the fire-list path: list + carried-over rows, perception sweep, MLP over the list, life mask.
     Without an alpha channel and with pair lists the perception sweep itself runs over the fired particles only and writes the
-    compact [A_c | Y_c] rows the MLP kernel reads (needs fb.A_c / fb.Y_c); otherwise the full sweep fills Y_s."""
+    compact [A_c | Y_c] rows the MLP kernel reads (needs fb.A_c / fb.Y_c); otherwise the full sweep fills Y_s.
+    draw = (u, rate): the fire bytes are made right here from the reference's `torch.rand(N)` values u (particle order) as
+    u <= rate and written to fire_s; on the fired-sweep path the static life mask is then applied by the list and MLP kernels
+    themselves (no separate mask pass)."""
     N = S.shape[0]
     if pl is False:
         pl = grid.pair_lists(x, v, blur=bool(use_alpha))
     fired_sweep = pl is not None and not use_alpha and fb.A_c is not None
-    _timed("fire_list", lib.sphnca_fire_list, N, ptr(fire_s), ptr(S), int(bool(use_alpha)), ptr(fb.rows), ptr(fb.count), ptr(Sn),
-           ptr(alive_s), ptr(pl["FLG"]) if fired_sweep else None, ptr(fb.flags) if fired_sweep else None, ptr(ws_fl), ws_fl.numel(), st)
+    fold = fired_sweep and draw is not None
+    flg, flags = (ptr(pl["FLG"]), ptr(fb.flags)) if fired_sweep else (None, None)
+    if draw is not None:
+        _timed("fire_list", lib.sphnca_fire_list_draw, g, ptr(draw[0]), float(draw[1]), ptr(fire_s), ptr(S), int(bool(use_alpha)),
+               ptr(fb.rows), ptr(fb.count), ptr(Sn), ptr(alive_s), flg, flags, int(fold), ptr(ws_fl), ws_fl.numel(), st)
+    else:
+        _timed("fire_list", lib.sphnca_fire_list, N, ptr(fire_s), ptr(S), int(bool(use_alpha)), ptr(fb.rows), ptr(fb.count), ptr(Sn),
+               ptr(alive_s), flg, flags, ptr(ws_fl), ws_fl.numel(), st)
     if fired_sweep:
         _timed("step_perceive", lib.sphnca_step_perceive_pairs_fired, g, ptr(fb.rows), ptr(fb.count), ptr(pl["slots"]), ptr(pl["base"]),
                ptr(pl["J"]), ptr(pl["WP"]), ptr(S), C.byref(p), ptr(fb.Y_c), ptr(fb.A_c), st)
         _timed("step_mlp", lib.sphnca_step_mlp_list, N, ptr(fb.rows), ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), C.byref(p), ptr(Sn),
-               ptr(alive_s), ptr(fb.O_c), ptr(fb.flags), ptr(fb.relu_c), None, None, 1, st)
+               ptr(alive_s), ptr(fb.O_c), ptr(fb.flags), ptr(fb.relu_c), None, None, 3 if fold else 1, st)
+        if fold:
+            return
     else:
         _perceive_pl(grid, pl, g, xv4, S, p, Y_s, fb.flags, st)
         _timed("step_mlp", lib.sphnca_step_mlp_list, N, ptr(fb.rows), ptr(fb.count), ptr(S), ptr(Y_s), C.byref(p), ptr(Sn), ptr(alive_s),
@@ -286,15 +297,19 @@ class _NCARollout(torch.autograd.Function):
         if fl:
             ws_fl = _fire_list_workspace(N, dev)
             Y_s = torch.empty((N, 32), **f32)                 # perception of the current step: scratch, the tape keeps Y_c
+        fire_s = None
         for _ in range(steps):
-            fire = torch.rand(N, device=dev) <= fire_rate
-            fire_s = grid.pack_bytes(fire.view(torch.uint8))
+            u = torch.rand(N, device=dev)                     # the reference's draw (nca.py:100), one call per step
             Sn = torch.empty((N, 16), **f32)
             if fl:
-                # MLP half over the fired rows only (firelist.cu); not-fired rows are carried over by the list kernel
+                # MLP half over the fired rows only (firelist.cu); not-fired rows are carried over by the list kernel,
+                # which also turns the draw into the (cell-sorted) fire bytes
                 if taped == 1 or fbuf is None:
                     fbuf = _FireBuffers(N, dev, compact_inputs=True)
-                _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, alive_s, fbuf, ws_fl, st)
+                if taped == 2 or fire_s is None:
+                    fire_s = torch.empty((N,), **u8)
+                _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, alive_s, fbuf, ws_fl, st,
+                                    draw=(u, fire_rate))
                 if taped == 1:
                     saved += fbuf.tensors()
                 elif taped == 2:
@@ -305,6 +320,7 @@ class _NCARollout(torch.autograd.Function):
                     states = [states[0], Sn]
                 S = Sn
                 continue
+            fire_s = grid.pack_bytes((u <= fire_rate).view(torch.uint8))
             if taped == 1 or Y_s is None:
                 Y_s = torch.empty((N, 32), **f32); O_s = torch.empty((N, 36), **f32)
                 flags_s = torch.empty((N,), **u8); relu_s = torch.empty((N, 8), dtype=torch.int32, device=dev)
