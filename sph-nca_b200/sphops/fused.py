@@ -300,6 +300,8 @@ class _NCARollout(torch.autograd.Function):
         fire_s = None
         for _ in range(steps):
             u = torch.rand(N, device=dev)                     # the reference's draw (nca.py:100), one call per step
+            if u.dtype != torch.float32 or not u.is_contiguous():
+                u = u.to(torch.float32).contiguous()
             Sn = torch.empty((N, 16), **f32)
             if fl:
                 # MLP half over the fired rows only (firelist.cu); not-fired rows are carried over by the list kernel,
