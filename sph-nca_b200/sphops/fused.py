@@ -6,6 +6,11 @@ perception sweep (+ previous life mask), MLP + gated update, life-mask sweep (+ 
 Backward: MLP backward (+ parameter gradients, deterministic) and the gather adjoint of the
 perception sweep.  All state is handled in cell-sorted order inside; inputs/outputs are in the
 caller's original particle order like every other sphops operator.
+
+`nca_rollout` runs K such steps as ONE autograd node with the state resident in cell-sorted order
+(`_NCARollout`): per step a fire list (the particles whose fire draw came up), the perception sweep
+and the MLP over those particles only, activation checkpointing on request -- the default path of
+`nca.sample_plane` / `SPHNCA.rollout` and of bench.py.
 """
 import ctypes as C
 
@@ -265,12 +270,14 @@ class _NCARollout(torch.autograd.Function):
     sweep adjoint, with the parameter gradients accumulated in place over all steps (fixed order:
     deterministic).  Outputs: the K+1 states S_0..S_K in SORTED order (unpack lazily, `RolloutStates`);
     a loss may read any subset of them -- missing output gradients are skipped, not materialised.
-    `taped`: 0 = no tape (inference), 1 = keep every step's perception / MLP output / ReLU bits / flags
-    (~305 B per particle-step besides the states), 2 = activation checkpointing: keep only the states and the
-    packed fire bytes (65 B per particle-step) and re-run perceive -> MLP -> mask of a step right before its
-    backward; the kernels are deterministic, so both modes give bit-identical gradients.
-    The fire mask of step k is drawn here by `torch.rand(N) <= fire_rate`, the same call, in the same
-    order, as the reference's `SPHNCA.forward` (nca.py:100)."""
+    `taped`: 0 = no tape (inference), 1 = keep every step's MLP input / output rows, ReLU bits, fire list and flags
+    (TAPE_BYTES = 373 B per particle-step besides the states), 2 = activation checkpointing: keep only the states and
+    the packed fire bytes (65 B per particle-step) and re-run list -> perceive -> MLP -> mask of a step right before
+    its backward; the kernels are deterministic, so both modes give bit-identical gradients.
+    With `FIRE_LISTS` (default) the MLP half of a step -- and, without an alpha channel, its perception sweep -- runs
+    over the particles whose fire draw came up only (csrc/firelist.cu); the others are carried over.
+    The fire mask of step k comes from `torch.rand(N)`, the same call, in the same order, as the reference's
+    `SPHNCA.forward` (nca.py:100), compared with the rate by the list kernel (`u <= fire_rate` in fp32, like torch)."""
 
     @staticmethod
     def forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_rate, keep_all, taped):
