@@ -148,6 +148,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 // Bounded wait: a protocol bug traps instead of hanging the GPU (try_wait itself sleeps in HW).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // not unrolled: the compiler otherwise emits ~32 try_wait/branch pairs per call site (768 in the forward MLP kernel), and
+    // ncu showed 13 % of that kernel's warp stalls as "no instructions" (instruction-cache misses)
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it)
         if (mbar_try_wait(bar, parity)) return;
     asm volatile("trap;");
