@@ -197,7 +197,12 @@ __device__ __forceinline__ void stage_batched(int total, int tid, int threads, L
 // development aid: per-role clock64 timestamps of CTA 0, 16 slots per tile/chunk iteration.  One buffer
 // per translation unit (no relocatable device code); each kernel file exports its own reader.
 static __device__ long long g_timeline[64 * 16];
+// (compiled in with `make EXTRA=-DSPHNCA_TIMELINE`; off by default: the stamps cost instructions and code size in every role)
+#ifdef SPHNCA_TIMELINE
 #define SPHNCA_TL(slot) do { if (blockIdx.x == 0 && it < 64) sphnca::g_timeline[it * 16 + (slot)] = clock64(); } while (0)
+#else
+#define SPHNCA_TL(slot) do { } while (0)
+#endif
 #define SPHNCA_TIMELINE_READER(name)                                                              \
     extern "C" int32_t name(long long* out_host, int32_t n) {                                     \
         if (n > 64 * 16) n = 64 * 16;                                                             \

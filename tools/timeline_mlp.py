@@ -1,4 +1,5 @@
 """In-kernel clock64 timeline of step_mlp_tc_kernel (CTA 0), development aid."""
+# needs a library built with the in-kernel time stamps: make -C sph-nca_b200/csrc clean && make -C sph-nca_b200/csrc EXTRA=-DSPHNCA_TIMELINE
 import ctypes as C, sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "sph-nca_b200"))
 import runpy, torch
