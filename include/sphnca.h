@@ -217,7 +217,8 @@ int32_t sphnca_step_adjoint(const sphnca_grid* g, const float* xv4, const float*
  * gradient reaches the MLP, so skipping them changes no result.  With fire rate 0.5 it halves the tensor-core work.
  *   sphnca_fire_list        rows[0..*count) = sorted positions of the fired particles in increasing order (deterministic
  *                           ordered compaction); not-fired rows: A_new_s = A_s, alive byte.  count is a DEVICE int32 that
- *                           the _list kernels read themselves: no host synchronisation.
+ *                           the _list kernels read themselves: no host synchronisation.  A_new_s = alive_s = NULL: the
+ *                           list only, no row is carried over (a second list over the same step, multigpu.py).
  *   sphnca_step_mlp_list    sphnca_step_mlp over the listed rows.  O_c [N,36], relu_c [N,8] and the optional compact
  *                           copies A_c [N,16], Y_c [N,32] (contiguous input of sphnca_mlp_wgrad_list) are indexed by
  *                           list position; A_new_s, alive_s, flags_s by particle.  inputs_by_list != 0: A_s / Y_s are
@@ -232,10 +233,10 @@ int32_t sphnca_step_adjoint(const sphnca_grid* g, const float* xv4, const float*
 int32_t sphnca_fire_list_workspace_bytes(int64_t N, size_t* bytes);
 int32_t sphnca_fire_list(int64_t N, const uint8_t* fire_s, const float* A_s, int32_t use_alpha, int32_t* rows,
                          int32_t* count, float* A_new_s, uint8_t* alive_s, const uint8_t* FLG, uint8_t* flags_s,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         int32_t fold_static_mask, void* workspace, size_t workspace_bytes, void* stream);
 /* sphnca_fire_list with the draw fused in: fire byte of sorted row p = (u[sorted_id[p]] <= rate), u = the reference's
  * `torch.rand(N)` in particle order (nca.py:100); fire_s [N] receives the bytes (kept for activation checkpointing).
- * fold_static_mask != 0 (no alpha channel, FLG given): the life mask of the step is applied right here and by
+ * fold_static_mask != 0 (both entries; no alpha channel, FLG given): the life mask of the step is applied right here and by
  * sphnca_step_mlp_list(inputs_by_list | 2) -- flag bits 0|1 set for living rows, dead rows multiplied by 0 -- so that
  * no sphnca_step_mask_static pass is needed. */
 int32_t sphnca_fire_list_draw(const sphnca_grid* g, const float* u, float rate, uint8_t* fire_s, const float* A_s,

@@ -322,17 +322,32 @@ def perceive(p: Pairs, v, A, cfg: StepConfig) -> torch.Tensor:
     return torch.cat([A.to(F64), gA[..., 0], gA[..., 1]], dim=-1)
 
 
-def nca_step(p: Pairs, v, A, params, update_mask, cfg: StepConfig, return_aux=False):
+def nca_step(p: Pairs, v, A, params, update_mask, cfg: StepConfig, return_aux=False, relu_bits=None):
     """One SPHNCA.forward (nca.py:87-117) with the stochastic fire mask supplied by the caller.
 
     params = (W1[Hd,3F], b1[Hd], W2[O,Hd], b2[O]); update_mask bool[N].
+    relu_bits: optional bool[N,Hd], or (rows, bool[len(rows),Hd]) for a subset of the rows -- the ReLU decisions of ANOTHER evaluation (the GPU's saved bits) imposed on this
+    one: hidden = pre * bit instead of max(pre, 0).  Where a pre-activation is within rounding of 0 the two evaluations
+    may decide differently, and a flipped unit changes a gradient row by O(1/Hd); with the bits imposed the comparison
+    measures arithmetic error only (the aux output reports every unit that differs and how close to 0 it is).
     """
     W1, b1, W2, b2 = [t.to(F64) for t in params]
     A = A.to(F64)
     nf = cfg.in_features
     prev_mask = life_mask(p, v, cell_activity(A, cfg.use_alpha)[:, None])
     y = perceive(p, v, A, cfg)
-    hid = torch.relu(y @ W1.T + b1)
+    pre = y @ W1.T + b1
+    if relu_bits is None:
+        bits = None
+        hid = torch.relu(pre)
+    else:
+        if isinstance(relu_bits, tuple):            # (rows i64[n], bits bool[n,Hd]): imposed on those rows only
+            rows, sub = relu_bits
+            bits = pre.detach() > 0
+            bits[rows] = sub
+        else:
+            bits = relu_bits
+        hid = pre * bits.to(F64)
     dA = hid @ W2.T + b2
     fire_rate = cfg.model_fire_rate if cfg.fire_rate is None else cfg.fire_rate
     if cfg.update_rule == "gated":
@@ -349,16 +364,35 @@ def nca_step(p: Pairs, v, A, params, update_mask, cfg: StepConfig, return_aux=Fa
     living = prev_mask & new_mask
     out = nA * living.to(F64)
     if return_aux:
-        return out, dict(prev_mask=prev_mask, new_mask=new_mask, y=y, dA=dA, nA_unmasked=nA)
+        with torch.no_grad():
+            # conditioning of every pre-activation: |pre| / (sum_k |y_k W1_nk| + |b1_n|); fp32 evaluations can only decide
+            # a ReLU differently where this is at rounding level
+            scale = y.abs() @ W1.abs().T + b1.abs()
+            margin = pre.abs() / scale.clamp_min(1e-300)
+        return out, dict(prev_mask=prev_mask, new_mask=new_mask, y=y, dA=dA, nA_unmasked=nA, pre=pre.detach(), margin=margin)
     return out
 
 
-def rollout(p: Pairs, v, A0, params, update_masks, cfg: StepConfig):
-    """K applications of nca_step (nca.py:138-141).  update_masks: bool[K, N].  Returns [A_0..A_K]."""
+def rollout(p: Pairs, v, A0, params, update_masks, cfg: StepConfig, relu_bits=None, aux_out=None, trajectory=None):
+    """K applications of nca_step (nca.py:138-141).  update_masks: bool[K, N].  Returns [A_0..A_K].
+    relu_bits: optional list of K bool[N,Hd] tensors imposed per step (see nca_step); aux_out: optional list that
+    receives every step's aux dict.
+    trajectory: optional list of K+1 states of ANOTHER evaluation (the GPU's fp32 states).  Step k is then evaluated AT
+    trajectory[k] (value substituted, gradient passed straight through to this rollout's own state), so out[k+1] is the
+    single-step result from identical inputs and the backward is the chain of THIS oracle's Jacobians along that
+    trajectory: rounding differences of earlier steps, which the dynamics amplify step by step, are taken out of both
+    comparisons (parity is defined per step from identical inputs)."""
     out = [A0.to(F64)]
     A = A0
     for k in range(update_masks.shape[0]):
-        A = nca_step(p, v, A, params, update_masks[k], cfg)
+        bits = None if relu_bits is None else relu_bits[k]
+        if trajectory is not None and k > 0:
+            A = A + (trajectory[k].to(F64) - A).detach()
+        if aux_out is not None:
+            A, aux = nca_step(p, v, A, params, update_masks[k], cfg, return_aux=True, relu_bits=bits)
+            aux_out.append(aux)
+        else:
+            A = nca_step(p, v, A, params, update_masks[k], cfg, relu_bits=bits)
         out.append(A)
     return out
 
@@ -377,12 +411,22 @@ def prepare(packed_x: torch.Tensor, sections, h, dims):
     return grid, pairs, volume(pairs)
 
 
-def rollout_fwd_bwd(packed_x, sections, h, dims, A0, params, update_masks, cfg: StepConfig):
-    """Grid build + volume + K steps + bench loss + backward.  Returns (A_K, loss, dA0, dparams)."""
-    grid, pairs, v = prepare(packed_x, sections, h, dims)
+def rollout_fwd_bwd(packed_x, sections, h, dims, A0, params, update_masks, cfg: StepConfig, relu_bits=None, prepared=None,
+                    return_all=False, trajectory=None):
+    """Grid build + volume + K steps + bench loss + backward.  Returns (A_K, loss, dA0, dparams)
+    [+ (states, per-step aux) with return_all].  relu_bits: per-step ReLU decisions to impose (see nca_step);
+    prepared: a (grid, pairs, v) tuple from `prepare` to reuse."""
+    grid, pairs, v = prepared if prepared is not None else prepare(packed_x, sections, h, dims)
     A0 = A0.detach().to(F64).requires_grad_(True)
     ps = [t.detach().to(F64).requires_grad_(True) for t in params]
-    states = rollout(pairs, v, A0, ps, update_masks, cfg)
-    loss = bench_loss(states[-1])
+    aux = [] if return_all else None
+    states = rollout(pairs, v, A0, ps, update_masks, cfg, relu_bits=relu_bits, aux_out=aux, trajectory=trajectory)
+    last = states[-1]
+    if trajectory is not None:          # the loss (and its gradient) at the other evaluation's final state too
+        last = last + (trajectory[-1].to(F64) - last).detach()
+    loss = bench_loss(last)
     loss.backward()
-    return states[-1].detach(), loss.detach(), A0.grad, [t.grad for t in ps]
+    res = (states[-1].detach(), loss.detach(), A0.grad, [t.grad for t in ps])
+    if return_all:
+        return res + ([s.detach() for s in states], aux)
+    return res

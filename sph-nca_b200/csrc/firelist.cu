@@ -137,6 +137,7 @@ fire_fill_kernel(int64_t n, const uint8_t* __restrict__ fire_s, const int32_t* _
         const bool live = FLG == nullptr || FLG[p] != 0;
         if (FLG != nullptr) flags_s[p] = live ? (fold_mask ? 3 : 1) : 0;
         if (f[k]) { rows[slot++] = (int32_t)p; continue; }
+        if (A_new_s == nullptr) continue;                   // list only (a second list over the same step: multigpu.py pass I)
         // not fired: the state is carried over unchanged (reference nca.py:107); fire bit of the flags stays 0
         const float4* a4 = reinterpret_cast<const float4*>(A_s + p * NF);
         float4* o4 = reinterpret_cast<float4*>(A_new_s + p * NF);
@@ -182,20 +183,23 @@ int32_t sphnca_fire_list_workspace_bytes(int64_t N, size_t* bytes) {
 
 int32_t sphnca_fire_list(int64_t N, const uint8_t* fire_s, const float* A_s, int32_t use_alpha, int32_t* rows,
                          int32_t* count, float* A_new_s, uint8_t* alive_s, const uint8_t* FLG, uint8_t* flags_s,
-                         void* workspace, size_t workspace_bytes, void* stream_) {
+                         int32_t fold_static_mask, void* workspace, size_t workspace_bytes, void* stream_) {
     SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
     SPHNCA_CHECK_ARG(count, "NULL argument");
     cudaStream_t stream = as_stream(stream_);
     if (N == 0) { SPHNCA_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), stream)); return SPHNCA_OK; }
-    SPHNCA_CHECK_ARG(fire_s && A_s && rows && A_new_s && alive_s, "NULL argument");
+    SPHNCA_CHECK_ARG(fire_s && A_s && rows, "NULL argument");
+    SPHNCA_CHECK_ARG((A_new_s == nullptr) == (alive_s == nullptr), "A_new_s and alive_s: both or neither");
     SPHNCA_CHECK_ARG(FLG == nullptr || flags_s != nullptr, "flags_s is required with FLG");
     SPHNCA_CHECK_ARG(((uintptr_t)fire_s & 3) == 0, "fire_s must be 4-byte aligned");
+    SPHNCA_CHECK_ARG(!fold_static_mask || (FLG != nullptr && !use_alpha), "the static life mask needs FLG and no alpha channel");
     const int nb = (int)((N + fl::BLOCK_ROWS - 1) / fl::BLOCK_ROWS);
     if (!workspace || workspace_bytes < (size_t)(nb + 1) * sizeof(int32_t)) { set_error("fire-list workspace too small"); return SPHNCA_ERR_WORKSPACE; }
     int32_t* bc = reinterpret_cast<int32_t*>(workspace);
     SPHNCA_LAUNCH(fire_count_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc);
     SPHNCA_LAUNCH(fire_scan_kernel, 1, 1024, 0, stream, nb, bc, count);
-    SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s, FLG, flags_s, 0);
+    SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s, FLG, flags_s,
+                  fold_static_mask ? 1 : 0);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

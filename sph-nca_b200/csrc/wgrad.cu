@@ -113,7 +113,7 @@ mlp_wgrad_kernel(int64_t n_total, const float* __restrict__ A_s, const float* __
 // stage 2: fixed-order sum over the CTA partials, accumulated into the gradient tensors
 __global__ void __launch_bounds__(256)
 mlp_wgrad_reduce_kernel(const float* __restrict__ partial, int num_partials, int n_out, float* __restrict__ dW1,
-                        float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2) {
+                        float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2, int w1_transposed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= WG_PART) return;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -124,7 +124,10 @@ mlp_wgrad_reduce_kernel(const float* __restrict__ partial, int num_partials, int
     }
     for (; g < num_partials; ++g) s0 += partial[(size_t)g * WG_PART + i];
     const float s = (s0 + s1) + (s2 + s3);
-    if (i < NH * NIN) dW1[i] += s;
+    if (i < NH * NIN) {
+        if (w1_transposed) dW1[(i % NH) * NIN + i / NH] += s;      // tensor-core partials hold dW1 as [k][h]
+        else dW1[i] += s;
+    }
     else if (i < NH * NIN + NH) db1[i - NH * NIN] += s;
     else if (i < NH * NIN + NH + NO_PAD * NH) {
         const int r = i - NH * NIN - NH, o = r / NH, n = r - o * NH;
@@ -176,7 +179,7 @@ int32_t sphnca_mlp_wgrad(int64_t N, const float* A_s, const float* Y_s, const fl
         float* partial = reinterpret_cast<float*>(workspace);
         int rc = launch_mlp_wgrad_tc(N, A_s, Y_s, dO_s, p, n_out, partial, WG_PART, streams, as_stream(stream_));
         if (rc) return rc;
-        SPHNCA_LAUNCH(mlp_wgrad_reduce_kernel, (WG_PART + 255) / 256, 256, 0, as_stream(stream_), partial, streams, n_out, dW1, db1, dW2, db2);
+        SPHNCA_LAUNCH(mlp_wgrad_reduce_kernel, (WG_PART + 255) / 256, 256, 0, as_stream(stream_), partial, streams, n_out, dW1, db1, dW2, db2, 1);
         SPHNCA_LAUNCH_CHECK();
         return SPHNCA_OK;
     }
@@ -185,7 +188,7 @@ int32_t sphnca_mlp_wgrad(int64_t N, const float* A_s, const float* Y_s, const fl
     cudaStream_t stream = as_stream(stream_);
     float* partial = reinterpret_cast<float*>(workspace);
     SPHNCA_LAUNCH(mlp_wgrad_kernel, grid, WG_THREADS, 0, stream, N, A_s, Y_s, dO_s, Ht, dHt, partial);
-    SPHNCA_LAUNCH(mlp_wgrad_reduce_kernel, (WG_PART + 255) / 256, 256, 0, stream, partial, grid, n_out, dW1, db1, dW2, db2);
+    SPHNCA_LAUNCH(mlp_wgrad_reduce_kernel, (WG_PART + 255) / 256, 256, 0, stream, partial, grid, n_out, dW1, db1, dW2, db2, 0);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }
@@ -203,7 +206,7 @@ int32_t sphnca_mlp_wgrad_list(int64_t N, const int32_t* count, const float* A_c,
     float* partial = reinterpret_cast<float*>(workspace);
     int rc = launch_mlp_wgrad_tc(N, A_c, Y_c, dO_c, p, n_out, partial, WG_PART, streams, as_stream(stream_), count);
     if (rc) return rc;
-    SPHNCA_LAUNCH(mlp_wgrad_reduce_kernel, (WG_PART + 255) / 256, 256, 0, as_stream(stream_), partial, streams, n_out, dW1, db1, dW2, db2);
+    SPHNCA_LAUNCH(mlp_wgrad_reduce_kernel, (WG_PART + 255) / 256, 256, 0, as_stream(stream_), partial, streams, n_out, dW1, db1, dW2, db2, 1);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

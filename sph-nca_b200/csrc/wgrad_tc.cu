@@ -13,8 +13,13 @@
 //               of the accumulator and dH_lo . y_hi adds to columns 0..63 -- 4 MMAs per k-step instead of 6.  An MMA
 //               with A from TMEM costs ~32 cycles + N/4 (probes/tc_timing4: N=64 57, N=128 71), so the stacked form
 //               takes 71 + 57 + 64 + 59 = 251 cycles per k-step instead of 3*57 + 3*59 = 348.
-//   the two accumulators (224 TMEM columns) live in TMEM for the whole CTA; the final dump adds the column groups,
-//   one partial per CTA pair is written and reduced in fixed order by mlp_wgrad_reduce_kernel (wgrad.cu).
+//   the two accumulators (224 TMEM columns) live in TMEM; every FLUSH chunks (and at the end) the epilogue warps drain them
+//   into the CTA's partial in global memory (+=, fp32 round-to-nearest, owner thread only) and the next accumulate MMA
+//   starts from zero: the tensor core's fp32 accumulation TRUNCATES, which biases a long same-sign sum towards zero by
+//   ~2e-8 x (number of accumulate steps) -- 3.2e-5 over the 886 steps of a 262,144-row launch, 9e-6 over 256
+//   (tests/test_gpu_parity_config_sizes.py::test_weight_gradient_accumulation_262144_rows_vs_fp64).  The drain adds the
+//   column groups; one partial per CTA pair (dW1 part stored transposed, [k][h], so that the drains are coalesced) is
+//   reduced in fixed order by mlp_wgrad_reduce_kernel (wgrad.cu).
 //
 // A CTA owns ONE hidden half (blockIdx.x & 1) and a contiguous range of 64-particle chunks, so the
 // weights it stages are halves: W1 48 KB + W2^T 32 KB (hi/lo); chunk operand tiles 96 KB.
@@ -38,6 +43,7 @@ constexpr int KO = 32;                                       // dO columns on th
 constexpr int NY = 64;                                       // rows of yT: 48 inputs + ones + pad
 constexpr int NOUT = 48;                                     // rows of dOT: 36 outputs + pad
 constexpr int ROW = NF + 2 * NF + NO_PAD;                    // 84 floats per particle: A 16 | Y 32 | dO 36
+constexpr int FLUSH = 16;                                    // chunks (1024 rows) accumulated in TMEM between two drains
 constexpr int KP = CH + 1;                                   // K-chunk pitch of the K-major chunk tiles in 16-byte units: one
                                                              // pad piece makes the "lanes over k-chunks" writes conflict-free
 constexpr uint32_t COL_R1 = 0, COL_HLO = 64, COL_R3 = 128, COL_DHLO = 192, COL_ACC1 = 256, COL_ACC2 = 384, TMEM_COLS = 512;
@@ -299,13 +305,18 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                 mbar_wait(&s.bar[T_FULL], it & 1);
                 fence_after_sync();
                 SPHNCA_TL(7);
+                const bool fresh = (it % FLUSH) == 0;        // the accumulators were drained (or never written): start from zero
+                if (fresh && it > 0) {                        // both warp groups drained before they converted their first quarter
+                    mbar_wait(&s.bar[HT_FULL + 1], it & 1);
+                    fence_after_sync();
+                }
 #pragma unroll
                 for (int ks = 0; ks < CH / 8; ++ks) {
                     if (ks > 0 && (ks & 1) == 0) { mbar_wait(&s.bar[HT_FULL + ks / 2], it & 1); fence_after_sync(); }   // next 16 columns converted
                     // one descriptor per tile: rows 0..N-1 of it are the hi tile, all 2N rows the stacked [hi ; lo] tile
                     const uint64_t y_t = make_smem_desc(smem_u32(s.yT) + chunk_off(2 * NY, 0, 2 * ks), 2 * NY * 16, 128);
                     const uint64_t o_t = make_smem_desc(smem_u32(s.dOT) + chunk_off(2 * NOUT, 0, 2 * ks), 2 * NOUT * 16, 128);
-                    const bool acc = (it | ks) > 0;
+                    const bool acc = !(fresh && ks == 0);
                     mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_R3 + 8 * ks, y_t, idA1c, acc, go);      // dH_hi . [y_hi ; y_lo]
                     mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_DHLO + 8 * ks, y_t, idA1, true, go);    // dH_lo . y_hi
                     mma_tf32_ts_e(tbase + COL_ACC2, tbase + COL_R1 + 8 * ks, o_t, idA2c, acc, go);      // H_hi . [dO_hi ; dO_lo]
@@ -322,11 +333,57 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
         const int col0 = (warp >> 2) * (CH / 4);              // first of this warp's two 16-column quarters
         const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
         const float b1h = s.b1[h], w2l = s.w2_last[h];
+        // drain of the accumulators into this CTA pair's partial: warp group 0 -> dW1 row h (48) | db1 (column 48),
+        // warp group 1 -> dW2[o][h] (column o of ACC2).  first = nothing drained yet (plain store), else +=.
+        float* out = partial + (size_t)stream_id * part_floats;
+        const int hg = hh * 128 + h;
+        auto drain = [&](const bool first) {
+            if (warp < 4) {
+#pragma unroll
+                for (int cc = 0; cc < NY; cc += 16) {
+                    uint32_t r[16], r2[16];                  // columns of the hi.(hi + lo of A) group and of the hi.lo group
+                    tmem_ld16(lane_addr + COL_ACC1 + cc, r); tmem_ld16(lane_addr + COL_ACC1 + NY + cc, r2);
+                    float prev[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = cc + j;
+                        prev[j] = (first || k > NIN) ? 0.f : out[k * NH + hg];        // dW1 TRANSPOSED [k][h] | db1 right behind it
+                    }
+                    wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = cc + j;
+                        const float val = prev[j] + (__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                        if (k <= NIN) out[k * NH + hg] = val;       // lanes = consecutive h: coalesced (148 CTAs drain in lockstep)
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < NOUT; cc += 16) {
+                    uint32_t r[16], r2[16];
+                    tmem_ld16(lane_addr + COL_ACC2 + cc, r); tmem_ld16(lane_addr + COL_ACC2 + NOUT + cc, r2);
+                    float prev[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int o = cc + j;
+                        prev[j] = (first || o >= NO_PAD) ? 0.f : out[NH * NIN + NH + o * NH + hg];
+                    }
+                    wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int o = cc + j;
+                        if (o < NO_PAD) out[NH * NIN + NH + o * NH + hg] = prev[j] + (__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                    }
+                }
+            }
+        };
         int it = 0;
         for (int64_t ch = c0; ch < c1; ++ch, ++it) {
             mbar_wait(&s.bar[R_FULL], it & 1);
             fence_after_sync();
             if (tid == 0) SPHNCA_TL(9);
+            // R_FULL(it) follows the accumulate MMAs of chunk it-1 in issue order: the accumulators are final up to there
+            if (it > 0 && (it % FLUSH) == 0) drain(it == FLUSH);
             // 16 particle columns per quarter; warp group g = warp >> 2 converts quarters g and g + 2, so quarters 0|1 and
             // 2|3 are produced in parallel and the accumulate MMAs over the first particles start while the later columns
             // are still being converted; the second quarter's TMEM loads are in flight during the first one's arithmetic
@@ -363,39 +420,12 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
             }
             if (tid == 0) SPHNCA_TL(10);
         }
-        // the accumulators: dW1 row h (48) | db1 (column 48)   and   dW2[o][h] (column o of ACC2)
-        float* out = partial + (size_t)stream_id * part_floats;
-        const int hg = hh * 128 + h;
-        if (warp >= 4) {
-            // second column-half warps have no share in the final dump
-        } else if (c0 < c1) {
+        if (c0 < c1) {
             mbar_wait(&s.bar[ACC_FULL], 0);
             fence_after_sync();
-#pragma unroll
-            for (int cc = 0; cc < NY; cc += 16) {
-                uint32_t r[16], r2[16];                      // columns of the hi.(hi + lo of A) group and of the hi.lo group
-                tmem_ld16(lane_addr + COL_ACC1 + cc, r); tmem_ld16(lane_addr + COL_ACC1 + NY + cc, r2); wait_ld();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int k = cc + j;
-                    const float val = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
-                    if (k < NIN) out[hg * NIN + k] = val;
-                    else if (k == NIN) out[NH * NIN + hg] = val;
-                }
-            }
-#pragma unroll
-            for (int cc = 0; cc < NOUT; cc += 16) {
-                uint32_t r[16], r2[16];
-                tmem_ld16(lane_addr + COL_ACC2 + cc, r); tmem_ld16(lane_addr + COL_ACC2 + NOUT + cc, r2); wait_ld();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int o = cc + j;
-                    if (o < NO_PAD) out[NH * NIN + NH + o * NH + hg] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
-                }
-            }
-        } else {
-            for (int k = 0; k < NIN; ++k) out[hg * NIN + k] = 0.f;
-            out[NH * NIN + hg] = 0.f;
+            drain(it <= FLUSH);                              // the chunks since the last drain (at least one)
+        } else if (warp < 4) {                               // a stream without chunks: zeros
+            for (int k = 0; k <= NIN; ++k) out[k * NH + hg] = 0.f;
             for (int o = 0; o < NO_PAD; ++o) out[NH * NIN + NH + o * NH + hg] = 0.f;
         }
     }

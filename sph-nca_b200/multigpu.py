@@ -26,15 +26,21 @@ def shard_sections(sections, world_size, rank):
     return lo, hi, p_lo, p_lo + sum(sections[lo:hi])
 
 
-def allreduce_gradients(params, group=None, average=True):
+def allreduce_gradients(params, group=None, average=True, weight=None):
     """One flat all-reduce of every parameter gradient.  No-op when not running distributed.
-    Parameters without a gradient contribute zeros (and receive the reduced value)."""
+    Parameters without a gradient contribute zeros (and receive the reduced value).
+    average=True divides the sum by the number of ranks: equal to the single-GPU gradient of a MEAN loss over the
+    concatenated batch only when every rank holds the same number of particles.  With unequal shards (B % world != 0,
+    `shard_sections`) pass `weight` = this rank's share of the batch (its particles / all particles): each rank's gradient
+    is scaled by it before the SUM and nothing is divided afterwards."""
     params = list(params)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return 0
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    if weight is not None:
+        flat = flat * float(weight)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    if average:
+    if average and weight is None:
         flat /= dist.get_world_size(group)
     off = 0
     for p in params:
@@ -53,49 +59,129 @@ class DataParallelSPHNCA(nca.SPHNCA):
 
     The reference's rollout drivers call `loss.backward(); model.normalize_grads(); optimizer.step()`
     (nca.py:151-153), so hooking the reduction here makes `nca.sample_plane` data-parallel without
-    changing it."""
+    changing it.  `shard_weight` (None = equal shards): this rank's share of the global batch, see allreduce_gradients.
+    N ranks reproduce the 1-rank gradient of the concatenated batch when the fire masks are the same (each rank draws
+    its own torch.rand stream otherwise): tests/test_gpu_multigpu.py::test_data_parallel_equals_single_gpu."""
+    shard_weight = None
 
     def normalize_grads(self):
-        allreduce_gradients(self.parameters())
+        allreduce_gradients(self.parameters(), weight=self.shard_weight)
         super().normalize_grads()
 
 
 # =====================================================================================================
 # Spatial slab sharding with a halo exchange (one huge cloud, inference) -- SURVEY.md 8e, BASELINE config 4
 # =====================================================================================================
+def counter_uniform(ids, ncols, seed, device=None):
+    """Counter-based uniforms in [0,1): value (i, c) depends on (ids[i], c, seed) only -- splitmix64 of the counter, top 24
+    bits -- so a quantity drawn per GLOBAL particle id (synthetic states, the per-step fire draw of a slab rollout) is the
+    same whatever the number of ranks and whichever rank owns the particle.  ids: int64 [n] -> float32 [n, ncols]."""
+    ids = ids.to(torch.int64)
+    if device is not None:
+        ids = ids.to(device)
+    M = (1 << 64) - 1
+
+    def s64(v):                                     # two's-complement int64 of an unsigned 64-bit constant
+        v &= M
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    z = ids[:, None] * ncols + torch.arange(ncols, device=ids.device, dtype=torch.int64)[None, :]
+    z = z + s64(0x9E3779B97F4A7C15 * (int(seed) + 1))
+    z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * s64(0xBF58476D1CE4E5B9)
+    z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * s64(0x94D049BB133111EB)
+    z = z ^ ((z >> 31) & ((1 << 33) - 1))
+    return ((z >> 40) & ((1 << 24) - 1)).to(torch.float32) * (1.0 / (1 << 24))
+
+
+def _row_ranges(nrow, world):
+    base, extra = divmod(nrow, world)
+    return [r * base + min(r, extra) for r in range(world + 1)]
+
+
+def cell_row(x_axis, h, nrow):
+    """int(floor(x/h)) mod dims in float64, exactly like the cell hash (single_impl.py:34-44)."""
+    return torch.remainder(torch.floor(x_axis.double() / float(h)).long(), nrow)
+
+
+def slab_lattice_2d(n_side, h, nrow, rank, world, device, seed=0, jitter=1.0):
+    """This rank's part of the synthetic n_side^2 jittered lattice (zero-padded to 3-D): the particles whose
+    cell row along y lies in the rank's slab or in the one-row halo either side, generated WITHOUT building the whole cloud
+    (16 M particles at BASELINE configs[3]).  Jitter comes from counter_uniform(global id), so the cloud is the same for
+    every rank count.  Returns (x [m,3], gid [m]) with gid = iy * n_side + ix ... ordered by gid."""
+    s = 2.0 / n_side
+    starts = _row_ranges(nrow, world)
+    lo, hi = starts[rank], starts[rank + 1]
+    need = torch.zeros(nrow, dtype=torch.bool, device=device)
+    need[lo:hi] = True
+    if world > 1:
+        need[(lo - 1) % nrow] = True
+        need[hi % nrow] = True
+    # lattice rows (index iy along y) that can land in a needed cell row for some jitter in [-0.5, 0.5) spacings
+    iy = torch.arange(n_side, device=device, dtype=torch.float64)
+    r_min = cell_row((iy + 0.5 - 0.5 * jitter) * s - 1.0, h, nrow)
+    r_max = cell_row((iy + 0.5 + 0.5 * jitter) * s - 1.0, h, nrow)
+    r_mid = cell_row((iy + 0.5) * s - 1.0, h, nrow)
+    keep_rows = torch.nonzero(need[r_min] | need[r_max] | need[r_mid]).flatten()
+    ix = torch.arange(n_side, device=device, dtype=torch.int64)
+    gid = (keep_rows[:, None] * n_side + ix[None, :]).reshape(-1)
+    u = counter_uniform(gid, 2, seed, device)
+    x = torch.empty((gid.numel(), 3), dtype=torch.float32, device=device)
+    # the lattice position in fp32 like tests/util.jittered_lattice: (i + 0.5) * s - 1 + (u - 0.5) * jitter * s
+    x[:, 0] = ((gid % n_side).to(torch.float32) + 0.5) * s - 1.0 + (u[:, 0] - 0.5) * (jitter * s)
+    x[:, 1] = ((gid // n_side).to(torch.float32) + 0.5) * s - 1.0 + (u[:, 1] - 0.5) * (jitter * s)
+    x[:, 2] = 0.0
+    sel = need[cell_row(x[:, 1], h, nrow)]
+    return x[sel].contiguous(), gid[sel].contiguous()
+
+
 class SlabPartition:
     """Ownership and halo bookkeeping of one packed cloud cut into slabs of cell rows.
 
     The cell hash is x + dims_x*(y + dims_y*z) (reference single_impl.py:34-44), the support radius equals the
-    cell size, and neighbour cells wrap modulo `dims` (single_impl.py:54-55).  Cutting along axis `axis` (the
-    last populated one) into contiguous ranges of cell indices therefore needs a halo of exactly ONE cell layer
-    on each side, taken from the ring neighbours (rank-1, rank+1 modulo world).
+    cell size, and neighbour cells wrap modulo `dims` (single_impl.py:54-55).  Cutting along axis `axis` into contiguous
+    ranges of cell indices therefore needs a halo of exactly ONE cell layer on each side, taken from the ring neighbours
+    (rank-1, rank+1 modulo world).  `axis=None` picks the last axis along which the particles span more than one cell
+    row (a zero-padded 2-D cloud has all its particles in ONE z row: cutting there would give one rank everything).
 
-    Local particle order on a rank: [interior | halo from the previous rank | halo from the next rank].
+    Two ways in: the whole cloud on every rank (`SlabPartition(x, ...)`, small clouds / tests), or only the particles of
+    this rank's rows + halo rows with their global ids (`SlabPartition.from_local`, e.g. from `slab_lattice_2d`).
+    Local particle order on a rank: [own (ascending global id) | halo from the previous rank | halo from the next rank],
+    halo particles in ascending global id too -- the order in which their owner sends them.
     `exchange(rows_of_my_particles)` fills the halo slots of a local tensor from the owners' current values.
     """
 
-    def __init__(self, x, h, dims, axis, rank, world, group=None):
-        import math
-        self.rank, self.world, self.group, self.axis = rank, world, group, axis
+    def __init__(self, x, h, dims, axis, rank, world, group=None, gid=None):
+        self.rank, self.world, self.group = rank, world, group
         D = x.shape[1]
         dims = [int(dims)] * D if isinstance(dims, int) else [int(d) for d in dims]
         self.dims = dims
+        if axis is None:
+            axis = self.pick_axis(x, h, dims)
+        self.axis = axis
         nrow = dims[axis]
-        # cell row of every particle: int(floor(x/h)) mod dims, in float64 like the hash (exact for these inputs)
-        row = torch.remainder(torch.floor(x[:, axis].double() / float(h)).long(), nrow)
-        base, extra = divmod(nrow, world)
-        starts = [r * base + min(r, extra) for r in range(world + 1)]
-        self.row_lo, self.row_hi = starts[rank], starts[rank + 1]            # my rows: [row_lo, row_hi)
-        owner_mask = (row >= self.row_lo) & (row < self.row_hi)
-        self.own_idx = torch.nonzero(owner_mask).flatten()                     # global indices I own (ascending)
-        own_rows = row[self.own_idx]
-        self.n_own = int(self.own_idx.numel())
-        if world > 1 and self.row_hi - self.row_lo < 1:
+        if world > 1 and nrow < world:
             raise ValueError("more ranks than cell rows")
+        row = cell_row(x[:, axis], h, nrow)
+        starts = _row_ranges(nrow, world)
+        self.row_lo, self.row_hi = starts[rank], starts[rank + 1]            # my rows: [row_lo, row_hi)
+        if gid is None:
+            gid = torch.arange(x.shape[0], device=x.device)
+            self._global = True
+        else:                                                                  # candidates: sort by global id once
+            order = torch.argsort(gid)
+            gid, row, x = gid[order], row[order], x[order]
+            self._global = False
+        own = (row >= self.row_lo) & (row < self.row_hi)
+        sel = torch.nonzero(own).flatten()
+        self.own_idx = gid[sel]                                                # global ids I own (ascending)
+        own_rows = row[sel]
+        self.n_own = int(sel.numel())
+        if world > 1 and self.n_own > 0.9 * x.shape[0] and self._global:
+            raise ValueError(f"rank {rank} owns {self.n_own} of {x.shape[0]} particles along axis {axis}: wrong slab axis?")
         # what I send: my first row goes to the previous rank (it is its upper halo), my last row to the next rank
         self.send_prev = torch.nonzero(own_rows == self.row_lo).flatten()      # positions inside own_idx
         self.send_next = torch.nonzero(own_rows == self.row_hi - 1).flatten()
+        self.boundary = (own_rows == self.row_lo) | (own_rows == self.row_hi - 1)   # own particles whose neighbourhood reaches a halo row
         self.prev, self.next = (rank - 1) % world, (rank + 1) % world
         if world > 1:
             cnt = torch.tensor([self.send_prev.numel(), self.send_next.numel()], dtype=torch.int64, device=x.device)
@@ -108,6 +194,29 @@ class SlabPartition:
         self.n_local = self.n_own + self.n_halo_prev + self.n_halo_next
         self.halo_prev = slice(self.n_own, self.n_own + self.n_halo_prev)
         self.halo_next = slice(self.n_own + self.n_halo_prev, self.n_local)
+        self._x_local = None
+        if not self._global:                               # the halo particles are among the candidates: no exchange needed for x
+            hp = torch.nonzero(row == (self.row_lo - 1) % nrow).flatten() if world > 1 else sel[:0]
+            hn = torch.nonzero(row == self.row_hi % nrow).flatten() if world > 1 else sel[:0]
+            if world > 1 and (hp.numel() != self.n_halo_prev or hn.numel() != self.n_halo_next):
+                raise ValueError("the local candidates do not hold the complete halo rows")
+            self._x_local = torch.cat([x[sel], x[hp], x[hn]]).contiguous()
+            self.halo_gid = torch.cat([gid[hp], gid[hn]])
+
+    @classmethod
+    def from_local(cls, x_cand, gid_cand, h, dims, axis, rank, world, group=None):
+        """Partition from the particles of this rank's rows + halo rows only (any order) and their global ids."""
+        return cls(x_cand, h, dims, axis, rank, world, group, gid=gid_cand)
+
+    @staticmethod
+    def pick_axis(x, h, dims):
+        for a in range(x.shape[1] - 1, -1, -1):
+            if dims[a] > 1 and int(torch.unique(cell_row(x[:, a], h, dims[a])).numel()) > 1:
+                return a
+        raise ValueError("the cloud occupies a single cell row along every axis: nothing to cut")
+
+    def own_global_ids(self):
+        return self.own_idx
 
     def exchange(self, own_rows_tensor, out_local):
         """out_local[halo slots] <- the owners' rows.  `own_rows_tensor` is indexed like own_idx (n_own rows);
@@ -121,7 +230,9 @@ class SlabPartition:
 
     def exchange_indexed(self, src, send_prev_idx, send_next_idx, dst, halo_prev_idx, halo_next_idx):
         """Generic form: rows src[send_*_idx] go to the ring neighbours, received rows land in dst[halo_*_idx].
-        Only halo-sized gathers / scatters are performed (the tensors may be in any order, e.g. cell-sorted)."""
+        Only halo-sized gathers / scatters are performed (the tensors may be in any order, e.g. cell-sorted).
+        Enqueued on the CURRENT stream (NCCL's stream is ordered after it and the current stream waits for NCCL): the
+        host does not block, and a caller may run it on a side stream to overlap it with compute."""
         if self.world == 1:
             return 0
         to_prev = src[send_prev_idx].contiguous()
@@ -139,26 +250,38 @@ class SlabPartition:
 
     def local_from_global(self, t_global):
         """[interior | halo_prev | halo_next] rows of a tensor every rank holds in full (setup only)."""
+        assert self._global, "this partition was built from local candidates: there is no global tensor to cut"
         out = torch.empty((self.n_local,) + tuple(t_global.shape[1:]), dtype=t_global.dtype, device=t_global.device)
         out[:self.n_own] = t_global[self.own_idx]
         self.exchange(out[:self.n_own], out)
         return out
 
+    def local_positions(self, x_global=None):
+        return self._x_local if self._x_local is not None else self.local_from_global(x_global.contiguous())
+
 
 class SlabShardedNCA:
-    """K-step inference rollout of one cloud sharded into slabs of cell rows (one process per GPU).
+    """K-step inference rollout of one cloud sharded into slabs of cell rows (one process per GPU), everything kept in the
+    cell-sorted order of the LOCAL particle set (own + halo), kernels unchanged.
 
-    Per rank and step, in the cell-sorted domain of the LOCAL particle set (interior + halo):
-      1. halo exchange of the state rows (64 B / halo particle)
-      2. perception sweep for every local particle (from the slab's pair lists when they fit) + tcgen05 MLP/update
-         for the fired ones (halo results are discarded)
-      3. halo exchange of the alive bytes of the updated state (1 B / halo particle)
-      4. life-mask sweep, masking of the new state
-    Volume: computed locally (interior exact), halo values fetched once from their owners.
-    Results for the interior equal the single-GPU results of the same kernels up to fp32 summation order.
-    """
+    Without an alpha channel (pair lists + fire lists; the benched path) a step is split so that the halo exchange hides
+    behind the interior work:
+      pass B  the BOUNDARY particles (own particles in the slab's first and last cell row: the only ones whose neighbourhood
+              reaches a halo row, and the only ones a neighbour rank needs) -- fire list, fired-rows perception, tcgen05 MLP;
+      exchange  of the NEW boundary rows into the neighbours' halo slots, on a side stream (NCCL P2P, 64 B / halo particle),
+              issued as soon as pass B is enqueued;
+      pass I  the INTERIOR particles (everything else: ~99 % of the slab at BASELINE configs[3]) on the main stream, while the
+              exchange is in flight; the next step's pass B waits for the exchange.
+    The not-fired rows are carried over by pass B's list kernel (pass I's list build leaves the state alone); halo particles
+    never fire.  With an alpha channel the life mask needs the neighbours' NEW alive bytes, so the step stays sequential:
+    exchange state -> full perception sweep -> MLP over the fire list -> exchange alive bytes -> mask sweep.
+    Volume: computed locally (own particles exact), halo values fetched once from their owners.
+    Fire draws: `fire_masks` (bool [steps, n_own]) or, by default, counter_uniform(global id, seed = fire_seed + step) <= rate:
+    the same global draw whatever the number of ranks, so an N-rank rollout equals the 1-rank rollout.
+    Results for the own particles equal the single-GPU results of the same kernels bit for bit (row-independent arithmetic,
+    identical neighbour order: cell-sorted local order restricted to a particle's neighbourhood is the global one)."""
 
-    def __init__(self, model, x, h, dims, axis=None, group=None):
+    def __init__(self, model, x, h, dims, axis=None, group=None, presharded=False, overlap=True, split_passes=None):
         import ctypes as C
         import sphops
         from sphops import _lib, fused
@@ -166,13 +289,19 @@ class SlabShardedNCA:
         self.model, self.h = model, float(h)
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
-        D = x.shape[1]
-        dims_l = [int(dims)] * D if isinstance(dims, int) else [int(d) for d in dims]
-        if axis is None:
-            axis = D - 1
-        self.part = SlabPartition(x, h, dims_l, axis, rank, world, group)
+        if presharded:
+            x_cand, gid = x
+            D = x_cand.shape[1]
+            dims_l = [int(dims)] * D if isinstance(dims, int) else [int(d) for d in dims]
+            self.part = SlabPartition.from_local(x_cand, gid, h, dims_l, axis, rank, world, group)
+            self.x_loc = self.part.local_positions()
+        else:
+            D = x.shape[1]
+            dims_l = [int(dims)] * D if isinstance(dims, int) else [int(d) for d in dims]
+            self.part = SlabPartition(x, h, dims_l, axis, rank, world, group)
+            self.x_loc = self.part.local_positions(x)
         p = self.part
-        self.x_loc = p.local_from_global(x.contiguous())
+        dev = self.x_loc.device
         self.grid = sphops.initialize_hashgrid(self.x_loc, (p.n_local,), h, tuple(dims_l))
         v = sphops.volume(self.x_loc, h, self.grid).clone()
         p.exchange(v[:p.n_own].clone(), v)                       # halo volumes from their owners
@@ -187,17 +316,46 @@ class SlabShardedNCA:
         self.send_next_pos = self.own_pos[p.send_next]
         self.halo_prev_pos = inv[p.n_own:p.n_own + p.n_halo_prev]
         self.halo_next_pos = inv[p.n_own + p.n_halo_prev:]
+        # per sorted position: global id (-1 for halo particles), boundary / interior membership of the own particles
+        gid_loc = torch.full((p.n_local,), -1, dtype=torch.int64, device=dev)
+        gid_loc[:p.n_own] = p.own_idx
+        self.gid_s = gid_loc[sid]
+        bnd_loc = torch.zeros((p.n_local,), dtype=torch.uint8, device=dev)
+        bnd_loc[:p.n_own] = p.boundary.to(torch.uint8)
+        own_loc = torch.zeros((p.n_local,), dtype=torch.uint8, device=dev)
+        own_loc[:p.n_own] = 1
+        self.bnd_s = bnd_loc[sid].contiguous()
+        self.int_s = (own_loc[sid] & (1 - self.bnd_s)).contiguous()
+        self.own_s = own_loc[sid].contiguous()
+        # boundary / interior passes: whenever there is a neighbour rank (split_passes=True forces them on one rank: tests)
+        self.split = world > 1 if split_passes is None else bool(split_passes)
+        self.overlap = bool(overlap) and world > 1
+        self.comm_stream = torch.cuda.Stream(device=dev) if (self.overlap and dev.type == "cuda") else None
+        self.exchange_mode = "none (1 rank)" if world == 1 else (
+            "NCCL P2P on a side stream, overlapped with the interior pass" if self.overlap else "NCCL P2P, blocking")
         self.bytes_per_step = 0
+        self.fire_seed = 0
+        self._rollouts = 0
 
     def _exchange_sorted(self, t_s):
         """halo exchange, in place, of a tensor held in cell-sorted order (rows = local particles)."""
         return self.part.exchange_indexed(t_s, self.send_prev_pos, self.send_next_pos, t_s, self.halo_prev_pos, self.halo_next_pos)
 
+    def _fire_bytes(self, k, fire_masks, fr, N, dev):
+        """Fire bytes of step k in sorted order (0 for halo particles)."""
+        p = self.part
+        if fire_masks is not None:
+            fire = torch.zeros((N,), dtype=torch.uint8, device=dev)
+            fire[:p.n_own] = fire_masks[k].to(torch.uint8)
+            return self.grid.pack_bytes(fire)
+        u = counter_uniform(self.gid_s, 1, self.fire_seed + 1000003 * self._run + k)[:, 0]
+        return ((u <= fr).to(torch.uint8) & self.own_s).contiguous()
+
     @torch.no_grad()
     def rollout(self, A_global_own, steps, fire_masks=None, fire_rate=None):
         """A_global_own: state rows of the particles this rank owns (ordered like part.own_idx).  Returns the
-        final state of the same particles.  fire_masks: optional bool [steps, n_own] (owned particles); by
-        default drawn per step with torch.rand like the reference (each rank its own stream)."""
+        final state of the same particles.  fire_masks: optional bool [steps, n_own] (owned particles); by default the
+        counter-based global draw (class docstring)."""
         C, _lib, fused = self.C, self._lib, self.fused
         lib, ptr, check = _lib.lib, _lib.ptr, _lib.check
         p, m = self.part, self.model
@@ -224,24 +382,16 @@ class SlabShardedNCA:
             count = torch.empty((1,), dtype=torch.int32, device=dev)
             ws_fl = fused._fire_list_workspace(N, dev)
         nbytes = 0
-        fb = None
+        self._run, self._rollouts = self._rollouts, self._rollouts + 1     # the draws of rollout r, step k: seed fire_seed + 1000003 r + k
+        if lists and not m.use_alpha and pl is not None:
+            out = self._rollout_split(A_s, An_s, Y_s, alive_s, flags_s, steps, fire_masks, fr, prm, pl, ws_fl, N, dev)
+            return out
         for k in range(steps):
             nbytes += self._exchange_sorted(A_s)
-            fire = torch.zeros((N,), dtype=torch.uint8, device=dev)
-            fire[:p.n_own] = (fire_masks[k] if fire_masks is not None else (torch.rand(p.n_own, device=dev) <= fr)).to(torch.uint8)
-            fire_s = self.grid.pack_bytes(fire)
-            if lists and not m.use_alpha:
-                # no alpha channel: list, perception sweep over the fired rows, MLP over compact rows, static life mask --
-                # the rollout node's forward step; halo rows never fire, so nothing at all is computed for them
-                if fb is None:
-                    fb = fused._FireBuffers(N, dev, compact_inputs=True)
-                fb.flags = flags_s
-                fused._step_forward_lists(self.grid, None, None, g, self.xv4, A_s, fire_s, prm, False, Y_s, An_s, alive_s, fb, ws_fl, st, pl=pl)
-                A_s, An_s = An_s, A_s
-                continue
+            fire_s = self._fire_bytes(k, fire_masks, fr, N, dev)
             if lists:
                 check(lib.sphnca_fire_list(N, ptr(fire_s), ptr(A_s), int(bool(m.use_alpha)), ptr(rows), ptr(count), ptr(An_s),
-                                           ptr(alive_s), None, None, ptr(ws_fl), ws_fl.numel(), st))
+                                           ptr(alive_s), None, None, 0, ptr(ws_fl), ws_fl.numel(), st))
             fused._perceive_pl(self.grid, pl, g, self.xv4, A_s, prm, Y_s, flags_s, st)
             if lists:
                 check(lib.sphnca_step_mlp_list(N, ptr(rows), ptr(count), ptr(A_s), ptr(Y_s), C.byref(prm), ptr(An_s), ptr(alive_s),
@@ -257,5 +407,52 @@ class SlabShardedNCA:
                 # no alpha channel: new life mask == previous one (include/sphnca.h), no sweep and no second halo round
                 check(lib.sphnca_step_mask_static(N, ptr(An_s), ptr(flags_s), st))
             A_s, An_s = An_s, A_s
+        self.bytes_per_step = nbytes // max(steps, 1)
+        return A_s[self.own_pos]
+
+    def _rollout_split(self, A_s, An_s, Y_s, alive_s, flags_s, steps, fire_masks, fr, prm, pl, ws_fl, N, dev):
+        """The no-alpha rollout: boundary pass -> exchange of the new boundary rows (side stream) || interior pass."""
+        C, _lib, fused = self.C, self._lib, self.fused
+        lib, ptr = _lib.lib, _lib.ptr
+        g = self.grid.c_grid()
+        main = torch.cuda.current_stream(dev)
+        st = _lib.stream_ptr()
+        fb = fused._FireBuffers(N, dev, compact_inputs=True)
+        fb.flags = flags_s
+        split = self.split
+        nbytes = self._exchange_sorted(A_s)                                 # halo rows of the initial state (no-op on one rank)
+        done = None
+        for k in range(steps):
+            fire_s = self._fire_bytes(k, fire_masks, fr, N, dev)
+            if not split:
+                fused._step_forward_lists(self.grid, None, None, g, self.xv4, A_s, fire_s, prm, False, Y_s, An_s, alive_s, fb, ws_fl, st, pl=pl)
+                A_s, An_s = An_s, A_s
+                continue
+            fire_b, fire_i = fire_s & self.bnd_s, fire_s & self.int_s
+            if done is not None:
+                main.wait_event(done)                                       # pass B reads the halo rows of the current state
+            # pass B: boundary particles; its list kernel also carries over every not-fired row and writes the static mask bits
+            fused._step_forward_lists(self.grid, None, None, g, self.xv4, A_s, fire_b, prm, False, Y_s, An_s, alive_s, fb, ws_fl, st, pl=pl)
+            # exchange of the NEW state's boundary rows into the neighbours' halo slots
+            if self.comm_stream is not None:
+                ready = torch.cuda.Event(); ready.record(main)
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(ready)
+                    nbytes += self._exchange_sorted(An_s)
+                    done = torch.cuda.Event(); done.record(self.comm_stream)
+            # pass I: interior particles (list build without carry-over / flag writes: NULL outputs)
+            fused._timed("fire_list", lib.sphnca_fire_list, N, ptr(fire_i), ptr(A_s), 0, ptr(fb.rows), ptr(fb.count), None, None, None, None, 0,
+                         ptr(ws_fl), ws_fl.numel(), st)
+            fused._timed("step_perceive", lib.sphnca_step_perceive_pairs_fired, g, ptr(fb.rows), ptr(fb.count), ptr(pl["slots"]), ptr(pl["base"]),
+                         ptr(pl["J"]), ptr(pl["WP"]), ptr(A_s), C.byref(prm), ptr(fb.Y_c), ptr(fb.A_c), st)
+            fused._timed("step_mlp", lib.sphnca_step_mlp_list, N, ptr(fb.rows), ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), C.byref(prm), ptr(An_s),
+                         ptr(alive_s), ptr(fb.O_c), ptr(fb.flags), ptr(fb.relu_c), None, None, 3, st)
+            if self.comm_stream is None:
+                nbytes += self._exchange_sorted(An_s)                       # blocking variant (overlap=False) / no-op on one rank
+            A_s, An_s = An_s, A_s
+        if done is not None:
+            main.wait_event(done)
+            # the side stream's temporaries were allocated under it: keep the allocator from handing them to the main stream early
+            A_s.record_stream(self.comm_stream); An_s.record_stream(self.comm_stream)
         self.bytes_per_step = nbytes // max(steps, 1)
         return A_s[self.own_pos]

@@ -138,12 +138,13 @@ class SPHNCA(nn.Module):
         new_mask = self.life_mask(x, v, cell_activity(nA, self.use_alpha)[..., None], h, grid)
         return x, nA * (prev_mask & new_mask).float()
 
-    def rollout(self, x, v, A, h, grid, steps, fire_rate=None, keep_all=True, checkpoint=None):
+    def rollout(self, x, v, A, h, grid, steps, fire_rate=None, keep_all=True, checkpoint=None, microbatch=None):
         """`steps` chained `forward` calls as one autograd node with the state kept cell-sorted on the
         device (sphops.fused.nca_rollout); returns the sequence of the steps+1 states, or None when the
         configuration is not the fused one (callers then loop over `forward`).  `checkpoint`: True = keep only
         the states + fire bytes and recompute each step in the backward, False = full tape, None = the
-        sphops.fused.CHECKPOINT default ("auto": by free device memory)."""
+        sphops.fused.CHECKPOINT default ("auto": by free device memory).  `microbatch`: sections per group when the
+        batch is run group by group (sphops.fused.plan_microbatches), None = sphops.fused.MICROBATCH ("auto")."""
         if not (USE_FUSED_ROLLOUT and self._fusable(x, A, None)):
             return None
         if fire_rate is None:
@@ -153,7 +154,7 @@ class SPHNCA(nn.Module):
             x, v, A, lin1.weight, lin1.bias, lin2.weight, lin2.bias, h, grid, steps, fire_rate,
             update_rule=self.update_rule, use_alpha=self.use_alpha,
             perception_scale=self.perception_scale(h), orig_rate=self.fire_rate / fire_rate, keep_all=keep_all,
-            checkpoint=checkpoint)
+            checkpoint=checkpoint, microbatch=microbatch)
 
     def normalize_grads(self):
         if not self.normalize_grad:

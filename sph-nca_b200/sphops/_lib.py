@@ -79,7 +79,7 @@ def _load():
         "sphnca_mlp_wgrad": ([I64, P, P, P, P, P, SP, P, P, P, P, P, C.c_size_t, P], I32),
         "sphnca_step_adjoint": ([G, P, P, P, SP, P, P], I32),
         "sphnca_fire_list_workspace_bytes": ([I64, C.POINTER(C.c_size_t)], I32),
-        "sphnca_fire_list": ([I64, P, P, I32, P, P, P, P, P, P, P, C.c_size_t, P], I32),
+        "sphnca_fire_list": ([I64, P, P, I32, P, P, P, P, P, P, I32, P, C.c_size_t, P], I32),
         "sphnca_fire_list_draw": ([G, P, C.c_float, P, P, I32, P, P, P, P, P, P, I32, P, C.c_size_t, P], I32),
         "sphnca_step_perceive_pairs_fired": ([G, P, P, P, P, P, P, P, SP, P, P, P], I32),
         "sphnca_step_mlp_list": ([I64, P, P, P, P, SP, P, P, P, P, P, P, P, I32, P], I32),

@@ -32,6 +32,13 @@ def _step_params(W1, b1, W2, b2, update_rule, use_alpha, perception_scale, orig_
     return p
 
 
+# Optional tape probe used by the parity tests: a list that receives, per taped (checkpoint=False) fire-list step of
+# `_NCARollout.forward`, the tuple (rows, count, relu_c, Y_c, O_c) -- the fired rows' sorted positions, their device-side
+# count, their 256 saved ReLU decisions (8 words per list position; bit b of word w = hidden unit 32 w + b), their perception
+# rows and MLP outputs -- so that the oracle can be evaluated with the GPU's own ReLU decisions imposed
+# (oracle.nca_step(relu_bits=...)) and the stages of a step compared one by one.  None = off (default).
+TAPE_PROBE = None
+
 # Optional per-kernel timing hook used by bench.py: a dict name -> list of (start, end) CUDA events
 # recorded on the launching (current) stream around each C-ABI call.  None = off (default).
 PROFILE = None
@@ -227,14 +234,14 @@ def _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, al
     if pl is False:
         pl = grid.pair_lists(x, v, blur=bool(use_alpha))
     fired_sweep = pl is not None and not use_alpha and fb.A_c is not None
-    fold = fired_sweep and draw is not None
+    fold = fired_sweep
     flg, flags = (ptr(pl["FLG"]), ptr(fb.flags)) if fired_sweep else (None, None)
     if draw is not None:
         _timed("fire_list", lib.sphnca_fire_list_draw, g, ptr(draw[0]), float(draw[1]), ptr(fire_s), ptr(S), int(bool(use_alpha)),
                ptr(fb.rows), ptr(fb.count), ptr(Sn), ptr(alive_s), flg, flags, int(fold), ptr(ws_fl), ws_fl.numel(), st)
     else:
         _timed("fire_list", lib.sphnca_fire_list, N, ptr(fire_s), ptr(S), int(bool(use_alpha)), ptr(fb.rows), ptr(fb.count), ptr(Sn),
-               ptr(alive_s), flg, flags, ptr(ws_fl), ws_fl.numel(), st)
+               ptr(alive_s), flg, flags, int(fold), ptr(ws_fl), ws_fl.numel(), st)
     if fired_sweep:
         _timed("step_perceive", lib.sphnca_step_perceive_pairs_fired, g, ptr(fb.rows), ptr(fb.count), ptr(pl["slots"]), ptr(pl["base"]),
                ptr(pl["J"]), ptr(pl["WP"]), ptr(S), C.byref(p), ptr(fb.Y_c), ptr(fb.A_c), st)
@@ -280,7 +287,10 @@ class _NCARollout(torch.autograd.Function):
     `SPHNCA.forward` (nca.py:100), compared with the rate by the list kernel (`u <= fire_rate` in fp32, like torch)."""
 
     @staticmethod
-    def forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_rate, keep_all, taped):
+    def forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_rate, keep_all, taped, groups=None):
+        if groups is not None:
+            return _microbatched_forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_rate, keep_all, taped, groups)
+        ctx.groups = None
         update_rule, use_alpha, perception_scale, orig_rate = cfg
         x = require_cuda_f32(x, "x"); v = require_cuda_f32(v, "v"); A0 = require_cuda_f32(A0, "A")
         W1c, b1c, W2c, b2c = [require_cuda_f32(t, n) for t, n in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"))]
@@ -321,6 +331,8 @@ class _NCARollout(torch.autograd.Function):
                                     draw=(u, fire_rate))
                 if taped == 1:
                     saved += fbuf.tensors()
+                    if TAPE_PROBE is not None:
+                        TAPE_PROBE.append((fbuf.rows, fbuf.count, fbuf.relu_c, fbuf.Y_c, fbuf.O_c))
                 elif taped == 2:
                     saved.append(fire_s)
                 if keep_all or taped:
@@ -360,6 +372,8 @@ class _NCARollout(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, *dstates):
+        if ctx.groups is not None:
+            return _microbatched_backward(ctx, dstates)
         K = ctx.steps
         t = ctx.saved_tensors
         xv4, W1, b1, W2, b2 = t[:5]
@@ -447,7 +461,179 @@ class _NCARollout(torch.autograd.Function):
         if need[2]:
             dA0 = grid.unpack_rows(gcur, 16) if gcur is not None else torch.zeros((N, 16), **f32)
         return (None, None, dA0, dW1 if need[3] else None, db1 if need[4] else None, dW2 if need[5] else None,
-                db2 if need[6] else None, None, None, None, None, None, None)
+                db2 if need[6] else None, None, None, None, None, None, None, None)
+
+
+# ---- micro-batches over sections ------------------------------------------------------------------------------------
+# Batch elements (`sections`) are independent through the whole rollout (reference operators_batch.py:34-42: separate
+# OFFSET / CELL_OFFSET ranges) and contiguous in the cell-sorted arrays.  When the pair lists (~0.8-1.1 KB per
+# particle) and the per-step work buffers of the WHOLE batch would not fit next to the K+1 saved states -- BASELINE
+# configs[4]: 64 clouds x 1,000,000 particles -- the node runs GROUPS of consecutive sections one after the other, group
+# outermost and step innermost: a group's pair lists and work buffers live only while that group runs (forward: built,
+# K steps, dropped; backward: rebuilt once, K steps back), the K+1 states and K fire-byte arrays of all particles are the only
+# O(N K) storage (65 B per particle-step: this mode always checkpoints), parameter gradients accumulate over groups in a
+# fixed order.  States and dL/dA0 are bit-identical to the whole-batch node (row-independent arithmetic, same lists); the
+# fire draws are the reference's: one torch.rand(N) per step, in step order (nca.py:100), drawn before the first group runs.
+MICROBATCH = "auto"            # "auto" | None (never) | int (sections per group; tests force small groups)
+MICROBATCH_WORK_BYTES = 373 + 128 + 16 + 144 + 128 + 64 + 128 + 64     # fire buffers, Y, Sn scratch, dO, dY, dAdir, gradient ping-pong, slack
+MICROBATCH_FRACTION = 0.30      # of the device memory torch does not hold and the states will not take
+
+
+def plan_microbatches(grid, steps, use_alpha, device, taped, setting=None):
+    """None = run the whole batch at once, else [(first section, last + 1)] groups of consecutive sections."""
+    setting = MICROBATCH if setting is None else setting
+    B, N = len(grid.sections), grid.num_particles
+    if setting is None or B <= 1 or N == 0 or not _fire_lists_on() or not _lib.USE_PAIR_LISTS or _lib.FORCE_SWEEP_PATH is not None:
+        return None
+    if isinstance(setting, int) and not isinstance(setting, bool):
+        per = max(1, setting)
+        return [(s, min(s + per, B)) for s in range(0, B, per)] if per < B else None
+    per_particle = grid.PAIR_SLOTS_ESTIMATE * grid.PAIR_ENTRY_BYTES[bool(use_alpha)] + MICROBATCH_WORK_BYTES
+    free = torch.cuda.get_device_properties(device).total_memory - torch.cuda.memory_allocated(device)
+    free -= N * (64 * (steps + 1) + steps) if taped else N * 128
+    budget = MICROBATCH_FRACTION * max(free, 0)
+    if N * per_particle <= budget:
+        return None
+    groups, s0, acc = [], 0, 0
+    for s, n in enumerate(grid.sections):
+        if s > s0 and (acc + n) * per_particle > budget:
+            groups.append((s0, s)); s0, acc = s, 0
+        acc += n
+    groups.append((s0, B))
+    return groups if len(groups) > 1 else None
+
+
+class _GroupWork:
+    """Work buffers of one micro-batch, sized for the largest group and reused by all groups."""
+
+    def __init__(self, n_max, dev, backward, want_w):
+        f32 = dict(dtype=torch.float32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        self.fb = _FireBuffers(n_max, dev, compact_inputs=True)
+        self.Y_s = torch.empty((n_max, 32), **f32)
+        self.alive_s = torch.empty((n_max,), **u8)
+        self.ws_fl = _fire_list_workspace(n_max, dev)
+        self.ping = [torch.empty((n_max, 16), **f32), torch.empty((n_max, 16), **f32)]   # state (inference) / gradient ping-pong
+        if backward:
+            self.dO_c = torch.empty((n_max, 36), **f32)
+            self.dY_s = torch.empty((n_max, 32), **f32)
+            self.dAdir_s = torch.empty((n_max, 16), **f32)
+            self.Sn_scr = torch.empty((n_max, 16), **f32)
+            self.nb = C.c_size_t(0)
+            self.ws = None
+            if want_w:
+                check(lib.sphnca_mlp_wgrad_workspace_bytes(max(n_max, 1), C.byref(self.nb)))
+                self.ws = torch.empty((self.nb.value,), **u8)
+
+
+def _group_lists(sub, xv, use_alpha):
+    # a group was sized to fit: build its lists unconditionally (the budget check of Hashgrid.pair_lists is for whole batches)
+    return sub.build_pair_lists(xv, blur=bool(use_alpha), budget_bytes=float("inf")) if sub.num_particles else None
+
+
+def _microbatched_forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_rate, keep_all, taped, groups):
+    update_rule, use_alpha, perception_scale, orig_rate = cfg
+    x = require_cuda_f32(x, "x"); v = require_cuda_f32(v, "v"); A0 = require_cuda_f32(A0, "A")
+    W1c, b1c, W2c, b2c = [require_cuda_f32(t, n) for t, n in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"))]
+    N = x.shape[0]
+    n_out = 33 if update_rule == "gated" else 16
+    if A0.shape != (N, 16) or W1c.shape != (256, 48) or W2c.shape != (n_out, 256):
+        raise ValueError("fused rollout needs A [N,16], W1 [256,48], W2 [33|16,256]")
+    dev = x.device
+    ctx.set_materialize_grads(False)
+    xv4 = grid.sorted_xv(x, v)
+    p = _step_params(W1c, b1c, W2c, b2c, update_rule, use_alpha, perception_scale, orig_rate)
+    st = stream_ptr()
+    S0 = grid.pack_rows(A0, 16)
+    # the reference's draws, one torch.rand(N) per step in step order, kept as bytes in PARTICLE order (N bytes per step)
+    fire_po = [(torch.rand(N, device=dev) <= fire_rate).view(torch.uint8) for _ in range(steps)]
+    every = bool(keep_all or taped)
+    f32 = dict(dtype=torch.float32, device=dev)
+    states = [S0] + [torch.empty((N, 16), **f32) for _ in range(steps if every else min(steps, 1))]
+    subs = [grid.subgrid(s0, s1) for s0, s1 in groups]
+    work = _GroupWork(max(s.num_particles for s in subs), dev, backward=False, want_w=False)
+    for sub in subs:
+        p0, p1 = sub.range
+        n = p1 - p0
+        if n == 0:
+            continue
+        g, xv = sub.c_grid(), xv4[p0:p1]
+        pl = _group_lists(sub, xv, use_alpha)
+        S = S0[p0:p1]
+        for k in range(steps):
+            fire_s = sub.pack_bytes(fire_po[k])
+            if every:
+                Sn = states[k + 1][p0:p1]
+            else:                                   # inference: only the final state is kept
+                Sn = states[-1][p0:p1] if k == steps - 1 else work.ping[k & 1][:n]
+            _step_forward_lists(sub, None, None, g, xv, S, fire_s, p, use_alpha, work.Y_s, Sn, work.alive_s, work.fb, work.ws_fl, st, pl=pl)
+            S = Sn
+        del pl
+    ctx.grid, ctx.cfg, ctx.steps, ctx.taped, ctx.fire_lists, ctx.groups = grid, cfg, steps, 2 if taped else 0, True, groups
+    ctx.pairs = None
+    if taped:
+        ctx.save_for_backward(xv4, W1c, b1c, W2c, b2c, *states, *fire_po)
+    return tuple(states)
+
+
+def _microbatched_backward(ctx, dstates):
+    K = ctx.steps
+    t = ctx.saved_tensors
+    xv4, W1, b1, W2, b2 = t[:5]
+    states, fire_po = t[5:5 + K + 1], t[5 + K + 1:]
+    grid, use_alpha = ctx.grid, ctx.cfg[1]
+    N, dev = xv4.shape[0], xv4.device
+    need = ctx.needs_input_grad
+    want_w = any(need[3:7])
+    p = _step_params(W1, b1, W2, b2, *ctx.cfg)
+    dW1 = db1 = dW2 = db2 = None
+    if want_w:
+        dW1, db1, dW2, db2 = torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2), torch.zeros_like(b2)
+    st = stream_ptr()
+    subs = [grid.subgrid(s0, s1) for s0, s1 in ctx.groups]
+    work = _GroupWork(max(s.num_particles for s in subs), dev, backward=True, want_w=want_w)
+    dstates = [None if d is None else require_cuda_f32(d, "dS") for d in dstates]
+    dA0_s = torch.zeros((N, 16), dtype=torch.float32, device=dev) if need[2] else None
+    if any(d is not None for d in dstates):
+        for sub in subs:
+            p0, p1 = sub.range
+            n = p1 - p0
+            if n == 0:
+                continue
+            g, xv = sub.c_grid(), xv4[p0:p1]
+            pl = _group_lists(sub, xv, use_alpha)
+            fb = work.fb
+            gcur = dstates[K][p0:p1] if dstates[K] is not None else None
+            for k in range(K - 1, -1, -1):
+                if gcur is not None:
+                    fire_s = sub.pack_bytes(fire_po[k])
+                    # the forward of step k again, from the saved state and fire bytes (activation checkpointing)
+                    _step_forward_lists(sub, None, None, g, xv, states[k][p0:p1], fire_s, p, use_alpha, work.Y_s, work.Sn_scr, work.alive_s,
+                                        fb, work.ws_fl, st, pl=pl)
+                    if pl is None:
+                        _timed("step_bwd_unfired", lib.sphnca_step_bwd_unfired, n, ptr(fb.flags), ptr(gcur), ptr(work.dY_s), ptr(work.dAdir_s), st)
+                    _timed("step_bwd", lib.sphnca_step_bwd_list, n, ptr(fb.rows), ptr(fb.count), ptr(fb.A_c), ptr(fb.O_c), ptr(fb.flags),
+                           ptr(fb.relu_c), ptr(gcur), C.byref(p), ptr(work.dO_c), ptr(work.dY_s), ptr(work.dAdir_s), st)
+                    if want_w:
+                        _timed("mlp_wgrad", lib.sphnca_mlp_wgrad_list, n, ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), ptr(work.dO_c), C.byref(p),
+                               ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(work.ws), work.nb.value, st)
+                    out = work.ping[k & 1][:n]
+                    if pl is not None:
+                        _timed("step_adjoint", lib.sphnca_step_adjoint_pairs_fired, g, ptr(pl["slots"]), ptr(pl["base"]), ptr(pl["J"]),
+                               ptr(pl["WA"]), ptr(pl["SXY"]), ptr(xv), ptr(work.dY_s), ptr(work.dAdir_s), ptr(fb.flags), ptr(gcur), C.byref(p),
+                               ptr(out), st)
+                    else:
+                        _adjoint(sub, None, xv, work.dY_s, work.dAdir_s, p, out, st)
+                    gcur = out
+                if dstates[k] is not None:
+                    dk = dstates[k][p0:p1]
+                    gcur = dk if gcur is None else gcur.add_(dk)
+            if dA0_s is not None and gcur is not None:
+                dA0_s[p0:p1].copy_(gcur)
+            del pl
+    dA0 = grid.unpack_rows(dA0_s, 16) if need[2] else None
+    return (None, None, dA0, dW1 if need[3] else None, db1 if need[4] else None, dW2 if need[5] else None,
+            db2 if need[6] else None, None, None, None, None, None, None, None)
 
 
 class RolloutStates:
@@ -495,9 +681,10 @@ def _tape_mode(N, steps, device, checkpoint):
 
 
 def nca_rollout(x, v, A, W1, b1, W2, b2, h, grid, steps, fire_rate, update_rule="gated", use_alpha=True,
-                perception_scale=1.0, orig_rate=1.0, keep_all=True, checkpoint=None):
+                perception_scale=1.0, orig_rate=1.0, keep_all=True, checkpoint=None, microbatch=None):
     """`steps` NCA steps from state A [N,16] as one autograd node -> RolloutStates (K+1 states if `keep_all`
-    or anything requires grad, else [first, last]).  `checkpoint`: None = module default `CHECKPOINT`."""
+    or anything requires grad, else [first, last]).  `checkpoint`: None = module default `CHECKPOINT`;
+    `microbatch`: None = module default `MICROBATCH` (see plan_microbatches)."""
     if "sphnca_step_fwd" in _lib.MISSING_SYMBOLS:
         raise RuntimeError("libsphnca.so was built without the fused step (step.cu)")
     hval = h.item() if isinstance(h, torch.Tensor) else float(h)
@@ -506,8 +693,9 @@ def nca_rollout(x, v, A, W1, b1, W2, b2, h, grid, steps, fire_rate, update_rule=
     taped = int(torch.is_grad_enabled() and any(t.requires_grad for t in (A, W1, b1, W2, b2)))
     if taped:
         taped = _tape_mode(x.shape[0], int(steps), x.device, checkpoint)
+    groups = plan_microbatches(grid, int(steps), use_alpha, x.device, taped, microbatch)
     states = _NCARollout.apply(x, v, A, W1, b1, W2, b2, grid, (update_rule, use_alpha, perception_scale, orig_rate),
-                               int(steps), fire_rate, keep_all, taped)
+                               int(steps), fire_rate, keep_all, taped, groups)
     return RolloutStates(states, grid)
 
 

@@ -126,30 +126,69 @@ class Hashgrid:
             self._pairs_key = None                                  # built without the blur weights: build again with them
         if self._pairs_key != key:
             self._pairs_key, self._pairs, self._pairs_ref = key, None, (x, v)
-            N = self.num_particles
-            if N:
-                dev = x.device
-                xv4 = self.sorted_xv(x, v)
-                ng = (N + 7) // 8                                   # list groups of 8 particles (csrc/pairs.cu)
-                slots = torch.empty((ng,), dtype=torch.int32, device=dev)
-                st = _lib.stream_ptr()
-                _lib.check(_lib.lib.sphnca_pairs_count(self.c_grid(), _lib.ptr(xv4), _lib.ptr(slots), st))
-                cum = torch.cumsum(slots, 0, dtype=torch.int64)
-                base = ((cum - slots) * 8).contiguous()
-                total = int(cum[-1].item()) * 8
-                # capacity minus torch's live tensors (host-side counters; cudaMemGetInfo stalls ~25 ms on a busy device)
-                free = torch.cuda.get_device_properties(dev).total_memory - torch.cuda.memory_allocated(dev)
-                if 0 < total and total * (28 if blur else 20) <= self.PAIR_LIST_MEMORY_FRACTION * free:
-                    f32 = dict(dtype=torch.float32, device=dev)
-                    J = torch.empty((total,), dtype=torch.int32, device=dev)
-                    WP, WA = (torch.empty((total, 2), **f32) for _ in range(2))
-                    WB = torch.empty((total, 2), **f32) if blur else None
-                    SXY = torch.empty((N, 2), **f32)
-                    FLG = torch.empty((N,), dtype=torch.uint8, device=dev)
-                    _lib.check(_lib.lib.sphnca_pairs_fill(self.c_grid(), _lib.ptr(xv4), _lib.ptr(slots), _lib.ptr(base), _lib.ptr(J),
-                                                          _lib.ptr(WP), _lib.ptr(WB), _lib.ptr(WA), _lib.ptr(SXY), _lib.ptr(FLG), st))
-                    self._pairs = dict(slots=slots, base=base, J=J, WP=WP, WB=WB, WA=WA, SXY=SXY, FLG=FLG, entries=total)
+            if self.num_particles:
+                self._pairs = self.build_pair_lists(self.sorted_xv(x, v), blur)
         return self._pairs
+
+    # what one list entry costs (J + WP + WA [+ WB]) and the measured entries per particle of the BASELINE workloads
+    # (35.9 slots in padded 2-D at h = 3.2 spacings, 39 in 3-D at h = 1.97 spacings): used to plan micro-batches
+    PAIR_ENTRY_BYTES = {False: 20, True: 28}
+    PAIR_SLOTS_ESTIMATE = 40
+
+    def build_pair_lists(self, xv4, blur=True, budget_bytes=None):
+        """The pair lists of this grid from its cell-sorted {x,y,z,v} array (uncached).  None when they would exceed
+        `budget_bytes` (default: PAIR_LIST_MEMORY_FRACTION of the device memory torch does not hold)."""
+        N, dev = self.num_particles, xv4.device
+        ng = (N + 7) // 8                                   # list groups of 8 particles (csrc/pairs.cu)
+        slots = torch.empty((ng,), dtype=torch.int32, device=dev)
+        st = _lib.stream_ptr()
+        _lib.check(_lib.lib.sphnca_pairs_count(self.c_grid(), _lib.ptr(xv4), _lib.ptr(slots), st))
+        cum = torch.cumsum(slots, 0, dtype=torch.int64)
+        base = ((cum - slots) * 8).contiguous()
+        total = int(cum[-1].item()) * 8
+        if budget_bytes is None:
+            # capacity minus torch's live tensors (host-side counters; cudaMemGetInfo stalls ~25 ms on a busy device)
+            free = torch.cuda.get_device_properties(dev).total_memory - torch.cuda.memory_allocated(dev)
+            budget_bytes = self.PAIR_LIST_MEMORY_FRACTION * free
+        if not (0 < total and total * self.PAIR_ENTRY_BYTES[bool(blur)] <= budget_bytes):
+            return None
+        f32 = dict(dtype=torch.float32, device=dev)
+        J = torch.empty((total,), dtype=torch.int32, device=dev)
+        WP, WA = (torch.empty((total, 2), **f32) for _ in range(2))
+        WB = torch.empty((total, 2), **f32) if blur else None
+        SXY = torch.empty((N, 2), **f32)
+        FLG = torch.empty((N,), dtype=torch.uint8, device=dev)
+        _lib.check(_lib.lib.sphnca_pairs_fill(self.c_grid(), _lib.ptr(xv4), _lib.ptr(slots), _lib.ptr(base), _lib.ptr(J),
+                                              _lib.ptr(WP), _lib.ptr(WB), _lib.ptr(WA), _lib.ptr(SXY), _lib.ptr(FLG), st))
+        return dict(slots=slots, base=base, J=J, WP=WP, WB=WB, WA=WA, SXY=SXY, FLG=FLG, entries=total)
+
+    # -- micro-batches over sections ---------------------------------------------------------
+    def section_ranges(self):
+        """[(first sorted position, last + 1)] per section: sections are contiguous, in order, in the sorted arrays."""
+        out, off = [], 0
+        for n in self.sections:
+            out.append((off, off + n))
+            off += n
+        return out
+
+    def subgrid(self, s0, s1):
+        """The grid of sections [s0, s1) alone, as a self-contained problem on SLICES of this grid's sorted arrays.
+        Batch elements are independent (reference operators_batch.py:34-42: separate OFFSET / CELL_OFFSET ranges) and
+        contiguous in cell-sorted order, so with row p0 = the first sorted position of section s0 re-based to 0 every
+        kernel runs unchanged on `array[p0:p1]`: cell offsets and cell ids are made relative here (two small copies),
+        `sorted_id` keeps the GLOBAL particle index (it is only used to gather from / scatter to particle-order arrays).
+        Used by the rollout node to hold pair lists for a few sections at a time (`sphops.fused`)."""
+        ranges = self.section_ranges()
+        p0, p1 = ranges[s0][0], ranges[s1 - 1][1]
+        C_ = self.total_cells
+        sub = Hashgrid(self.h, self.dims, self.total_cells, self.sections[s0:s1], self.device)
+        sub._dims_host = self._dims_host
+        sub.cell_off = (self.cell_off[s0 * C_: s1 * C_ + 1] - p0).contiguous()
+        sub.sorted_cell = (self.sorted_cell[p0:p1] - s0 * C_).contiguous()
+        sub.sorted_id = self.sorted_id[p0:p1]
+        sub.num_points = self.num_points[s0:s1]
+        sub.range = (p0, p1)
+        return sub
 
     def staged_sweep_ok(self):
         """True when (nearly) every 128-particle tile of this grid fits the shared-memory staging buffer of

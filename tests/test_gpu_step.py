@@ -693,7 +693,7 @@ def test_fire_list_is_the_ordered_compaction(n, rate):
     _lib.check(_lib.lib.sphnca_fire_list_workspace_bytes(n, C.byref(nb)))
     ws = torch.empty((nb.value,), dtype=torch.uint8, device=DEV)
     _lib.check(_lib.lib.sphnca_fire_list(n, _lib.ptr(fire), _lib.ptr(A), 1, _lib.ptr(rows), _lib.ptr(count), _lib.ptr(An), _lib.ptr(alive),
-                                         None, None, _lib.ptr(ws), nb.value, _lib.stream_ptr()))
+                                         None, None, 0, _lib.ptr(ws), nb.value, _lib.stream_ptr()))
     want = torch.nonzero(fire)[:, 0].to(torch.int32)
     assert int(count.item()) == want.numel()
     assert torch.equal(rows[:want.numel()], want)
@@ -794,12 +794,18 @@ def test_static_life_mask_equals_sweep_when_no_alpha():
     import sphops
     from sphops import _lib, fused
     gen = torch.Generator().manual_seed(11)
-    x = torch.nn.functional.pad(jittered_lattice(90, 2, gen), (0, 1))
-    # a few isolated far-away particles in otherwise empty cells next to a dense blob: life mask may drop to 0 there
-    blob = torch.rand(4000, 3, generator=gen) * torch.tensor([0.05, 0.05, 0.0]) + torch.tensor([0.5, 0.5, 0.0])
-    x = torch.cat([x, blob])
-    N = x.shape[0]
     h = 3.2 * 2 / 90
+    x = torch.nn.functional.pad(jittered_lattice(90, 2, gen), (0, 1))
+    # particles whose life mask IS 0 (blur of the all-ones activity <= 0.1): a ring of 16 isolated particles at 0.8 h
+    # around a very dense, very tight blob, in a region cleared of lattice particles.  Their own volume is tiny (the blob
+    # sits inside their support) and the blob's volumes are tiny too: blur = 0.0625 (fp64 oracle), far from the threshold.
+    c = torch.tensor([0.5, 0.5, 0.0])
+    x = x[((x - c) ** 2).sum(-1) > (2.5 * h) ** 2]
+    blob = (torch.rand(4000, 3, generator=gen) - 0.5) * torch.tensor([0.002, 0.002, 0.0]) + c
+    ang = torch.arange(16) * (2 * math.pi / 16)
+    ring = c + 0.8 * h * torch.stack([torch.cos(ang), torch.sin(ang), torch.zeros(16)], -1)
+    x = torch.cat([x, blob, ring])
+    N = x.shape[0]
     xd = x.to(DEV)
     grid = sphops.initialize_hashgrid(xd, (N,), h, math.ceil(2 / h))
     v = sphops.volume(xd, h, grid)
@@ -826,8 +832,12 @@ def test_static_life_mask_equals_sweep_when_no_alpha():
         torch.cuda.synchronize()
         res.append((An, fl))
     assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][0], res[1][0])
-    dead = int(((res[0][1] & 1) == 0).sum())
-    print("particles with life mask 0:", dead)
+    dead = (res[0][1] & 1) == 0
+    fired = fire_s.bool()
+    # the 16 ring particles are dead; both the fired-and-dead and the not-fired-and-dead (carry-over) branches are exercised
+    assert int(dead.sum()) == 16, int(dead.sum())
+    assert int((dead & fired).sum()) > 0 and int((dead & ~fired).sum()) > 0
+    assert bool((res[1][0][dead] == 0).all()), "a dead particle kept a non-zero state"
 
 
 def test_staged_sweep_is_chosen_per_grid():
@@ -844,3 +854,79 @@ def test_staged_sweep_is_chosen_per_grid():
         assert g2.staged_sweep_ok() is True and g3.staged_sweep_ok() is False
     else:
         assert g2.staged_sweep_ok() is False
+
+
+@pytest.mark.parametrize("use_alpha", [False, True], ids=["noalpha", "alpha"])
+@pytest.mark.parametrize("per_group", [1, 2], ids=["one_section_per_group", "two_sections_per_group"])
+def test_rollout_node_microbatched_over_sections_equals_whole_batch(use_alpha, per_group):
+    """Micro-batching over sections (sphops.fused.plan_microbatches: groups of consecutive batch elements run one after the
+    other with their own pair lists; BASELINE configs[4] needs it) against the whole-batch node: every state and dL/dA0
+    bit-identical, parameter gradients equal up to the summation order over groups; same fire draws (one torch.rand(N)
+    per step).  Ragged sections, none of them a multiple of 4 or 8 (slices of the sorted arrays start anywhere)."""
+    import nca
+    from sphops import fused
+    gen = torch.Generator().manual_seed(31)
+    n_side = 110
+    x = torch.nn.functional.pad(jittered_lattice(n_side, 2, gen), (0, 1))
+    N = x.shape[0]
+    sections = (3001, 2047, 777, 4099, N - 3001 - 2047 - 777 - 4099)
+    h = 3.2 * 2 / n_side
+    dims = math.ceil(2 / h)
+    w = load_golden("weights_gecko" if use_alpha else "weights_zebra")
+    params = [torch.from_numpy(w[k]) for k in ("W1", "b1", "W2", "b2")]
+    if use_alpha:
+        d2 = (x ** 2).sum(-1)
+        A0 = (torch.clamp(1 - d2 / 0.6 ** 2, 0, 1) ** 3)[:, None].repeat(1, 16) + 0.05 * torch.rand(N, 16, generator=gen)
+    else:
+        A0 = torch.rand(N, 16, generator=gen)
+    K = 3
+    masks = torch.rand(K, N, generator=gen) <= 0.5
+    nca.USE_FUSED_STEP = True
+    m = nca.SPHNCA(16, 0.5, use_alpha=use_alpha, normalize_perception=1.0 / h).to(DEV)
+    with torch.no_grad():
+        for t, src in zip((m.model[0].weight, m.model[0].bias, m.model[2].weight, m.model[2].bias), params):
+            t.copy_(src)
+    xd = x.to(DEV)
+    res = {}
+    for mb in (None, per_group):
+        m.zero_grad()
+        grid, v = m.init_grid(xd, sections, h, dims)
+        A = A0.to(DEV).requires_grad_(True)
+        prev, fused.MICROBATCH = fused.MICROBATCH, None          # "whole batch" must really be the whole batch
+        try:
+            with forced_fire_masks(list(masks)):
+                out = m.rollout(xd, v, A, h, grid, K, checkpoint=True, microbatch=mb)
+        finally:
+            fused.MICROBATCH = prev
+        loss = (out[-1][:, :4] ** 2).mean() + 0.1 * (out[1][:, :4] ** 2).mean()
+        loss.backward()
+        res[mb] = ([out[k].detach().clone() for k in range(K + 1)], A.grad.clone(), [p.grad.clone() for p in m.parameters()])
+        # inference through the same groups: only [first, last] are kept
+        with torch.no_grad(), forced_fire_masks(list(masks)):
+            o2 = m.rollout(xd, v, A0.to(DEV), h, grid, K, keep_all=False, microbatch=mb)
+        assert len(o2) == 2 and torch.equal(o2[-1], res[mb][0][-1])
+    for a, b in zip(res[None][0], res[per_group][0]):
+        assert torch.equal(a, b)
+    assert torch.equal(res[None][1], res[per_group][1])
+    for a, b, nm in zip(res[None][2], res[per_group][2], ("dW1", "db1", "dW2", "db2")):
+        assert_close(b, a, rtol=GRAD_RTOL, what=nm)
+
+
+def test_microbatch_plan_follows_memory(monkeypatch):
+    """plan_microbatches: whole batch while lists + work buffers fit the budget, else groups of consecutive sections that do."""
+    import sphops
+    from sphops import fused
+    gen = torch.Generator().manual_seed(1)
+    x = torch.nn.functional.pad(jittered_lattice(64, 2, gen), (0, 1)).to(DEV)
+    sections = (1024,) * 4
+    grid = sphops.initialize_hashgrid(x, sections, 0.1, 20)
+    assert fused.plan_microbatches(grid, 8, False, x.device, 2, "auto") is None
+    per = grid.PAIR_SLOTS_ESTIMATE * grid.PAIR_ENTRY_BYTES[False] + fused.MICROBATCH_WORK_BYTES
+
+    class Props:
+        total_memory = int(torch.cuda.memory_allocated(x.device) + 4096 * (64 * 9 + 8) + 2.5 * 1024 * per / fused.MICROBATCH_FRACTION)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: Props)
+    assert fused.plan_microbatches(grid, 8, False, x.device, 2, "auto") == [(0, 2), (2, 4)]
+    assert fused.plan_microbatches(grid, 8, False, x.device, 2, 3) == [(0, 3), (3, 4)]
+    monkeypatch.setattr(fused, "MICROBATCH", None)
+    assert fused.plan_microbatches(grid, 8, False, x.device, 2, None) is None

@@ -94,3 +94,51 @@ def test_slab_partition_halo_world2():
         assert err < 1e-12, err                                      # identical neighbour sets -> identical fp64 sums
         assert hp > 0 and hn > 0 and hi > lo
     assert ret[0][5] == ret[1][4]                                    # contiguous row ranges
+
+
+def test_counter_uniform_is_a_function_of_the_global_id():
+    import multigpu
+    ids = torch.arange(0, 100000, dtype=torch.int64)
+    u = multigpu.counter_uniform(ids, 3, seed=5)
+    assert u.shape == (100000, 3) and u.dtype == torch.float32
+    assert float(u.min()) >= 0.0 and float(u.max()) < 1.0
+    assert abs(float(u.mean()) - 0.5) < 5e-3 and abs(float((u <= 0.5).float().mean()) - 0.5) < 5e-3
+    perm = torch.randperm(100000, generator=torch.Generator().manual_seed(0))
+    assert torch.equal(multigpu.counter_uniform(ids[perm], 3, seed=5), u[perm])          # any subset, any order, any rank
+    assert not torch.equal(multigpu.counter_uniform(ids, 3, seed=6), u)
+    # columns and neighbouring ids are uncorrelated
+    c = torch.corrcoef(torch.stack([u[:-1, 0], u[1:, 0], u[:-1, 1]]))
+    assert float(c[0, 1].abs()) < 0.02 and float(c[0, 2].abs()) < 0.02
+
+
+def _presharded_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import math
+    import multigpu
+    n = 64
+    h = 3.2 * 2 / n
+    d = math.ceil(2 / h)
+    dims = (d, d, 3)
+    xg, gidg = multigpu.slab_lattice_2d(n, h, d, 0, 1, "cpu", seed=2)                     # the whole cloud (what 1 rank generates)
+    glob = multigpu.SlabPartition(xg, h, dims, None, rank, world)                         # axis picked: y (z holds one cell row)
+    xl, gidl = multigpu.slab_lattice_2d(n, h, d, rank, world, "cpu", seed=2)              # this rank's rows + halo rows only
+    loc = multigpu.SlabPartition.from_local(xl, gidl, h, dims, 1, rank, world)
+    same = (glob.axis == 1 and torch.equal(glob.own_idx, loc.own_idx) and torch.equal(glob.send_prev, loc.send_prev)
+            and torch.equal(glob.send_next, loc.send_next) and (glob.n_halo_prev, glob.n_halo_next) == (loc.n_halo_prev, loc.n_halo_next)
+            and torch.equal(glob.local_from_global(xg), loc.local_positions()))
+    ret[rank] = (bool(same), int(xl.shape[0]), int(xg.shape[0]), loc.n_own, int(loc.boundary.sum()))
+    dist.destroy_process_group()
+
+
+def test_presharded_partition_equals_global_partition_world2():
+    """slab_lattice_2d(rank, world) + SlabPartition.from_local: same ownership, send sets, halo order and local positions as
+    cutting the whole cloud -- without any rank ever holding the whole cloud."""
+    world = 2
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_presharded_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret[0][3] + ret[1][3] == 64 * 64
+    for r in range(world):
+        same, n_loc, n_glob, n_own, n_bnd = ret[r]
+        assert same
+        assert n_own < n_loc < n_glob and 0 < n_bnd < n_own
