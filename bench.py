@@ -280,6 +280,15 @@ class Ctx:
             torch.distributed.destroy_process_group()
 
 
+def release_memory():
+    """Between workloads: drop autograd garbage and hand torch's cached blocks back, so that the next workload does not
+    start inside an allocator full of the previous one's 100+ GB."""
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+
 def run_slab(ctx, args, name, wl, steps, warmup):
     """Forward-only rollout of ONE cloud sharded into slabs of cell rows (multigpu.SlabShardedNCA): strong scaling."""
     import nca
@@ -315,7 +324,7 @@ def run_slab(ctx, args, name, wl, steps, warmup):
                       "exchange": sh.exchange_mode, "l2": "state per rank >> 126 MB L2"},
            "gpu_launches": launches, "clocks": clk.stop() if clk else None}
     del sh, A0
-    torch.cuda.empty_cache()
+    release_memory()
     return rec
 
 
@@ -385,7 +394,7 @@ def run_train(ctx, args, name, wl, steps, warmup, detail):
     if not detail:
         rec["clocks"] = clk.stop() if clk else None
         del x_dev, A_dev, model, opt
-        torch.cuda.empty_cache()
+        release_memory()
         return rec
 
     # per-kernel durations: the same K steps once more with a CUDA-event pair (on the launching stream) around
@@ -478,7 +487,7 @@ def run_train(ctx, args, name, wl, steps, warmup, detail):
     rec["kernel_timing"] = {"how": "second timed pass of the same steps with a CUDA-event pair around every hot kernel launch "
                                    "(kept out of the pass `value` is measured on)", "ms_per_step_instrumented": ms_instr / steps}
     del x_dev, A_dev, model, opt
-    torch.cuda.empty_cache()
+    release_memory()
     return rec
 
 
@@ -558,7 +567,7 @@ def main():
                     args.use_alpha = saved
             except Exception as e:  # noqa: BLE001  (a sub-record must not take the headline down; the error is the record)
                 subs[name] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
-                torch.cuda.empty_cache()
+                release_memory()
     ctx.barrier()
     if ctx.rank != 0:
         ctx.close()

@@ -47,6 +47,19 @@ typedef struct sphnca_grid {
     const int32_t* cell_off;   /* [B*cells + 1] global sorted offset of every cell (exclusive scan) */
     const int32_t* sorted_id;  /* [N] original (global packed) index of sorted position p */
     const int32_t* sorted_cell;/* [N] global cell id (section*cells + hash) of sorted position p */
+    double period[3];          /* > 0: the cloud is PERIODIC along that axis with this period (== dims * h, so that the hash grid's
+                                * modulo wrap, single_impl.py:54-55, is the period): a neighbour found through the wrap is taken at
+                                * x_j +- period -- the ghost particles of reference nca.py:200-227 without ghost particles.
+                                * Honoured by sphnca_volume_fwd, sphnca_pairs_count / _fill (and, through the lists, by every
+                                * list-based step kernel); every other sweep entry rejects a periodic grid.  0 = open (default). */
+    /* Ghost-volume emulation for periodic planes (x and y axes; NULL = plain periodic volumes).  The reference builds grid and
+     * volumes ONCE on the ghost-padded cloud (nca.py:262-263), so a ghost copy carries the volume of ITS OWN, outward-truncated
+     * neighbourhood, not its source's, and own particles near an edge see those volumes.  image_volume [N][9] (cell-sorted;
+     * entry (sx+1)*3 + (sy+1) = volume of the copy shifted by (sx, sy) periods, entry 4 = the particle's own volume) is written
+     * by sphnca_volume_images and read by sphnca_pairs_fill; a copy (sx, sy) of a particle exists iff, per axis, s = 0, or
+     * s = +1 and x <= band_lo, or s = -1 and x >= band_hi (nca.py:182-197: within h of the lower / upper edge). */
+    const float* image_volume;
+    double band_lo[3], band_hi[3];
 } sphnca_grid;
 
 int32_t sphnca_abi_version(void);
@@ -82,6 +95,9 @@ int32_t sphnca_pack_bytes(const sphnca_grid* g, const uint8_t* src, uint8_t* dst
 /* volume_forward (:16-77): v_i = 1/(Cw sum_j (h^2-d^2)^3_+).  Reads xyz of xv4; writes v (original
  * order) and xv4_out[p] = {x,y,z,v} (sorted order; a buffer distinct from xv4). */
 int32_t sphnca_volume_fwd(const sphnca_grid* g, const float* xv4, float* v, float* xv4_out, void* stream);
+/* Volumes of the ghost copies of a periodic plane (see sphnca_grid.image_volume): xv4 = {x,y,z,v} with the particles' own
+ * (periodic) volumes, image_volume [N][9] out.  g->image_volume is ignored here; band_lo / band_hi / period are read. */
+int32_t sphnca_volume_images(const sphnca_grid* g, const float* xv4, float* image_volume, void* stream);
 /* volume_backward (:79-151): dLdx [N,D] original order; dLdv_s sorted order */
 int32_t sphnca_volume_bwd(const sphnca_grid* g, const float* xv4, const float* dLdv_s, float* dLdx, void* stream);
 /* count_forward (:536-597) */
@@ -254,6 +270,13 @@ int32_t sphnca_step_bwd_list(int64_t N, const int32_t* rows, const int32_t* coun
                              const sphnca_step_params* p, float* dO_c, float* dY_s, float* dAdir_s, void* stream);
 int32_t sphnca_step_bwd_unfired(int64_t N, const uint8_t* flags_s, const float* dA_next_s, float* dY_s, float* dAdir_s,
                                 void* stream);
+/* Counter-based fire bytes of one step for slab-sharded rollouts (multigpu.py; no reference counterpart -- the reference draws
+ * torch.rand(N) on its single GPU, nca.py:100): fire_s[p] = gid_s[p] >= 0 && U(gid_s[p], seed) <= rate, U = top 24 bits of
+ * splitmix64(gid + 0x9E3779B97F4A7C15 (seed + 1)) / 2^24 -- a function of the GLOBAL particle id, so N ranks draw what 1 rank
+ * draws.  gid_s [N] int64 in cell-sorted order, -1 = halo particle (never fires).  Optional: bnd_s [N] (1 = boundary particle)
+ * -> fire_b = fire & bnd, fire_i = fire & ~bnd (the two passes of a split step). */
+int32_t sphnca_fire_bytes_counter(int64_t N, const int64_t* gid_s, int64_t seed, float rate, const uint8_t* bnd_s, uint8_t* fire_s,
+                                  uint8_t* fire_b, uint8_t* fire_i, void* stream);
 /* sphnca_step_adjoint_pairs for a fire-list step: rows of dY_s / dAdir_s are read only for the particles whose flag byte has the
  * fire bit (4); for the others dL/dY is zero and the direct part is (living ? dA_next_s : 0), taken from flags_s / dA_next_s --
  * no sphnca_step_bwd_unfired pass is needed and the row gathers of not-fired neighbours are skipped. */

@@ -47,9 +47,35 @@ struct GridView {
     const int32_t* __restrict__ cell_off;
     const int32_t* __restrict__ sorted_id;
     const int32_t* __restrict__ sorted_cell;
+    float period[3];  // > 0: periodic along that axis (sphnca_grid.period)
+    int periodic;
+    const float* __restrict__ image_volume;   // ghost-volume emulation (sphnca_grid.image_volume), may be NULL
+    float band_lo[2], band_hi[2];
 };
 
-inline int make_view(const sphnca_grid* g, GridView* v) {
+// Does the ghost copy of the particle at b, shifted by (sx, sy) periods, exist in the reference's ghost-padded cloud?
+__device__ __forceinline__ bool image_exists(const GridView& g, const float4& b, int sx, int sy) {
+    const bool okx = sx == 0 || (sx == 1 ? b.x <= g.band_lo[0] : b.x >= g.band_hi[0]);
+    const bool oky = sy == 0 || (sy == 1 ? b.y <= g.band_lo[1] : b.y >= g.band_hi[1]);
+    return okx && oky;
+}
+// shift (in periods, -1 / 0 / +1 per axis) that nearest_image applied to b
+__device__ __forceinline__ void image_shift(const float4& b, const float4& b_img, int& sx, int& sy) {
+    sx = b_img.x > b.x ? 1 : (b_img.x < b.x ? -1 : 0);
+    sy = b_img.y > b.y ? 1 : (b_img.y < b.y ? -1 : 0);
+}
+
+// The neighbour's position as the reference's ghost copy would hold it (nca.py:214-217: x_w = x + (+-gsize), one fp32 add): the image
+// of b closest to a along every periodic axis.  Open axes (period 0) are left alone.
+__device__ __forceinline__ float4 nearest_image(const GridView& g, const float4& a, float4 b) {
+    if (g.period[0] > 0.f) { const float d = b.x - a.x; if (d > 0.5f * g.period[0]) b.x -= g.period[0]; else if (d < -0.5f * g.period[0]) b.x += g.period[0]; }
+    if (g.period[1] > 0.f) { const float d = b.y - a.y; if (d > 0.5f * g.period[1]) b.y -= g.period[1]; else if (d < -0.5f * g.period[1]) b.y += g.period[1]; }
+    if (g.period[2] > 0.f) { const float d = b.z - a.z; if (d > 0.5f * g.period[2]) b.z -= g.period[2]; else if (d < -0.5f * g.period[2]) b.z += g.period[2]; }
+    return b;
+}
+
+// allow_periodic: only the entries that implement the periodic neighbour search (or never look at positions) pass true
+inline int make_view(const sphnca_grid* g, GridView* v, bool allow_periodic = false) {
     if (!g) { set_error("grid is NULL"); return SPHNCA_ERR_INVALID; }
     if (g->dim != 2 && g->dim != 3) { set_error("grid.dim must be 2 or 3, got %d", g->dim); return SPHNCA_ERR_INVALID; }
     if (g->num_particles < 0 || g->num_particles >= (int64_t(1) << 31)) { set_error("num_particles out of range"); return SPHNCA_ERR_INVALID; }
@@ -60,6 +86,23 @@ inline int make_view(const sphnca_grid* g, GridView* v) {
     v->cells = (int)g->cells_per_section;
     for (int d = 0; d < 3; ++d) v->dims[d] = d < g->dim ? (int)g->dims[d] : 1;
     v->cell_off = g->cell_off; v->sorted_id = g->sorted_id; v->sorted_cell = g->sorted_cell;
+    v->periodic = 0;
+    for (int d = 0; d < 3; ++d) {
+        v->period[d] = (d < g->dim && g->period[d] > 0.0) ? (float)g->period[d] : 0.f;
+        if (v->period[d] > 0.f) {
+            v->periodic = 1;
+            // the modulo wrap of the cell hash must BE the period (and a stencil must not meet itself)
+            const double cells = g->period[d] / g->h;
+            if (g->dims[d] < 3 || cells < (double)g->dims[d] - 1e-6 * g->dims[d] || cells > (double)g->dims[d] + 1e-6 * g->dims[d]) {
+                set_error("periodic axis %d: period %g must equal dims (%lld) x h (%g), dims >= 3", d, g->period[d], (long long)g->dims[d], g->h);
+                return SPHNCA_ERR_INVALID;
+            }
+        }
+    }
+    v->image_volume = v->periodic ? g->image_volume : nullptr;
+    for (int d = 0; d < 2; ++d) { v->band_lo[d] = (float)g->band_lo[d]; v->band_hi[d] = (float)g->band_hi[d]; }
+    if (v->image_volume != nullptr && v->period[2] > 0.f) { set_error("ghost-volume emulation is for periodic PLANES (x, y)"); return SPHNCA_ERR_INVALID; }
+    if (v->periodic && !allow_periodic) { set_error("this entry does not implement periodic grids (sphnca_grid.period)"); return SPHNCA_ERR_INVALID; }
     return SPHNCA_OK;
 }
 

@@ -150,6 +150,42 @@ fire_fill_kernel(int64_t n, const uint8_t* __restrict__ fire_s, const int32_t* _
     }
 }
 
+// Counter-based fire bytes for slab rollouts (multigpu.py): fire byte of sorted row p = gid[p] >= 0 && U(gid[p], seed) <= rate with
+// U = the top 24 bits of splitmix64(gid + golden * (seed + 1)) -- multigpu.counter_uniform(ids, 1, seed), bit for bit -- so
+// the draw of a particle depends on its GLOBAL id only (any rank count).  Also emits the two masked copies the boundary /
+// interior passes need.  One thread = 4 rows.
+__global__ void __launch_bounds__(256)
+fire_bytes_counter_kernel(int64_t n, const int64_t* __restrict__ gid_s, uint64_t seed_term, float rate,
+                          const uint8_t* __restrict__ bnd_s, uint8_t* __restrict__ fire_s, uint8_t* __restrict__ fire_b,
+                          uint8_t* __restrict__ fire_i) {
+    const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (base >= n) return;
+    uint32_t f = 0, fb = 0, fi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t p = base + k;
+        if (p >= n) break;
+        const int64_t g = gid_s[p];
+        uint64_t z = (uint64_t)g + seed_term;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        const float u = (float)(uint32_t)((z >> 40) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+        const uint32_t fire = (g >= 0 && u <= rate) ? 1u : 0u;
+        const uint32_t b = bnd_s != nullptr ? (uint32_t)bnd_s[p] : 0u;
+        f |= fire << (8 * k); fb |= (fire & b) << (8 * k); fi |= (fire & (b ^ 1u)) << (8 * k);
+    }
+    if (base + 4 <= n) {
+        *reinterpret_cast<uint32_t*>(fire_s + base) = f;
+        if (fire_b != nullptr) { *reinterpret_cast<uint32_t*>(fire_b + base) = fb; *reinterpret_cast<uint32_t*>(fire_i + base) = fi; }
+    } else {
+        for (int k = 0; k < 4 && base + k < n; ++k) {
+            fire_s[base + k] = (uint8_t)((f >> (8 * k)) & 1u);
+            if (fire_b != nullptr) { fire_b[base + k] = (uint8_t)((fb >> (8 * k)) & 1u); fire_i[base + k] = (uint8_t)((fi >> (8 * k)) & 1u); }
+        }
+    }
+}
+
 // backward of the not-fired rows: thread = one 16-byte piece of a row's (dAdir 4 | dY 8) pieces, coalesced
 __global__ void __launch_bounds__(256)
 step_bwd_unfired_kernel(int64_t n, const uint8_t* __restrict__ flags_s, const float* __restrict__ dAn_s,
@@ -208,7 +244,7 @@ int32_t sphnca_fire_list_draw(const sphnca_grid* g, const float* u, float rate, 
                               int32_t use_alpha, int32_t* rows, int32_t* count, float* A_new_s, uint8_t* alive_s,
                               const uint8_t* FLG, uint8_t* flags_s, int32_t fold_static_mask, void* workspace,
                               size_t workspace_bytes, void* stream_) {
-    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    GridView gv; { int rc = make_view(g, &gv, true); if (rc) return rc; }
     const int64_t N = gv.n;
     SPHNCA_CHECK_ARG(count, "NULL argument");
     cudaStream_t stream = as_stream(stream_);
@@ -224,6 +260,21 @@ int32_t sphnca_fire_list_draw(const sphnca_grid* g, const float* u, float rate, 
     SPHNCA_LAUNCH(fire_scan_kernel, 1, 1024, 0, stream, nb, bc, count);
     SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s, FLG, flags_s,
                   fold_static_mask ? 1 : 0);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_fire_bytes_counter(int64_t N, const int64_t* gid_s, int64_t seed, float rate, const uint8_t* bnd_s, uint8_t* fire_s,
+                                  uint8_t* fire_b, uint8_t* fire_i, void* stream_) {
+    SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
+    if (N == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(gid_s && fire_s, "NULL argument");
+    SPHNCA_CHECK_ARG((fire_b == nullptr) == (fire_i == nullptr) && (fire_b == nullptr || bnd_s != nullptr), "fire_b / fire_i / bnd_s: all or none");
+    SPHNCA_CHECK_ARG((((uintptr_t)fire_s | (uintptr_t)fire_b | (uintptr_t)fire_i) & 3) == 0, "fire byte arrays must be 4-byte aligned");
+    const uint64_t seed_term = 0x9E3779B97F4A7C15ull * (uint64_t)(seed + 1);
+    const int64_t threads = (N + 3) / 4;
+    SPHNCA_LAUNCH(fire_bytes_counter_kernel, (unsigned)((threads + 255) / 256), 256, 0, as_stream(stream_), N, gid_s, seed_term, rate, bnd_s,
+                  fire_s, fire_b, fire_i);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

@@ -346,7 +346,7 @@ int32_t sphnca_hashgrid_build(const float* x, int64_t N, int32_t D, const int64_
 }
 
 int32_t sphnca_pack_xv(const sphnca_grid* g, const float* x, const float* v, float* xv4, void* stream) {
-    GridView gv; int rc = make_view(g, &gv); if (rc) return rc;
+    GridView gv; int rc = make_view(g, &gv, true); if (rc) return rc;
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(x && xv4, "x/xv4 is NULL");
     SPHNCA_LAUNCH(pack_xv_kernel, (int)((gv.n + 255) / 256), 256, 0, as_stream(stream), x, v, gv.sorted_id, (int)gv.n, gv.dim, (float4*)xv4);
@@ -355,7 +355,7 @@ int32_t sphnca_pack_xv(const sphnca_grid* g, const float* x, const float* v, flo
 }
 
 static int32_t permute_rows(const sphnca_grid* g, const float* src, int32_t row, float* dst, void* stream, bool pack) {
-    GridView gv; int rc = make_view(g, &gv); if (rc) return rc;
+    GridView gv; int rc = make_view(g, &gv, true); if (rc) return rc;
     SPHNCA_CHECK_ARG(row > 0, "row must be positive");
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(src && dst, "src/dst is NULL");
@@ -383,7 +383,7 @@ int32_t sphnca_unpack_rows(const sphnca_grid* g, const float* src, int32_t row, 
     return permute_rows(g, src, row, dst, stream, false);
 }
 int32_t sphnca_pack_bytes(const sphnca_grid* g, const uint8_t* src, uint8_t* dst, void* stream) {
-    GridView gv; int rc = make_view(g, &gv); if (rc) return rc;
+    GridView gv; int rc = make_view(g, &gv, true); if (rc) return rc;
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_LAUNCH(pack_bytes_kernel, (int)((gv.n + 255) / 256), 256, 0, as_stream(stream), src, dst, gv.sorted_id, (int)gv.n);
     SPHNCA_LAUNCH_CHECK();

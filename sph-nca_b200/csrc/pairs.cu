@@ -39,7 +39,9 @@ pairs_count_kernel(GridView g, const float4* __restrict__ xv4, float h2, int32_t
         const float4 xi = xv4[p];
         for_each_candidate<D>(g, g.sorted_cell[p], [&](int q) {
             float rx, ry;
-            if (pair_d2<D>(xi, __ldg(&xv4[q]), rx, ry) < h2) ++cnt;
+            float4 xj = __ldg(&xv4[q]);
+            if (g.periodic) xj = nearest_image(g, xi, xj);
+            if (pair_d2<D>(xi, xj, rx, ry) < h2) ++cnt;
         });
     }
     // max over the 8 lanes of the group
@@ -67,7 +69,23 @@ pairs_fill_kernel(GridView g, const float4* __restrict__ xv4, float h, float h2,
         float sx = 0.f, sy = 0.f, blur1 = 0.f;
         for_each_candidate<D>(g, g.sorted_cell[p], [&](int q) {
             float rx, ry;
-            const float4 xj = __ldg(&xv4[q]);
+            float4 xj = __ldg(&xv4[q]);
+            float self_ratio = 1.f;
+            if (g.periodic) {
+                const float4 xo = xj;
+                xj = nearest_image(g, xi, xj);                   // the ghost copy's position (periodic planes, nca.py:200-227)
+                if (g.image_volume != nullptr) {
+                    int tx, ty;
+                    image_shift(xo, xj, tx, ty);
+                    if (tx | ty) {
+                        // a neighbour through the wrap is the reference's GHOST copy (tx, ty) of q, which carries the volume of its own
+                        // truncated neighbourhood; its counterpart in q's list is the copy (-tx, -ty) of this particle, whose volume
+                        // multiplies this row's share of the adjoint (that ghost row's gradient is gathered back into this row)
+                        xj.w = __ldg(g.image_volume + (size_t)q * 9 + (tx + 1) * 3 + (ty + 1));
+                        self_ratio = __ldg(g.image_volume + (size_t)p * 9 + (1 - tx) * 3 + (1 - ty)) / xi.w;
+                    }
+                }
+            }
             const float d2 = pair_d2<D>(xi, xj, rx, ry);
             if (d2 < h2) {
                 const float t = h2 - d2;
@@ -82,6 +100,7 @@ pairs_fill_kernel(GridView g, const float4* __restrict__ xv4, float h, float h2,
                     const float ma = 3.f * hd * hd * inv;
                     wa = make_float2(ma * rx, ma * ry);
                     sx = fmaf(wa.x, xj.w, sx); sy = fmaf(wa.y, xj.w, sy);
+                    if (self_ratio != 1.f) wa = make_float2(wa.x * self_ratio, wa.y * self_ratio);
                 }
                 J[e] = q; WP[e] = wp; WA[e] = wa;
                 if (WB != nullptr) WB[e] = make_float2(xj.w, t * t * t);
@@ -283,7 +302,7 @@ extern "C" {
 using namespace sphnca;
 
 int32_t sphnca_pairs_count(const sphnca_grid* g, const float* xv4, int32_t* group_slots, void* stream_) {
-    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    GridView gv; { int rc = make_view(g, &gv, true); if (rc) return rc; }
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(xv4 && group_slots, "NULL argument");
     const int blocks = (int)((gv.n + 127) / 128);
@@ -296,7 +315,7 @@ int32_t sphnca_pairs_count(const sphnca_grid* g, const float* xv4, int32_t* grou
 
 int32_t sphnca_pairs_fill(const sphnca_grid* g, const float* xv4, const int32_t* group_slots, const int64_t* group_base,
                           int32_t* J, float* WP, float* WB, float* WA, float* SXY, uint8_t* FLG, void* stream_) {
-    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    GridView gv; { int rc = make_view(g, &gv, true); if (rc) return rc; }
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(xv4 && group_slots && group_base && J && WP && WA && SXY && FLG, "NULL argument");   // WB may be NULL
     const float cw = (float)poly6_norm(g->dim, g->h);
@@ -313,7 +332,7 @@ int32_t sphnca_pairs_fill(const sphnca_grid* g, const float* xv4, const int32_t*
 int32_t sphnca_step_perceive_pairs(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
                                    const float* WP, const float* WB, const uint8_t* FLG, const float* A_s,
                                    const sphnca_step_params* p, float* Y_s, uint8_t* flags_s, void* stream_) {
-    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    GridView gv; { int rc = make_view(g, &gv, true); if (rc) return rc; }
     StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(group_slots && group_base && J && WP && FLG && A_s && Y_s && flags_s, "NULL argument");
@@ -330,7 +349,7 @@ int32_t sphnca_step_perceive_pairs(const sphnca_grid* g, const int32_t* group_sl
 int32_t sphnca_step_perceive_pairs_fired(const sphnca_grid* g, const int32_t* rows, const int32_t* count, const int32_t* group_slots,
                                          const int64_t* group_base, const int32_t* J, const float* WP, const float* A_s,
                                          const sphnca_step_params* p, float* Y_c, float* A_c, void* stream_) {
-    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    GridView gv; { int rc = make_view(g, &gv, true); if (rc) return rc; }
     StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(rows && count && group_slots && group_base && J && WP && A_s && Y_c && A_c, "NULL argument");
@@ -345,7 +364,7 @@ int32_t sphnca_step_perceive_pairs_fired(const sphnca_grid* g, const int32_t* ro
 static int launch_adjoint_pairs(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
                                 const float* WA, const float* SXY, const float* xv4, const float* dY_s, const float* dAdir_s,
                                 const sphnca_step_params* p, float* dA_s, const uint8_t* flags_s, const float* dAn_s, void* stream_) {
-    GridView gv; { int rc = make_view(g, &gv); if (rc) return rc; }
+    GridView gv; { int rc = make_view(g, &gv, true); if (rc) return rc; }
     StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(group_slots && group_base && J && WA && SXY && xv4 && dY_s && dAdir_s && dA_s, "NULL argument");

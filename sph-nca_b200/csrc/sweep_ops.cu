@@ -51,13 +51,61 @@ __global__ void __launch_bounds__(kSweepThreads) volume_fwd_kernel(GridView g, c
     double sum = 0.0;
     for_each_candidate<D>(g, g.sorted_cell[p], [&](int q) {
         float rx, ry, rz;
-        const float4 xj = __ldg(&xv4[q]);
+        float4 xj = __ldg(&xv4[q]);
+        if (g.periodic) xj = nearest_image(g, xi, xj);
         double t = h2 - (double)dist2<D>(xi, xj, rx, ry, rz);
         sum += t > 0.0 ? t * t * t : 0.0;
     });
     const float vi = __frcp_rn((float)(norm * sum));
     v[g.sorted_id[p]] = vi;
     xv4_out[p] = make_float4(xi.x, xi.y, xi.z, vi);
+}
+
+// Volumes of the ghost copies of a periodic plane (sphnca_grid.image_volume).  The copy of particle i shifted by s = (sx, sy)
+// periods sits at x_i + s*period in the ghost-padded cloud; its neighbours there are the own particles and the EXISTING copies
+// within h: for a periodic neighbour k of i, seen from i at shift t, that is the copy s' = s + t of k (the particle itself when
+// s' = 0), if it exists.  A particle lies in at most one band per axis, so it has at most 3 copies: (bx,0), (0,by), (bx,by).
+template <int D>
+__global__ void __launch_bounds__(kSweepThreads) volume_images_kernel(GridView g, const float4* __restrict__ xv4, double h2, double norm,
+                                                                      float* __restrict__ vimg) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.n) return;
+    const float4 xi = xv4[p];
+    const int bx = xi.x <= g.band_lo[0] ? 1 : (xi.x >= g.band_hi[0] ? -1 : 0);
+    const int by = xi.y <= g.band_lo[1] ? 1 : (xi.y >= g.band_hi[1] ? -1 : 0);
+    const int isx[3] = {bx, 0, bx}, isy[3] = {0, by, by};
+    const bool have[3] = {bx != 0, by != 0, bx != 0 && by != 0};
+    double sum[3] = {0.0, 0.0, 0.0};
+    if (have[0] || have[1]) {
+        for_each_candidate<D>(g, g.sorted_cell[p], [&](int q) {
+            const float4 xk = __ldg(&xv4[q]);
+            const float4 xk_img = nearest_image(g, xi, xk);
+            int tx, ty;
+            image_shift(xk, xk_img, tx, ty);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (!have[c]) continue;
+                const int sx = isx[c] + tx, sy = isy[c] + ty;          // the copy of k next to copy c of i
+                if (sx < -1 || sx > 1 || sy < -1 || sy > 1 || !image_exists(g, xk, sx, sy)) continue;
+                // positions as the ghost-padded cloud holds them: one fp32 add of the shift each (nca.py:214-217)
+                float4 pi = xi, pk = xk;
+                if (isx[c]) pi.x += (float)isx[c] * g.period[0];
+                if (isy[c]) pi.y += (float)isy[c] * g.period[1];
+                if (sx) pk.x += (float)sx * g.period[0];
+                if (sy) pk.y += (float)sy * g.period[1];
+                float rx, ry, rz;
+                const double t = h2 - (double)dist2<D>(pi, pk, rx, ry, rz);
+                sum[c] += t > 0.0 ? t * t * t : 0.0;
+            }
+        });
+    }
+    float* o = vimg + (size_t)p * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k] = 0.f;
+    o[4] = xi.w;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        if (have[c]) o[(isx[c] + 1) * 3 + (isy[c] + 1)] = __frcp_rn((float)(norm * sum[c]));
 }
 
 // dL/dx_i = Cw sum_j (v_i^2 g_i + v_j^2 g_j) * (-6 (h^2-d^2)^2) * r      (operators_batch.py:137-150)
@@ -321,9 +369,10 @@ static void for_each_chunk(int F, Launch&& launch) {
 
 using namespace sphnca;
 
-#define SPHNCA_PROLOGUE()                                  \
+#define SPHNCA_PROLOGUE() SPHNCA_PROLOGUE_P(false)
+#define SPHNCA_PROLOGUE_P(allow_periodic)                  \
     GridView gv;                                           \
-    { int rc_ = make_view(g, &gv); if (rc_) return rc_; }  \
+    { int rc_ = make_view(g, &gv, allow_periodic); if (rc_) return rc_; }  \
     cudaStream_t stream = as_stream(stream_);              \
     if (gv.n == 0) return SPHNCA_OK;                       \
     const double hd = g->h;                                \
@@ -334,11 +383,22 @@ using namespace sphnca;
 extern "C" {
 
 int32_t sphnca_volume_fwd(const sphnca_grid* g, const float* xv4, float* v, float* xv4_out, void* stream_) {
-    SPHNCA_PROLOGUE();
+    SPHNCA_PROLOGUE_P(true);
     SPHNCA_CHECK_ARG(xv4 && v && xv4_out, "NULL argument");
     const double norm = poly6_norm(gv.dim, hd);
     if (gv.dim == 3) SPHNCA_LAUNCH(volume_fwd_kernel<3>, blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, hd * hd, norm, v, (float4*)xv4_out);
     else SPHNCA_LAUNCH(volume_fwd_kernel<2>, blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, hd * hd, norm, v, (float4*)xv4_out);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_volume_images(const sphnca_grid* g, const float* xv4, float* image_volume, void* stream_) {
+    SPHNCA_PROLOGUE_P(true);
+    SPHNCA_CHECK_ARG(xv4 && image_volume, "NULL argument");
+    SPHNCA_CHECK_ARG(gv.period[0] > 0.f && gv.period[1] > 0.f && gv.period[2] == 0.f, "ghost volumes are defined for planes periodic in x and y");
+    const double norm = poly6_norm(gv.dim, hd);
+    if (gv.dim == 3) SPHNCA_LAUNCH(volume_images_kernel<3>, blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, hd * hd, norm, image_volume);
+    else SPHNCA_LAUNCH(volume_images_kernel<2>, blocks, kSweepThreads, 0, stream, gv, (const float4*)xv4, hd * hd, norm, image_volume);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

@@ -319,7 +319,7 @@ class SlabShardedNCA:
         # per sorted position: global id (-1 for halo particles), boundary / interior membership of the own particles
         gid_loc = torch.full((p.n_local,), -1, dtype=torch.int64, device=dev)
         gid_loc[:p.n_own] = p.own_idx
-        self.gid_s = gid_loc[sid]
+        self.gid_s = gid_loc[sid].contiguous()
         bnd_loc = torch.zeros((p.n_local,), dtype=torch.uint8, device=dev)
         bnd_loc[:p.n_own] = p.boundary.to(torch.uint8)
         own_loc = torch.zeros((p.n_local,), dtype=torch.uint8, device=dev)
@@ -334,6 +334,7 @@ class SlabShardedNCA:
         self.exchange_mode = "none (1 rank)" if world == 1 else (
             "NCCL P2P on a side stream, overlapped with the interior pass" if self.overlap else "NCCL P2P, blocking")
         self.bytes_per_step = 0
+        self._work = None
         self.fire_seed = 0
         self._rollouts = 0
 
@@ -341,15 +342,23 @@ class SlabShardedNCA:
         """halo exchange, in place, of a tensor held in cell-sorted order (rows = local particles)."""
         return self.part.exchange_indexed(t_s, self.send_prev_pos, self.send_next_pos, t_s, self.halo_prev_pos, self.halo_next_pos)
 
-    def _fire_bytes(self, k, fire_masks, fr, N, dev):
-        """Fire bytes of step k in sorted order (0 for halo particles)."""
+    def _fire_bytes(self, k, fire_masks, fr, N, dev, split=False):
+        """Fire bytes of step k in sorted order (0 for halo particles); split: also the boundary / interior copies."""
         p = self.part
         if fire_masks is not None:
             fire = torch.zeros((N,), dtype=torch.uint8, device=dev)
             fire[:p.n_own] = fire_masks[k].to(torch.uint8)
-            return self.grid.pack_bytes(fire)
-        u = counter_uniform(self.gid_s, 1, self.fire_seed + 1000003 * self._run + k)[:, 0]
-        return ((u <= fr).to(torch.uint8) & self.own_s).contiguous()
+            fire_s = self.grid.pack_bytes(fire)
+            return (fire_s, fire_s & self.bnd_s, fire_s & self.int_s) if split else fire_s
+        # counter_uniform(gid, 1, seed) <= rate in one kernel (csrc/firelist.cu), bit for bit
+        _lib = self._lib
+        u8 = dict(dtype=torch.uint8, device=dev)
+        fire_s = torch.empty((N,), **u8)
+        fire_b, fire_i = (torch.empty((N,), **u8), torch.empty((N,), **u8)) if split else (None, None)
+        _lib.check(_lib.lib.sphnca_fire_bytes_counter(N, _lib.ptr(self.gid_s), self.fire_seed + 1000003 * self._run + k, float(fr),
+                                                      _lib.ptr(self.bnd_s) if split else None, _lib.ptr(fire_s), _lib.ptr(fire_b),
+                                                      _lib.ptr(fire_i), _lib.stream_ptr()))
+        return (fire_s, fire_b, fire_i) if split else fire_s
 
     @torch.no_grad()
     def rollout(self, A_global_own, steps, fire_masks=None, fire_rate=None):
@@ -361,13 +370,25 @@ class SlabShardedNCA:
         p, m = self.part, self.model
         dev = A_global_own.device
         N = p.n_local
-        A_loc = torch.zeros((N, 16), dtype=torch.float32, device=dev)
-        A_loc[:p.n_own] = A_global_own
-        A_s = self.grid.pack_rows(A_loc, 16)
         f32 = dict(dtype=torch.float32, device=dev)
-        An_s = torch.empty((N, 16), **f32); Y_s = torch.empty((N, 32), **f32); O_s = torch.empty((N, 36), **f32)
-        flags_s = torch.empty((N,), dtype=torch.uint8, device=dev); alive_s = torch.empty((N,), dtype=torch.uint8, device=dev)
-        relu_s = torch.empty((N, 8), dtype=torch.int32, device=dev)
+        if self._work is None:
+            # work buffers of a rollout, allocated once per partition (several GB at 16 M particles: re-allocating them per
+            # rollout would make the timing depend on the state of torch's caching allocator)
+            split_path = fused._fire_lists_on() and not m.use_alpha
+            self._work = dict(
+                A_loc=torch.zeros((N, 16), **f32), A=torch.empty((N, 16), **f32), An=torch.empty((N, 16), **f32),
+                Y=torch.empty((N, 32), **f32), flags=torch.empty((N,), dtype=torch.uint8, device=dev),
+                alive=torch.empty((N,), dtype=torch.uint8, device=dev),
+                O=None if split_path else torch.empty((N, 36), **f32),
+                relu=None if split_path else torch.empty((N, 8), dtype=torch.int32, device=dev),
+                fb=fused._FireBuffers(N, dev, compact_inputs=True) if split_path else None)
+        w = self._work
+        A_loc = w["A_loc"]
+        A_loc[:p.n_own] = A_global_own
+        A_s, An_s = w["A"], w["An"]
+        if N:
+            _lib.check(_lib.lib.sphnca_pack_rows(self.grid.c_grid(), _lib.ptr(A_loc), 16, _lib.ptr(A_s), _lib.stream_ptr()))
+        Y_s, O_s, flags_s, alive_s, relu_s = w["Y"], w["O"], w["flags"], w["alive"], w["relu"]
         lin1, lin2 = m.model[0], m.model[2]
         fr = m.fire_rate if fire_rate is None else fire_rate
         prm = fused._step_params(lin1.weight.detach(), lin1.bias.detach(), lin2.weight.detach(), lin2.bias.detach(),
@@ -417,18 +438,18 @@ class SlabShardedNCA:
         g = self.grid.c_grid()
         main = torch.cuda.current_stream(dev)
         st = _lib.stream_ptr()
-        fb = fused._FireBuffers(N, dev, compact_inputs=True)
+        fb = self._work["fb"]
         fb.flags = flags_s
         split = self.split
         nbytes = self._exchange_sorted(A_s)                                 # halo rows of the initial state (no-op on one rank)
         done = None
         for k in range(steps):
-            fire_s = self._fire_bytes(k, fire_masks, fr, N, dev)
             if not split:
+                fire_s = self._fire_bytes(k, fire_masks, fr, N, dev)
                 fused._step_forward_lists(self.grid, None, None, g, self.xv4, A_s, fire_s, prm, False, Y_s, An_s, alive_s, fb, ws_fl, st, pl=pl)
                 A_s, An_s = An_s, A_s
                 continue
-            fire_b, fire_i = fire_s & self.bnd_s, fire_s & self.int_s
+            _, fire_b, fire_i = self._fire_bytes(k, fire_masks, fr, N, dev, split=True)
             if done is not None:
                 main.wait_event(done)                                       # pass B reads the halo rows of the current state
             # pass B: boundary particles; its list kernel also carries over every not-fired row and writes the static mask bits

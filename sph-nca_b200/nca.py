@@ -23,6 +23,9 @@ import sphops
 USE_3D = False
 # set to False to force the operator-by-operator path (used by the parity tests)
 USE_FUSED_STEP = True
+# set to False to run periodic planes (sample_plane_wrapped) on ghost particles like the reference even where the native periodic
+# neighbour search applies (no alpha channel, period == dims * h)
+USE_NATIVE_PERIODIC = True
 # set to False to run rollouts as K separate fused steps (one autograd node per step, states permuted back
 # to particle order after every step) instead of one cell-sorted-resident K-step node
 USE_FUSED_ROLLOUT = True
@@ -138,7 +141,7 @@ class SPHNCA(nn.Module):
         new_mask = self.life_mask(x, v, cell_activity(nA, self.use_alpha)[..., None], h, grid)
         return x, nA * (prev_mask & new_mask).float()
 
-    def rollout(self, x, v, A, h, grid, steps, fire_rate=None, keep_all=True, checkpoint=None, microbatch=None):
+    def rollout(self, x, v, A, h, grid, steps, fire_rate=None, keep_all=True, checkpoint=None, microbatch=None, fire_index=None):
         """`steps` chained `forward` calls as one autograd node with the state kept cell-sorted on the
         device (sphops.fused.nca_rollout); returns the sequence of the steps+1 states, or None when the
         configuration is not the fused one (callers then loop over `forward`).  `checkpoint`: True = keep only
@@ -154,7 +157,7 @@ class SPHNCA(nn.Module):
             x, v, A, lin1.weight, lin1.bias, lin2.weight, lin2.bias, h, grid, steps, fire_rate,
             update_rule=self.update_rule, use_alpha=self.use_alpha,
             perception_scale=self.perception_scale(h), orig_rate=self.fire_rate / fire_rate, keep_all=keep_all,
-            checkpoint=checkpoint, microbatch=microbatch)
+            checkpoint=checkpoint, microbatch=microbatch, fire_index=fire_index)
 
     def normalize_grads(self):
         if not self.normalize_grad:
@@ -298,6 +301,53 @@ def unwrap_tensors(tensors, sections, orig_sections):
     return [t[keep.to(t.device)] for t in tensors]
 
 
+class _GatheredStates:
+    """The reference's `out_wrapped` list (ghost-padded state after every step) as a lazy view: wrapped row r = own row src[r]."""
+
+    def __init__(self, states, src):
+        self._s, self._src = states, src
+
+    def __len__(self):
+        return len(self._s)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self._s)))]
+        return self._s[k][self._src]
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self._s)))
+
+
+def _native_periodic_rollout(model, x, A, sections, h, dims, gmin, gsize, plan, iter_n, fire_rate, keep_all):
+    """The K steps of a periodic plane on the N real particles (periodic hash grid, sphops Hashgrid.set_periodic), or None
+    when this configuration needs the ghost particles: an alpha channel (the reference evolves ghosts on their own within a
+    step and reads THEIR new alpha in the life mask), a plane whose size is not dims x h (the cell hash then does not wrap
+    with the plane), or a step the fused node does not take."""
+    if not (USE_NATIVE_PERIODIC and USE_FUSED_ROLLOUT and hasattr(model, "rollout") and not model.use_alpha):
+        return None
+    if not model._fusable(x, A, None):
+        return None
+    from sphops.hashgrid import Hashgrid
+    from sphops.preprocess import _host_dims
+    hval = h.item() if isinstance(h, torch.Tensor) else float(h)
+    gs = [float(g) for g in torch.as_tensor(gsize).flatten().tolist()][:2]
+    period = (gs[0], gs[1], 0.0)
+    dims_host = _host_dims(dims, 3)
+    if not Hashgrid.periodic_compatible(hval, dims_host, period):
+        return None
+    # which particles have ghost copies: the very comparisons of get_wrapped_points_index (reference nca.py:182-197)
+    gmin_t = torch.as_tensor(gmin, dtype=x.dtype, device=x.device).flatten()[:2]
+    gmax_t = gmin_t + torch.as_tensor(gsize, dtype=x.dtype, device=x.device).flatten()[:2]
+    band = ((gmin_t + hval).tolist(), (gmax_t - hval).tolist())
+    grid = sphops.initialize_hashgrid(x, sections, h, dims).set_periodic(period, band=band)
+    v = sphops.volume(x, h, grid)
+    # the reference draws torch.rand over the WRAPPED particles every step (nca.py:100 on x_w); the real ones come first in
+    # every wrapped section (`plan.own`)
+    n_wrapped = int(plan.src.numel())
+    return model.rollout(x, v, A, h, grid, iter_n, fire_rate, keep_all=keep_all, fire_index=(n_wrapped, plan.own))
+
+
 def sample_plane_wrapped(model, x, A, sections, h, dims, gmin, gsize, out_steps=False, iter_n=None, loss_fn=None,
                          img=None, optimizer=None, scheduler=None, out_wrapped=False, fire_rate=None):
     """Rollout on a periodic plane (reference nca.py:245-299): ghost copies of the particles within h of an
@@ -310,6 +360,26 @@ def sample_plane_wrapped(model, x, A, sections, h, dims, gmin, gsize, out_steps=
     idxs = get_wrapped_points_index(x, A, sections, gmin, gsize, h)
     plan = _WrapPlan(sections, idxs, gsize, x.device)
     x_w = plan.wrap_positions(x)
+
+    native = _native_periodic_rollout(model, x, A, sections, h, dims, gmin, gsize, plan, iter_n, fire_rate,
+                                      keep_all=out_steps or loss_fn is not None)
+    if native is not None:
+        # Periodic neighbour search instead of ghost particles: N particles, ONE autograd node, fire lists, no per-step
+        # gathers.  Own-particle results are the reference's (same pairs at the same fp32 offsets; the wrapped states are
+        # the own states gathered, which is what the reference's per-step ghost refresh makes them).
+        out = native
+        A = out[-1]
+        loss = 0.0
+        if loss_fn is not None:
+            if xdim == 2:
+                x = x[..., :2]
+            loss = _train_on(loss_fn, x, A, img, out, model, optimizer, scheduler)
+        if USE_3D and xdim == 2:
+            x = x[..., :2]
+        if out_steps:
+            return loss, x, out, x_w, _GatheredStates(out, plan.src)
+        return loss, x, A
+
     A_w = A[plan.src]
     grid, v_w = model.init_grid(x_w, plan.sections, h, dims)
 
@@ -419,13 +489,39 @@ def add_radial_seed(x3, A3, N=None, T=None, R=0.2, idx=None, center=None):
     """Add a smooth bump (1 - d^2/R^2)^3 around a particle or a given centre to every channel, in place
     (reference nca.py:383-398); optionally seed the tangent of the closest particle."""
     if idx is None:
-        idx = int(torch.randint(0, x3.shape[0], (1,)))
+        import numpy as np
+        idx = int(np.random.randint(0, x3.shape[0]))           # the reference's draw (np.random, seeded by train.py:252)
     c = x3[idx, :] if center is None else center
     d2 = ((x3 - c) ** 2).sum(dim=-1)
     A3 += (torch.clamp(1 - d2 / R ** 2, 0, 1) ** 3)[..., None]
     if N is not None:
         i = torch.argmin(d2)
         T[i, :] = orthogonalize(N[i, :], torch.randn((x3.shape[-1],), device=T.device))
+
+
+def BNC2BCHW(A, H, W, B=None):
+    """[B*N, C] (with B given) or [B, N, C] particle rows of a lattice, particle n = w*H + h (the order of the reference's
+    `geometry.grange`) -> image batch [B, C, H, W] (reference nca.py:555-561; used by the image-space losses of losses.py)."""
+    C_ = A.shape[-1]
+    if B is not None:
+        A = A.reshape(B, -1, C_)
+    return A.reshape(A.shape[0], W, H, C_).permute(0, 3, 2, 1)
+
+
+# Downstream of the per-timestep path (SURVEY.md 2 rows 9-19, 8 "out of scope"): the VGG / optimal-transport / CLIP image losses
+# of reference nca.py:470-715.  `train.py --loss mse_simple` needs none of them; `--loss ot|clip_multiscale` needs the
+# reference's own implementations (pretrained VGG19 / open_clip weights), which this module does not re-implement.
+_NOT_ON_THE_PATH = ("get_style_loss", "eval_style_loss", "OptimalTransportLoss", "StyleLoss", "Normalization", "gram_matrix",
+                    "get_clip_loss")
+
+
+def __getattr__(name):
+    if name in _NOT_ON_THE_PATH:
+        raise AttributeError(
+            f"nca.{name} is an image-space loss helper of the reference (code/nca.py:470-715), downstream of the particle update "
+            "this package replaces; it is not re-implemented here.  Take it from the reference's nca.py (e.g. "
+            "`import importlib.util` on that file) -- `train.py --loss mse_simple` does not need it.")
+    raise AttributeError(f"module 'nca' has no attribute {name!r}")
 
 
 def get_rgba(A, margin=None):

@@ -23,6 +23,8 @@ class CGrid(C.Structure):
         ("dim", C.c_int32), ("num_sections", C.c_int32), ("num_particles", C.c_int64),
         ("cells_per_section", C.c_int64), ("dims", C.c_int64 * 3), ("h", C.c_double),
         ("cell_off", C.c_void_p), ("sorted_id", C.c_void_p), ("sorted_cell", C.c_void_p),
+        ("period", C.c_double * 3),
+        ("image_volume", C.c_void_p), ("band_lo", C.c_double * 3), ("band_hi", C.c_double * 3),
     ]
 
 
@@ -55,6 +57,7 @@ def _load():
         "sphnca_pack_bytes": ([G, P, P, P], I32),
         "sphnca_volume_fwd": ([G, P, P, P, P], I32),
         "sphnca_volume_bwd": ([G, P, P, P, P], I32),
+        "sphnca_volume_images": ([G, P, P, P], I32),
         "sphnca_count_fwd": ([G, P, P, P], I32),
         "sphnca_gradient_fwd": ([G, P, P, I32, P, P], I32),
         "sphnca_gradient_bwd": ([G, P, P, I32, P, P], I32),
@@ -85,6 +88,7 @@ def _load():
         "sphnca_step_mlp_list": ([I64, P, P, P, P, SP, P, P, P, P, P, P, P, I32, P], I32),
         "sphnca_step_bwd_list": ([I64, P, P, P, P, P, P, P, SP, P, P, P, P], I32),
         "sphnca_step_bwd_unfired": ([I64, P, P, P, P, P], I32),
+        "sphnca_fire_bytes_counter": ([I64, P, I64, C.c_float, P, P, P, P, P], I32),
         "sphnca_mlp_wgrad_list": ([I64, P, P, P, P, SP, P, P, P, P, P, C.c_size_t, P], I32),
         "sphnca_launch_count": ([], I64),
         "sphnca_set_mlp_path": ([I32], I32),

@@ -256,6 +256,16 @@ def _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, al
     _mask(use_alpha, g, N, xv4, alive_s, Sn, fb.flags, st)
 
 
+def _draw(N, dev, fire_index):
+    """One step's fire draw: torch.rand(N), or -- fire_index = (n_draw, index [N]) -- entries `index` of torch.rand(n_draw): the
+    periodic planes draw for their ghost particles too (reference nca.py:100 inside :245-299), so the draws of the N real
+    particles are a subset of a longer call; consuming the generator identically keeps seeded runs comparable."""
+    if fire_index is None:
+        return torch.rand(N, device=dev)
+    n_draw, index = fire_index
+    return torch.rand(n_draw, device=dev)[index]
+
+
 class _UnpackRows(torch.autograd.Function):
     """cell-sorted rows -> the caller's particle order (adjoint: the inverse permutation)."""
 
@@ -287,9 +297,9 @@ class _NCARollout(torch.autograd.Function):
     `SPHNCA.forward` (nca.py:100), compared with the rate by the list kernel (`u <= fire_rate` in fp32, like torch)."""
 
     @staticmethod
-    def forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_rate, keep_all, taped, groups=None):
+    def forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_rate, keep_all, taped, groups=None, fire_index=None):
         if groups is not None:
-            return _microbatched_forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_rate, keep_all, taped, groups)
+            return _microbatched_forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_rate, keep_all, taped, groups, fire_index)
         ctx.groups = None
         update_rule, use_alpha, perception_scale, orig_rate = cfg
         x = require_cuda_f32(x, "x"); v = require_cuda_f32(v, "v"); A0 = require_cuda_f32(A0, "A")
@@ -316,7 +326,7 @@ class _NCARollout(torch.autograd.Function):
             Y_s = torch.empty((N, 32), **f32)                 # perception of the current step: scratch, the tape keeps Y_c
         fire_s = None
         for _ in range(steps):
-            u = torch.rand(N, device=dev)                     # the reference's draw (nca.py:100), one call per step
+            u = _draw(N, dev, fire_index)                     # the reference's draw (nca.py:100), one call per step
             if u.dtype != torch.float32 or not u.is_contiguous():
                 u = u.to(torch.float32).contiguous()
             Sn = torch.empty((N, 16), **f32)
@@ -461,7 +471,7 @@ class _NCARollout(torch.autograd.Function):
         if need[2]:
             dA0 = grid.unpack_rows(gcur, 16) if gcur is not None else torch.zeros((N, 16), **f32)
         return (None, None, dA0, dW1 if need[3] else None, db1 if need[4] else None, dW2 if need[5] else None,
-                db2 if need[6] else None, None, None, None, None, None, None, None)
+                db2 if need[6] else None, None, None, None, None, None, None, None, None)
 
 
 # ---- micro-batches over sections ------------------------------------------------------------------------------------
@@ -476,7 +486,8 @@ class _NCARollout(torch.autograd.Function):
 # fire draws are the reference's: one torch.rand(N) per step, in step order (nca.py:100), drawn before the first group runs.
 MICROBATCH = "auto"            # "auto" | None (never) | int (sections per group; tests force small groups)
 MICROBATCH_WORK_BYTES = 373 + 128 + 16 + 144 + 128 + 64 + 128 + 64     # fire buffers, Y, Sn scratch, dO, dY, dAdir, gradient ping-pong, slack
-MICROBATCH_FRACTION = 0.30      # of the device memory torch does not hold and the states will not take
+MICROBATCH_FRACTION = 0.20      # of the device memory torch does not hold and the states will not take (the loss side of a
+                                # training iteration unpacks the states it reads and holds their gradients: ~10 x 64 B per particle)
 
 
 def plan_microbatches(grid, steps, use_alpha, device, taped, setting=None):
@@ -531,7 +542,7 @@ def _group_lists(sub, xv, use_alpha):
     return sub.build_pair_lists(xv, blur=bool(use_alpha), budget_bytes=float("inf")) if sub.num_particles else None
 
 
-def _microbatched_forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_rate, keep_all, taped, groups):
+def _microbatched_forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_rate, keep_all, taped, groups, fire_index=None):
     update_rule, use_alpha, perception_scale, orig_rate = cfg
     x = require_cuda_f32(x, "x"); v = require_cuda_f32(v, "v"); A0 = require_cuda_f32(A0, "A")
     W1c, b1c, W2c, b2c = [require_cuda_f32(t, n) for t, n in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"))]
@@ -546,7 +557,7 @@ def _microbatched_forward(ctx, x, v, A0, W1, b1, W2, b2, grid, cfg, steps, fire_
     st = stream_ptr()
     S0 = grid.pack_rows(A0, 16)
     # the reference's draws, one torch.rand(N) per step in step order, kept as bytes in PARTICLE order (N bytes per step)
-    fire_po = [(torch.rand(N, device=dev) <= fire_rate).view(torch.uint8) for _ in range(steps)]
+    fire_po = [(_draw(N, dev, fire_index) <= fire_rate).view(torch.uint8) for _ in range(steps)]
     every = bool(keep_all or taped)
     f32 = dict(dtype=torch.float32, device=dev)
     states = [S0] + [torch.empty((N, 16), **f32) for _ in range(steps if every else min(steps, 1))]
@@ -633,7 +644,7 @@ def _microbatched_backward(ctx, dstates):
             del pl
     dA0 = grid.unpack_rows(dA0_s, 16) if need[2] else None
     return (None, None, dA0, dW1 if need[3] else None, db1 if need[4] else None, dW2 if need[5] else None,
-            db2 if need[6] else None, None, None, None, None, None, None, None)
+            db2 if need[6] else None, None, None, None, None, None, None, None, None)
 
 
 class RolloutStates:
@@ -681,10 +692,10 @@ def _tape_mode(N, steps, device, checkpoint):
 
 
 def nca_rollout(x, v, A, W1, b1, W2, b2, h, grid, steps, fire_rate, update_rule="gated", use_alpha=True,
-                perception_scale=1.0, orig_rate=1.0, keep_all=True, checkpoint=None, microbatch=None):
+                perception_scale=1.0, orig_rate=1.0, keep_all=True, checkpoint=None, microbatch=None, fire_index=None):
     """`steps` NCA steps from state A [N,16] as one autograd node -> RolloutStates (K+1 states if `keep_all`
     or anything requires grad, else [first, last]).  `checkpoint`: None = module default `CHECKPOINT`;
-    `microbatch`: None = module default `MICROBATCH` (see plan_microbatches)."""
+    `microbatch`: None = module default `MICROBATCH` (see plan_microbatches); `fire_index`: see _draw."""
     if "sphnca_step_fwd" in _lib.MISSING_SYMBOLS:
         raise RuntimeError("libsphnca.so was built without the fused step (step.cu)")
     hval = h.item() if isinstance(h, torch.Tensor) else float(h)
@@ -695,7 +706,7 @@ def nca_rollout(x, v, A, W1, b1, W2, b2, h, grid, steps, fire_rate, update_rule=
         taped = _tape_mode(x.shape[0], int(steps), x.device, checkpoint)
     groups = plan_microbatches(grid, int(steps), use_alpha, x.device, taped, microbatch)
     states = _NCARollout.apply(x, v, A, W1, b1, W2, b2, grid, (update_rule, use_alpha, perception_scale, orig_rate),
-                               int(steps), fire_rate, keep_all, taped, groups)
+                               int(steps), fire_rate, keep_all, taped, groups, fire_index)
     return RolloutStates(states, grid)
 
 

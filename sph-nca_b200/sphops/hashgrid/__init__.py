@@ -37,6 +37,42 @@ class Hashgrid:
         self._staged_ok = None
         self._pairs_key = None
         self._pairs = None
+        self.period = (0.0, 0.0, 0.0)
+        self.band = None
+        self._vimg = None
+
+    def set_periodic(self, period, band=None):
+        """Declare the cloud periodic: period[d] > 0 = the period along axis d, which must equal dims[d] * h (then the modulo
+        wrap of the cell hash, reference single_impl.py:54-55, IS the period) -- what `nca.sample_plane_wrapped` emulates with
+        ghost particles (reference nca.py:200-299).  Neighbours found through the wrap are taken at x_j +- period by
+        `sphops.volume` and by the pair lists (so by every kernel of the fused rollout); the other operators refuse a
+        periodic grid.  Call before the first use of the grid.
+        band = ((lo_x, lo_y), (hi_x, hi_y)): ghost-volume emulation for periodic PLANES -- the reference builds its grid and
+        volumes once on the ghost-padded cloud (nca.py:262-263), so a ghost copy (of a particle with x <= lo / x >= hi, nca.py:182-197)
+        carries the volume of its own, outward-truncated neighbourhood; with `band` the pair lists reproduce exactly that
+        (include/sphnca.h: sphnca_grid.image_volume).  Without it neighbours through the wrap keep their own volume."""
+        per = [float(p) for p in period] + [0.0] * (3 - len(period))
+        D = int(self.dims.shape[0])
+        for d in range(D):
+            if per[d] > 0 and (self._dims_host[d] < 3 or abs(per[d] / self.h - self._dims_host[d]) > 1e-6 * self._dims_host[d]):
+                raise ValueError(f"periodic axis {d}: period {per[d]} must equal dims ({self._dims_host[d]}) x h ({self.h}), dims >= 3")
+        self.period = tuple(per[:3])
+        if band is not None:
+            if per[2] > 0 or not (per[0] > 0 and per[1] > 0):
+                raise ValueError("ghost-volume emulation is defined for planes periodic in x and y")
+            band = (tuple(float(b) for b in band[0]), tuple(float(b) for b in band[1]))
+        self.band = band
+        self._c = self._pairs_key = self._pairs = self._vimg = None
+        return self
+
+    @property
+    def periodic(self):
+        return any(p > 0 for p in self.period)
+
+    @staticmethod
+    def periodic_compatible(h, dims_host, period):
+        """True when `set_periodic(period)` would accept this grid (period == dims * h on every periodic axis, dims >= 3)."""
+        return all(p <= 0 or (d >= 3 and abs(p / h - d) <= 1e-6 * d) for p, d in zip(period, dims_host))
 
     # -- reference API -------------------------------------------------------------------
     def get_num_blocks(self, block_size):
@@ -79,6 +115,11 @@ class Hashgrid:
             for d in range(3):
                 g.dims[d] = self._dims_host[d] if d < D else 1
             g.h = self.h
+            for d in range(3):
+                g.period[d] = self.period[d]
+                g.band_lo[d] = self.band[0][d] if (self.band and d < 2) else 0.0
+                g.band_hi[d] = self.band[1][d] if (self.band and d < 2) else 0.0
+            g.image_volume = self._vimg.data_ptr() if self._vimg is not None else None
             g.cell_off = self.cell_off.data_ptr()
             g.sorted_id = self.sorted_id.data_ptr()
             g.sorted_cell = self.sorted_cell.data_ptr()
@@ -120,6 +161,8 @@ class Hashgrid:
         blur weights WB (8 of the 28 bytes per pair; only models with an alpha channel read them); lists built without
         them are rebuilt when a later caller needs them."""
         if not _lib.USE_PAIR_LISTS or _lib.FORCE_SWEEP_PATH is not None or "sphnca_pairs_fill" in _lib.MISSING_SYMBOLS:
+            if self.periodic:
+                raise RuntimeError("a periodic grid needs the pair lists (SPHNCA_PAIRS=0 / SPHNCA_SWEEP_PATH are set)")
             return None
         key = (self._key(x), self._key(v))
         if self._pairs_key == key and self._pairs is not None and blur and self._pairs["WB"] is None:
@@ -127,7 +170,8 @@ class Hashgrid:
         if self._pairs_key != key:
             self._pairs_key, self._pairs, self._pairs_ref = key, None, (x, v)
             if self.num_particles:
-                self._pairs = self.build_pair_lists(self.sorted_xv(x, v), blur)
+                # a periodic grid has no cell-sweep fallback: its lists are built whatever they cost
+                self._pairs = self.build_pair_lists(self.sorted_xv(x, v), blur, float("inf") if self.periodic else None)
         return self._pairs
 
     # what one list entry costs (J + WP + WA [+ WB]) and the measured entries per particle of the BASELINE workloads
@@ -139,6 +183,10 @@ class Hashgrid:
         """The pair lists of this grid from its cell-sorted {x,y,z,v} array (uncached).  None when they would exceed
         `budget_bytes` (default: PAIR_LIST_MEMORY_FRACTION of the device memory torch does not hold)."""
         N, dev = self.num_particles, xv4.device
+        if self.band is not None and self._vimg is None:    # periodic plane with ghost-volume emulation: the copies' volumes first
+            vimg = torch.empty((N, 9), dtype=torch.float32, device=dev)
+            _lib.check(_lib.lib.sphnca_volume_images(self.c_grid(), _lib.ptr(xv4), _lib.ptr(vimg), _lib.stream_ptr()))
+            self._vimg, self._c = vimg, None
         ng = (N + 7) // 8                                   # list groups of 8 particles (csrc/pairs.cu)
         slots = torch.empty((ng,), dtype=torch.int32, device=dev)
         st = _lib.stream_ptr()
@@ -187,6 +235,8 @@ class Hashgrid:
         sub.sorted_cell = (self.sorted_cell[p0:p1] - s0 * C_).contiguous()
         sub.sorted_id = self.sorted_id[p0:p1]
         sub.num_points = self.num_points[s0:s1]
+        sub.period, sub.band = self.period, self.band
+        sub._vimg = self._vimg[p0:p1] if self._vimg is not None else None
         sub.range = (p0, p1)
         return sub
 

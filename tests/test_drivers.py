@@ -108,3 +108,64 @@ def test_sample_mesh_matches_reference():
     for k in range(3):
         assert_close(out[k], g["states"][k], what=f"state {k}")
     assert_close(T, g["T_final"], rtol=2e-5, what="diffused tangents")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("native", [True, False], ids=["periodic_grid", "ghost_particles"])
+def test_sample_plane_wrapped_periodic_matches_reference_with_gradients(native, monkeypatch):
+    """The periodic plane as train.py / test.py set it up (dims = ceil(2 / h), so dims x h is the plane size), forward states AND
+    the gradients through the K steps, against the unmodified reference (tests/golden/make_golden_drivers.py::
+    wrapped_periodic_case): the NATIVE periodic path (periodic hash grid: N particles, one rollout node with fire lists, no
+    ghosts, no per-step gathers) and the reference-shaped ghost path."""
+    import nca
+    g = load_golden("wrapped_periodic_k3")
+    nca.USE_3D, nca.USE_FUSED_STEP = True, True
+    monkeypatch.setattr(nca, "USE_NATIVE_PERIODIC", native)
+    taken = []
+    orig = nca._native_periodic_rollout
+    monkeypatch.setattr(nca, "_native_periodic_rollout", lambda *a, **k: taken.append(orig(*a, **k)) or taken[-1])
+    m = _model(g, update_rule="gated", use_alpha=False, normalize_perception=float(g["normalize_perception"]))
+    x = torch.from_numpy(g["x"]).to(DEV)
+    A0 = torch.from_numpy(g["A0"]).to(DEV).requires_grad_(True)
+    gmin, gsize = torch.tensor([-1.0, -1.0], device=DEV), torch.tensor([2.0, 2.0], device=DEV)
+    with forced_fire_masks([torch.from_numpy(mk) for mk in g["masks"]]):
+        loss, x_out, out, x_w, out_w = nca.sample_plane_wrapped(m, x, A0, tuple(g["sections"]), float(g["h"]), int(g["dims"]), gmin, gsize,
+                                                                out_steps=True, iter_n=3)
+    assert (taken[0] is not None) == native
+    assert np.array_equal(x_w.cpu().numpy(), g["x_wrapped"])
+    for k in range(4):
+        assert_close(out[k], g["states"][k], what=f"state {k}")
+    assert_close(out_w[-1], g["states_wrapped_last"], what="wrapped final state")
+    L = (out[-1][:, :4] ** 2).mean() + 0.1 * (out[1][:, :4] ** 2).mean()
+    L.backward()
+    assert abs(float(L) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert_close(A0.grad, g["dA0"], rtol=2e-5, what="dL/dA0")
+    P = dict(m.named_parameters())
+    for key, pn in (("dW1", "model.0.weight"), ("db1", "model.0.bias"), ("dW2", "model.2.weight"), ("db2", "model.2.bias")):
+        assert_close(P[pn].grad, g[key], rtol=2e-5, what=key)
+
+
+@pytest.mark.gpu
+def test_periodic_grid_is_refused_where_it_is_not_implemented():
+    """A plane that is not dims x h wide keeps the ghost particles; operators without a periodic neighbour search refuse a
+    periodic grid instead of silently ignoring the wrap."""
+    import nca
+    import sphops
+    from sphops._lib import SphncaError
+    g = load_golden("wrapped_zebra_k3")                     # h = 0.4, dims = 7: 2.8 != 2
+    m = _model(g, update_rule="gated", use_alpha=False, normalize_perception=2.5)
+    x = torch.nn.functional.pad(torch.from_numpy(g["x"]), (0, 1)).to(DEV)
+    sections = tuple(int(s) for s in g["sections"])
+    plan = nca._WrapPlan(sections, nca.get_wrapped_points_index(x, None, sections, torch.tensor([-1.0, -1.0]), torch.tensor([2.0, 2.0]), 0.4),
+                         torch.tensor([2.0, 2.0]), x.device)
+    assert nca._native_periodic_rollout(m, x, torch.from_numpy(g["A0"]).to(DEV), sections, 0.4, 7, torch.tensor([-1.0, -1.0]),
+                                        torch.tensor([2.0, 2.0]), plan, 2, None, True) is None
+    grid = sphops.initialize_hashgrid(x, sections, 0.4, 5)
+    with pytest.raises(ValueError):
+        grid.set_periodic((2.0, 2.0, 2.0))                  # z: dims 5 x 0.4 == 2 is fine, but (2.8, ...) is not
+        grid.set_periodic((2.8, 2.0, 0.0))
+    grid.set_periodic((2.0, 2.0, 0.0))
+    v = sphops.volume(x, 0.4, grid)                          # implemented
+    assert torch.isfinite(v).all()
+    with pytest.raises(SphncaError):
+        sphops.count(x, 0.4, grid)                           # not implemented for periodic grids
