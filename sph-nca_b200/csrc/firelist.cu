@@ -264,6 +264,24 @@ int32_t sphnca_fire_list_draw(const sphnca_grid* g, const float* u, float rate, 
     return SPHNCA_OK;
 }
 
+int32_t sphnca_step_fwd_fired(const sphnca_grid* g, const uint8_t* fire_s, const float* A_s, const int32_t* group_slots,
+                              const int64_t* group_base, const int32_t* J, const float* WP, const uint8_t* FLG,
+                              const sphnca_step_params* p, int32_t carry_over, int32_t* rows, int32_t* count, float* Y_c, float* A_c,
+                              float* A_new_s, uint8_t* alive_s, float* O_c, uint8_t* flags_s, uint32_t* relu_c, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    SPHNCA_CHECK_ARG(g && p && !p->use_alpha, "sphnca_step_fwd_fired is the no-alpha step (static life mask)");
+    SPHNCA_CHECK_ARG(A_new_s && alive_s && flags_s && FLG, "NULL argument");
+    const int64_t N = g->num_particles;
+    // list of the fired rows (+ carry-over of the others and the static mask bits, unless this is a second list over the same step)
+    int rc = sphnca_fire_list(N, fire_s, A_s, 0, rows, count, carry_over ? A_new_s : nullptr, carry_over ? alive_s : nullptr,
+                              carry_over ? FLG : nullptr, carry_over ? flags_s : nullptr, carry_over ? 1 : 0, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    if (N == 0) return SPHNCA_OK;
+    rc = sphnca_step_perceive_pairs_fired(g, rows, count, group_slots, group_base, J, WP, A_s, p, Y_c, A_c, stream);
+    if (rc) return rc;
+    return sphnca_step_mlp_list(N, rows, count, A_c, Y_c, p, A_new_s, alive_s, O_c, flags_s, relu_c, nullptr, nullptr, 3, stream);
+}
+
 int32_t sphnca_fire_bytes_counter(int64_t N, const int64_t* gid_s, int64_t seed, float rate, const uint8_t* bnd_s, uint8_t* fire_s,
                                   uint8_t* fire_b, uint8_t* fire_i, void* stream_) {
     SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");

@@ -335,6 +335,9 @@ class SlabShardedNCA:
             "NCCL P2P on a side stream, overlapped with the interior pass" if self.overlap else "NCCL P2P, blocking")
         self.bytes_per_step = 0
         self._work = None
+        self._xchg = None
+        self._fire_buf = None
+        self._events = (torch.cuda.Event(), torch.cuda.Event()) if dev.type == "cuda" else (None, None)
         self.fire_seed = 0
         self._rollouts = 0
 
@@ -352,9 +355,10 @@ class SlabShardedNCA:
             return (fire_s, fire_s & self.bnd_s, fire_s & self.int_s) if split else fire_s
         # counter_uniform(gid, 1, seed) <= rate in one kernel (csrc/firelist.cu), bit for bit
         _lib = self._lib
-        u8 = dict(dtype=torch.uint8, device=dev)
-        fire_s = torch.empty((N,), **u8)
-        fire_b, fire_i = (torch.empty((N,), **u8), torch.empty((N,), **u8)) if split else (None, None)
+        if self._fire_buf is None:
+            self._fire_buf = [torch.empty((N,), dtype=torch.uint8, device=dev) for _ in range(3)]
+        fire_s = self._fire_buf[0]
+        fire_b, fire_i = (self._fire_buf[1], self._fire_buf[2]) if split else (None, None)
         _lib.check(_lib.lib.sphnca_fire_bytes_counter(N, _lib.ptr(self.gid_s), self.fire_seed + 1000003 * self._run + k, float(fr),
                                                       _lib.ptr(self.bnd_s) if split else None, _lib.ptr(fire_s), _lib.ptr(fire_b),
                                                       _lib.ptr(fire_i), _lib.stream_ptr()))
@@ -431,49 +435,76 @@ class SlabShardedNCA:
         self.bytes_per_step = nbytes // max(steps, 1)
         return A_s[self.own_pos]
 
+    def _state_exchange(self, dev):
+        """Persistent buffers + P2P op list of the per-step state-row exchange (built once: the op objects, the index tensors and the
+        send / receive buffers are reused by every step, which keeps the host side of a step short)."""
+        if self._xchg is None and self.part.world > 1:
+            p = self.part
+            f32 = dict(dtype=torch.float32, device=dev)
+            to_prev, to_next = torch.empty((self.send_prev_pos.numel(), 16), **f32), torch.empty((self.send_next_pos.numel(), 16), **f32)
+            from_prev, from_next = torch.empty((p.n_halo_prev, 16), **f32), torch.empty((p.n_halo_next, 16), **f32)
+            ops = [dist.P2POp(dist.isend, to_prev, p.prev, p.group), dist.P2POp(dist.isend, to_next, p.next, p.group),
+                   dist.P2POp(dist.irecv, from_next, p.next, p.group), dist.P2POp(dist.irecv, from_prev, p.prev, p.group)]
+            self._xchg = dict(to_prev=to_prev, to_next=to_next, from_prev=from_prev, from_next=from_next, ops=ops,
+                              nbytes=(to_prev.numel() + to_next.numel()) * 4)
+        return self._xchg
+
+    def _exchange_state(self, t_s, dev):
+        """halo exchange of the state rows of t_s (cell-sorted), on the current stream, through the persistent buffers."""
+        x = self._state_exchange(dev)
+        if x is None:
+            return 0
+        torch.index_select(t_s, 0, self.send_prev_pos, out=x["to_prev"])
+        torch.index_select(t_s, 0, self.send_next_pos, out=x["to_next"])
+        for w in dist.batch_isend_irecv(x["ops"]):
+            w.wait()
+        t_s.index_copy_(0, self.halo_prev_pos, x["from_prev"])
+        t_s.index_copy_(0, self.halo_next_pos, x["from_next"])
+        return x["nbytes"]
+
     def _rollout_split(self, A_s, An_s, Y_s, alive_s, flags_s, steps, fire_masks, fr, prm, pl, ws_fl, N, dev):
-        """The no-alpha rollout: boundary pass -> exchange of the new boundary rows (side stream) || interior pass."""
-        C, _lib, fused = self.C, self._lib, self.fused
-        lib, ptr = _lib.lib, _lib.ptr
+        """The no-alpha rollout: boundary pass -> exchange of the new boundary rows (side stream) || interior pass.  One C-ABI call
+        per pass (sphnca_step_fwd_fired), persistent exchange buffers, two reused events: ~15 host-side operations per step."""
+        C, _lib = self.C, self._lib
+        lib, ptr, check = _lib.lib, _lib.ptr, _lib.check
         g = self.grid.c_grid()
         main = torch.cuda.current_stream(dev)
         st = _lib.stream_ptr()
         fb = self._work["fb"]
-        fb.flags = flags_s
         split = self.split
-        nbytes = self._exchange_sorted(A_s)                                 # halo rows of the initial state (no-op on one rank)
-        done = None
+        nbytes = self._exchange_state(A_s, dev)                              # halo rows of the initial state (no-op on one rank)
+        ready, done = self._events
+        waiting = False
+        pargs = (ptr(pl["slots"]), ptr(pl["base"]), ptr(pl["J"]), ptr(pl["WP"]), ptr(pl["FLG"]), C.byref(prm))
+        targs = (ptr(fb.rows), ptr(fb.count), ptr(fb.Y_c), ptr(fb.A_c))
+        oargs = (ptr(alive_s), ptr(fb.O_c), ptr(flags_s), ptr(fb.relu_c), ptr(ws_fl), ws_fl.numel(), st)
+        pA, pAn = ptr(A_s), ptr(An_s)
         for k in range(steps):
             if not split:
                 fire_s = self._fire_bytes(k, fire_masks, fr, N, dev)
-                fused._step_forward_lists(self.grid, None, None, g, self.xv4, A_s, fire_s, prm, False, Y_s, An_s, alive_s, fb, ws_fl, st, pl=pl)
-                A_s, An_s = An_s, A_s
+                check(lib.sphnca_step_fwd_fired(g, ptr(fire_s), pA, *pargs, 1, *targs, pAn, *oargs))
+                A_s, An_s, pA, pAn = An_s, A_s, pAn, pA
                 continue
             _, fire_b, fire_i = self._fire_bytes(k, fire_masks, fr, N, dev, split=True)
-            if done is not None:
+            if waiting:
                 main.wait_event(done)                                       # pass B reads the halo rows of the current state
+                waiting = False
             # pass B: boundary particles; its list kernel also carries over every not-fired row and writes the static mask bits
-            fused._step_forward_lists(self.grid, None, None, g, self.xv4, A_s, fire_b, prm, False, Y_s, An_s, alive_s, fb, ws_fl, st, pl=pl)
+            check(lib.sphnca_step_fwd_fired(g, ptr(fire_b), pA, *pargs, 1, *targs, pAn, *oargs))
             # exchange of the NEW state's boundary rows into the neighbours' halo slots
             if self.comm_stream is not None:
-                ready = torch.cuda.Event(); ready.record(main)
+                ready.record(main)
                 with torch.cuda.stream(self.comm_stream):
                     self.comm_stream.wait_event(ready)
-                    nbytes += self._exchange_sorted(An_s)
-                    done = torch.cuda.Event(); done.record(self.comm_stream)
-            # pass I: interior particles (list build without carry-over / flag writes: NULL outputs)
-            fused._timed("fire_list", lib.sphnca_fire_list, N, ptr(fire_i), ptr(A_s), 0, ptr(fb.rows), ptr(fb.count), None, None, None, None, 0,
-                         ptr(ws_fl), ws_fl.numel(), st)
-            fused._timed("step_perceive", lib.sphnca_step_perceive_pairs_fired, g, ptr(fb.rows), ptr(fb.count), ptr(pl["slots"]), ptr(pl["base"]),
-                         ptr(pl["J"]), ptr(pl["WP"]), ptr(A_s), C.byref(prm), ptr(fb.Y_c), ptr(fb.A_c), st)
-            fused._timed("step_mlp", lib.sphnca_step_mlp_list, N, ptr(fb.rows), ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), C.byref(prm), ptr(An_s),
-                         ptr(alive_s), ptr(fb.O_c), ptr(fb.flags), ptr(fb.relu_c), None, None, 3, st)
+                    nbytes += self._exchange_state(An_s, dev)
+                    done.record(self.comm_stream)
+                waiting = True
+            # pass I: interior particles (a second list over the same step: no carry-over, no flag writes)
+            check(lib.sphnca_step_fwd_fired(g, ptr(fire_i), pA, *pargs, 0, *targs, pAn, *oargs))
             if self.comm_stream is None:
-                nbytes += self._exchange_sorted(An_s)                       # blocking variant (overlap=False) / no-op on one rank
-            A_s, An_s = An_s, A_s
-        if done is not None:
+                nbytes += self._exchange_state(An_s, dev)                   # blocking variant (overlap=False) / no-op on one rank
+            A_s, An_s, pA, pAn = An_s, A_s, pAn, pA
+        if waiting:
             main.wait_event(done)
-            # the side stream's temporaries were allocated under it: keep the allocator from handing them to the main stream early
-            A_s.record_stream(self.comm_stream); An_s.record_stream(self.comm_stream)
         self.bytes_per_step = nbytes // max(steps, 1)
         return A_s[self.own_pos]

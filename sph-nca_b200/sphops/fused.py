@@ -408,6 +408,15 @@ class _NCARollout(torch.autograd.Function):
         st = stream_ptr()
         recompute = ctx.taped == 2
         fl = ctx.fire_lists
+        # The weight-gradient kernel of step k (tensor-core bound) and its adjoint sweep (latency bound) both depend on the
+        # data-gradient kernel only: with OVERLAP_WGRAD the weight-gradient kernels run on a side stream (serialised there, so the
+        # parameter gradients accumulate in the same fixed order) beside the adjoint sweep and the next step's data gradient.
+        # (Not while bench.py times the kernels one by one: PROFILE.)  Measured on configs[1]: 808 -> 830 M particle-steps/s; the
+        # weight-gradient CTAs (416 threads x 128 registers, 223 KB shared memory) leave room for only 2 of the 10 adjoint CTAs an
+        # SM normally holds, so the two kernels overlap by ~0.03 ms per step, not by the 0.15 ms the shorter one lasts.
+        side = _side_stream(dev) if (OVERLAP_WGRAD and PROFILE is None and fl and want_w and not recompute and N) else None
+        dO_alt = torch.empty((N, 36), **f32) if side is not None else None       # dO double buffer: step k-1 writes while wgrad(k) reads
+        wg_done = [None, None]
         if fl:
             g = grid.c_grid()
             dO_c = dO_s                                       # dL/d(MLP output) of the listed rows, by list position
@@ -436,9 +445,19 @@ class _NCARollout(torch.autograd.Function):
                 pl = ctx.pairs
                 if pl is None:      # the cell-sweep adjoint reads every row: the not-fired ones are written first
                     _timed("step_bwd_unfired", lib.sphnca_step_bwd_unfired, N, ptr(fb.flags), ptr(gcur), ptr(dY_s), ptr(dAdir_s), st)
+                if side is not None:
+                    dO_c = dO_s if (k & 1) else dO_alt
+                    if wg_done[k & 1] is not None:          # the weight-gradient kernel that last read this dO buffer
+                        torch.cuda.current_stream(dev).wait_event(wg_done[k & 1])
                 _timed("step_bwd", lib.sphnca_step_bwd_list, N, ptr(fb.rows), ptr(fb.count), ptr(fb.A_c), ptr(fb.O_c), ptr(fb.flags),
                        ptr(fb.relu_c), ptr(gcur), C.byref(p), ptr(dO_c), ptr(dY_s), ptr(dAdir_s), st)
-                if want_w:
+                if want_w and side is not None:
+                    ready = torch.cuda.Event(); ready.record(torch.cuda.current_stream(dev))
+                    side.wait_event(ready)
+                    check(lib.sphnca_mlp_wgrad_list(N, ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), ptr(dO_c), C.byref(p),
+                                                    ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value, C.c_void_p(side.cuda_stream)))
+                    wg_done[k & 1] = torch.cuda.Event(); wg_done[k & 1].record(side)
+                elif want_w:
                     _timed("mlp_wgrad", lib.sphnca_mlp_wgrad_list, N, ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), ptr(dO_c), C.byref(p),
                            ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value, st)
                 out = own[k & 1]
@@ -467,6 +486,8 @@ class _NCARollout(torch.autograd.Function):
             if dstates[k] is not None:
                 dk = require_cuda_f32(dstates[k], "dS")
                 gcur = dk if gcur is None else gcur.add_(dk)
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
         dA0 = None
         if need[2]:
             dA0 = grid.unpack_rows(gcur, 16) if gcur is not None else torch.zeros((N, 16), **f32)
@@ -671,6 +692,18 @@ class RolloutStates:
 
     def __iter__(self):
         return (self[k] for k in range(len(self._s)))
+
+
+# Run the weight-gradient kernels of a taped backward on a side stream, beside the adjoint sweeps (see _NCARollout.backward).
+OVERLAP_WGRAD = __import__("os").environ.get("SPHNCA_OVERLAP_WGRAD", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
 
 
 # Activation checkpointing inside the rollout node: True / False, or "auto" = checkpoint when
