@@ -141,4 +141,9 @@ def require_cuda_f32(t, name):
     if t.dtype != torch.float32:
         raise TypeError(f"{name} must be float32 (got {t.dtype}); the reference's dtype map "
                         "(func.py:12-16) also lists fp16/fp64 but only fp32 is implemented")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are launched on the CURRENT device's current stream (stream_ptr): a tensor of another device would be
+        # dereferenced in the wrong context (an illegal address at best)
+        raise RuntimeError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                           "call torch.cuda.set_device(...) / use `with torch.cuda.device(t.device)` around sphops calls")
     return t.detach().contiguous()

@@ -134,13 +134,16 @@ def test_rollout_node_matches_reference(name, checkpoint):
 
 
 def test_rollout_node_matches_oracle_midsize_and_is_reproducible():
-    """The default rollout node vs the fp64 oracle at 14 k 3-D particles with the BASELINE neighbour count (K=4, fwd+bwd), and
-    a second run of it: bit-identical states and gradients (ordered fire lists, fixed-order reductions, gather adjoints)."""
+    """The default rollout node vs the fp64 oracle at 14 k 3-D particles with the BASELINE neighbour count (K=4, fwd+bwd) -- with
+    the GPU's ReLU decisions imposed on the oracle and every step compared from identical inputs (tests/
+    test_gpu_parity_config_sizes.py: states, loss, dL/dA0 and the four parameter gradients at the fp32 bars, no allowance for
+    flipped kinks) -- and a second run of it: bit-identical states and gradients (ordered fire lists, fixed-order reductions,
+    gather adjoints)."""
     import nca
-    from oracle import sphnca_oracle as O
+    from tests.test_gpu_parity_config_sizes import compare_with_imposed_bits
     K = 4
     x, sections, h, dims, A0, params, masks, cfg = oracle_case(24, True, False, K, seed=21)
-    A_ref, loss_ref, dA0_ref, dP_ref = O.rollout_fwd_bwd(x, sections, h, dims, A0, params, masks, cfg)
+    compare_with_imposed_bits(x, sections, h, dims, A0, params, masks, cfg, "3-D 14k")
     nca.USE_FUSED_STEP = True
     m = nca.SPHNCA(16, 0.5, use_alpha=False, normalize_perception=cfg.normalize_perception).to(DEV)
     with torch.no_grad():
@@ -159,18 +162,6 @@ def test_rollout_node_matches_oracle_midsize_and_is_reproducible():
         runs.append([out[-1].detach().clone(), A.grad.clone()] + [p.grad.clone() for p in m.parameters()])
     for a, b in zip(*runs):
         assert torch.equal(a, b)
-    A_K, dA0 = runs[0][0], runs[0][1]
-    ref = A_ref.numpy()
-    diff = np.abs(A_K.cpu().numpy().astype(np.float64) - ref).max(-1)
-    assert (diff > 1e-4 * np.abs(ref).max()).mean() == 0.0
-    assert_close(A_K, A_ref, rtol=2e-5, what="A_K")
-    assert abs(float(loss.detach()) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
-    gref = dA0_ref.numpy()
-    gerr = np.abs(dA0.cpu().numpy().astype(np.float64) - gref).max(-1) / np.abs(gref).max()
-    frac = (gerr > 5e-5).mean()         # ReLU-kink flips, see test_fused_rollout_matches_oracle_midsize
-    assert frac <= 2e-2 and gerr.max() <= 2e-2, f"dL/dA0: {frac:.3%} rows > 5e-5, worst {gerr.max():.2e}"
-    for t, r, nm in zip(runs[0][2:], dP_ref, ("dW1", "db1", "dW2", "db2")):
-        assert_close(t, r, rtol=5e-4, what=nm)
 
 
 def test_sample_plane_driver_matches_reference_call_pattern():
@@ -222,45 +213,13 @@ def oracle_case(n_side, dim3, use_alpha, K, seed):
 
 @pytest.mark.parametrize("dim3,use_alpha,n_side", [(True, False, 24), (False, True, 100)], ids=["3d_14k", "2d_10k_alpha"])
 def test_fused_rollout_matches_oracle_midsize(dim3, use_alpha, n_side):
-    """K=4 fused rollout fwd+bwd vs the fp64 oracle at the BASELINE neighbour counts."""
-    import nca
-    from oracle import sphnca_oracle as O
-    K = 4
-    x, sections, h, dims, A0, params, masks, cfg = oracle_case(n_side, dim3, use_alpha, K, seed=21)
-    A_ref, loss_ref, dA0_ref, dP_ref = O.rollout_fwd_bwd(x, sections, h, dims, A0, params, masks, cfg)
-
-    nca.USE_FUSED_STEP = True
-    m = nca.SPHNCA(16, 0.5, use_alpha=use_alpha, normalize_perception=cfg.normalize_perception).to(DEV)
-    with torch.no_grad():
-        for t, src in zip((m.model[0].weight, m.model[0].bias, m.model[2].weight, m.model[2].bias), params):
-            t.copy_(src)
-    xd = x.to(DEV)
-    grid, v = m.init_grid(xd, sections, h, dims)
-    A = A0.to(DEV).requires_grad_(True)
-    A_in = A
-    with forced_fire_masks(list(masks)):
-        for _ in range(K):
-            _, A = m(xd, v, A, h, grid)
-    loss = (A[:, :4] ** 2).mean()
-    loss.backward()
-    ref = A_ref.numpy()
-    diff = np.abs(A.detach().cpu().numpy().astype(np.float64) - ref).max(-1)
-    flipped = (diff > 1e-4 * np.abs(ref).max()).mean()
-    assert flipped <= 1e-3, f"{flipped:.3%} of particles differ after {K} steps (life-mask threshold flips)"
-    if flipped == 0.0:
-        assert_close(A, A_ref, rtol=2e-5, what="A_K")
-        assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
-        # dL/dA0: an fp32-vs-fp64 rounding difference can flip a ReLU whose pre-activation is ~0
-        # (14k particles x 256 units x K steps of kinks); a flip moves that particle's row by ~1/256
-        # of its size and leaks to its neighbours through the adjoint sweeps.  Measured: the ORACLE
-        # ITSELF run in fp32 vs fp64 on this case gives 0.29% rows > 5e-5, worst 1.0e-3, parameter
-        # gradients up to 7.9e-5.  So: <= 2% of rows above 5e-5, every row within 2e-2.
-        gref = dA0_ref.numpy()
-        gerr = np.abs(A_in.grad.cpu().numpy().astype(np.float64) - gref).max(-1) / np.abs(gref).max()
-        frac = (gerr > 5e-5).mean()
-        assert frac <= 2e-2 and gerr.max() <= 2e-2, f"dL/dA0: {frac:.3%} rows > 5e-5, worst {gerr.max():.2e}"
-        for t, r, nm in zip((m.model[0].weight, m.model[0].bias, m.model[2].weight, m.model[2].bias), dP_ref, ("dW1", "db1", "dW2", "db2")):
-            assert_close(t.grad, r, rtol=5e-4, what=nm)
+    """K=4 rollout fwd+bwd vs the fp64 oracle at the BASELINE neighbour counts (two sections in 2-D; the alpha-channel model
+    with its life-mask sweeps): the GPU's ReLU decisions imposed, every step from identical inputs, fp32 bars on every state
+    and gradient (tests/test_gpu_parity_config_sizes.py).  The single-step autograd nodes (`SPHNCA.forward`) are tied to
+    this path bit for bit by test_rollout_node_equals_stepwise_tape."""
+    from tests.test_gpu_parity_config_sizes import compare_with_imposed_bits
+    x, sections, h, dims, A0, params, masks, cfg = oracle_case(n_side, dim3, use_alpha, 4, seed=21)
+    compare_with_imposed_bits(x, sections, h, dims, A0, params, masks, cfg, "mid-size " + ("alpha 2-D" if use_alpha else "3-D"))
 
 
 def test_fused_equals_ops_path_bitwise_masks():
