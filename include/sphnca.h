@@ -179,12 +179,20 @@ int32_t sphnca_stage_fit(const sphnca_grid* g, int32_t* counts, void* stream);
  *   sphnca_pairs_fill    J int32 [E], WP / WB / WA float [E,2], SXY float [N,2], FLG uint8 [N] (the life mask of an
  *                        all-alive field: what the perception sweep reports when use_alpha == 0); WB (the life-mask blur
  *                        weights, 8 of the 28 bytes per pair) may be NULL when no model with an alpha channel will use the
- *                        lists -- sphnca_step_perceive_pairs then requires use_alpha == 0
+ *                        lists -- sphnca_step_perceive_pairs then requires use_alpha == 0; WPZ float [E] (optional, NULL = not
+ *                        built): the z component of the perception weight, read by sphnca_step_perceive_pairs_frame only
  *   sphnca_step_perceive_pairs / sphnca_step_adjoint_pairs: same outputs, bit for bit, as sphnca_step_perceive /
  *   sphnca_step_adjoint (same visiting order, same floats), from the lists. */
 int32_t sphnca_pairs_count(const sphnca_grid* g, const float* xv4, int32_t* group_slots, void* stream);
 int32_t sphnca_pairs_fill(const sphnca_grid* g, const float* xv4, const int32_t* group_slots, const int64_t* group_base,
-                          int32_t* J, float* WP, float* WB, float* WA, float* SXY, uint8_t* FLG, void* stream);
+                          int32_t* J, float* WP, float* WB, float* WA, float* SXY, uint8_t* FLG, float* WPZ, void* stream);
+/* Perception in a per-particle tangent frame (surface clouds: reference nca.py:325-336 `project_tangent_space` applied to the
+ * gradient of every channel, then `[..., 0]` and `[..., 1]` kept by the default feature process): Y_s = [A-gradient along T_i |
+ * along B_i], frame_s [N][8] = {T_i, 0, B_i = N_i x T_i, 0} in cell-sorted order.  The projection is applied to the pair weights
+ * (w . T_i, w . B_i), so the sweep costs what the planar one costs and feeds the same MLP kernel. */
+int32_t sphnca_step_perceive_pairs_frame(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
+                                         const float* WP, const float* WPZ, const float* WB, const uint8_t* FLG, const float* frame_s,
+                                         const float* A_s, const sphnca_step_params* p, float* Y_s, uint8_t* flags_s, void* stream);
 int32_t sphnca_step_perceive_pairs(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
                                    const float* WP, const float* WB, const uint8_t* FLG, const float* A_s,
                                    const sphnca_step_params* p, float* Y_s, uint8_t* flags_s, void* stream);

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128)
 pairs_fill_kernel(GridView g, const float4* __restrict__ xv4, float h, float h2, const int32_t* __restrict__ group_slots,
                   const int64_t* __restrict__ group_base, int32_t* __restrict__ J, float2* __restrict__ WP,
                   float2* __restrict__ WB, float2* __restrict__ WA, float2* __restrict__ SXY, float cw,
-                  uint8_t* __restrict__ FLG) {
+                  uint8_t* __restrict__ FLG, float* __restrict__ WPZ) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t grp = p / PG;
     if (grp * PG >= g.n) return;
@@ -104,6 +104,11 @@ pairs_fill_kernel(GridView g, const float4* __restrict__ xv4, float h, float h2,
                 }
                 J[e] = q; WP[e] = wp; WA[e] = wa;
                 if (WB != nullptr) WB[e] = make_float2(xj.w, t * t * t);
+                if (WPZ != nullptr) {                                    // z component of the perception weight (tangent-frame sweeps)
+                    float wz = 0.f;
+                    if (D == 3 && d2 > 0.f) { const float inv = rsqrtf(d2); const float hd = h - d2 * inv; wz = 3.f * hd * hd * inv * xj.w * (xj.z - xi.z); }
+                    WPZ[e] = wz;
+                }
                 e += PG; ++cnt;
             }
         });
@@ -113,6 +118,7 @@ pairs_fill_kernel(GridView g, const float4* __restrict__ xv4, float h, float h2,
     for (; cnt < slots; ++cnt, e += PG) {                 // zero-weight self pairs up to the group's slot count
         J[e] = (int32_t)self; WP[e] = make_float2(0.f, 0.f); WA[e] = make_float2(0.f, 0.f);
         if (WB != nullptr) WB[e] = make_float2(0.f, 0.f);
+        if (WPZ != nullptr) WPZ[e] = 0.f;
     }
 }
 
@@ -150,6 +156,67 @@ step_perceive_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, c
         for (int u = 0; u < 4; ++u) {
             const int src = u * PG + q;
             const float wxs = __shfl_sync(0xffffffffu, wpc.x, src), wys = __shfl_sync(0xffffffffu, wpc.y, src);
+            if (ALPHA) {
+                const float bv = __shfl_sync(0xffffffffu, wbc.x, src), bt = __shfl_sync(0xffffffffu, wbc.y, src);
+                const float alive = Aj[u].w > 0.1f ? 1.f : 0.f;                    // channel 3: meaningful in part 0 only
+                blur = fmaf(alive * bv, bt, blur);
+            }
+            const float2 wx = make_float2(wxs, wxs), wy = make_float2(wys, wys);
+            const float2 d0 = fsub2(make_float2(Aj[u].x, Aj[u].y), make_float2(Ai.x, Ai.y));
+            const float2 d1 = fsub2(make_float2(Aj[u].z, Aj[u].w), make_float2(Ai.z, Ai.w));
+            float2 t;
+            t = ffma2(d0, wx, make_float2(gx.x, gx.y)); gx.x = t.x; gx.y = t.y;
+            t = ffma2(d1, wx, make_float2(gx.z, gx.w)); gx.z = t.x; gx.w = t.y;
+            t = ffma2(d0, wy, make_float2(gy.x, gy.y)); gy.x = t.x; gy.y = t.y;
+            t = ffma2(d1, wy, make_float2(gy.z, gy.w)); gy.z = t.x; gy.w = t.y;
+        }
+    }
+    if (p >= n) return;
+    float4* y4 = reinterpret_cast<float4*>(Y_s + (size_t)p * 2 * NF);
+    y4[part] = make_float4(gx.x * c.kg, gx.y * c.kg, gx.z * c.kg, gx.w * c.kg);
+    y4[4 + part] = make_float4(gy.x * c.kg, gy.y * c.kg, gy.z * c.kg, gy.w * c.kg);
+    if (part == 0) flags_s[p] = ALPHA ? (blur * c.cw > 0.1f ? 1 : 0) : FLG[p];
+}
+
+// Perception in a per-particle TANGENT FRAME (surface point clouds, reference nca.py:325-336,364: `feature_process_tangent` projects the
+// 3-D gradient of every channel onto (T_i, B_i = N_i x T_i) after the sweep): the projection is linear, so it is applied to the pair
+// WEIGHT instead -- w_t = w . T_i, w_b = w . B_i, 6 FMAs per pair in the lane that loaded the entry -- and the sweep itself is the
+// planar one: Y = [sum_j (A_j - A_i) w_t | sum_j (A_j - A_i) w_b].  frame_s [N][8] = {T, 0, B, 0} in cell-sorted order.
+template <bool ALPHA>
+__global__ void __launch_bounds__(128)
+step_perceive_pairs_frame_kernel(int64_t n, const int32_t* __restrict__ group_slots, const int64_t* __restrict__ group_base,
+                                 const int32_t* __restrict__ J, const float2* __restrict__ WP, const float* __restrict__ WPZ,
+                                 const float2* __restrict__ WB, const uint8_t* __restrict__ FLG, const float4* __restrict__ frame_s,
+                                 const float* __restrict__ A_s, StepConsts c, float* __restrict__ Y_s, uint8_t* __restrict__ flags_s) {
+    const int64_t grp = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (grp * PG >= n) return;
+    const int lane = threadIdx.x & 31, part = lane & 3, q = lane >> 2;
+    const int64_t p = grp * PG + q;
+    const int64_t pi = p < n ? p : n - 1;
+    const int batches = group_slots[grp] >> 2;            // 4 slots per batch
+    const int64_t e0 = group_base[grp] + lane;
+    // the frame of the particle whose list entries THIS lane loads (column lane % 8 of the group)
+    const int64_t pe = grp * PG + (lane & 7) < n ? grp * PG + (lane & 7) : n - 1;
+    const float4 T = __ldg(frame_s + pe * 2), B = __ldg(frame_s + pe * 2 + 1);
+    const float4* __restrict__ A4 = reinterpret_cast<const float4*>(A_s);
+    const float4 Ai = __ldg(A4 + (size_t)pi * 4 + part);
+    float4 gx = make_float4(0.f, 0.f, 0.f, 0.f), gy = make_float4(0.f, 0.f, 0.f, 0.f);
+    float blur = 0.f;
+    int jv = 0; float2 wp = make_float2(0.f, 0.f), wb = make_float2(0.f, 0.f); float wz = 0.f;
+    if (batches > 0) { jv = __ldcs(J + e0); wp = __ldcs(WP + e0); wz = __ldcs(WPZ + e0); if (ALPHA) wb = __ldcs(WB + e0); }
+#pragma unroll 1
+    for (int b = 0; b < batches; ++b) {
+        float4 Aj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) Aj[u] = __ldg(A4 + (size_t)__shfl_sync(0xffffffffu, jv, u * PG + q) * 4 + part);
+        // projected weights of this lane's entry
+        const float wt = fmaf(wz, T.z, fmaf(wp.y, T.y, wp.x * T.x)), wbn = fmaf(wz, B.z, fmaf(wp.y, B.y, wp.x * B.x));
+        const float2 wbc = wb;
+        if (b + 1 < batches) { const int64_t e = e0 + (int64_t)(b + 1) * 32; jv = __ldcs(J + e); wp = __ldcs(WP + e); wz = __ldcs(WPZ + e); if (ALPHA) wb = __ldcs(WB + e); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int src = u * PG + q;
+            const float wxs = __shfl_sync(0xffffffffu, wt, src), wys = __shfl_sync(0xffffffffu, wbn, src);
             if (ALPHA) {
                 const float bv = __shfl_sync(0xffffffffu, wbc.x, src), bt = __shfl_sync(0xffffffffu, wbc.y, src);
                 const float alive = Aj[u].w > 0.1f ? 1.f : 0.f;                    // channel 3: meaningful in part 0 only
@@ -314,7 +381,7 @@ int32_t sphnca_pairs_count(const sphnca_grid* g, const float* xv4, int32_t* grou
 }
 
 int32_t sphnca_pairs_fill(const sphnca_grid* g, const float* xv4, const int32_t* group_slots, const int64_t* group_base,
-                          int32_t* J, float* WP, float* WB, float* WA, float* SXY, uint8_t* FLG, void* stream_) {
+                          int32_t* J, float* WP, float* WB, float* WA, float* SXY, uint8_t* FLG, float* WPZ, void* stream_) {
     GridView gv; { int rc = make_view(g, &gv, true); if (rc) return rc; }
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(xv4 && group_slots && group_base && J && WP && WA && SXY && FLG, "NULL argument");   // WB may be NULL
@@ -322,9 +389,9 @@ int32_t sphnca_pairs_fill(const sphnca_grid* g, const float* xv4, const int32_t*
     const int blocks = (int)((gv.n + 127) / 128);
     const float h = (float)g->h, h2 = (float)(g->h * g->h);
     if (gv.dim == 3) SPHNCA_LAUNCH(pairs_fill_kernel<3>, blocks, 128, 0, as_stream(stream_), gv, (const float4*)xv4, h, h2, group_slots, group_base,
-                                   J, (float2*)WP, (float2*)WB, (float2*)WA, (float2*)SXY, cw, FLG);
+                                   J, (float2*)WP, (float2*)WB, (float2*)WA, (float2*)SXY, cw, FLG, WPZ);
     else SPHNCA_LAUNCH(pairs_fill_kernel<2>, blocks, 128, 0, as_stream(stream_), gv, (const float4*)xv4, h, h2, group_slots, group_base,
-                       J, (float2*)WP, (float2*)WB, (float2*)WA, (float2*)SXY, cw, FLG);
+                       J, (float2*)WP, (float2*)WB, (float2*)WA, (float2*)SXY, cw, FLG, WPZ);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }
@@ -342,6 +409,24 @@ int32_t sphnca_step_perceive_pairs(const sphnca_grid* g, const int32_t* group_sl
                                    (const float2*)WP, (const float2*)WB, FLG, A_s, c, Y_s, flags_s);
     else SPHNCA_LAUNCH(step_perceive_pairs_kernel<false>, blocks, 128, 0, as_stream(stream_), gv.n, group_slots, group_base, J,
                        (const float2*)WP, (const float2*)WB, FLG, A_s, c, Y_s, flags_s);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
+int32_t sphnca_step_perceive_pairs_frame(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
+                                         const float* WP, const float* WPZ, const float* WB, const uint8_t* FLG, const float* frame_s,
+                                         const float* A_s, const sphnca_step_params* p, float* Y_s, uint8_t* flags_s, void* stream_) {
+    GridView gv; { int rc = make_view(g, &gv, true); if (rc) return rc; }
+    StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
+    if (gv.n == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(group_slots && group_base && J && WP && WPZ && FLG && frame_s && A_s && Y_s && flags_s, "NULL argument");
+    SPHNCA_CHECK_ARG(WB != nullptr || !p->use_alpha, "the blur weights WB are required with an alpha channel");
+    SPHNCA_CHECK_ARG(((uintptr_t)frame_s & 15) == 0, "frame_s must be 16-byte aligned");
+    const int blocks = (int)((gv.n + 31) / 32);
+    if (c.use_alpha) SPHNCA_LAUNCH(step_perceive_pairs_frame_kernel<true>, blocks, 128, 0, as_stream(stream_), gv.n, group_slots, group_base, J,
+                                   (const float2*)WP, WPZ, (const float2*)WB, FLG, (const float4*)frame_s, A_s, c, Y_s, flags_s);
+    else SPHNCA_LAUNCH(step_perceive_pairs_frame_kernel<false>, blocks, 128, 0, as_stream(stream_), gv.n, group_slots, group_base, J,
+                       (const float2*)WP, WPZ, (const float2*)WB, FLG, (const float4*)frame_s, A_s, c, Y_s, flags_s);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

@@ -112,9 +112,36 @@ class SPHNCA(nn.Module):
                 and self.in_features == 16 and self.hidden_features == 256
                 and x.shape[-1] == 3 and A.is_cuda and sphops.fused_available())
 
+    def _tangent_frame(self, x, v, A, grid, feature_process):
+        """[N,8] = {T, 0, N x T, 0} when `feature_process` is a `feature_process_tangent(N, T)` hook and this step can run on the
+        fused kernels without a tape (inference), else None."""
+        NT = getattr(feature_process, "tangent_frame", None)
+        if NT is None or not self._fusable(x, A, None):
+            return None
+        if torch.is_grad_enabled() and (A.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return None                                   # training through a surface rollout: the operator-by-operator path has the tape
+        if not sphops.fused.frame_step_available(grid, x, v):
+            return None
+        Nn, T = NT
+        frame = torch.zeros((x.shape[0], 8), dtype=torch.float32, device=x.device)
+        frame[:, 0:3] = T
+        frame[:, 4:7] = torch.linalg.cross(Nn, T)
+        return frame
+
     def forward(self, x, v, A, h, grid, fire_rate=None, feature_process=None):
         if fire_rate is None:
             fire_rate = self.fire_rate
+        frame = self._tangent_frame(x, v, A, grid, feature_process)
+        if frame is not None:
+            # surface clouds: the tangent-frame projection of `feature_process_tangent` runs INSIDE the perception sweep (weights
+            # projected per pair), the MLP / update / life mask on the fused kernels -- no operator-by-operator step, no library GEMM
+            update_mask = torch.rand(x.shape[0], device=x.device) <= fire_rate
+            lin1, lin2 = self.model[0], self.model[2]
+            nA = sphops.fused.nca_step(
+                x, v, A, update_mask, lin1.weight, lin1.bias, lin2.weight, lin2.bias, h, grid,
+                update_rule=self.update_rule, use_alpha=self.use_alpha,
+                perception_scale=self.perception_scale(h), orig_rate=self.fire_rate / fire_rate, frame=frame)
+            return x, nA
         if self._fusable(x, A, feature_process):
             update_mask = torch.rand(x.shape[0], device=x.device) <= fire_rate
             lin1, lin2 = self.model[0], self.model[2]
@@ -450,6 +477,7 @@ def project_tangent_space(Av, N, T):
 def feature_process_tangent(N, T):
     def func(features):
         return [(As, project_tangent_space(Av, N, T)) for As, Av in features]
+    func.tangent_frame = (N, T)          # lets SPHNCA.forward run the projection inside the perception sweep
     return func
 
 

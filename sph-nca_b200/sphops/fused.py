@@ -95,7 +95,7 @@ def _mask(use_alpha, g, N, xv4, alive_s, An_s, flags_s, st):
 
 class _NCAStep(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, v, A, update_mask, W1, b1, W2, b2, h, grid, update_rule, use_alpha, perception_scale, orig_rate):
+    def forward(ctx, x, v, A, update_mask, W1, b1, W2, b2, h, grid, update_rule, use_alpha, perception_scale, orig_rate, frame=None):
         x = require_cuda_f32(x, "x"); v = require_cuda_f32(v, "v"); A_ = require_cuda_f32(A, "A")
         W1c, b1c, W2c, b2c = [require_cuda_f32(t, n) for t, n in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"))]
         N = x.shape[0]
@@ -116,7 +116,15 @@ class _NCAStep(torch.autograd.Function):
         p = _step_params(W1c, b1c, W2c, b2c, update_rule, use_alpha, perception_scale, orig_rate)
         if N:
             g, st = grid.c_grid(), stream_ptr()
-            if SPLIT_FORWARD:
+            if frame is not None:
+                # perception projected onto the particles' tangent frames inside the sweep (inference only; surface clouds)
+                pl = grid.pair_lists(x, v, blur=bool(use_alpha), z=True)
+                frame_s = grid.pack_rows(frame, 8)
+                _timed("step_perceive", lib.sphnca_step_perceive_pairs_frame, g, ptr(pl["slots"]), ptr(pl["base"]), ptr(pl["J"]), ptr(pl["WP"]),
+                       ptr(pl["WPZ"]), ptr(pl["WB"]), ptr(pl["FLG"]), ptr(frame_s), ptr(A_s), C.byref(p), ptr(Y_s), ptr(flags_s), st)
+                _timed("step_mlp", lib.sphnca_step_mlp, N, ptr(A_s), ptr(Y_s), ptr(fire_s), C.byref(p), ptr(An_s),
+                       ptr(alive_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
+            elif SPLIT_FORWARD:
                 _perceive(grid, x, v, g, xv4, A_s, p, Y_s, flags_s, st)
                 _timed("step_mlp", lib.sphnca_step_mlp, N, ptr(A_s), ptr(Y_s), ptr(fire_s), C.byref(p), ptr(An_s),
                        ptr(alive_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
@@ -125,6 +133,9 @@ class _NCAStep(torch.autograd.Function):
                        ptr(alive_s), ptr(Y_s), ptr(O_s), ptr(flags_s), ptr(relu_s), st)
             _mask(use_alpha, g, N, xv4, alive_s, An_s, flags_s, st)
         out = grid.unpack_rows(An_s, 16)
+        if frame is not None:                        # no tape: the frame sweep has no adjoint (callers fall back when gradients are needed)
+            ctx.mark_non_differentiable(out)
+            return out
         ctx.grid = grid
         ctx.pairs = grid.pair_lists(x, v, blur=bool(use_alpha)) if N else None     # cached by the grid; the adjoint sweep reads the same lists
         ctx.cfg = (update_rule, use_alpha, perception_scale, orig_rate)
@@ -178,7 +189,7 @@ class _NCAStep(torch.autograd.Function):
             _adjoint(grid, ctx.pairs, xv4, dY_s, dAdir_s, p, dA_s, st)
         dA = grid.unpack_rows(dA_s, 16) if g[2] else None
         return (None, None, dA, None, dW1 if g[4] else None, db1 if g[5] else None,
-                dW2 if g[6] else None, db2 if g[7] else None, None, None, None, None, None, None)
+                dW2 if g[6] else None, db2 if g[7] else None, None, None, None, None, None, None, None)
 
 
 # The MLP half of a rollout step runs over the fired rows only (csrc/firelist.cu) when the tensor-core kernels are the
@@ -753,13 +764,26 @@ SIMT_BACKWARD = False
 WGRAD_CHUNK = 4 * 1024 * 1024
 
 
+def frame_step_available(grid, x, v):
+    """The tangent-frame step needs the pair lists (with the z weights); False when they are off or do not fit."""
+    return "sphnca_step_perceive_pairs_frame" not in _lib.MISSING_SYMBOLS and x.shape[0] > 0 \
+        and grid.pair_lists(x, v, blur=True, z=True) is not None
+
+
 def nca_step(x, v, A, update_mask, W1, b1, W2, b2, h, grid, update_rule="gated", use_alpha=True,
-             perception_scale=1.0, orig_rate=1.0):
-    """One NCA step.  x [N,3], v [N], A [N,16], update_mask bool [N] (the fire draw) -> new A [N,16]."""
+             perception_scale=1.0, orig_rate=1.0, frame=None):
+    """One NCA step.  x [N,3], v [N], A [N,16], update_mask bool [N] (the fire draw) -> new A [N,16].
+    frame [N,8] = {T, 0, B, 0} per particle: the perception gradients are taken along T and B instead of x and y
+    (surface clouds, `nca.feature_process_tangent`); forward only."""
     if "sphnca_step_fwd" in _lib.MISSING_SYMBOLS:
         raise RuntimeError("libsphnca.so was built without the fused step (step.cu)")
     hval = h.item() if isinstance(h, torch.Tensor) else float(h)
     if abs(hval - grid.h) > 1e-9 * abs(grid.h):
         raise ValueError(f"h={hval} differs from the grid's cell size {grid.h}")
+    if frame is not None:
+        frame = require_cuda_f32(frame, "frame")
+        with torch.no_grad():
+            return _NCAStep.apply(x, v, A, update_mask, W1, b1, W2, b2, h, grid, update_rule, use_alpha,
+                                  perception_scale, orig_rate, frame)
     return _NCAStep.apply(x, v, A, update_mask, W1, b1, W2, b2, h, grid, update_rule, use_alpha,
                           perception_scale, orig_rate)

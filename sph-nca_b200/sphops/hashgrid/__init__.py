@@ -154,7 +154,7 @@ class Hashgrid:
     # fraction of the free device memory the pair lists of one grid may take (about 1.3 KB per particle)
     PAIR_LIST_MEMORY_FRACTION = 0.4
 
-    def pair_lists(self, x, v, blur=True):
+    def pair_lists(self, x, v, blur=True, z=False):
         """Per-pair neighbour lists and kernel weights of this grid (csrc/pairs.cu), cached per (x, v) pair; None when
         disabled or when they would not fit the memory budget.  Building them reads back ONE integer (the total number
         of list entries) -- the only host synchronisation besides `staged_sweep_ok`.  blur=False leaves out the life-mask
@@ -165,13 +165,14 @@ class Hashgrid:
                 raise RuntimeError("a periodic grid needs the pair lists (SPHNCA_PAIRS=0 / SPHNCA_SWEEP_PATH are set)")
             return None
         key = (self._key(x), self._key(v))
-        if self._pairs_key == key and self._pairs is not None and blur and self._pairs["WB"] is None:
-            self._pairs_key = None                                  # built without the blur weights: build again with them
+        if self._pairs_key == key and self._pairs is not None and ((blur and self._pairs["WB"] is None) or (z and self._pairs["WPZ"] is None)):
+            blur, z = blur or self._pairs["WB"] is not None, z or self._pairs["WPZ"] is not None
+            self._pairs_key = None                                  # built without the blur / z weights: build again with them
         if self._pairs_key != key:
             self._pairs_key, self._pairs, self._pairs_ref = key, None, (x, v)
             if self.num_particles:
                 # a periodic grid has no cell-sweep fallback: its lists are built whatever they cost
-                self._pairs = self.build_pair_lists(self.sorted_xv(x, v), blur, float("inf") if self.periodic else None)
+                self._pairs = self.build_pair_lists(self.sorted_xv(x, v), blur, float("inf") if self.periodic else None, z=z)
         return self._pairs
 
     # what one list entry costs (J + WP + WA [+ WB]) and the measured entries per particle of the BASELINE workloads
@@ -179,7 +180,7 @@ class Hashgrid:
     PAIR_ENTRY_BYTES = {False: 20, True: 28}
     PAIR_SLOTS_ESTIMATE = 40
 
-    def build_pair_lists(self, xv4, blur=True, budget_bytes=None):
+    def build_pair_lists(self, xv4, blur=True, budget_bytes=None, z=False):
         """The pair lists of this grid from its cell-sorted {x,y,z,v} array (uncached).  None when they would exceed
         `budget_bytes` (default: PAIR_LIST_MEMORY_FRACTION of the device memory torch does not hold)."""
         N, dev = self.num_particles, xv4.device
@@ -198,17 +199,18 @@ class Hashgrid:
             # capacity minus torch's live tensors (host-side counters; cudaMemGetInfo stalls ~25 ms on a busy device)
             free = torch.cuda.get_device_properties(dev).total_memory - torch.cuda.memory_allocated(dev)
             budget_bytes = self.PAIR_LIST_MEMORY_FRACTION * free
-        if not (0 < total and total * self.PAIR_ENTRY_BYTES[bool(blur)] <= budget_bytes):
+        if not (0 < total and total * (self.PAIR_ENTRY_BYTES[bool(blur)] + (4 if z else 0)) <= budget_bytes):
             return None
         f32 = dict(dtype=torch.float32, device=dev)
         J = torch.empty((total,), dtype=torch.int32, device=dev)
         WP, WA = (torch.empty((total, 2), **f32) for _ in range(2))
         WB = torch.empty((total, 2), **f32) if blur else None
+        WPZ = torch.empty((total,), **f32) if z else None            # tangent-frame sweeps only (surface clouds)
         SXY = torch.empty((N, 2), **f32)
         FLG = torch.empty((N,), dtype=torch.uint8, device=dev)
         _lib.check(_lib.lib.sphnca_pairs_fill(self.c_grid(), _lib.ptr(xv4), _lib.ptr(slots), _lib.ptr(base), _lib.ptr(J),
-                                              _lib.ptr(WP), _lib.ptr(WB), _lib.ptr(WA), _lib.ptr(SXY), _lib.ptr(FLG), st))
-        return dict(slots=slots, base=base, J=J, WP=WP, WB=WB, WA=WA, SXY=SXY, FLG=FLG, entries=total)
+                                              _lib.ptr(WP), _lib.ptr(WB), _lib.ptr(WA), _lib.ptr(SXY), _lib.ptr(FLG), _lib.ptr(WPZ), st))
+        return dict(slots=slots, base=base, J=J, WP=WP, WB=WB, WA=WA, SXY=SXY, FLG=FLG, WPZ=WPZ, entries=total)
 
     # -- micro-batches over sections ---------------------------------------------------------
     def section_ranges(self):

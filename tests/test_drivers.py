@@ -93,10 +93,19 @@ def test_sample_plane_wrapped_matches_reference():
 
 
 @pytest.mark.gpu
-def test_sample_mesh_matches_reference():
+@pytest.mark.parametrize("fused", [True, False], ids=["frame_sweep", "operators"])
+def test_sample_mesh_matches_reference(fused, monkeypatch):
+    """Surface rollout (reference nca.py:338-381) against the reference golden: with the tangent-frame projection inside the
+    perception sweep + fused MLP / update / mask kernels (default for inference), and operator by operator."""
     import nca
+    from sphops import fused as F
     g = load_golden("mesh_gecko_k2")
     nca.USE_3D = True
+    calls = []
+    orig = F.nca_step
+    monkeypatch.setattr(F, "nca_step", lambda *a, **k: calls.append(k.get("frame") is not None) or orig(*a, **k))
+    if not fused:
+        monkeypatch.setattr(F, "frame_step_available", lambda *a: False)
     m = _model(g, update_rule="gated", use_alpha=True, normalize_perception=float(g["normalize_perception"]))
     x = torch.from_numpy(g["x"]).to(DEV)
     N = torch.from_numpy(g["N"]).to(DEV)
@@ -105,6 +114,7 @@ def test_sample_mesh_matches_reference():
     with torch.no_grad(), forced_fire_masks([torch.from_numpy(mk) for mk in g["masks"]]):
         loss, x_out, out = nca.sample_mesh(m, x, torch.from_numpy(g["A0"]).to(DEV), N, T, (n,), float(g["h"]), int(g["dims"]),
                                            out_steps=True, iter_n=2)
+    assert calls == ([True, True] if fused else []), calls
     for k in range(3):
         assert_close(out[k], g["states"][k], what=f"state {k}")
     assert_close(T, g["T_final"], rtol=2e-5, what="diffused tangents")
