@@ -404,21 +404,43 @@ def run_train(ctx, args, name, wl, steps, warmup, detail):
     prof, fused.PROFILE = fused.PROFILE, None
     rec["clocks"] = clk.stop() if clk else None
 
+    # End to end: every step's inputs come from pinned host memory and its final state + loss go back to the host, all inside the
+    # timed region.  The copies run on a copy stream, double buffered like an input pipeline would: the H2D of step i+1 and the D2H
+    # of step i-1's result overlap step i's kernels; every step still consumes a copy made for it and the region ends with a
+    # synchronize that covers the last D2H.
     out_pin = torch.empty_like(A_pin).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
 
-    def one_step_e2e():
-        x0 = x_pin.to(dev, non_blocking=True)
-        A0 = A_pin.to(dev, non_blocking=True)
-        loss, _, A = one_step(x0, A0)
-        out_pin.copy_(A.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return loss
+    def fetch():
+        with torch.cuda.stream(copy_stream):
+            x0 = x_pin.to(dev, non_blocking=True)
+            A0 = A_pin.to(dev, non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(copy_stream)
+        return x0, A0, ev
 
-    for _ in range(2):
-        one_step_e2e()
-    ms_e2e = ctx.timed(one_step_e2e, steps)
+    def e2e_steps(n):
+        nxt = fetch()
+        for i in range(n):
+            x0, A0, ev = nxt
+            main_stream.wait_event(ev)
+            x0.record_stream(main_stream); A0.record_stream(main_stream)
+            if i + 1 < n:
+                nxt = fetch()
+            loss, _, A = one_step(x0, A0)                       # ends with loss.item(): the loss is on the host
+            done = torch.cuda.Event(); done.record(main_stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                A = A.detach()
+                A.record_stream(copy_stream)
+                out_pin.copy_(A, non_blocking=True)
+        copy_stream.synchronize()
+
+    e2e_steps(2)
+    ms_e2e = ctx.timed(lambda: e2e_steps(steps), 1)
     rec["e2e"] = {"value": units * steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
-                  "h2d_bytes_per_step": x_pin.numel() * 4 + A_pin.numel() * 4, "d2h_bytes_per_step": out_pin.numel() * 4 + 4}
+                  "h2d_bytes_per_step": x_pin.numel() * 4 + A_pin.numel() * 4, "d2h_bytes_per_step": out_pin.numel() * 4 + 4,
+                  "copies": "pinned host buffers; H2D / D2H on a copy stream, double buffered (overlap the neighbouring steps' kernels)"}
     if rank != 0:
         return rec
 
