@@ -279,13 +279,16 @@ int32_t sphnca_step_bwd_list(int64_t N, const int32_t* rows, const int32_t* coun
 int32_t sphnca_step_bwd_unfired(int64_t N, const uint8_t* flags_s, const float* dA_next_s, float* dY_s, float* dAdir_s,
                                 void* stream);
 /* The whole forward of a no-alpha fire-list step in ONE call (host overhead: 1 instead of 3 C-ABI calls): sphnca_fire_list
- * (fold_static_mask = 1) -> sphnca_step_perceive_pairs_fired -> sphnca_step_mlp_list(inputs_by_list | fold).  carry_over = 0: a
- * SECOND list over the same step (multigpu.py pass I): the list kernel neither carries rows over nor writes flag bytes. */
+ * (fold_static_mask = 1) -> sphnca_step_perceive_pairs_fired -> sphnca_step_mlp_list(inputs_by_list | fold).  A step may be split
+ * into several lists (multigpu.py: boundary particles first, interior particles while the halo exchange runs): carry_sel [N]
+ * (NULL = all) selects the rows THIS call carries over when they did not fire, write_flags = 1 on the first list of a step (the
+ * static mask bits of all rows), max_fired = an upper bound of this list's length when the caller knows one (0 = N; sizes the
+ * grids of the list kernels). */
 int32_t sphnca_step_fwd_fired(const sphnca_grid* g, const uint8_t* fire_s, const float* A_s, const int32_t* group_slots,
                               const int64_t* group_base, const int32_t* J, const float* WP, const uint8_t* FLG,
-                              const sphnca_step_params* p, int32_t carry_over, int32_t* rows, int32_t* count, float* Y_c, float* A_c,
-                              float* A_new_s, uint8_t* alive_s, float* O_c, uint8_t* flags_s, uint32_t* relu_c, void* workspace,
-                              size_t workspace_bytes, void* stream);
+                              const sphnca_step_params* p, const uint8_t* carry_sel, int32_t write_flags, int64_t max_fired,
+                              int32_t* rows, int32_t* count, float* Y_c, float* A_c, float* A_new_s, uint8_t* alive_s, float* O_c,
+                              uint8_t* flags_s, uint32_t* relu_c, void* workspace, size_t workspace_bytes, void* stream);
 /* Counter-based fire bytes of one step for slab-sharded rollouts (multigpu.py; no reference counterpart -- the reference draws
  * torch.rand(N) on its single GPU, nca.py:100): fire_s[p] = gid_s[p] >= 0 && U(gid_s[p], seed) <= rate, U = top 24 bits of
  * splitmix64(gid + 0x9E3779B97F4A7C15 (seed + 1)) / 2^24 -- a function of the GLOBAL particle id, so N ranks draw what 1 rank

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(fl::THREADS)
 fire_fill_kernel(int64_t n, const uint8_t* __restrict__ fire_s, const int32_t* __restrict__ block_off,
                  const float* __restrict__ A_s, int use_alpha, int32_t* __restrict__ rows,
                  float* __restrict__ A_new_s, uint8_t* __restrict__ alive_s, const uint8_t* __restrict__ FLG,
-                 uint8_t* __restrict__ flags_s, int fold_mask) {
+                 uint8_t* __restrict__ flags_s, int fold_mask, const uint8_t* __restrict__ carry_sel) {
     using namespace fl;
     const int64_t base = (int64_t)blockIdx.x * BLOCK_ROWS + (int64_t)threadIdx.x * PER_THREAD;
     bool f[PER_THREAD];
@@ -135,9 +135,10 @@ fire_fill_kernel(int64_t n, const uint8_t* __restrict__ fire_s, const int32_t* _
         // static life mask (no alpha channel): the previous-mask bit of every row; fold_mask: the new mask is the same bit
         // (step_mask_static_kernel), so bit 1 is set here too and dead rows are zeroed below / by the MLP kernel
         const bool live = FLG == nullptr || FLG[p] != 0;
-        if (FLG != nullptr) flags_s[p] = live ? (fold_mask ? 3 : 1) : 0;
+        if (FLG != nullptr && flags_s != nullptr) flags_s[p] = live ? (fold_mask ? 3 : 1) : 0;
         if (f[k]) { rows[slot++] = (int32_t)p; continue; }
-        if (A_new_s == nullptr) continue;                   // list only (a second list over the same step: multigpu.py pass I)
+        if (A_new_s == nullptr) continue;                   // list only
+        if (carry_sel != nullptr && carry_sel[p] == 0) continue;   // this row is carried over by the other list of the step (multigpu.py)
         // not fired: the state is carried over unchanged (reference nca.py:107); fire bit of the flags stays 0
         const float4* a4 = reinterpret_cast<const float4*>(A_s + p * NF);
         float4* o4 = reinterpret_cast<float4*>(A_new_s + p * NF);
@@ -217,16 +218,15 @@ int32_t sphnca_fire_list_workspace_bytes(int64_t N, size_t* bytes) {
     return SPHNCA_OK;
 }
 
-int32_t sphnca_fire_list(int64_t N, const uint8_t* fire_s, const float* A_s, int32_t use_alpha, int32_t* rows,
-                         int32_t* count, float* A_new_s, uint8_t* alive_s, const uint8_t* FLG, uint8_t* flags_s,
-                         int32_t fold_static_mask, void* workspace, size_t workspace_bytes, void* stream_) {
+static int32_t fire_list_impl(int64_t N, const uint8_t* fire_s, const float* A_s, int32_t use_alpha, int32_t* rows,
+                              int32_t* count, float* A_new_s, uint8_t* alive_s, const uint8_t* FLG, uint8_t* flags_s,
+                              int32_t fold_static_mask, const uint8_t* carry_sel, void* workspace, size_t workspace_bytes, void* stream_) {
     SPHNCA_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31), "bad N");
     SPHNCA_CHECK_ARG(count, "NULL argument");
     cudaStream_t stream = as_stream(stream_);
     if (N == 0) { SPHNCA_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), stream)); return SPHNCA_OK; }
     SPHNCA_CHECK_ARG(fire_s && A_s && rows, "NULL argument");
     SPHNCA_CHECK_ARG((A_new_s == nullptr) == (alive_s == nullptr), "A_new_s and alive_s: both or neither");
-    SPHNCA_CHECK_ARG(FLG == nullptr || flags_s != nullptr, "flags_s is required with FLG");
     SPHNCA_CHECK_ARG(((uintptr_t)fire_s & 3) == 0, "fire_s must be 4-byte aligned");
     SPHNCA_CHECK_ARG(!fold_static_mask || (FLG != nullptr && !use_alpha), "the static life mask needs FLG and no alpha channel");
     const int nb = (int)((N + fl::BLOCK_ROWS - 1) / fl::BLOCK_ROWS);
@@ -235,9 +235,17 @@ int32_t sphnca_fire_list(int64_t N, const uint8_t* fire_s, const float* A_s, int
     SPHNCA_LAUNCH(fire_count_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc);
     SPHNCA_LAUNCH(fire_scan_kernel, 1, 1024, 0, stream, nb, bc, count);
     SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s, FLG, flags_s,
-                  fold_static_mask ? 1 : 0);
+                  fold_static_mask ? 1 : 0, carry_sel);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
+}
+
+int32_t sphnca_fire_list(int64_t N, const uint8_t* fire_s, const float* A_s, int32_t use_alpha, int32_t* rows,
+                         int32_t* count, float* A_new_s, uint8_t* alive_s, const uint8_t* FLG, uint8_t* flags_s,
+                         int32_t fold_static_mask, void* workspace, size_t workspace_bytes, void* stream_) {
+    SPHNCA_CHECK_ARG(FLG == nullptr || flags_s != nullptr, "flags_s is required with FLG");
+    return fire_list_impl(N, fire_s, A_s, use_alpha, rows, count, A_new_s, alive_s, FLG, flags_s, fold_static_mask, nullptr, workspace,
+                          workspace_bytes, stream_);
 }
 
 int32_t sphnca_fire_list_draw(const sphnca_grid* g, const float* u, float rate, uint8_t* fire_s, const float* A_s,
@@ -259,27 +267,31 @@ int32_t sphnca_fire_list_draw(const sphnca_grid* g, const float* u, float rate, 
     SPHNCA_LAUNCH(fire_draw_count_kernel, nb, fl::THREADS, 0, stream, N, u, rate, gv.sorted_id, fire_s, bc);
     SPHNCA_LAUNCH(fire_scan_kernel, 1, 1024, 0, stream, nb, bc, count);
     SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s, FLG, flags_s,
-                  fold_static_mask ? 1 : 0);
+                  fold_static_mask ? 1 : 0, nullptr);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }
 
 int32_t sphnca_step_fwd_fired(const sphnca_grid* g, const uint8_t* fire_s, const float* A_s, const int32_t* group_slots,
                               const int64_t* group_base, const int32_t* J, const float* WP, const uint8_t* FLG,
-                              const sphnca_step_params* p, int32_t carry_over, int32_t* rows, int32_t* count, float* Y_c, float* A_c,
-                              float* A_new_s, uint8_t* alive_s, float* O_c, uint8_t* flags_s, uint32_t* relu_c, void* workspace,
-                              size_t workspace_bytes, void* stream) {
+                              const sphnca_step_params* p, const uint8_t* carry_sel, int32_t write_flags, int64_t max_fired,
+                              int32_t* rows, int32_t* count, float* Y_c, float* A_c, float* A_new_s, uint8_t* alive_s, float* O_c,
+                              uint8_t* flags_s, uint32_t* relu_c, void* workspace, size_t workspace_bytes, void* stream) {
     SPHNCA_CHECK_ARG(g && p && !p->use_alpha, "sphnca_step_fwd_fired is the no-alpha step (static life mask)");
     SPHNCA_CHECK_ARG(A_new_s && alive_s && flags_s && FLG, "NULL argument");
     const int64_t N = g->num_particles;
-    // list of the fired rows (+ carry-over of the others and the static mask bits, unless this is a second list over the same step)
-    int rc = sphnca_fire_list(N, fire_s, A_s, 0, rows, count, carry_over ? A_new_s : nullptr, carry_over ? alive_s : nullptr,
-                              carry_over ? FLG : nullptr, carry_over ? flags_s : nullptr, carry_over ? 1 : 0, workspace, workspace_bytes, stream);
+    // list of the fired rows; the not-fired rows (of carry_sel, when given) are carried over; the static mask bits of ALL rows are
+    // written when write_flags is set (the first list of a step)
+    int rc = fire_list_impl(N, fire_s, A_s, 0, rows, count, A_new_s, alive_s, FLG, write_flags ? flags_s : nullptr, 1, carry_sel,
+                            workspace, workspace_bytes, stream);
     if (rc) return rc;
     if (N == 0) return SPHNCA_OK;
-    rc = sphnca_step_perceive_pairs_fired(g, rows, count, group_slots, group_base, J, WP, A_s, p, Y_c, A_c, stream);
+    // the list kernels size their grids for an upper bound of the list length: the caller may know a much smaller one
+    sphnca_grid gb = *g;
+    if (max_fired > 0 && max_fired < N) gb.num_particles = max_fired;
+    rc = sphnca_step_perceive_pairs_fired(&gb, rows, count, group_slots, group_base, J, WP, A_s, p, Y_c, A_c, stream);
     if (rc) return rc;
-    return sphnca_step_mlp_list(N, rows, count, A_c, Y_c, p, A_new_s, alive_s, O_c, flags_s, relu_c, nullptr, nullptr, 3, stream);
+    return sphnca_step_mlp_list(gb.num_particles, rows, count, A_c, Y_c, p, A_new_s, alive_s, O_c, flags_s, relu_c, nullptr, nullptr, 3, stream);
 }
 
 int32_t sphnca_fire_bytes_counter(int64_t N, const int64_t* gid_s, int64_t seed, float rate, const uint8_t* bnd_s, uint8_t* fire_s,

@@ -267,13 +267,13 @@ class SlabShardedNCA:
     Without an alpha channel (pair lists + fire lists; the benched path) a step is split so that the halo exchange hides
     behind the interior work:
       pass B  the BOUNDARY particles (own particles in the slab's first and last cell row: the only ones whose neighbourhood
-              reaches a halo row, and the only ones a neighbour rank needs) -- fire list, fired-rows perception, tcgen05 MLP;
+              reaches a halo row, and the only ones a neighbour rank needs) -- fire list, fired-rows perception, tcgen05 MLP, with
+              grids sized for the boundary rows and only the boundary rows carried over;
       exchange  of the NEW boundary rows into the neighbours' halo slots, on a side stream (NCCL P2P, 64 B / halo particle),
               issued as soon as pass B is enqueued;
       pass I  the INTERIOR particles (everything else: ~99 % of the slab at BASELINE configs[3]) on the main stream, while the
               exchange is in flight; the next step's pass B waits for the exchange.
-    The not-fired rows are carried over by pass B's list kernel (pass I's list build leaves the state alone); halo particles
-    never fire.  With an alpha channel the life mask needs the neighbours' NEW alive bytes, so the step stays sequential:
+    Each pass's list kernel carries over its own not-fired rows; halo rows are written by the exchange only (pass I runs beside it).  With an alpha channel the life mask needs the neighbours' NEW alive bytes, so the step stays sequential:
     exchange state -> full perception sweep -> MLP over the fire list -> exchange alive bytes -> mask sweep.
     Volume: computed locally (own particles exact), halo values fetched once from their owners.
     Fire draws: `fire_masks` (bool [steps, n_own]) or, by default, counter_uniform(global id, seed = fire_seed + step) <= rate:
@@ -327,6 +327,7 @@ class SlabShardedNCA:
         self.bnd_s = bnd_loc[sid].contiguous()
         self.int_s = (own_loc[sid] & (1 - self.bnd_s)).contiguous()
         self.own_s = own_loc[sid].contiguous()
+        self.n_bnd = int(p.boundary.sum())                        # upper bound of pass B's list length (sizes its grids)
         # boundary / interior passes: whenever there is a neighbour rank (split_passes=True forces them on one rank: tests)
         self.split = world > 1 if split_passes is None else bool(split_passes)
         self.overlap = bool(overlap) and world > 1
@@ -479,18 +480,24 @@ class SlabShardedNCA:
         targs = (ptr(fb.rows), ptr(fb.count), ptr(fb.Y_c), ptr(fb.A_c))
         oargs = (ptr(alive_s), ptr(fb.O_c), ptr(flags_s), ptr(fb.relu_c), ptr(ws_fl), ws_fl.numel(), st)
         pA, pAn = ptr(A_s), ptr(An_s)
+        timed = self.fused._timed                     # per-phase CUDA events when sphops.fused.PROFILE is set (tools/slab_profile.py)
         for k in range(steps):
             if not split:
                 fire_s = self._fire_bytes(k, fire_masks, fr, N, dev)
-                check(lib.sphnca_step_fwd_fired(g, ptr(fire_s), pA, *pargs, 1, *targs, pAn, *oargs))
+                check(lib.sphnca_step_fwd_fired(g, ptr(fire_s), pA, *pargs, None, 1, 0, *targs, pAn, *oargs))
                 A_s, An_s, pA, pAn = An_s, A_s, pAn, pA
                 continue
             _, fire_b, fire_i = self._fire_bytes(k, fire_masks, fr, N, dev, split=True)
             if waiting:
+                if self.fused.PROFILE is not None:                          # how long the main stream sits waiting for the exchange
+                    a = torch.cuda.Event(enable_timing=True); a.record(main)
                 main.wait_event(done)                                       # pass B reads the halo rows of the current state
+                if self.fused.PROFILE is not None:
+                    b = torch.cuda.Event(enable_timing=True); b.record(main)
+                    self.fused.PROFILE.setdefault("wait_exchange", []).append((a, b))
                 waiting = False
             # pass B: boundary particles; its list kernel also carries over every not-fired row and writes the static mask bits
-            check(lib.sphnca_step_fwd_fired(g, ptr(fire_b), pA, *pargs, 1, *targs, pAn, *oargs))
+            timed("pass_B", lib.sphnca_step_fwd_fired, g, ptr(fire_b), pA, *pargs, ptr(self.bnd_s), 1, self.n_bnd, *targs, pAn, *oargs)
             # exchange of the NEW state's boundary rows into the neighbours' halo slots
             if self.comm_stream is not None:
                 ready.record(main)
@@ -500,7 +507,7 @@ class SlabShardedNCA:
                     done.record(self.comm_stream)
                 waiting = True
             # pass I: interior particles (a second list over the same step: no carry-over, no flag writes)
-            check(lib.sphnca_step_fwd_fired(g, ptr(fire_i), pA, *pargs, 0, *targs, pAn, *oargs))
+            timed("pass_I", lib.sphnca_step_fwd_fired, g, ptr(fire_i), pA, *pargs, ptr(self.int_s), 0, 0, *targs, pAn, *oargs)
             if self.comm_stream is None:
                 nbytes += self._exchange_state(An_s, dev)                   # blocking variant (overlap=False) / no-op on one rank
             A_s, An_s, pA, pAn = An_s, A_s, pAn, pA
