@@ -179,3 +179,28 @@ def test_periodic_grid_is_refused_where_it_is_not_implemented():
     assert torch.isfinite(v).all()
     with pytest.raises(SphncaError):
         sphops.count(x, 0.4, grid)                           # not implemented for periodic grids
+
+
+@pytest.mark.gpu
+def test_periodic_rollout_microbatched_over_sections_equals_whole_batch():
+    """A periodic grid cut into micro-batches of sections (Hashgrid.subgrid carries the period, the ghost-copy band and its slice of
+    the ghost volumes): states bit-identical to the whole-batch periodic rollout."""
+    import nca
+    import sphops
+    g = load_golden("wrapped_periodic_k3")
+    m = _model(g, update_rule="gated", use_alpha=False, normalize_perception=float(g["normalize_perception"]))
+    x = torch.nn.functional.pad(torch.from_numpy(g["x"]), (0, 1)).to(DEV)
+    A0 = torch.from_numpy(g["A0"]).to(DEV)
+    sections = tuple(int(s) for s in g["sections"])
+    h = float(g["h"])
+    band = ((-1.0 + h, -1.0 + h), (1.0 - h, 1.0 - h))
+    outs = []
+    for mb in (None, 1):
+        grid = sphops.initialize_hashgrid(x, sections, h, int(g["dims"])).set_periodic((2.0, 2.0, 0.0), band=band)
+        v = sphops.volume(x, h, grid)
+        torch.manual_seed(3)
+        with torch.no_grad():
+            out = m.rollout(x, v, A0, h, grid, 3, microbatch=mb)
+        outs.append([out[k].clone() for k in range(4)])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
