@@ -186,6 +186,14 @@ int32_t sphnca_stage_fit(const sphnca_grid* g, int32_t* counts, void* stream);
 int32_t sphnca_pairs_count(const sphnca_grid* g, const float* xv4, int32_t* group_slots, void* stream);
 int32_t sphnca_pairs_fill(const sphnca_grid* g, const float* xv4, const int32_t* group_slots, const int64_t* group_base,
                           int32_t* J, float* WP, float* WB, float* WA, float* SXY, uint8_t* FLG, float* WPZ, void* stream);
+/* Life mask of a model WITH an alpha channel from the pair lists: the F = 1 blur of nca.py:71-79 alone (12 list bytes + one alive
+ * byte per neighbour), so that the 16-channel perception can run over the fired rows only.  mode 0: flags_s = bit 0 (previous
+ * mask; alive_in = alive bytes of the current state).  mode 1: flags_s |= bit 1 (new mask; alive_in = alive bytes of the unmasked
+ * new state), A_new_s rows with !(prev & new) are multiplied by 0, alive_out (optional) = alive bytes of the masked new state.
+ * Bit-identical to the masks of sphnca_step_perceive_pairs / sphnca_step_mask. */
+int32_t sphnca_step_mask_pairs(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
+                               const float* WB, const uint8_t* alive_in, int32_t mode, uint8_t* flags_s, float* A_new_s,
+                               uint8_t* alive_out, void* stream);
 /* Perception in a per-particle tangent frame (surface clouds: reference nca.py:325-336 `project_tangent_space` applied to the
  * gradient of every channel, then `[..., 0]` and `[..., 1]` kept by the default feature process): Y_s = [A-gradient along T_i |
  * along B_i], frame_s [N][8] = {T_i, 0, B_i = N_i x T_i, 0} in cell-sorted order.  The projection is applied to the pair weights
@@ -247,8 +255,8 @@ int32_t sphnca_step_adjoint(const sphnca_grid* g, const float* xv4, const float*
  *                           copies A_c [N,16], Y_c [N,32] (contiguous input of sphnca_mlp_wgrad_list) are indexed by
  *                           list position; A_new_s, alive_s, flags_s by particle.  inputs_by_list != 0: A_s / Y_s are
  *                           such compact arrays already (written by sphnca_step_perceive_pairs_fired), A_c = Y_c = NULL.
- *   sphnca_step_perceive_pairs_fired  the perception sweep for the listed particles only (no alpha channel: the
- *                           perception vector feeds nothing but the MLP); writes Y_c and the compact state rows A_c by
+ *   sphnca_step_perceive_pairs_fired  the perception sweep for the listed particles only (the perception vector feeds nothing
+ *                           but the MLP; with an alpha channel the life mask comes from sphnca_step_mask_pairs); writes Y_c and the compact state rows A_c by
  *                           list position, bit-identical to the rows of the full sweep.  sphnca_fire_list's FLG / flags_s
  *                           pair (optional, both or neither) copies the static life-mask bit of every row meanwhile.
  *   sphnca_step_bwd_list    sphnca_step_bwd over the listed rows (dO_c by list position, dY_s / dAdir_s by particle);

@@ -178,6 +178,48 @@ step_perceive_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, c
     if (part == 0) flags_s[p] = ALPHA ? (blur * c.cw > 0.1f ? 1 : 0) : FLG[p];
 }
 
+// Life mask from the pair lists (models with an alpha channel): blur_i = cw * sum_j alive_j v_j (h^2 - d_ij^2)^3 > 0.1 over the
+// list (J, WB = {v_j, (h^2 - d^2)^3}), one thread per particle -- the F = 1 blur of reference nca.py:71-79 without its 16-channel
+// company: 12 list bytes + one byte gather per neighbour.  Same terms in the same order as the blur inside
+// step_perceive_pairs_kernel<true> and as step_mask_kernel: bit-identical masks.
+//   MODE 0  previous mask of a step: alive_in = alive bytes of the CURRENT state; flags_s = bit 0.
+//   MODE 1  new mask of a step: alive_in = alive bytes of the unmasked NEW state; flags_s |= bit 1; rows that are not living
+//           (prev & new) are multiplied by 0; alive_out = alive bytes of the masked new state (the next step's MODE 0 input).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+step_mask_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, const int64_t* __restrict__ group_base,
+                       const int32_t* __restrict__ J, const float2* __restrict__ WB, const uint8_t* __restrict__ alive_in, float cw,
+                       uint8_t* __restrict__ flags_s, float* __restrict__ An_s, uint8_t* __restrict__ alive_out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int64_t grp = p >> 3;
+    const int slots = group_slots[grp];
+    int64_t e = group_base[grp] + (p & 7);
+    float blur = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < slots; ++s, e += PG) {
+        const int j = __ldcs(J + e);
+        const float2 wb = __ldcs(WB + e);
+        const float alive = __ldg(alive_in + j) ? 1.f : 0.f;
+        blur = fmaf(alive * wb.x, wb.y, blur);
+    }
+    const bool on = blur * cw > 0.1f;
+    if (MODE == 0) {
+        flags_s[p] = on ? 1 : 0;
+    } else {
+        uint8_t fl = flags_s[p];
+        if (on) fl |= 2;
+        flags_s[p] = fl;
+        const bool living = (fl & 1) && on;
+        if (!living) {
+            float4* a4 = reinterpret_cast<float4*>(An_s + (size_t)p * NF);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { float4 t = a4[k]; a4[k] = make_float4(t.x * 0.f, t.y * 0.f, t.z * 0.f, t.w * 0.f); }
+        }
+        if (alive_out != nullptr) alive_out[p] = living ? alive_in[p] : (uint8_t)0;
+    }
+}
+
 // Perception in a per-particle TANGENT FRAME (surface point clouds, reference nca.py:325-336,364: `feature_process_tangent` projects the
 // 3-D gradient of every channel onto (T_i, B_i = N_i x T_i) after the sweep): the projection is linear, so it is applied to the pair
 // WEIGHT instead -- w_t = w . T_i, w_b = w . B_i, 6 FMAs per pair in the lane that loaded the entry -- and the sweep itself is the
@@ -413,6 +455,23 @@ int32_t sphnca_step_perceive_pairs(const sphnca_grid* g, const int32_t* group_sl
     return SPHNCA_OK;
 }
 
+int32_t sphnca_step_mask_pairs(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
+                               const float* WB, const uint8_t* alive_in, int32_t mode, uint8_t* flags_s, float* A_new_s,
+                               uint8_t* alive_out, void* stream_) {
+    GridView gv; { int rc = make_view(g, &gv, true); if (rc) return rc; }
+    if (gv.n == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(group_slots && group_base && J && WB && alive_in && flags_s, "NULL argument");
+    SPHNCA_CHECK_ARG(mode == 0 || (mode == 1 && A_new_s != nullptr), "mode 0 (previous mask) or 1 (new mask: needs A_new_s)");
+    const float cw = (float)poly6_norm(g->dim, g->h);
+    const int blocks = (int)((gv.n + 255) / 256);
+    if (mode == 0) SPHNCA_LAUNCH(step_mask_pairs_kernel<0>, blocks, 256, 0, as_stream(stream_), gv.n, group_slots, group_base, J, (const float2*)WB,
+                                 alive_in, cw, flags_s, A_new_s, alive_out);
+    else SPHNCA_LAUNCH(step_mask_pairs_kernel<1>, blocks, 256, 0, as_stream(stream_), gv.n, group_slots, group_base, J, (const float2*)WB,
+                       alive_in, cw, flags_s, A_new_s, alive_out);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
 int32_t sphnca_step_perceive_pairs_frame(const sphnca_grid* g, const int32_t* group_slots, const int64_t* group_base, const int32_t* J,
                                          const float* WP, const float* WPZ, const float* WB, const uint8_t* FLG, const float* frame_s,
                                          const float* A_s, const sphnca_step_params* p, float* Y_s, uint8_t* flags_s, void* stream_) {
@@ -438,7 +497,7 @@ int32_t sphnca_step_perceive_pairs_fired(const sphnca_grid* g, const int32_t* ro
     StepConsts c; { int rc = make_consts(g, p, &c); if (rc) return rc; }
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(rows && count && group_slots && group_base && J && WP && A_s && Y_c && A_c, "NULL argument");
-    SPHNCA_CHECK_ARG(!p->use_alpha, "the fired-rows sweep has no life-mask part: use sphnca_step_perceive_pairs with an alpha channel");
+    // (with an alpha channel the previous life mask must come from sphnca_step_mask_pairs: this sweep has no mask part)
     const int blocks = (int)((gv.n + 31) / 32);           // sized for all N particles; warps past *count exit at once
     SPHNCA_LAUNCH(step_perceive_pairs_fired_kernel, blocks, 128, 0, as_stream(stream_), rows, count, group_slots, group_base, J,
                   (const float2*)WP, A_s, c, Y_c, A_c);

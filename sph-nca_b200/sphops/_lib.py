@@ -70,6 +70,7 @@ def _load():
         "sphnca_stage_fit": ([G, P, P], I32),
         "sphnca_pairs_count": ([G, P, P, P], I32),
         "sphnca_pairs_fill": ([G, P, P, P, P, P, P, P, P, P, P, P], I32),
+        "sphnca_step_mask_pairs": ([G, P, P, P, P, P, I32, P, P, P, P], I32),
         "sphnca_step_perceive_pairs_frame": ([G, P, P, P, P, P, P, P, P, P, SP, P, P, P], I32),
         "sphnca_step_perceive_pairs": ([G, P, P, P, P, P, P, P, SP, P, P, P], I32),
         "sphnca_step_adjoint_pairs": ([G, P, P, P, P, P, P, P, P, SP, P, P], I32),

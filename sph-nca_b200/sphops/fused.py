@@ -234,7 +234,12 @@ class _FireBuffers:
         return self
 
 
-def _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, alive_s, fb, ws_fl, st, pl=False, draw=None):
+# With an alpha channel: the two life masks of a step from their own light list sweeps (sphnca_step_mask_pairs) and the 16-channel
+# perception over the fired rows only, instead of the full perception sweep (+ blur) over all rows and the cell-sweep mask.
+ALPHA_MASK_LISTS = __import__("os").environ.get("SPHNCA_ALPHA_MASK_LISTS", "1") != "0"
+
+
+def _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, alive_s, fb, ws_fl, st, pl=False, draw=None, alive_io=None):
     """One forward step on the fire-list path: list + carried-over rows, perception sweep, MLP over the list, life mask.
     Without an alpha channel and with pair lists the perception sweep itself runs over the fired particles only and writes the
     compact [A_c | Y_c] rows the MLP kernel reads (needs fb.A_c / fb.Y_c); otherwise the full sweep fills Y_s.
@@ -244,6 +249,25 @@ def _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, al
     N = S.shape[0]
     if pl is False:
         pl = grid.pair_lists(x, v, blur=bool(use_alpha))
+    if use_alpha and ALPHA_MASK_LISTS and pl is not None and pl["WB"] is not None and fb.A_c is not None \
+            and "sphnca_step_mask_pairs" not in _lib.MISSING_SYMBOLS:
+        # alive_io = (alive bytes of S, buffer for the alive bytes of the masked new state): chained by the forward loop; a lone
+        # step (recompute in the backward) derives the former from the state
+        alive_cur, alive_next = alive_io if alive_io is not None else ((S[:, 3] > 0.1).view(torch.uint8).contiguous(), None)
+        lists = (ptr(pl["slots"]), ptr(pl["base"]), ptr(pl["J"]))
+        _timed("step_mask", lib.sphnca_step_mask_pairs, g, *lists, ptr(pl["WB"]), ptr(alive_cur), 0, ptr(fb.flags), None, None, st)
+        if draw is not None:
+            _timed("fire_list", lib.sphnca_fire_list_draw, g, ptr(draw[0]), float(draw[1]), ptr(fire_s), ptr(S), 1, ptr(fb.rows), ptr(fb.count),
+                   ptr(Sn), ptr(alive_s), None, None, 0, ptr(ws_fl), ws_fl.numel(), st)
+        else:
+            _timed("fire_list", lib.sphnca_fire_list, N, ptr(fire_s), ptr(S), 1, ptr(fb.rows), ptr(fb.count), ptr(Sn), ptr(alive_s), None, None, 0,
+                   ptr(ws_fl), ws_fl.numel(), st)
+        _timed("step_perceive", lib.sphnca_step_perceive_pairs_fired, g, ptr(fb.rows), ptr(fb.count), *lists, ptr(pl["WP"]), ptr(S), C.byref(p),
+               ptr(fb.Y_c), ptr(fb.A_c), st)
+        _timed("step_mlp", lib.sphnca_step_mlp_list, N, ptr(fb.rows), ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), C.byref(p), ptr(Sn), ptr(alive_s),
+               ptr(fb.O_c), ptr(fb.flags), ptr(fb.relu_c), None, None, 1, st)
+        _timed("step_mask", lib.sphnca_step_mask_pairs, g, *lists, ptr(pl["WB"]), ptr(alive_s), 1, ptr(fb.flags), ptr(Sn), ptr(alive_next), st)
+        return
     fired_sweep = pl is not None and not use_alpha and fb.A_c is not None
     fold = fired_sweep
     flg, flags = (ptr(pl["FLG"]), ptr(fb.flags)) if fired_sweep else (None, None)
@@ -336,6 +360,7 @@ class _NCARollout(torch.autograd.Function):
             ws_fl = _fire_list_workspace(N, dev)
             Y_s = torch.empty((N, 32), **f32)                 # perception of the current step: scratch, the tape keeps Y_c
         fire_s = None
+        alive_cur = None
         for _ in range(steps):
             u = _draw(N, dev, fire_index)                     # the reference's draw (nca.py:100), one call per step
             if u.dtype != torch.float32 or not u.is_contiguous():
@@ -348,8 +373,15 @@ class _NCARollout(torch.autograd.Function):
                     fbuf = _FireBuffers(N, dev, compact_inputs=True)
                 if taped == 2 or fire_s is None:
                     fire_s = torch.empty((N,), **u8)
+                alive_io = None
+                if use_alpha:                                 # alive bytes of the state chained from step to step (mask list sweeps)
+                    if alive_cur is None:
+                        alive_cur = (S[:, 3] > 0.1).view(torch.uint8).contiguous()
+                    alive_io = (alive_cur, torch.empty((N,), **u8))
                 _step_forward_lists(grid, x, v, g, xv4, S, fire_s, p, use_alpha, Y_s, Sn, alive_s, fbuf, ws_fl, st,
-                                    draw=(u, fire_rate))
+                                    draw=(u, fire_rate), alive_io=alive_io)
+                if use_alpha:
+                    alive_cur = alive_io[1]
                 if taped == 1:
                     saved += fbuf.tensors()
                     if TAPE_PROBE is not None:
