@@ -210,7 +210,7 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 for (int ks = 0; ks < 128 / 8; ++ks) {
                     const uint64_t b = make_smem_desc(w + chunk_off(2 * NIN, 0, 2 * ks), 2 * NIN * 16, 128);
                     if (half == 0 && ks == 0) mma_tf32_ts_e(tbase + COL_DY, tbase + COL_DHLO, b, idesc4c, false, go);
-                    else mma_tf32_ts_e(tbase + COL_DY, tbase + COL_DHLO + 8 * ks, b, idesc4, true, go);         // dH_lo . W_hi
+                    else mma_tf32_ts_e(tbase + COL_DY + NIN, tbase + COL_DHLO + 8 * ks, b, idesc4, true, go);   // dH_lo . W_hi -> second group (see step_mlp_tc.cu)
                 }
                 mma_commit_e(&s.bar[DH_EMPTY], go);                                                             // dH_lo region free again
 #pragma unroll

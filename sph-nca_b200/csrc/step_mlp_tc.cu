@@ -195,7 +195,9 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 for (int ks = 0; ks < 128 / 8; ++ks) {
                     const uint64_t b = make_smem_desc(w + chunk_off(2 * N2, 0, 2 * ks), 2 * N2 * 16, 128);
                     if (half == 0 && ks == 0) mma_tf32_ts_e(d2, tbase + COL_HLO, b, idesc2c, false, go);
-                    else mma_tf32_ts_e(d2, tbase + COL_HLO + 8 * ks, b, idesc2, true, go);              // H_lo . W_hi
+                    // H_lo . W_hi goes to the SECOND column group (with H_hi . W_lo): the first group then accumulates the large
+                    // H_hi . W_hi terms only -- half as many adds in the chain whose TRUNCATING fp32 accumulation biases the result
+                    else mma_tf32_ts_e(d2 + N2, tbase + COL_HLO + 8 * ks, b, idesc2, true, go);
                 }
                 mma_commit_e(&s.bar[H_EMPTY], go);                                                      // H_lo region free again
 #pragma unroll

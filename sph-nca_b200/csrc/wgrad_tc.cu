@@ -318,9 +318,10 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                     const uint64_t o_t = make_smem_desc(smem_u32(s.dOT) + chunk_off(2 * NOUT, 0, 2 * ks), 2 * NOUT * 16, 128);
                     const bool acc = !(fresh && ks == 0);
                     mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_R3 + 8 * ks, y_t, idA1c, acc, go);      // dH_hi . [y_hi ; y_lo]
-                    mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_DHLO + 8 * ks, y_t, idA1, true, go);    // dH_lo . y_hi
+                    mma_tf32_ts_e(tbase + COL_ACC1 + NY, tbase + COL_DHLO + 8 * ks, y_t, idA1, true, go);   // dH_lo . y_hi -> second group: the first one
+                                                                                                           // holds the large hi . hi terms only (half the truncating adds)
                     mma_tf32_ts_e(tbase + COL_ACC2, tbase + COL_R1 + 8 * ks, o_t, idA2c, acc, go);      // H_hi . [dO_hi ; dO_lo]
-                    mma_tf32_ts_e(tbase + COL_ACC2, tbase + COL_HLO + 8 * ks, o_t, idA2, true, go);     // H_lo . dO_hi
+                    mma_tf32_ts_e(tbase + COL_ACC2 + NOUT, tbase + COL_HLO + 8 * ks, o_t, idA2, true, go);  // H_lo . dO_hi -> second group
                 }
                 mma_commit_e(&s.bar[T_EMPTY], go);
                 SPHNCA_TL(8);
