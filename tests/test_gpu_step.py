@@ -889,3 +889,39 @@ def test_microbatch_plan_follows_memory(monkeypatch):
     assert fused.plan_microbatches(grid, 8, False, x.device, 2, 3) == [(0, 3), (3, 4)]
     monkeypatch.setattr(fused, "MICROBATCH", None)
     assert fused.plan_microbatches(grid, 8, False, x.device, 2, None) is None
+
+
+@pytest.mark.parametrize("use_alpha", [False, True], ids=["noalpha", "alpha"])
+def test_microbatched_rollout_with_empty_and_tiny_sections(use_alpha):
+    """Micro-batches whose groups hold an empty section, a 1-particle section and a section that is not a multiple of the list
+    group size: forward states and gradients equal the whole-batch node (bitwise states / dL/dA0)."""
+    import nca
+    gen = torch.Generator().manual_seed(8)
+    x = torch.nn.functional.pad(jittered_lattice(40, 2, gen), (0, 1))
+    N = x.shape[0]
+    sections = (0, 1, 613, 0, N - 614)
+    h = 3.2 * 2 / 40
+    dims = math.ceil(2 / h)
+    w = load_golden("weights_gecko" if use_alpha else "weights_zebra")
+    nca.USE_FUSED_STEP = True
+    m = nca.SPHNCA(16, 0.5, use_alpha=use_alpha, normalize_perception=1.0 / h).to(DEV)
+    with torch.no_grad():
+        for t, k in zip((m.model[0].weight, m.model[0].bias, m.model[2].weight, m.model[2].bias), ("W1", "b1", "W2", "b2")):
+            t.copy_(torch.from_numpy(w[k]))
+    A0 = (0.3 + 0.7 * torch.rand(N, 16, generator=gen))
+    masks = torch.rand(3, N, generator=gen) <= 0.5
+    xd = x.to(DEV)
+    res = []
+    for mb in (None, 2):
+        m.zero_grad()
+        grid, v = m.init_grid(xd, sections, h, dims)
+        A = A0.to(DEV).requires_grad_(True)
+        with forced_fire_masks(list(masks)):
+            out = m.rollout(xd, v, A, h, grid, 3, checkpoint=True, microbatch=mb)
+        (out[-1][:, :4] ** 2).mean().backward()
+        res.append(([out[k].detach().clone() for k in range(4)], A.grad.clone(), [p.grad.clone() for p in m.parameters()]))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    assert torch.equal(res[0][1], res[1][1])
+    for a, b, nm in zip(res[0][2], res[1][2], ("dW1", "db1", "dW2", "db2")):
+        assert_close(b, a, rtol=GRAD_RTOL, what=nm)

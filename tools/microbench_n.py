@@ -18,7 +18,7 @@ def timeit(fn, reps=20):
     for _ in range(reps): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
-for N in (1024, 32768, 131072, 262144, 524288):
+for N in (128, 1024, 18944, 32768, 131072, 262144, 524288):
     f32 = dict(dtype=torch.float32, device=dev)
     A = torch.rand(N, 16, **f32); Y = torch.randn(N, 32, **f32); O = torch.randn(N, 36, **f32); dO = torch.randn(N, 36, **f32) * 1e-3
     An = torch.empty(N, 16, **f32); dAn = torch.randn(N, 16, **f32); dY = torch.empty(N, 32, **f32); dAd = torch.empty(N, 16, **f32)
