@@ -124,6 +124,10 @@ def main():
                 draws.append(u.detach().cpu())
                 return u
             model.zero_grad(set_to_none=True)
+            with torch.no_grad():       # the timed iterations above were TRAINING iterations (Adam updated the weights): start over
+                for t, src in zip((model.model[0].weight, model.model[0].bias, model.model[2].weight, model.model[2].bias),
+                                  bench.load_weights("gecko" if use_alpha else "zebra")):
+                    t.copy_(src)
             A0 = A_dev.clone().requires_grad_(True)
             torch.rand = rec
             try:
@@ -136,10 +140,15 @@ def main():
                 torch.rand = orig_rand
             loss = bench.bench_loss(xp, A, None)
             loss.backward()
+            with torch.no_grad():       # the two stages of the first step on their own: the sphops gradient op, the torch MLP on top of it
+                gA0 = sphops.gradient(xp, v, A_dev, h, grid)
+                y0 = model.base_feature_process(model.perceive(xp, v, A_dev, h, grid))
+                mlp0 = model.model(y0)
             P = dict(model.named_parameters())
             np.savez_compressed(args.dump, x=xp.cpu().numpy(), A0=A_cpu.numpy(), v=v.cpu().numpy(), h=h, dims=dims,
                                 sections=np.asarray(sections), masks=np.stack([(u <= 0.5).numpy() for u in draws]),
                                 states=np.stack(states), loss=float(loss), dA0=A0.grad.cpu().numpy(),
+                                gA0=gA0.cpu().numpy(), y0=y0.cpu().numpy(), mlp0=mlp0.cpu().numpy(),
                                 dW1=P["model.0.weight"].grad.cpu().numpy(), db1=P["model.0.bias"].grad.cpu().numpy(),
                                 dW2=P["model.2.weight"].grad.cpu().numpy(), db2=P["model.2.bias"].grad.cpu().numpy())
             out["dump"] = args.dump
