@@ -73,18 +73,31 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
 
     const int n_mma = c.n_out < KO ? c.n_out : KO;
     // W2 [o][h] -> W2t[half] (rows h, K = o)
-    stage_batched<8>(KO * NH, tid, THREADS, [&](int i) { return i / NH < n_mma ? __ldg(prm.W2 + i) : 0.f; }, [&](int i, float w) {
-        const int o_ = i / NH, h = i - o_ * NH;
-        float hi, lo; split_tf32(w, hi, lo);
-        const uint32_t o = fidx(128, h & 127, o_);
-        s.W2t_hi[h >> 7][o] = hi; s.W2t_lo[h >> 7][o] = lo;
-    });
-    // W1 [h][k] -> W1t[half] (rows k, K = h)
-    stage_batched<8>(NH * NIN, tid, THREADS, [&](int i) { return __ldg(prm.W1 + i); }, [&](int i, float w) {
-        const int h = i / NIN, k = i - h * NIN;
-        float hi, lo; split_tf32(w, hi, lo);
-        s.W1t[h >> 7][fidx(2 * NIN, k, h & 127)] = hi; s.W1t[h >> 7][fidx(2 * NIN, NIN + k, h & 127)] = lo;
-    });
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        // W2 [o][h] -> W2t_hi / W2t_lo [half]: rows = h, K = o (4 global rows per chunk, consecutive lanes along h)
+        stage_chunks<2>(128 * (KO / 4), tid, THREADS, [&](int idx) {
+            int row, ck; stage_map(idx, 128 / 8, row, ck);
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = 4 * ck + e < n_mma ? __ldg(prm.W2 + (size_t)(4 * ck + e) * NH + half * 128 + row) : 0.f;
+            return make_float4(v[0], v[1], v[2], v[3]);
+        }, [&](int idx, float4 hi, float4 lo) {
+            int row, ck; stage_map(idx, 128 / 8, row, ck);
+            const uint32_t o = chunk_off(128, row, ck) / 4;
+            *reinterpret_cast<float4*>(&s.W2t_hi[half][o]) = hi; *reinterpret_cast<float4*>(&s.W2t_lo[half][o]) = lo;
+        });
+        // W1 [h][k] -> W1t[half]: rows 0..47 = k hi, 48..95 = k lo, K = h within the half
+        stage_chunks<3>(NIN * (128 / 4), tid, THREADS, [&](int idx) {
+            int row, ck; stage_map(idx, NIN / 8, row, ck);
+            const float* w = prm.W1 + (size_t)(half * 128 + 4 * ck) * NIN + row;
+            return make_float4(__ldg(w), __ldg(w + NIN), __ldg(w + 2 * NIN), __ldg(w + 3 * NIN));
+        }, [&](int idx, float4 hi, float4 lo) {
+            int row, ck; stage_map(idx, NIN / 8, row, ck);
+            *reinterpret_cast<float4*>(&s.W1t[half][chunk_off(2 * NIN, row, ck) / 4]) = hi;
+            *reinterpret_cast<float4*>(&s.W1t[half][chunk_off(2 * NIN, NIN + row, ck) / 4]) = lo;
+        });
+    }
     for (int i = tid; i < NH; i += THREADS) s.w2_last[i] = c.n_out > KO ? __ldg(prm.W2 + (size_t)KO * NH + i) : 0.f;
     if (tid == 0) {
         mbar_init(&s.bar[DO_FULL], LOAD_WARPS * 32); mbar_init(&s.bar[DO_EMPTY], 1);
@@ -185,16 +198,17 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
         {   // warp-uniform issue: every lane runs the loop, one elected lane issues (tc_common.cuh)
             const uint32_t go = elect_one();
             const uint32_t idesc3 = make_idesc_tf32(TILE, 128), idesc4 = make_idesc_tf32(TILE, NIN), idesc4c = make_idesc_tf32(TILE, 2 * NIN);
-            const uint32_t ah = smem_u32(s.dO_hi), al = smem_u32(s.dO_lo);
+            // base descriptors, built once (desc_advance, tc_common.cuh)
+            const uint64_t dOh = make_smem_desc(smem_u32(s.dO_hi), TILE * 16, 128), dOl = make_smem_desc(smem_u32(s.dO_lo), TILE * 16, 128);
+            const uint64_t dW2h[2] = {make_smem_desc(smem_u32(s.W2t_hi[0]), 128 * 16, 128), make_smem_desc(smem_u32(s.W2t_hi[1]), 128 * 16, 128)};
+            const uint64_t dW2l[2] = {make_smem_desc(smem_u32(s.W2t_lo[0]), 128 * 16, 128), make_smem_desc(smem_u32(s.W2t_lo[1]), 128 * 16, 128)};
+            const uint64_t dW1t[2] = {make_smem_desc(smem_u32(s.W1t[0]), 2 * NIN * 16, 128), make_smem_desc(smem_u32(s.W1t[1]), 2 * NIN * 16, 128)};
             auto gemm3 = [&](const int half) {
-                const uint32_t wh = smem_u32(s.W2t_hi[half]), wl = smem_u32(s.W2t_lo[half]);
                 const uint32_t d3 = tbase + (half ? COL_DB : COL_DA);
 #pragma unroll
                 for (int ks = 0; ks < KO / 8; ++ks) {
-                    const uint64_t a_hi = make_smem_desc(ah + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
-                    const uint64_t a_lo = make_smem_desc(al + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
-                    const uint64_t b_hi = make_smem_desc(wh + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                    const uint64_t b_lo = make_smem_desc(wl + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
+                    const uint64_t a_hi = desc_advance(dOh, chunk_off(TILE, 0, 2 * ks)), a_lo = desc_advance(dOl, chunk_off(TILE, 0, 2 * ks));
+                    const uint64_t b_hi = desc_advance(dW2h[half], chunk_off(128, 0, 2 * ks)), b_lo = desc_advance(dW2l[half], chunk_off(128, 0, 2 * ks));
                     mma_tf32_ss_e(d3, a_lo, b_hi, idesc3, ks > 0, go);
                     mma_tf32_ss_e(d3, a_hi, b_lo, idesc3, true, go);
                     mma_tf32_ss_e(d3, a_hi, b_hi, idesc3, true, go);
@@ -202,20 +216,19 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 mma_commit_e(&s.bar[D3_FULL + half], go);
             };
             auto gemm4 = [&](const int half) {
-                const uint32_t w = smem_u32(s.W1t[half]);
                 const uint32_t dhhi = tbase + (half ? COL_DB : COL_DA);
                 // rows 0..47 of a W1^T tile = hi, all 96 rows = the stacked [hi ; lo] tile.  dH_lo part first; the very first
                 // MMA of a tile initialises all 96 Dy columns (its extra dH_lo . W_lo block is the term the split drops anyway)
 #pragma unroll
                 for (int ks = 0; ks < 128 / 8; ++ks) {
-                    const uint64_t b = make_smem_desc(w + chunk_off(2 * NIN, 0, 2 * ks), 2 * NIN * 16, 128);
+                    const uint64_t b = desc_advance(dW1t[half], chunk_off(2 * NIN, 0, 2 * ks));
                     if (half == 0 && ks == 0) mma_tf32_ts_e(tbase + COL_DY, tbase + COL_DHLO, b, idesc4c, false, go);
                     else mma_tf32_ts_e(tbase + COL_DY + NIN, tbase + COL_DHLO + 8 * ks, b, idesc4, true, go);   // dH_lo . W_hi -> second group (see step_mlp_tc.cu)
                 }
                 mma_commit_e(&s.bar[DH_EMPTY], go);                                                             // dH_lo region free again
 #pragma unroll
                 for (int ks = 0; ks < 128 / 8; ++ks) {
-                    const uint64_t b = make_smem_desc(w + chunk_off(2 * NIN, 0, 2 * ks), 2 * NIN * 16, 128);
+                    const uint64_t b = desc_advance(dW1t[half], chunk_off(2 * NIN, 0, 2 * ks));
                     mma_tf32_ts_e(tbase + COL_DY, dhhi + 8 * ks, b, idesc4c, true, go);                         // dH_hi . [W_hi ; W_lo]
                 }
             };

@@ -37,7 +37,7 @@ __device__ __forceinline__ void load16(const float* __restrict__ p, float (&o)[N
 inline int make_consts(const sphnca_grid* g, const sphnca_step_params* p, StepConsts* c) {
     if (!p || !p->W1 || !p->b1 || !p->W2 || !p->b2) { set_error("step params / weights are NULL"); return SPHNCA_ERR_INVALID; }
     if (p->update_rule != 0 && p->update_rule != 1) { set_error("update_rule must be 0 (gated) or 1 (orig)"); return SPHNCA_ERR_INVALID; }
-    if (((uintptr_t)p->W1 & 15) != 0) { set_error("W1 must be 16-byte aligned"); return SPHNCA_ERR_INVALID; }
+    if ((((uintptr_t)p->W1 | (uintptr_t)p->W2) & 15) != 0) { set_error("W1 and W2 must be 16-byte aligned"); return SPHNCA_ERR_INVALID; }
     c->h = (float)g->h; c->h2 = (float)(g->h * g->h);
     c->cw = (float)poly6_norm(g->dim, g->h);
     c->kg = (float)(spiky_norm(g->dim, g->h) * (double)p->perception_scale);

@@ -41,6 +41,7 @@ struct Smem {
     float Y_hi[TILE * NIN], Y_lo[TILE * NIN];
     float b1[NH], w2_last[NH], b2[NO_PAD];
     float o32[2][2][TILE];              // [slot][column-half group] partial scalar-gate sums
+    float ostage[FIN_WARPS][16 * NO_PAD];  // finalizer: 16 output rows per warp on their way to a coalesced store
     uint64_t bar[NUM_BARS];
     uint32_t tmem_base;
 };
@@ -84,24 +85,62 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    SPHNCA_TL_PHASE(0);
 
-    stage_batched<8>(NH * NIN, tid, THREADS, [&](int i) { return __ldg(prm.W1 + i); }, [&](int i, float w) {
-        const int n = i / NIN, k = i - n * NIN;
-        float hi, lo; split_tf32(w, hi, lo);
-        const uint32_t o = fidx(128, n & 127, k);
-        s.W1_hi[n >> 7][o] = hi; s.W1_lo[n >> 7][o] = lo;
-    });
+    // Loader warps: lane mapping and the row loads of a tile (see the loader role below).  The loads of the CTA's FIRST tile are
+    // issued here, in front of the weight staging, so that their global-memory latency runs beside it.
+    const bool is_loader = warp >= LOAD_WARP0 && warp < FIN_WARP0;
+    const int lw = warp - LOAD_WARP0, r8 = lane & 7, c4 = lane >> 3;
+    float4 v[NIN / 4];                                        // [3 * g + {0: A chunk c4, 1: Y chunk c4, 2: Y chunk 4 + c4}], row 32 lw + 8 g + r8
+    auto load_rows = [&](const int tile) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int j = tile * TILE + 32 * lw + 8 * g + r8;
+            if (j < n_total) {
+                const int p = (rows && !in_by_list) ? __ldg(rows + j) : j;
+                const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)p * NF);
+                const float4* y4 = reinterpret_cast<const float4*>(Y_s + (size_t)p * 2 * NF);
+                v[3 * g] = __ldg(a4 + c4); v[3 * g + 1] = __ldg(y4 + c4); v[3 * g + 2] = __ldg(y4 + 4 + c4);
+                if (A_c != nullptr) {                         // compact copies for the backward
+                    reinterpret_cast<float4*>(A_c + (size_t)j * NF)[c4] = v[3 * g];
+                    float4* yc = reinterpret_cast<float4*>(Y_c + (size_t)j * 2 * NF);
+                    yc[c4] = v[3 * g + 1]; yc[4 + c4] = v[3 * g + 2];
+                }
+            } else {
+                v[3 * g] = v[3 * g + 1] = v[3 * g + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    if (is_loader && (int)blockIdx.x < num_tiles) load_rows(blockIdx.x);
+
     const int n_mma = c.n_out < N2 ? c.n_out : N2;
-    stage_batched<8>(N2 * NH, tid, THREADS, [&](int i) { return i / NH < n_mma ? __ldg(prm.W2 + i) : 0.f; }, [&](int i, float w) {
-        const int o_ = i / NH, k = i - o_ * NH;
-        float hi, lo; split_tf32(w, hi, lo);
-        s.W2[k >> 7][fidx(2 * N2, o_, k & 127)] = hi; s.W2[k >> 7][fidx(2 * N2, N2 + o_, k & 127)] = lo;
-    });
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        // W1 [h][k] -> W1_hi / W1_lo [half]: rows = h, K = k (contiguous in global memory: one LDG.128 per chunk)
+        stage_chunks<3>(128 * (NIN / 4), tid, THREADS, [&](int idx) {
+            int row, ck; stage_map(idx, 128 / 8, row, ck);
+            return __ldg(reinterpret_cast<const float4*>(prm.W1 + (size_t)(half * 128 + row) * NIN) + ck);
+        }, [&](int idx, float4 hi, float4 lo) {
+            int row, ck; stage_map(idx, 128 / 8, row, ck);
+            const uint32_t o = chunk_off(128, row, ck) / 4;
+            *reinterpret_cast<float4*>(&s.W1_hi[half][o]) = hi; *reinterpret_cast<float4*>(&s.W1_lo[half][o]) = lo;
+        });
+        // W2 [o][h] -> W2[half]: rows 0..31 = o hi, 32..63 = o lo, K = h within the half
+        stage_chunks<2>(N2 * (128 / 4), tid, THREADS, [&](int idx) {
+            int row, ck; stage_map(idx, N2 / 8, row, ck);
+            return row < n_mma ? __ldg(reinterpret_cast<const float4*>(prm.W2 + (size_t)row * NH + half * 128) + ck) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }, [&](int idx, float4 hi, float4 lo) {
+            int row, ck; stage_map(idx, N2 / 8, row, ck);
+            *reinterpret_cast<float4*>(&s.W2[half][chunk_off(2 * N2, row, ck) / 4]) = hi;
+            *reinterpret_cast<float4*>(&s.W2[half][chunk_off(2 * N2, N2 + row, ck) / 4]) = lo;
+        });
+    }
     for (int i = tid; i < NH; i += THREADS) {
         s.b1[i] = __ldg(prm.b1 + i);
         s.w2_last[i] = c.n_out > N2 ? __ldg(prm.W2 + (size_t)N2 * NH + i) : 0.f;
     }
     if (tid < NO_PAD) s.b2[tid] = tid < c.n_out ? __ldg(prm.b2 + tid) : 0.f;
+    SPHNCA_TL_PHASE(1);
     if (tid == 0) {
         mbar_init(&s.bar[Y_FULL], LOAD_WARPS * 32); mbar_init(&s.bar[Y_EMPTY], 1);
         mbar_init(&s.bar[D1_FULL], 1);              mbar_init(&s.bar[D1_FULL1], 1);
@@ -117,49 +156,38 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     __syncthreads();
     fence_after_sync();
     const uint32_t tbase = s.tmem_base;
+    SPHNCA_TL_PHASE(2);
 
-    if (warp >= LOAD_WARP0 && warp < FIN_WARP0) {
+    if (is_loader) {
         // ===================== loader: rows [A | Y] -> tf32 hi/lo A tile, one tile ahead =====================
-        const int m = tid - LOAD_WARP0 * 32;
+        // Lane mapping: a warp owns 32 tile rows; one warp-level LDG.128 fetches 4 consecutive 16-byte chunks of EIGHT rows
+        // (lane = 8 * chunk + row): 64 contiguous bytes per row, 8 lines per instruction.  With a thread per row (12 loads of
+        // 32 different lines each) the loader alone put 1536 L1 wavefronts per tile on the LSU pipe -- which the epilogue's
+        // LDS, the finalizer's stores and the tensor-core issue all share -- against 384 this way.  The shared-memory side is
+        // unchanged: the 8 lanes of a quarter warp write 8 consecutive rows of one K chunk, 128 contiguous bytes.
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int j = tile * TILE + m;
-            float4 v[NIN / 4];
-            if (j < n_total) {
-                const int p = (rows && !in_by_list) ? __ldg(rows + j) : j;
-                const float4* a4 = reinterpret_cast<const float4*>(A_s + (size_t)p * NF);
-                const float4* y4 = reinterpret_cast<const float4*>(Y_s + (size_t)p * 2 * NF);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = __ldg(a4 + k);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[4 + k] = __ldg(y4 + k);
-                if (A_c != nullptr) {                         // compact copies for the backward
-                    float4* ac = reinterpret_cast<float4*>(A_c + (size_t)j * NF);
-                    float4* yc = reinterpret_cast<float4*>(Y_c + (size_t)j * 2 * NF);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) ac[k] = v[k];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) yc[k] = v[4 + k];
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < NIN / 4; ++k) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (m == 0) SPHNCA_TL(12);
+            if (it > 0) load_rows(tile);
+            if (tid == LOAD_WARP0 * 32) SPHNCA_TL(12);
             mbar_wait(&s.bar[Y_EMPTY], (it & 1) ^ 1);
-            if (m == 0) SPHNCA_TL(13);
+            if (tid == LOAD_WARP0 * 32) SPHNCA_TL(13);
 #pragma unroll
-            for (int ch = 0; ch < NIN / 4; ++ch) {
-                float hi[4], lo[4];
-                split_tf32(v[ch].x, hi[0], lo[0]); split_tf32(v[ch].y, hi[1], lo[1]);
-                split_tf32(v[ch].z, hi[2], lo[2]); split_tf32(v[ch].w, hi[3], lo[3]);
-                const uint32_t o = chunk_off(TILE, m, ch) / 4;
-                *reinterpret_cast<float4*>(&s.Y_hi[o]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(&s.Y_lo[o]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            for (int g = 0; g < 4; ++g) {
+                const int m = 32 * lw + 8 * g + r8;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const float4 x = v[3 * g + q];
+                    float hi[4], lo[4];
+                    split_tf32(x.x, hi[0], lo[0]); split_tf32(x.y, hi[1], lo[1]);
+                    split_tf32(x.z, hi[2], lo[2]); split_tf32(x.w, hi[3], lo[3]);
+                    const uint32_t o = chunk_off(TILE, m, (q == 0 ? 0 : 4 * q) + c4) / 4;      // K chunks 0..3 = A, 4..11 = Y
+                    *reinterpret_cast<float4*>(&s.Y_hi[o]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(&s.Y_lo[o]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
             }
             fence_proxy_async_smem();
             mbar_arrive(&s.bar[Y_FULL]);
-            if (m == 0) SPHNCA_TL(0);
+            if (tid == LOAD_WARP0 * 32) SPHNCA_TL(0);
         }
     } else if (warp == MMA_WARP) {
         {   // warp-uniform issue: every lane runs the loop, one elected lane issues (tc_common.cuh)
@@ -170,16 +198,21 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             // H_lo MMAs first and releases the shared H_lo region (H_EMPTY) before its H_hi MMAs.
             const uint32_t go = elect_one();
             const uint32_t idesc1 = make_idesc_tf32(TILE, 128), idesc2 = make_idesc_tf32(TILE, N2), idesc2c = make_idesc_tf32(TILE, 2 * N2);
-            const uint32_t yh = smem_u32(s.Y_hi), yl = smem_u32(s.Y_lo);
+            // base descriptors, built once (desc_advance, tc_common.cuh)
+            const uint64_t dYh = make_smem_desc(smem_u32(s.Y_hi), TILE * 16, 128), dYl = make_smem_desc(smem_u32(s.Y_lo), TILE * 16, 128);
+            const uint64_t dW1h[2] = {make_smem_desc(smem_u32(s.W1_hi[0]), 128 * 16, 128), make_smem_desc(smem_u32(s.W1_hi[1]), 128 * 16, 128)};
+            const uint64_t dW1l[2] = {make_smem_desc(smem_u32(s.W1_lo[0]), 128 * 16, 128), make_smem_desc(smem_u32(s.W1_lo[1]), 128 * 16, 128)};
+            const uint64_t dW2[2] = {make_smem_desc(smem_u32(s.W2[0]), 2 * N2 * 16, 128), make_smem_desc(smem_u32(s.W2[1]), 2 * N2 * 16, 128)};
+            // The issue loops are ROLLED (a few MMAs per iteration): 136 unrolled MMAs are 7 KB of straight-line code that the
+            // MMA warp walks through once per tile, through an instruction cache it shares with four other roles.
             auto gemm1 = [&](const int half) {
-                const uint32_t wh = smem_u32(s.W1_hi[half]), wl = smem_u32(s.W1_lo[half]);
                 const uint32_t d1 = tbase + (half ? COL_DB : COL_DA);
-#pragma unroll
+                const uint64_t wh = dW1h[half], wl = dW1l[half];
+#pragma unroll 1
                 for (int ks = 0; ks < NIN / 8; ++ks) {
-                    const uint64_t a_hi = make_smem_desc(yh + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
-                    const uint64_t a_lo = make_smem_desc(yl + chunk_off(TILE, 0, 2 * ks), TILE * 16, 128);
-                    const uint64_t b_hi = make_smem_desc(wh + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                    const uint64_t b_lo = make_smem_desc(wl + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
+                    const uint32_t oa = chunk_off(TILE, 0, 2) * ks, ob = chunk_off(128, 0, 2) * ks;
+                    const uint64_t a_hi = desc_advance(dYh, oa), a_lo = desc_advance(dYl, oa);
+                    const uint64_t b_hi = desc_advance(wh, ob), b_lo = desc_advance(wl, ob);
                     mma_tf32_ss_e(d1, a_lo, b_hi, idesc1, ks > 0, go);
                     mma_tf32_ss_e(d1, a_hi, b_lo, idesc1, true, go);
                     mma_tf32_ss_e(d1, a_hi, b_hi, idesc1, true, go);
@@ -187,24 +220,21 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 mma_commit_e(&s.bar[D1_FULL + half], go);
             };
             auto gemm2 = [&](const int half, const uint32_t d2) {
-                const uint32_t w = smem_u32(s.W2[half]);
                 const uint32_t hhi = tbase + (half ? COL_DB : COL_DA);
+                const uint64_t w = dW2[half];
                 // rows 0..31 of a W2 tile = hi, all 64 rows = the stacked [hi ; lo] tile.  H_lo part first; the very first MMA of
                 // a tile initialises all 64 columns of the slot (its extra H_lo . W_lo block is the term the split drops anyway)
-#pragma unroll
-                for (int ks = 0; ks < 128 / 8; ++ks) {
-                    const uint64_t b = make_smem_desc(w + chunk_off(2 * N2, 0, 2 * ks), 2 * N2 * 16, 128);
-                    if (half == 0 && ks == 0) mma_tf32_ts_e(d2, tbase + COL_HLO, b, idesc2c, false, go);
+                if (half == 0) mma_tf32_ts_e(d2, tbase + COL_HLO, w, idesc2c, false, go);
+#pragma unroll 1
+                for (int ks = (half == 0 ? 1 : 0); ks < 128 / 8; ++ks) {
                     // H_lo . W_hi goes to the SECOND column group (with H_hi . W_lo): the first group then accumulates the large
                     // H_hi . W_hi terms only -- half as many adds in the chain whose TRUNCATING fp32 accumulation biases the result
-                    else mma_tf32_ts_e(d2 + N2, tbase + COL_HLO + 8 * ks, b, idesc2, true, go);
+                    mma_tf32_ts_e(d2 + N2, tbase + COL_HLO + 8 * ks, desc_advance(w, chunk_off(2 * N2, 0, 2) * ks), idesc2, true, go);
                 }
                 mma_commit_e(&s.bar[H_EMPTY], go);                                                      // H_lo region free again
-#pragma unroll
-                for (int ks = 0; ks < 128 / 8; ++ks) {
-                    const uint64_t b = make_smem_desc(w + chunk_off(2 * N2, 0, 2 * ks), 2 * N2 * 16, 128);
-                    mma_tf32_ts_e(d2, hhi + 8 * ks, b, idesc2c, true, go);                              // H_hi . [W_hi ; W_lo]
-                }
+#pragma unroll 2
+                for (int ks = 0; ks < 128 / 8; ++ks)
+                    mma_tf32_ts_e(d2, hhi + 8 * ks, desc_advance(w, chunk_off(2 * N2, 0, 2) * ks), idesc2c, true, go);   // H_hi . [W_hi ; W_lo]
             };
             int it = 0;
             if (blockIdx.x < num_tiles) {
@@ -313,13 +343,34 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 float4* o4 = reinterpret_cast<float4*>(An_s + (size_t)p * NF);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) o4[k] = make_float4(nA[4 * k], nA[4 * k + 1], nA[4 * k + 2], nA[4 * k + 3]);
-                float4* oo4 = reinterpret_cast<float4*>(O_s + (size_t)j * NO_PAD);
-#pragma unroll
-                for (int k = 0; k < NO_PAD / 4; ++k) oo4[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
                 // fold_mask (no alpha channel, sphnca_fire_list_draw set bits 0|1 of the living rows): the static life mask is applied
                 // here instead of by step_mask_static_kernel -- dead rows are multiplied by 0 exactly like there
                 flags_s[p] = (uint8_t)((flag_raw & (fold_mask ? 3u : 1u)) | (fire ? 4u : 0u));
                 alive_s[p] = c.use_alpha ? (nA[3] > 0.1f ? 1 : 0) : 1;
+            }
+            // The pre-gate outputs O (36 floats per row, rows consecutive in j) leave through shared memory: 16 rows of the warp
+            // at a time are laid down as they are in global memory (row pitch 144 B: the 8 lanes of a quarter warp hit distinct
+            // banks) and go out as 512 contiguous bytes per warp-level STG.128 -- 36 L1 wavefronts and 36 full-line L2 writes per
+            // warp and tile instead of 288 wavefronts and 288 half-sector writes with a thread per row.
+            {
+                float4* st4 = reinterpret_cast<float4*>(s.ostage[warp - FIN_WARP0]);
+                const int jw = tile * TILE + (warp & 3) * 32;
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    if ((lane >> 4) == sub) {
+#pragma unroll
+                        for (int k = 0; k < NO_PAD / 4; ++k) st4[(lane & 15) * (NO_PAD / 4) + k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+                    }
+                    __syncwarp();
+                    const int j0 = jw + sub * 16;
+                    float4* g4 = reinterpret_cast<float4*>(O_s + (size_t)j0 * NO_PAD);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const int cidx = k * 32 + lane;
+                        if (cidx < 16 * (NO_PAD / 4) && j0 + cidx / (NO_PAD / 4) < n_total) g4[cidx] = st4[cidx];
+                    }
+                    __syncwarp();
+                }
             }
             if (tid == (FIN_WARP0 + 3) * 32) SPHNCA_TL(11);
         }
@@ -338,50 +389,63 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             uint32_t rmask[NH / 64];                          // this warp's 4 ReLU words: (half, chalf) -> word 4*half + 2*chalf + {0,1}
 #pragma unroll
             for (int wd = 0; wd < NH / 64; ++wd) rmask[wd] = 0u;
+            // One 16-column block: bias + ReLU (+ its bits), the partial scalar-gate dot product, H as tf32 hi / lo.
+            // Packed fp32 pairs (FADD2 / FFMA2) for the bias add, the dot product and the lo remainder.
+            auto convert = [&](const uint32_t (&r)[16], const float* __restrict__ b1p, const float* __restrict__ w2p,
+                               uint32_t (&hi)[16], uint32_t (&lo)[16]) -> uint32_t {
+                uint32_t bits = 0;
 #pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const float2 pre = fadd2(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), *reinterpret_cast<const float2*>(b1p + j));
+                    bits |= (pre.x > 0.f ? 1u : 0u) << j;
+                    bits |= (pre.y > 0.f ? 1u : 0u) << (j + 1);
+                    const float2 hv = make_float2(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f));
+                    o32p = ffma2(hv, *reinterpret_cast<const float2*>(w2p + j), o32p);
+                    const float2 h_ = make_float2(__uint_as_float((__float_as_uint(hv.x) + 0x1000u) & 0xffffe000u),
+                                                  __uint_as_float((__float_as_uint(hv.y) + 0x1000u) & 0xffffe000u));   // split_tf32
+                    const float2 l_ = fsub2(hv, h_);
+                    hi[j] = __float_as_uint(h_.x); hi[j + 1] = __float_as_uint(h_.y);
+                    lo[j] = __float_as_uint(l_.x); lo[j + 1] = __float_as_uint(l_.y);
+                }
+                return bits;
+            };
+            // ROLLED loops over the two hidden halves and the two 32-column pairs of a half: the conversion code exists twice
+            // (one copy per register set of the TMEM-load double buffer), not eight times.  Fully unrolled, the epilogue alone
+            // was 18 KB of straight-line code per tile, five roles share each scheduler's instruction cache, and ncu showed
+            // "no instruction" as the epilogue warps' first stall reason (25 % of their samples).
+#pragma unroll 1
             for (int half = 0; half < 2; ++half) {
-                const uint32_t d1 = lane_addr + (half ? COL_DB : COL_DA);
+                const uint32_t d1 = lane_addr + COL_DA + half * (COL_DB - COL_DA);
                 mbar_wait(&s.bar[D1_FULL + half], it & 1);
                 fence_after_sync();
                 if (tid == 0) SPHNCA_TL(6 + 2 * half);
-                // the next 16 columns are in flight while the current ones are converted (two register sets)
-                uint32_t r[2][16];
-                tmem_ld16(d1 + chalf * 64, r[0]);
-                // (a generic lambda per 16-column block: the block index must be a compile-time constant for the register sets)
-                auto block = [&](auto C4) {
-                    constexpr int c4 = decltype(C4)::value;
-                    const int cc = chalf * 64 + c4 * 16;
+                uint32_t r0[16], r1[16];                      // the next 16 columns are in flight while the current ones are converted
+                tmem_ld16(d1 + chalf * 64, r0);
+                uint32_t word[2];
+#pragma unroll 1
+                for (int pair = 0; pair < 2; ++pair) {
+                    const int cc = chalf * 64 + pair * 32;
+                    const float* b1p = s.b1 + half * 128 + cc;
+                    const float* w2p = s.w2_last + half * 128 + cc;
                     uint32_t hi[16], lo[16];
                     wait_ld();
-                    if (c4 < 3) tmem_ld16(d1 + cc + 16, r[(c4 + 1) & 1]);
-                    uint32_t bits = 0;
-                    // packed fp32 pairs (FADD2 / FFMA2) for the bias add, the scalar-gate dot product and the lo remainder:
-                    // the 8 epilogue warps are issue-bound, every instruction saved per element counts
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        const int n = half * 128 + cc + j;
-                        const float2 pre = fadd2(make_float2(__uint_as_float(r[c4 & 1][j]), __uint_as_float(r[c4 & 1][j + 1])),
-                                                 *reinterpret_cast<const float2*>(&s.b1[n]));
-                        bits |= (pre.x > 0.f ? 1u : 0u) << j;
-                        bits |= (pre.y > 0.f ? 1u : 0u) << (j + 1);
-                        const float2 hv = make_float2(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f));
-                        o32p = ffma2(hv, *reinterpret_cast<const float2*>(&s.w2_last[n]), o32p);
-                        const float2 h_ = make_float2(__uint_as_float((__float_as_uint(hv.x) + 0x1000u) & 0xffffe000u),
-                                                      __uint_as_float((__float_as_uint(hv.y) + 0x1000u) & 0xffffe000u));   // split_tf32
-                        const float2 l_ = fsub2(hv, h_);
-                        hi[j] = __float_as_uint(h_.x); hi[j + 1] = __float_as_uint(h_.y);
-                        lo[j] = __float_as_uint(l_.x); lo[j + 1] = __float_as_uint(l_.y);
-                    }
-                    rmask[2 * half + (c4 >> 1)] |= bits << ((c4 & 1) * 16);
+                    tmem_ld16(d1 + cc + 16, r1);
+                    const uint32_t bits_a = convert(r0, b1p, w2p, hi, lo);
                     tmem_st16(d1 + cc, hi);                   // in place: pre-activations -> H_hi
-                    if (c4 == 0) {                            // the shared H_lo region: free once the previous GEMM2 half's H_lo MMAs are done
+                    if (pair == 0) {                          // the shared H_lo region: free once the previous GEMM2 half's H_lo MMAs are done
                         mbar_wait(&s.bar[H_EMPTY], half ^ 1);
                         fence_after_sync();
                     }
                     tmem_st16(lane_addr + COL_HLO + cc, lo);
-                };
-                block(std::integral_constant<int, 0>{}); block(std::integral_constant<int, 1>{});
-                block(std::integral_constant<int, 2>{}); block(std::integral_constant<int, 3>{});
+                    wait_ld();
+                    if (pair == 0) tmem_ld16(d1 + cc + 32, r0);
+                    const uint32_t bits_b = convert(r1, b1p + 16, w2p + 16, hi, lo);
+                    tmem_st16(d1 + cc + 16, hi);
+                    tmem_st16(lane_addr + COL_HLO + cc + 16, lo);
+                    const uint32_t w = bits_a | (bits_b << 16);
+                    if (pair == 0) word[0] = w; else word[1] = w;
+                }
+                if (half == 0) { rmask[0] = word[0]; rmask[1] = word[1]; } else { rmask[2] = word[0]; rmask[3] = word[1]; }
                 wait_st();
                 fence_before_sync();
                 mbar_arrive(&s.bar[H_FULL + half]);
@@ -402,6 +466,7 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
     }
     fence_before_sync();
     __syncthreads();
+    SPHNCA_TL_PHASE(3);
     if (warp == MMA_WARP) tmem_dealloc(tbase, mt::TMEM_COLS);
 }
 

@@ -28,6 +28,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;                                                // base_offset 0, lbo_mode 0, SWIZZLE_NONE (0) in [61,64)
 }
 
+// The descriptor of the same tile `bytes` further on (bytes % 16 == 0, address stays below 256 KB: no carry out of the 14-bit field).
+// Build the base descriptors ONCE, before the tile loop, and advance them with this: base + constant stays in uniform registers
+// (one UIADD3 per MMA or none), whereas make_smem_desc(address + offset) inside the issue loop re-derives every descriptor with
+// vector ALU instructions and an R2UR -- a 6-instruction dependent chain per MMA that crawls when the epilogue warps of the same
+// scheduler partition are busy (measured: 155 cycles per N=128 MMA issued, against the tensor pipe's 65).
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+
 // kind::tf32, D = fp32, A and B K-major, dense
 __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -192,6 +199,40 @@ __device__ __forceinline__ void stage_batched(int total, int tid, int threads, L
     }
 }
 
+// Weight staging into the K-major tile layout (chunk_off) as tf32 hi / lo, one 16-byte K chunk (4 K-consecutive values of
+// one tile row) per thread and step.  Lane mapping inside a warp: 8 consecutive rows x 4 consecutive chunks -- each quarter
+// warp writes 128 contiguous bytes (no bank conflict) and, where K is the fast dimension in global memory, a warp-level load
+// covers 64 contiguous bytes of 8 rows.  stage_batched's per-element form with consecutive threads along K put 32 lanes on 4
+// banks (8-way conflict on both stores): 11,900 cycles per launch for the forward kernel's 84 KB of weights -- a third of an
+// empty launch.  Tiles need rows % 8 == 0 and chunks % 4 == 0.
+// lane mapping of the idx-th chunk of a tile with `rgroups` groups of 8 rows (see above)
+__device__ __forceinline__ void stage_map(int idx, int rgroups, int& row, int& chunk) {
+    const int blk = idx >> 5, l = idx & 31, q = blk / rgroups, g = blk - q * rgroups;
+    row = 8 * g + (l & 7); chunk = 4 * q + (l >> 3);
+}
+// get4(idx) loads chunk idx of a tile (U loads of a thread in flight at once); put(idx, hi, lo) stores its tf32 hi / lo parts.
+// One call per tile with U = chunks per thread: enumerating ALL tiles of a launch in one index space (10 loads in flight, one
+// round trip) was measured SLOWER (9,200 vs 7,700 cycles for the forward kernel's prologue) -- the unrolled code is twice as
+// long and a cold launch fetches it line by line.
+template <int U, typename G, typename P>
+__device__ __forceinline__ void stage_chunks(int total, int tid, int threads, G get4, P put) {
+    for (int u0 = tid; u0 < total; u0 += threads * U) {
+        float4 w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int idx = u0 + u * threads; if (idx < total) w[u] = get4(idx); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = u0 + u * threads;
+            if (idx < total) {
+                float hi[4], lo[4];
+                split_tf32(w[u].x, hi[0], lo[0]); split_tf32(w[u].y, hi[1], lo[1]);
+                split_tf32(w[u].z, hi[2], lo[2]); split_tf32(w[u].w, hi[3], lo[3]);
+                put(idx, make_float4(hi[0], hi[1], hi[2], hi[3]), make_float4(lo[0], lo[1], lo[2], lo[3]));
+            }
+        }
+    }
+}
+
 }  // namespace tc
 
 // development aid: per-role clock64 timestamps of CTA 0, 16 slots per tile/chunk iteration.  One buffer
@@ -199,9 +240,12 @@ __device__ __forceinline__ void stage_batched(int total, int tid, int threads, L
 static __device__ long long g_timeline[64 * 16];
 // (compiled in with `make EXTRA=-DSPHNCA_TIMELINE`; off by default: the stamps cost instructions and code size in every role)
 #ifdef SPHNCA_TIMELINE
-#define SPHNCA_TL(slot) do { if (blockIdx.x == 0 && it < 64) sphnca::g_timeline[it * 16 + (slot)] = clock64(); } while (0)
+#define SPHNCA_TL(slot) do { if (blockIdx.x == 0 && it < 63) sphnca::g_timeline[it * 16 + (slot)] = clock64(); } while (0)
+// launch phases of CTA 0 (row 63 of the table): 0 entry, 1 weights staged, 2 barriers + TMEM ready, 3 all roles done
+#define SPHNCA_TL_PHASE(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) sphnca::g_timeline[63 * 16 + (k)] = clock64(); } while (0)
 #else
 #define SPHNCA_TL(slot) do { } while (0)
+#define SPHNCA_TL_PHASE(k) do { } while (0)
 #endif
 #define SPHNCA_TIMELINE_READER(name)                                                              \
     extern "C" int32_t name(long long* out_host, int32_t n) {                                     \

@@ -174,6 +174,7 @@ int32_t sphnca_mlp_wgrad(int64_t N, const float* A_s, const float* Y_s, const fl
     if (Ht == nullptr) {
         // tensor-core path: hidden layer recomputed in the transposed orientation (wgrad_tc.cu)
         SPHNCA_CHECK_ARG(p->W1 && p->b1 && p->W2, "weights are required by the recompute path");
+        SPHNCA_CHECK_ARG(((uintptr_t)p->W1 & 15) == 0, "W1 must be 16-byte aligned");
         const int streams = wgrad_tc_streams(N);
         if (!workspace || workspace_bytes < (size_t)streams * WG_PART * sizeof(float)) { set_error("wgrad workspace too small"); return SPHNCA_ERR_WORKSPACE; }
         float* partial = reinterpret_cast<float*>(workspace);
@@ -201,6 +202,7 @@ int32_t sphnca_mlp_wgrad_list(int64_t N, const int32_t* count, const float* A_c,
     if (N == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(count && A_c && Y_c && dO_c && dW1 && db1 && dW2 && db2, "NULL argument");
     SPHNCA_CHECK_ARG(p->W1 && p->b1 && p->W2, "weights are required by the recompute path");
+    SPHNCA_CHECK_ARG(((uintptr_t)p->W1 & 15) == 0, "W1 must be 16-byte aligned");
     const int streams = wgrad_tc_streams(N);
     if (!workspace || workspace_bytes < (size_t)streams * WG_PART * sizeof(float)) { set_error("wgrad workspace too small"); return SPHNCA_ERR_WORKSPACE; }
     float* partial = reinterpret_cast<float*>(workspace);

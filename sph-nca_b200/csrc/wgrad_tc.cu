@@ -85,18 +85,26 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
     const int64_t c0 = chunks_total * stream_id / num_streams, c1 = chunks_total * (stream_id + 1) / num_streams;
     const int n_mma = n_out < KO ? n_out : KO;
 
-    stage_batched<8>(128 * NIN, tid, THREADS, [&](int i) { return __ldg(prm.W1 + (size_t)hh * 128 * NIN + i); }, [&](int i, float w) {
-        const int h = i / NIN, k = i - h * NIN;
-        float hi, lo; split_tf32(w, hi, lo);
-        const uint32_t o = fidx(128, h, k);
-        s.W1_hi[o] = hi; s.W1_lo[o] = lo;
+    // W1 [h][k] of this CTA's hidden half -> W1_hi / W1_lo: rows = h, K = k
+    stage_chunks<4>(128 * (NIN / 4), tid, THREADS, [&](int idx) {
+        int row, ck; stage_map(idx, 128 / 8, row, ck);
+        return __ldg(reinterpret_cast<const float4*>(prm.W1 + (size_t)(hh * 128 + row) * NIN) + ck);
+    }, [&](int idx, float4 hi, float4 lo) {
+        int row, ck; stage_map(idx, 128 / 8, row, ck);
+        const uint32_t o = chunk_off(128, row, ck) / 4;
+        *reinterpret_cast<float4*>(&s.W1_hi[o]) = hi; *reinterpret_cast<float4*>(&s.W1_lo[o]) = lo;
     });
-    stage_batched<8>(KO * 128, tid, THREADS, [&](int i) { return (i >> 7) < n_mma ? __ldg(prm.W2 + (size_t)(i >> 7) * NH + hh * 128 + (i & 127)) : 0.f; },
-                     [&](int i, float w) {
-        const int o_ = i / 128, h = i - o_ * 128;
-        float hi, lo; split_tf32(w, hi, lo);
-        const uint32_t o = fidx(128, h, o_);
-        s.W2t_hi[o] = hi; s.W2t_lo[o] = lo;
+    // W2 [o][h] -> W2t_hi / W2t_lo: rows = h, K = o
+    stage_chunks<3>(128 * (KO / 4), tid, THREADS, [&](int idx) {
+        int row, ck; stage_map(idx, 128 / 8, row, ck);
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = 4 * ck + e < n_mma ? __ldg(prm.W2 + (size_t)(4 * ck + e) * NH + hh * 128 + row) : 0.f;
+        return make_float4(v[0], v[1], v[2], v[3]);
+    }, [&](int idx, float4 hi, float4 lo) {
+        int row, ck; stage_map(idx, 128 / 8, row, ck);
+        const uint32_t o = chunk_off(128, row, ck) / 4;
+        *reinterpret_cast<float4*>(&s.W2t_hi[o]) = hi; *reinterpret_cast<float4*>(&s.W2t_lo[o]) = lo;
     });
     for (int i = tid; i < 128; i += THREADS) {
         s.b1[i] = __ldg(prm.b1 + hh * 128 + i);
@@ -271,6 +279,12 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
             const uint32_t go = elect_one();
             const uint32_t idR = make_idesc_tf32(128, CH), idA1 = make_idesc_tf32(128, NY), idA2 = make_idesc_tf32(128, NOUT);
             const uint32_t idA1c = make_idesc_tf32(128, 2 * NY), idA2c = make_idesc_tf32(128, 2 * NOUT);   // stacked [hi ; lo] B tiles
+            // base descriptors, built once (desc_advance, tc_common.cuh)
+            const uint64_t dW1h = make_smem_desc(smem_u32(s.W1_hi), 128 * 16, 128), dW1l = make_smem_desc(smem_u32(s.W1_lo), 128 * 16, 128);
+            const uint64_t dW2h = make_smem_desc(smem_u32(s.W2t_hi), 128 * 16, 128), dW2l = make_smem_desc(smem_u32(s.W2t_lo), 128 * 16, 128);
+            const uint64_t dyKh = make_smem_desc(smem_u32(s.yK_hi), KP * 16, 128), dyKl = make_smem_desc(smem_u32(s.yK_lo), KP * 16, 128);
+            const uint64_t dOKh = make_smem_desc(smem_u32(s.dOK_hi), KP * 16, 128), dOKl = make_smem_desc(smem_u32(s.dOK_lo), KP * 16, 128);
+            const uint64_t dyT = make_smem_desc(smem_u32(s.yT), 2 * NY * 16, 128), dOT = make_smem_desc(smem_u32(s.dOT), 2 * NOUT * 16, 128);
             int it = 0;
             for (int64_t ch = c0; ch < c1; ++ch, ++it) {
                 mbar_wait(&s.bar[K_FULL], it & 1);
@@ -279,20 +293,16 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                 // recompute (the TMEM chunk regions were last read by the accumulate MMAs issued before: in order)
 #pragma unroll
                 for (int ks = 0; ks < NIN / 8; ++ks) {
-                    const uint64_t a_hi = make_smem_desc(smem_u32(s.W1_hi) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                    const uint64_t a_lo = make_smem_desc(smem_u32(s.W1_lo) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                    const uint64_t b_hi = make_smem_desc(smem_u32(s.yK_hi) + 2 * ks * KP * 16, KP * 16, 128);
-                    const uint64_t b_lo = make_smem_desc(smem_u32(s.yK_lo) + 2 * ks * KP * 16, KP * 16, 128);
+                    const uint64_t a_hi = desc_advance(dW1h, chunk_off(128, 0, 2 * ks)), a_lo = desc_advance(dW1l, chunk_off(128, 0, 2 * ks));
+                    const uint64_t b_hi = desc_advance(dyKh, 2 * ks * KP * 16), b_lo = desc_advance(dyKl, 2 * ks * KP * 16);
                     mma_tf32_ss_e(tbase + COL_R1, a_lo, b_hi, idR, ks > 0, go);
                     mma_tf32_ss_e(tbase + COL_R1, a_hi, b_lo, idR, true, go);
                     mma_tf32_ss_e(tbase + COL_R1, a_hi, b_hi, idR, true, go);
                 }
 #pragma unroll
                 for (int ks = 0; ks < KO / 8; ++ks) {
-                    const uint64_t a_hi = make_smem_desc(smem_u32(s.W2t_hi) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                    const uint64_t a_lo = make_smem_desc(smem_u32(s.W2t_lo) + chunk_off(128, 0, 2 * ks), 128 * 16, 128);
-                    const uint64_t b_hi = make_smem_desc(smem_u32(s.dOK_hi) + 2 * ks * KP * 16, KP * 16, 128);
-                    const uint64_t b_lo = make_smem_desc(smem_u32(s.dOK_lo) + 2 * ks * KP * 16, KP * 16, 128);
+                    const uint64_t a_hi = desc_advance(dW2h, chunk_off(128, 0, 2 * ks)), a_lo = desc_advance(dW2l, chunk_off(128, 0, 2 * ks));
+                    const uint64_t b_hi = desc_advance(dOKh, 2 * ks * KP * 16), b_lo = desc_advance(dOKl, 2 * ks * KP * 16);
                     mma_tf32_ss_e(tbase + COL_R3, a_lo, b_hi, idR, ks > 0, go);
                     mma_tf32_ss_e(tbase + COL_R3, a_hi, b_lo, idR, true, go);
                     mma_tf32_ss_e(tbase + COL_R3, a_hi, b_hi, idR, true, go);
@@ -314,8 +324,7 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                 for (int ks = 0; ks < CH / 8; ++ks) {
                     if (ks > 0 && (ks & 1) == 0) { mbar_wait(&s.bar[HT_FULL + ks / 2], it & 1); fence_after_sync(); }   // next 16 columns converted
                     // one descriptor per tile: rows 0..N-1 of it are the hi tile, all 2N rows the stacked [hi ; lo] tile
-                    const uint64_t y_t = make_smem_desc(smem_u32(s.yT) + chunk_off(2 * NY, 0, 2 * ks), 2 * NY * 16, 128);
-                    const uint64_t o_t = make_smem_desc(smem_u32(s.dOT) + chunk_off(2 * NOUT, 0, 2 * ks), 2 * NOUT * 16, 128);
+                    const uint64_t y_t = desc_advance(dyT, chunk_off(2 * NY, 0, 2 * ks)), o_t = desc_advance(dOT, chunk_off(2 * NOUT, 0, 2 * ks));
                     const bool acc = !(fresh && ks == 0);
                     mma_tf32_ts_e(tbase + COL_ACC1, tbase + COL_R3 + 8 * ks, y_t, idA1c, acc, go);      // dH_hi . [y_hi ; y_lo]
                     mma_tf32_ts_e(tbase + COL_ACC1 + NY, tbase + COL_DHLO + 8 * ks, y_t, idA1, true, go);   // dH_lo . y_hi -> second group: the first one
