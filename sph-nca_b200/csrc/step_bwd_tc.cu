@@ -48,6 +48,7 @@ struct Smem {
     float dO32[2][TILE];
     uint32_t relu[2][TILE][NH / 32];
     float w2_last[NH];
+    float fstage[FIN_WARPS][8 * 52];                      // finalizer: 8 result rows [dAdir 16 | dY 32 | pad 4] per warp, on their way out
     uint64_t bar[NUM_BARS];
     uint32_t tmem_base;
 };
@@ -285,14 +286,38 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             for (int k = 0; k < 4; ++k) dir[k] = *reinterpret_cast<const float4*>(&s.dAdir[slot][m][4 * k]);
             fence_before_sync();
             mbar_arrive(&s.bar[DY_EMPTY]);                    // Dy and this slot's dAdir rows are in registers
-            if (valid) {
-                float4* d4 = reinterpret_cast<float4*>(dAdir_s + (size_t)p * NF);
+            // The result rows (64 B of dAdir and 128 B of dL/dY at the particle's place) leave through shared memory, 8 rows of the
+            // warp at a time (row pitch 208 B: the 8 writing lanes hit distinct banks), as contiguous 16-byte pieces: a warp-level
+            // store then touches ~6 lines instead of 32.  With a thread per row these 12 stores cost the kernel 14 of its 78 us
+            // (measured by compiling them out) -- the LSU pipe they clog is shared with the prologue's loads and the epilogue's LDS.
+            {
+                float4* st4 = reinterpret_cast<float4*>(s.fstage[warp - FIN_WARP0]);
+                float4* dA4 = reinterpret_cast<float4*>(dAdir_s);
+                float4* dY4 = reinterpret_cast<float4*>(dY_s);
+                const int jw = tile * TILE + (warp & 3) * 32;
+#pragma unroll 1
+                for (int sub = 0; sub < 4; ++sub) {
+                    if ((lane >> 3) == sub) {
+                        float4* r = st4 + (lane & 7) * 13;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    d4[k] = make_float4(dir[k].x + dy[4*k], dir[k].y + dy[4*k+1], dir[k].z + dy[4*k+2], dir[k].w + dy[4*k+3]);
-                float4* g4 = reinterpret_cast<float4*>(dY_s + (size_t)p * 2 * NF);
+                        for (int k = 0; k < 4; ++k)
+                            r[k] = make_float4(dir[k].x + dy[4*k], dir[k].y + dy[4*k+1], dir[k].z + dy[4*k+2], dir[k].w + dy[4*k+3]);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) g4[k] = make_float4(dy[NF+4*k], dy[NF+4*k+1], dy[NF+4*k+2], dy[NF+4*k+3]);
+                        for (int k = 0; k < 8; ++k) r[4 + k] = make_float4(dy[NF+4*k], dy[NF+4*k+1], dy[NF+4*k+2], dy[NF+4*k+3]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int idx = k * 32 + lane, row = idx / 12, cq = idx - 12 * row;
+                        const int jr = jw + sub * 8 + row;
+                        if (jr < n_total) {
+                            const size_t pr = rows ? (size_t)__ldg(rows + jr) : (size_t)jr;
+                            const float4 v = st4[row * 13 + cq];
+                            if (cq < 4) dA4[pr * 4 + cq] = v; else dY4[pr * 8 + (cq - 4)] = v;
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
     } else {
