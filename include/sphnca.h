@@ -261,7 +261,9 @@ int32_t sphnca_step_adjoint(const sphnca_grid* g, const float* xv4, const float*
  *                           pair (optional, both or neither) copies the static life-mask bit of every row meanwhile.
  *   sphnca_step_bwd_list    sphnca_step_bwd over the listed rows (dO_c by list position, dY_s / dAdir_s by particle);
  *   sphnca_step_bwd_unfired the not-fired rows of the same step: dY_s = 0, dAdir_s = living ? dA_next_s : 0.
- *   sphnca_mlp_wgrad_list   sphnca_mlp_wgrad over the first *count rows of the compact arrays (workspace sized for N). */
+ *   sphnca_mlp_wgrad_list   sphnca_mlp_wgrad over the first *count rows of the compact arrays (workspace sized for N).
+ * The fire-list workspace (sphnca_fire_list_workspace_bytes, 8-byte aligned) holds the look-back state of the one-launch ordered
+ * compaction: it must be ZERO before its first use; every call leaves it zeroed again (calls on one workspace must not overlap). */
 int32_t sphnca_fire_list_workspace_bytes(int64_t N, size_t* bytes);
 int32_t sphnca_fire_list(int64_t N, const uint8_t* fire_s, const float* A_s, int32_t use_alpha, int32_t* rows,
                          int32_t* count, float* A_new_s, uint8_t* alive_s, const uint8_t* FLG, uint8_t* flags_s,

@@ -6,7 +6,7 @@
 // to dW1, db1, dW2, db2 and to dL/dY).  With the default fire rate 0.5 that is half of all tensor-core work.
 //
 //   fire_list        rows[0..count) = sorted positions of the fired particles, in increasing order (ordered
-//                    compaction: block counts -> single-block scan -> in-block ranks; no atomics, deterministic);
+//                    compaction in ONE launch: block counts chained by a look-back over the preceding blocks; deterministic);
 //                    the not-fired rows get their new state right here: A_new = A, alive byte from A; optionally the
 //                    static life-mask bit of every row (no alpha channel: pairs.cu FLG) is copied into the flag bytes.
 //   bwd_unfired      the backward of those rows: dL/dY = 0, direct dL/dA = (living ? dL/dA_new : 0).
@@ -21,133 +21,151 @@ namespace fl {
 constexpr int THREADS = 256, PER_THREAD = 4, BLOCK_ROWS = THREADS * PER_THREAD;   // 1024 rows per block
 }
 
-__global__ void __launch_bounds__(fl::THREADS)
-fire_count_kernel(int64_t n, const uint8_t* __restrict__ fire_s, int32_t* __restrict__ block_count) {
-    using namespace fl;
-    const int64_t base = (int64_t)blockIdx.x * BLOCK_ROWS + (int64_t)threadIdx.x * PER_THREAD;
-    int c = 0;
-    if (base + PER_THREAD <= n) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(fire_s + base);      // 4 bytes, 4-aligned (base % 4 == 0)
-        c = ((w & 0xffu) != 0) + ((w & 0xff00u) != 0) + ((w & 0xff0000u) != 0) + ((w & 0xff000000u) != 0);
-    } else {
-        for (int k = 0; k < PER_THREAD; ++k) c += (base + k < n && fire_s[base + k] != 0) ? 1 : 0;
-    }
-    __shared__ int wsum[THREADS / 32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-#pragma unroll
-        for (int w = 0; w < THREADS / 32; ++w) t += wsum[w];
-        block_count[blockIdx.x] = t;
-    }
+// ---- one launch: fire bytes (drawn or given) -> ordered list + carry-over of the not-fired rows ------------------------------
+// Single-pass ordered compaction: a block takes a ticket (blocks are numbered in the order they START, so every predecessor is
+// already running -- no deadlock whatever the residency), counts its fired rows, publishes the count in its state word and sums
+// its predecessors' words (see below).  Sums of integers: the list is the same whatever the timing.  Replaces three launches (draw + block counts | one-block scan |
+// fill); the not-fired rows' 64-byte state copies are done as coalesced 16-byte pieces (4 lanes per row) instead of a thread
+// per row.  State words and the two counters live in the caller's workspace: ZERO before the first use, left zero by every
+// launch (the block that finishes last clears them).
+namespace fl {
+constexpr unsigned long long FLAG_AGG = 1ull << 32, VALUE_MASK = 0xffffffffull;
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+}  // namespace fl
 
-// The draw itself, fused with the count: fire byte of sorted row p = (u[sorted_id[p]] <= rate), u = the reference's
-// `torch.rand(N)` in particle order (nca.py:100) -- replaces torch's compare, the byte permutation and fire_count_kernel.
+template <bool DRAW>
 __global__ void __launch_bounds__(fl::THREADS)
-fire_draw_count_kernel(int64_t n, const float* __restrict__ u, float rate, const int32_t* __restrict__ sorted_id,
-                       uint8_t* __restrict__ fire_s, int32_t* __restrict__ block_count) {
+fire_list_onepass_kernel(int64_t n, int nb, const float* __restrict__ u, float rate, const int32_t* __restrict__ sorted_id,
+                         uint8_t* __restrict__ fire_s, const float* __restrict__ A_s, int use_alpha, int32_t* __restrict__ rows,
+                         int32_t* __restrict__ count, float* __restrict__ A_new_s, uint8_t* __restrict__ alive_s,
+                         const uint8_t* __restrict__ FLG, uint8_t* __restrict__ flags_s, int fold_mask,
+                         const uint8_t* __restrict__ carry_sel, unsigned long long* __restrict__ state, int* __restrict__ ctr) {
     using namespace fl;
-    const int64_t base = (int64_t)blockIdx.x * BLOCK_ROWS + (int64_t)threadIdx.x * PER_THREAD;
-    int c = 0;
+    __shared__ int s_ticket, s_excl, wsum[THREADS / 32];
+    __shared__ uint8_t s_copy[BLOCK_ROWS];                    // per row: 0 nothing to copy, 1 copy, 2 copy times zero (dead, static mask folded)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(&ctr[0], 1);
+    __syncthreads();
+    const int b = s_ticket;
+    const int64_t base = (int64_t)b * BLOCK_ROWS + (int64_t)tid * PER_THREAD;
+    // ---- fire bits of this thread's 4 rows
     uint32_t packed = 0;
+    if (DRAW) {
 #pragma unroll
-    for (int k = 0; k < PER_THREAD; ++k) {
-        const int64_t p = base + k;
-        const uint32_t f = (p < n && __ldg(u + __ldg(sorted_id + p)) <= rate) ? 1u : 0u;
-        packed |= f << (8 * k); c += (int)f;
-    }
-    if (base + PER_THREAD <= n) *reinterpret_cast<uint32_t*>(fire_s + base) = packed;
-    else for (int k = 0; k < PER_THREAD; ++k) if (base + k < n) fire_s[base + k] = (uint8_t)((packed >> (8 * k)) & 1u);
-    __shared__ int wsum[THREADS / 32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-#pragma unroll
-        for (int w = 0; w < THREADS / 32; ++w) t += wsum[w];
-        block_count[blockIdx.x] = t;
-    }
-}
-
-// exclusive scan of the block counts in place (one block; fixed order), total -> count[0]
-__global__ void __launch_bounds__(1024)
-fire_scan_kernel(int nb, int32_t* __restrict__ block_count, int32_t* __restrict__ count) {
-    __shared__ int wsum[32];
-    __shared__ int carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int b0 = 0; b0 < nb; b0 += 1024) {
-        const int i = b0 + threadIdx.x;
-        const int v = i < nb ? block_count[i] : 0;
-        int x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            int w = wsum[threadIdx.x];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += y; }
-            wsum[threadIdx.x] = w;
+        for (int k = 0; k < PER_THREAD; ++k) {
+            const int64_t p = base + k;
+            packed |= ((p < n && __ldg(u + __ldg(sorted_id + p)) <= rate) ? 1u : 0u) << (8 * k);
         }
-        __syncthreads();
-        const int carry = carry_s;
-        const int incl = x + (threadIdx.x >= 32 ? wsum[(threadIdx.x >> 5) - 1] : 0);
-        if (i < nb) block_count[i] = carry + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + incl;
-        __syncthreads();
+        if (base + PER_THREAD <= n) *reinterpret_cast<uint32_t*>(fire_s + base) = packed;
+        else for (int k = 0; k < PER_THREAD; ++k) if (base + k < n) fire_s[base + k] = (uint8_t)((packed >> (8 * k)) & 1u);
+    } else {
+        if (base + PER_THREAD <= n) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(fire_s + base);
+            packed = ((w & 0xffu) ? 1u : 0u) | ((w & 0xff00u) ? 0x100u : 0u) | ((w & 0xff0000u) ? 0x10000u : 0u) | ((w & 0xff000000u) ? 0x1000000u : 0u);
+        } else {
+            for (int k = 0; k < PER_THREAD; ++k) if (base + k < n && fire_s[base + k] != 0) packed |= 1u << (8 * k);
+        }
     }
-    if (threadIdx.x == 0) count[0] = carry_s;
-}
-
-__global__ void __launch_bounds__(fl::THREADS)
-fire_fill_kernel(int64_t n, const uint8_t* __restrict__ fire_s, const int32_t* __restrict__ block_off,
-                 const float* __restrict__ A_s, int use_alpha, int32_t* __restrict__ rows,
-                 float* __restrict__ A_new_s, uint8_t* __restrict__ alive_s, const uint8_t* __restrict__ FLG,
-                 uint8_t* __restrict__ flags_s, int fold_mask, const uint8_t* __restrict__ carry_sel) {
-    using namespace fl;
-    const int64_t base = (int64_t)blockIdx.x * BLOCK_ROWS + (int64_t)threadIdx.x * PER_THREAD;
-    bool f[PER_THREAD];
-    int c = 0;
-#pragma unroll
-    for (int k = 0; k < PER_THREAD; ++k) { f[k] = base + k < n && fire_s[base + k] != 0; c += f[k] ? 1 : 0; }
-    // exclusive rank of this thread's first row among the block's fired rows
-    __shared__ int wsum[THREADS / 32];
+    const int c = __popc(packed);
+    // ---- ranks inside the block
     int x = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[warp] = x;
     __syncthreads();
-    int before = x - c;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += wsum[w];
-    int slot = block_off[blockIdx.x] + before;
+    int before = x - c, total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) { const int t = wsum[w]; if (w < warp) before += t; total += t; }
+    // ---- the block's count goes into its state word at once; the sums over the preceding blocks are only read after the carry-over
+    // copies below (nothing but the list positions depends on them), when every block that started earlier has published its own
+    if (tid == 0) fl::st_state(state + b, fl::FLAG_AGG | (unsigned long long)(uint32_t)total);
+    // ---- per-row work that needs no prefix: static-mask flag bytes, what to copy
 #pragma unroll
     for (int k = 0; k < PER_THREAD; ++k) {
         const int64_t p = base + k;
-        if (p >= n) break;
-        // static life mask (no alpha channel): the previous-mask bit of every row; fold_mask: the new mask is the same bit
-        // (step_mask_static_kernel), so bit 1 is set here too and dead rows are zeroed below / by the MLP kernel
-        const bool live = FLG == nullptr || FLG[p] != 0;
-        if (FLG != nullptr && flags_s != nullptr) flags_s[p] = live ? (fold_mask ? 3 : 1) : 0;
-        if (f[k]) { rows[slot++] = (int32_t)p; continue; }
-        if (A_new_s == nullptr) continue;                   // list only
-        if (carry_sel != nullptr && carry_sel[p] == 0) continue;   // this row is carried over by the other list of the step (multigpu.py)
-        // not fired: the state is carried over unchanged (reference nca.py:107); fire bit of the flags stays 0
-        const float4* a4 = reinterpret_cast<const float4*>(A_s + p * NF);
-        float4* o4 = reinterpret_cast<float4*>(A_new_s + p * NF);
-        const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), a2 = __ldg(a4 + 2), a3 = __ldg(a4 + 3);
-        if (fold_mask && !live) {                           // the product with 0 of step_mask_static_kernel, bit for bit
-            o4[0] = make_float4(a0.x * 0.f, a0.y * 0.f, a0.z * 0.f, a0.w * 0.f); o4[1] = make_float4(a1.x * 0.f, a1.y * 0.f, a1.z * 0.f, a1.w * 0.f);
-            o4[2] = make_float4(a2.x * 0.f, a2.y * 0.f, a2.z * 0.f, a2.w * 0.f); o4[3] = make_float4(a3.x * 0.f, a3.y * 0.f, a3.z * 0.f, a3.w * 0.f);
-        } else { o4[0] = a0; o4[1] = a1; o4[2] = a2; o4[3] = a3; }
-        alive_s[p] = use_alpha ? (a0.w > 0.1f ? 1 : 0) : 1;
+        uint8_t cp = 0;
+        if (p < n) {
+            // static life mask (no alpha channel): the previous-mask bit of every row; fold_mask: the new mask is the same bit
+            // (step_mask_static_kernel), so bit 1 is set here too and dead rows are zeroed below / by the MLP kernel
+            const bool live = FLG == nullptr || FLG[p] != 0;
+            if (FLG != nullptr && flags_s != nullptr) flags_s[p] = live ? (fold_mask ? 3 : 1) : 0;
+            const bool fired = (packed >> (8 * k)) & 1u;
+            // not fired: the state is carried over unchanged (reference nca.py:107); fire bit of the flags stays 0.
+            // carry_sel: rows carried over by the other list of the step are skipped (multigpu.py)
+            if (!fired && A_new_s != nullptr && (carry_sel == nullptr || carry_sel[p] != 0)) cp = (fold_mask && !live) ? 2 : 1;
+        }
+        s_copy[tid * PER_THREAD + k] = cp;
+    }
+    __syncthreads();
+    // ---- carry-over copies: 4 lanes per row, 16 bytes each
+    if (A_new_s != nullptr) {
+        const float4* a4 = reinterpret_cast<const float4*>(A_s) + (int64_t)b * BLOCK_ROWS * 4;
+        float4* o4 = reinterpret_cast<float4*>(A_new_s) + (int64_t)b * BLOCK_ROWS * 4;
+        uint8_t* al = alive_s + (int64_t)b * BLOCK_ROWS;
+#pragma unroll 8
+        for (int i = tid; i < BLOCK_ROWS * 4; i += THREADS) {
+            const int r = i >> 2;
+            const uint8_t cp = s_copy[r];
+            if (cp == 0) continue;
+            float4 v = __ldg(a4 + i);
+            if ((i & 3) == 0) al[r] = use_alpha ? (v.w > 0.1f ? 1 : 0) : 1;
+            if (cp == 2) v = make_float4(v.x * 0.f, v.y * 0.f, v.z * 0.f, v.w * 0.f);   // the product with 0 of step_mask_static_kernel, bit for bit
+            o4[i] = v;
+        }
+    }
+    // ---- exclusive prefix of the block: the sum over the preceding blocks' state words is read
+    // back in PARALLEL in two levels (<= 255 words of its own group of 256 blocks + one total per preceding group, published by
+    // each group's last block): two global-memory round trips however many blocks there are.  (The textbook chained look-back
+    // serialises here: all blocks of a launch run at once, none has a prefix yet, and block b would walk back b/32 windows --
+    // 12 us for 512 blocks.)
+    {
+        unsigned long long* gstate = state + nb;
+        const int g = b >> 8, b0 = g << 8;
+        auto spin_value = [&](const unsigned long long* w) -> int {
+            unsigned long long v = ld_state(w);
+            for (uint32_t spins = 0; (v >> 32) == 0; v = ld_state(w))
+                if (++spins > (1u << 26)) asm volatile("trap;");                        // a protocol bug traps instead of hanging the GPU
+            return (int)(v & VALUE_MASK);
+        };
+        auto block_sum = [&](int v) -> int {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            __syncthreads();                                                            // wsum free again
+            if (lane == 0) wsum[warp] = v;
+            __syncthreads();
+            int t = 0;
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; ++w) t += wsum[w];
+            return t;
+        };
+        const int in_group = block_sum(tid < b - b0 ? spin_value(state + b0 + tid) : 0);
+        if ((b & 255) == 255 && tid == 0) st_state(gstate + g, FLAG_AGG | (unsigned long long)(uint32_t)(in_group + total));
+        int prev = 0;
+        for (int gi = tid; gi < g; gi += THREADS) prev += spin_value(gstate + gi);
+        const int excl = in_group + block_sum(prev);
+        if (tid == 0) { s_excl = excl; if (b == nb - 1) count[0] = excl + total; }
+    }
+    __syncthreads();
+    // ---- the list
+    {
+        int slot = s_excl + before;
+#pragma unroll
+        for (int k = 0; k < PER_THREAD; ++k) if ((packed >> (8 * k)) & 1u) rows[slot++] = (int32_t)(base + k);
+    }
+    // ---- the block that finishes last leaves the workspace zeroed for the next launch
+    __syncthreads();
+    if (tid == 0) { __threadfence(); s_ticket = atomicAdd(&ctr[1], 1); }
+    __syncthreads();
+    if (s_ticket == nb - 1) {
+        for (int i = tid; i < nb + ((nb + 255) >> 8); i += THREADS) st_state(state + i, 0ull);
+        if (tid == 0) { ctr[0] = 0; ctr[1] = 0; }
     }
 }
 
@@ -210,11 +228,17 @@ step_bwd_unfired_kernel(int64_t n, const uint8_t* __restrict__ flags_s, const fl
 
 using namespace sphnca;
 
+// state words of the blocks, of the groups of 256 blocks, {ticket, finished} counters
+static size_t fl_workspace_bytes(int64_t N) {
+    const size_t nb = (size_t)((N + fl::BLOCK_ROWS - 1) / fl::BLOCK_ROWS);
+    return (nb + ((nb + 255) >> 8) + 1) * sizeof(unsigned long long);
+}
+
 extern "C" {
 
 int32_t sphnca_fire_list_workspace_bytes(int64_t N, size_t* bytes) {
     SPHNCA_CHECK_ARG(N >= 0 && bytes, "bad argument");
-    *bytes = (size_t)((N + fl::BLOCK_ROWS - 1) / fl::BLOCK_ROWS + 1) * sizeof(int32_t);
+    *bytes = fl_workspace_bytes(N);
     return SPHNCA_OK;
 }
 
@@ -230,12 +254,12 @@ static int32_t fire_list_impl(int64_t N, const uint8_t* fire_s, const float* A_s
     SPHNCA_CHECK_ARG(((uintptr_t)fire_s & 3) == 0, "fire_s must be 4-byte aligned");
     SPHNCA_CHECK_ARG(!fold_static_mask || (FLG != nullptr && !use_alpha), "the static life mask needs FLG and no alpha channel");
     const int nb = (int)((N + fl::BLOCK_ROWS - 1) / fl::BLOCK_ROWS);
-    if (!workspace || workspace_bytes < (size_t)(nb + 1) * sizeof(int32_t)) { set_error("fire-list workspace too small"); return SPHNCA_ERR_WORKSPACE; }
-    int32_t* bc = reinterpret_cast<int32_t*>(workspace);
-    SPHNCA_LAUNCH(fire_count_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc);
-    SPHNCA_LAUNCH(fire_scan_kernel, 1, 1024, 0, stream, nb, bc, count);
-    SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s, FLG, flags_s,
-                  fold_static_mask ? 1 : 0, carry_sel);
+    if (!workspace || workspace_bytes < fl_workspace_bytes(N)) { set_error("fire-list workspace too small"); return SPHNCA_ERR_WORKSPACE; }
+    SPHNCA_CHECK_ARG(((uintptr_t)workspace & 7) == 0, "the fire-list workspace must be 8-byte aligned");
+    unsigned long long* state = reinterpret_cast<unsigned long long*>(workspace);
+    SPHNCA_LAUNCH(fire_list_onepass_kernel<false>, nb, fl::THREADS, 0, stream, N, nb, (const float*)nullptr, 0.f, (const int32_t*)nullptr,
+                  const_cast<uint8_t*>(fire_s), A_s, use_alpha, rows, count, A_new_s, alive_s, FLG, flags_s, fold_static_mask ? 1 : 0, carry_sel,
+                  state, reinterpret_cast<int*>(state + nb + ((nb + 255) >> 8)));
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }
@@ -262,12 +286,11 @@ int32_t sphnca_fire_list_draw(const sphnca_grid* g, const float* u, float rate, 
     SPHNCA_CHECK_ARG(FLG == nullptr || flags_s != nullptr, "flags_s is required with FLG");
     SPHNCA_CHECK_ARG(!fold_static_mask || (FLG != nullptr && !use_alpha), "the static life mask needs FLG and no alpha channel");
     const int nb = (int)((N + fl::BLOCK_ROWS - 1) / fl::BLOCK_ROWS);
-    if (!workspace || workspace_bytes < (size_t)(nb + 1) * sizeof(int32_t)) { set_error("fire-list workspace too small"); return SPHNCA_ERR_WORKSPACE; }
-    int32_t* bc = reinterpret_cast<int32_t*>(workspace);
-    SPHNCA_LAUNCH(fire_draw_count_kernel, nb, fl::THREADS, 0, stream, N, u, rate, gv.sorted_id, fire_s, bc);
-    SPHNCA_LAUNCH(fire_scan_kernel, 1, 1024, 0, stream, nb, bc, count);
-    SPHNCA_LAUNCH(fire_fill_kernel, nb, fl::THREADS, 0, stream, N, fire_s, bc, A_s, use_alpha, rows, A_new_s, alive_s, FLG, flags_s,
-                  fold_static_mask ? 1 : 0, nullptr);
+    if (!workspace || workspace_bytes < fl_workspace_bytes(N)) { set_error("fire-list workspace too small"); return SPHNCA_ERR_WORKSPACE; }
+    SPHNCA_CHECK_ARG(((uintptr_t)workspace & 7) == 0, "the fire-list workspace must be 8-byte aligned");
+    unsigned long long* state = reinterpret_cast<unsigned long long*>(workspace);
+    SPHNCA_LAUNCH(fire_list_onepass_kernel<true>, nb, fl::THREADS, 0, stream, N, nb, u, rate, gv.sorted_id, fire_s, A_s, use_alpha, rows, count,
+                  A_new_s, alive_s, FLG, flags_s, fold_static_mask ? 1 : 0, (const uint8_t*)nullptr, state, reinterpret_cast<int*>(state + nb + ((nb + 255) >> 8)));
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

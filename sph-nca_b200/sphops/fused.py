@@ -205,7 +205,8 @@ def _fire_lists_on():
 def _fire_list_workspace(N, dev):
     nb = C.c_size_t(0)
     check(lib.sphnca_fire_list_workspace_bytes(N, C.byref(nb)))
-    return torch.empty((nb.value,), dtype=torch.uint8, device=dev)
+    # zero before the first use (look-back state words of the one-launch compaction); every call leaves it zeroed again
+    return torch.zeros((nb.value,), dtype=torch.uint8, device=dev)
 
 
 class _FireBuffers:

@@ -635,7 +635,7 @@ def test_rollout_node_auto_checkpoint_follows_free_memory(monkeypatch):
     assert fused._tape_mode(n_small, 8, torch.device(DEV), None) == 2
 
 
-@pytest.mark.parametrize("n,rate", [(1, 1.0), (5, 0.0), (1023, 0.5), (1024, 0.5), (1025, 0.3), (300_000, 0.5), (2_100_000, 0.9)])
+@pytest.mark.parametrize("n,rate", [(1, 1.0), (5, 0.0), (1023, 0.5), (1024, 0.5), (1025, 0.3), (300_000, 0.5), (2_100_000, 0.9), (6_000_000, 0.5)])
 def test_fire_list_is_the_ordered_compaction(n, rate):
     """sphnca_fire_list: rows[0..count) == nonzero(fire) in increasing order, count on the device; not-fired rows carry
     their state over and get their alive byte; fired rows of A_new are left to the MLP kernel."""
@@ -650,15 +650,21 @@ def test_fire_list_is_the_ordered_compaction(n, rate):
     alive = torch.full((n,), 9, dtype=torch.uint8, device=DEV)
     nb = C.c_size_t(0)
     _lib.check(_lib.lib.sphnca_fire_list_workspace_bytes(n, C.byref(nb)))
-    ws = torch.empty((nb.value,), dtype=torch.uint8, device=DEV)
-    _lib.check(_lib.lib.sphnca_fire_list(n, _lib.ptr(fire), _lib.ptr(A), 1, _lib.ptr(rows), _lib.ptr(count), _lib.ptr(An), _lib.ptr(alive),
-                                         None, None, 0, _lib.ptr(ws), nb.value, _lib.stream_ptr()))
-    want = torch.nonzero(fire)[:, 0].to(torch.int32)
-    assert int(count.item()) == want.numel()
-    assert torch.equal(rows[:want.numel()], want)
-    off = fire == 0
-    assert torch.equal(An[off], A[off]) and bool((An[~off] == -5.0).all())
-    assert torch.equal(alive[off], (A[off][:, 3] > 0.1).to(torch.uint8)) and bool((alive[~off] == 9).all())
+    ws = torch.zeros((nb.value,), dtype=torch.uint8, device=DEV)           # zero before the first use (include/sphnca.h)
+    # three calls on the same workspace: the launch leaves its look-back state zeroed for the next one
+    for rep in range(3):
+        if rep:
+            fire = (torch.rand(n, generator=gen) < rate).to(torch.uint8).to(DEV)
+            rows.fill_(-1); count.fill_(-7); An.fill_(-5.0); alive.fill_(9)
+        _lib.check(_lib.lib.sphnca_fire_list(n, _lib.ptr(fire), _lib.ptr(A), 1, _lib.ptr(rows), _lib.ptr(count), _lib.ptr(An), _lib.ptr(alive),
+                                             None, None, 0, _lib.ptr(ws), nb.value, _lib.stream_ptr()))
+        want = torch.nonzero(fire)[:, 0].to(torch.int32)
+        assert int(count.item()) == want.numel()
+        assert torch.equal(rows[:want.numel()], want)
+        off = fire == 0
+        assert torch.equal(An[off], A[off]) and bool((An[~off] == -5.0).all())
+        assert torch.equal(alive[off], (A[off][:, 3] > 0.1).to(torch.uint8)) and bool((alive[~off] == 9).all())
+        assert not bool(ws.any())
 
 
 @pytest.mark.parametrize("use_alpha", [False, True], ids=["noalpha", "alpha"])

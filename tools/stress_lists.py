@@ -30,7 +30,7 @@ for it in range(iters):
     rows = torch.empty(N, dtype=torch.int32, device=dev); cnt = torch.zeros(1, dtype=torch.int32, device=dev)
     An2 = torch.full((N, 16), -3.0, **f32); al2 = torch.empty(N, dtype=torch.uint8, device=dev)
     nb = C.c_size_t(0); check(lib.sphnca_fire_list_workspace_bytes(N, C.byref(nb)))
-    ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    ws = torch.zeros(nb.value, dtype=torch.uint8, device=dev)
     check(lib.sphnca_fire_list(N, ptr(fire), ptr(A), 0, ptr(rows), ptr(cnt), ptr(An2), ptr(al2), None, None, 0, ptr(ws), nb.value, st))
     O2 = torch.zeros(N, 36, **f32); rl2 = torch.zeros(N, 8, dtype=torch.int32, device=dev); fl2 = flags0.clone()
     Ac = torch.zeros(N, 16, **f32); Yc = torch.zeros(N, 32, **f32)
