@@ -316,6 +316,16 @@ int32_t sphnca_step_adjoint_pairs_fired(const sphnca_grid* g, const int32_t* gro
 int32_t sphnca_mlp_wgrad_list(int64_t N, const int32_t* count, const float* A_c, const float* Y_c, const float* dO_c,
                               const sphnca_step_params* p, float* dW1, float* db1, float* dW2, float* db2,
                               void* workspace, size_t workspace_bytes, void* stream);
+/* sphnca_mlp_wgrad_list in two halves, for the backward of a whole rollout (replaces per-step Linear.backward accumulation into
+ * .grad, code/nca.py:62-79 through torch autograd): every step's call ADDS its rows' contribution to the per-stream partial sums
+ * in `workspace` (accumulate = 0 on the first call of a series: plain stores), sphnca_mlp_wgrad_reduce then adds the partials
+ * to the parameter gradients ONCE, in a fixed order.  All calls of a series use the same N (it fixes the stream count) and the
+ * same workspace (sphnca_mlp_wgrad_workspace_bytes(N)). */
+int32_t sphnca_mlp_wgrad_list_partial(int64_t N, const int32_t* count, const float* A_c, const float* Y_c, const float* dO_c,
+                                      const sphnca_step_params* p, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+int32_t sphnca_mlp_wgrad_reduce(int64_t N, const sphnca_step_params* p, float* dW1, float* db1, float* dW2, float* db2,
+                                const void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,6 @@ int launch_step_bwd_tc(int64_t N, const StepConsts& c, const sphnca_step_params*
 int wgrad_tc_streams(int64_t N);
 int launch_mlp_wgrad_tc(int64_t N, const float* A_s, const float* Y_s, const float* dO_s, const sphnca_step_params* p,
                         int n_out, float* partial, int part_floats, int streams, cudaStream_t stream,
-                        const int32_t* count = nullptr);
+                        const int32_t* count = nullptr, int acc_in = 0);
 
 }  // namespace sphnca

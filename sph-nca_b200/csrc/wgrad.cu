@@ -213,4 +213,36 @@ int32_t sphnca_mlp_wgrad_list(int64_t N, const int32_t* count, const float* A_c,
     return SPHNCA_OK;
 }
 
+// The same in two halves, for a rollout's backward: every step ADDS to the per-stream partials (accumulate = 0 on the first
+// call of a series: plain stores), and ONE fixed-order reduction at the end adds them to the parameter gradients -- instead of a
+// 6 MB reduction pass per step.  All calls of a series use the same N (it fixes the number of streams) and workspace.
+int32_t sphnca_mlp_wgrad_list_partial(int64_t N, const int32_t* count, const float* A_c, const float* Y_c, const float* dO_c,
+                                      const sphnca_step_params* p, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                                      void* stream_) {
+    SPHNCA_CHECK_ARG(N >= 0 && p && (p->update_rule == 0 || p->update_rule == 1), "bad N / params");
+    const int n_out = p->update_rule == 0 ? 2 * NF + 1 : NF;
+    if (N == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(count && A_c && Y_c && dO_c, "NULL argument");
+    SPHNCA_CHECK_ARG(p->W1 && p->b1 && p->W2, "weights are required by the recompute path");
+    SPHNCA_CHECK_ARG(((uintptr_t)p->W1 & 15) == 0, "W1 must be 16-byte aligned");
+    const int streams = wgrad_tc_streams(N);
+    if (!workspace || workspace_bytes < (size_t)streams * WG_PART * sizeof(float)) { set_error("wgrad workspace too small"); return SPHNCA_ERR_WORKSPACE; }
+    return launch_mlp_wgrad_tc(N, A_c, Y_c, dO_c, p, n_out, reinterpret_cast<float*>(workspace), WG_PART, streams, as_stream(stream_), count,
+                               accumulate ? 1 : 0);
+}
+
+int32_t sphnca_mlp_wgrad_reduce(int64_t N, const sphnca_step_params* p, float* dW1, float* db1, float* dW2, float* db2,
+                                const void* workspace, size_t workspace_bytes, void* stream_) {
+    SPHNCA_CHECK_ARG(N >= 0 && p && (p->update_rule == 0 || p->update_rule == 1), "bad N / params");
+    const int n_out = p->update_rule == 0 ? 2 * NF + 1 : NF;
+    if (N == 0) return SPHNCA_OK;
+    SPHNCA_CHECK_ARG(dW1 && db1 && dW2 && db2, "NULL argument");
+    const int streams = wgrad_tc_streams(N);
+    if (!workspace || workspace_bytes < (size_t)streams * WG_PART * sizeof(float)) { set_error("wgrad workspace too small"); return SPHNCA_ERR_WORKSPACE; }
+    SPHNCA_LAUNCH(mlp_wgrad_reduce_kernel, (WG_PART + 255) / 256, 256, 0, as_stream(stream_), reinterpret_cast<const float*>(workspace), streams,
+                  n_out, dW1, db1, dW2, db2, 1);
+    SPHNCA_LAUNCH_CHECK();
+    return SPHNCA_OK;
+}
+
 }  // extern "C"

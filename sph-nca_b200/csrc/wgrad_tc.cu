@@ -73,7 +73,7 @@ __device__ __forceinline__ uint32_t fidx(uint32_t rows, uint32_t m, uint32_t k) 
 __global__ void __launch_bounds__(wg::THREADS, 1)
 mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float* __restrict__ Y_s,
                     const float* __restrict__ dO_s, sphnca_step_params prm, int n_out, float* __restrict__ partial,
-                    int part_floats, const int32_t* __restrict__ count_ptr) {
+                    int part_floats, const int32_t* __restrict__ count_ptr, int acc_in) {
     using namespace wg;
     if (count_ptr != nullptr) n_total = __ldg(count_ptr);     // fire-list mode: the first *count rows of the compact arrays
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -272,7 +272,10 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
                 }
                 asm volatile("bar.sync 1, %0;" :: "r"(LOADERS) : "memory");
             }
-            if (lt < NO_PAD) partial[(size_t)stream_id * part_floats + NH * NIN + NH + NO_PAD * NH + lt] = red[0][lt];
+            if (lt < NO_PAD) {                               // acc_in: the partials of earlier launches stay (one reduction per rollout)
+                float* d = partial + (size_t)stream_id * part_floats + NH * NIN + NH + NO_PAD * NH + lt;
+                *d = acc_in ? *d + red[0][lt] : red[0][lt];
+            }
         }
     } else if (warp == MMA_WARP) {
         {   // warp-uniform issue: every lane runs the loop, one elected lane issues (tc_common.cuh)
@@ -393,7 +396,7 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
             fence_after_sync();
             if (tid == 0) SPHNCA_TL(9);
             // R_FULL(it) follows the accumulate MMAs of chunk it-1 in issue order: the accumulators are final up to there
-            if (it > 0 && (it % FLUSH) == 0) drain(it == FLUSH);
+            if (it > 0 && (it % FLUSH) == 0) drain(it == FLUSH && !acc_in);
             // 16 particle columns per quarter; warp group g = warp >> 2 converts quarters g and g + 2, so quarters 0|1 and
             // 2|3 are produced in parallel and the accumulate MMAs over the first particles start while the later columns
             // are still being converted; the second quarter's TMEM loads are in flight during the first one's arithmetic
@@ -433,8 +436,8 @@ mlp_wgrad_tc_kernel(int64_t n_total, const float* __restrict__ A_s, const float*
         if (c0 < c1) {
             mbar_wait(&s.bar[ACC_FULL], 0);
             fence_after_sync();
-            drain(it <= FLUSH);                              // the chunks since the last drain (at least one)
-        } else if (warp < 4) {                               // a stream without chunks: zeros
+            drain(it <= FLUSH && !acc_in);                   // the chunks since the last drain (at least one)
+        } else if (warp < 4 && !acc_in) {                    // a stream without chunks: zeros
             for (int k = 0; k <= NIN; ++k) out[k * NH + hg] = 0.f;
             for (int o = 0; o < NO_PAD; ++o) out[NH * NIN + NH + o * NH + hg] = 0.f;
         }
@@ -457,10 +460,10 @@ int wgrad_tc_streams(int64_t N) {
 }
 
 int launch_mlp_wgrad_tc(int64_t N, const float* A_s, const float* Y_s, const float* dO_s, const sphnca_step_params* p,
-                        int n_out, float* partial, int part_floats, int streams, cudaStream_t stream, const int32_t* count) {
+                        int n_out, float* partial, int part_floats, int streams, cudaStream_t stream, const int32_t* count, int acc_in) {
     const size_t smem = sizeof(wg::Smem);
     SPHNCA_CUDA(cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SPHNCA_LAUNCH(mlp_wgrad_tc_kernel, 2 * streams, wg::THREADS, smem, stream, N, A_s, Y_s, dO_s, *p, n_out, partial, part_floats, count);
+    SPHNCA_LAUNCH(mlp_wgrad_tc_kernel, 2 * streams, wg::THREADS, smem, stream, N, A_s, Y_s, dO_s, *p, n_out, partial, part_floats, count, acc_in);
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

@@ -93,6 +93,8 @@ def _load():
         "sphnca_fire_bytes_counter": ([I64, P, I64, C.c_float, P, P, P, P, P], I32),
         "sphnca_step_fwd_fired": ([G, P, P, P, P, P, P, P, SP, P, I32, I64, P, P, P, P, P, P, P, P, P, P, C.c_size_t, P], I32),
         "sphnca_mlp_wgrad_list": ([I64, P, P, P, P, SP, P, P, P, P, P, C.c_size_t, P], I32),
+        "sphnca_mlp_wgrad_list_partial": ([I64, P, P, P, P, SP, I32, P, C.c_size_t, P], I32),
+        "sphnca_mlp_wgrad_reduce": ([I64, SP, P, P, P, P, P, C.c_size_t, P], I32),
         "sphnca_launch_count": ([], I64),
         "sphnca_set_mlp_path": ([I32], I32),
         "sphnca_get_mlp_path": ([], I32),

@@ -461,6 +461,7 @@ class _NCARollout(torch.autograd.Function):
         side = _side_stream(dev) if (OVERLAP_WGRAD and PROFILE is None and fl and want_w and not recompute and N) else None
         dO_alt = torch.empty((N, 36), **f32) if side is not None else None       # dO double buffer: step k-1 writes while wgrad(k) reads
         wg_done = [None, None]
+        wg_calls = 0                                          # launches that added to the weight-gradient partials in `ws`
         if fl:
             g = grid.c_grid()
             dO_c = dO_s                                       # dL/d(MLP output) of the listed rows, by list position
@@ -498,12 +499,15 @@ class _NCARollout(torch.autograd.Function):
                 if want_w and side is not None:
                     ready = torch.cuda.Event(); ready.record(torch.cuda.current_stream(dev))
                     side.wait_event(ready)
-                    check(lib.sphnca_mlp_wgrad_list(N, ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), ptr(dO_c), C.byref(p),
-                                                    ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value, C.c_void_p(side.cuda_stream)))
+                    # per-stream partial sums accumulate over the steps; ONE reduction into the gradients after the loop
+                    check(lib.sphnca_mlp_wgrad_list_partial(N, ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), ptr(dO_c), C.byref(p), wg_calls > 0,
+                                                            ptr(ws), nb.value, C.c_void_p(side.cuda_stream)))
+                    wg_calls += 1
                     wg_done[k & 1] = torch.cuda.Event(); wg_done[k & 1].record(side)
                 elif want_w:
-                    _timed("mlp_wgrad", lib.sphnca_mlp_wgrad_list, N, ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), ptr(dO_c), C.byref(p),
-                           ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value, st)
+                    _timed("mlp_wgrad", lib.sphnca_mlp_wgrad_list_partial, N, ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), ptr(dO_c), C.byref(p),
+                           wg_calls > 0, ptr(ws), nb.value, st)
+                    wg_calls += 1
                 out = own[k & 1]
                 if pl is not None:  # fire-aware list adjoint: rows of not-fired particles come from their flag byte
                     _timed("step_adjoint", lib.sphnca_step_adjoint_pairs_fired, grid.c_grid(), ptr(pl["slots"]), ptr(pl["base"]), ptr(pl["J"]),
@@ -530,6 +534,9 @@ class _NCARollout(torch.autograd.Function):
             if dstates[k] is not None:
                 dk = require_cuda_f32(dstates[k], "dS")
                 gcur = dk if gcur is None else gcur.add_(dk)
+        if wg_calls:
+            check(lib.sphnca_mlp_wgrad_reduce(N, C.byref(p), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), nb.value,
+                                              C.c_void_p(side.cuda_stream) if side is not None else st))
         if side is not None:
             torch.cuda.current_stream(dev).wait_stream(side)
         dA0 = None
@@ -680,6 +687,7 @@ def _microbatched_backward(ctx, dstates):
             pl = _group_lists(sub, xv, use_alpha)
             fb = work.fb
             gcur = dstates[K][p0:p1] if dstates[K] is not None else None
+            wg_calls = 0                                      # a group's steps add to ITS partials (the stream count follows n)
             for k in range(K - 1, -1, -1):
                 if gcur is not None:
                     fire_s = sub.pack_bytes(fire_po[k])
@@ -691,8 +699,9 @@ def _microbatched_backward(ctx, dstates):
                     _timed("step_bwd", lib.sphnca_step_bwd_list, n, ptr(fb.rows), ptr(fb.count), ptr(fb.A_c), ptr(fb.O_c), ptr(fb.flags),
                            ptr(fb.relu_c), ptr(gcur), C.byref(p), ptr(work.dO_c), ptr(work.dY_s), ptr(work.dAdir_s), st)
                     if want_w:
-                        _timed("mlp_wgrad", lib.sphnca_mlp_wgrad_list, n, ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), ptr(work.dO_c), C.byref(p),
-                               ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(work.ws), work.nb.value, st)
+                        _timed("mlp_wgrad", lib.sphnca_mlp_wgrad_list_partial, n, ptr(fb.count), ptr(fb.A_c), ptr(fb.Y_c), ptr(work.dO_c),
+                               C.byref(p), wg_calls > 0, ptr(work.ws), work.nb.value, st)
+                        wg_calls += 1
                     out = work.ping[k & 1][:n]
                     if pl is not None:
                         _timed("step_adjoint", lib.sphnca_step_adjoint_pairs_fired, g, ptr(pl["slots"]), ptr(pl["base"]), ptr(pl["J"]),
@@ -704,6 +713,8 @@ def _microbatched_backward(ctx, dstates):
                 if dstates[k] is not None:
                     dk = dstates[k][p0:p1]
                     gcur = dk if gcur is None else gcur.add_(dk)
+            if wg_calls:
+                check(lib.sphnca_mlp_wgrad_reduce(n, C.byref(p), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(work.ws), work.nb.value, st))
             if dA0_s is not None and gcur is not None:
                 dA0_s[p0:p1].copy_(gcur)
             del pl
