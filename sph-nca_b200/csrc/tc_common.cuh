@@ -29,10 +29,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // The descriptor of the same tile `bytes` further on (bytes % 16 == 0, address stays below 256 KB: no carry out of the 14-bit field).
-// Build the base descriptors ONCE, before the tile loop, and advance them with this: base + constant stays in uniform registers
-// (one UIADD3 per MMA or none), whereas make_smem_desc(address + offset) inside the issue loop re-derives every descriptor with
-// vector ALU instructions and an R2UR -- a 6-instruction dependent chain per MMA that crawls when the epilogue warps of the same
-// scheduler partition are busy (measured: 155 cycles per N=128 MMA issued, against the tensor pipe's 65).
+// Build the base descriptors ONCE, before the tile loop, and advance them with this: base + constant, instead of re-deriving
+// every descriptor from its address (shift, mask, or) in front of its MMA.  10 % fewer instructions in the forward kernel,
+// -2.5 % kernel time; the MMA issue rate itself was not what limited the kernels.
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 
 // kind::tf32, D = fp32, A and B K-major, dense
@@ -59,8 +58,8 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 // Operands derived from warp-uniform values then stay in uniform registers (UIADD3.64 + UTCHMMA, ~3 SASS
 // instructions per MMA); issuing from `if (lane == 0)` instead makes ptxas move every descriptor through
 // R2UR inside a BRA.U.ANY convergence loop (~16 instructions) and the issuing thread, not the tensor core,
-// becomes the floor: 72-90 cycles per M128 x N<=128 x K8 MMA vs 42 (N=32) .. 66 (N=128) with this form
-// (csrc/probes/tc_timing3.cu vs tc_timing4.cu).
+// becomes the floor: 72-90 cycles per M128 x N<=128 x K8 MMA vs the tensor pipe's own N/2 cycles with this form
+// (csrc/probes/tc_timing3.cu vs tc_timing4.cu / tc_timing5.cu).
 __device__ __forceinline__ uint32_t elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));

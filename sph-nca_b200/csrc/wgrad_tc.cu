@@ -10,9 +10,11 @@
 //               dW2t_half[128h x 48] += H^T . dO            (B operands = K-major TRANSPOSED copies yT, dOT)
 //               The hi and lo B tiles are stacked along N ([y_hi ; y_lo] = 128 rows, [dO_hi ; dO_lo] = 96 rows), so the
 //               two passes that share the A operand are ONE MMA: dH_hi . [y_hi ; y_lo] lands in columns 0..63 | 64..127
-//               of the accumulator and dH_lo . y_hi adds to columns 0..63 -- 4 MMAs per k-step instead of 6.  An MMA
-//               with A from TMEM costs ~32 cycles + N/4 (probes/tc_timing4: N=64 57, N=128 71), so the stacked form
-//               takes 71 + 57 + 64 + 59 = 251 cycles per k-step instead of 3*57 + 3*59 = 348.
+//               of the accumulator and dH_lo . y_hi adds to columns 64..127 -- 4 MMAs per k-step instead of 6 (an M128 x K8 tf32
+//               MMA occupies the tensor pipe for N/2 cycles, probes/tc_timing5.cu: stacking saves instructions and A-operand
+//               reads, not pipe time).  The RECOMPUTE MMAs take both operands from shared memory: the 4 KB weight tile (A) alone
+//               is 32 cycles of the 128 B/clk port per MMA, 48 with the particle tile, against 33 cycles of pipe time at N = 64
+//               -- that GEMM is bound by operand fetch.
 //   the two accumulators (224 TMEM columns) live in TMEM; every FLUSH chunks (and at the end) the epilogue warps drain them
 //   into the CTA's partial in global memory (+=, fp32 round-to-nearest, owner thread only) and the next accumulate MMA
 //   starts from zero: the tensor core's fp32 accumulation TRUNCATES, which biases a long same-sign sum towards zero by
