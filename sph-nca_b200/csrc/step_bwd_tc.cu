@@ -48,7 +48,7 @@ struct Smem {
     float dO32[2][TILE];
     uint32_t relu[2][TILE][NH / 32];
     float w2_last[NH];
-    float fstage[FIN_WARPS][8 * 52];                      // finalizer: 8 result rows [dAdir 16 | dY 32 | pad 4] per warp, on their way out
+    float fstage[FIN_WARPS][8 * 52];                      // finalizer: 8 result rows [dAdir 16 | dY 32 | particle, pad 3] per warp, on their way out
     uint64_t bar[NUM_BARS];
     uint32_t tmem_base;
 };
@@ -118,10 +118,18 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
         // ======================= prologue: dL/d(MLP output) and the direct dL/dA part =======================
         const int m = tid - LOAD_WARP0 * 32;
         int it = 0;
+        // fire-list mode: the row's particle index is fetched ONE TILE AHEAD -- the loads below depend on it, and a cold list
+        // read in front of them put a second global-memory round trip on this role's critical path (+8 us per 262,144 rows)
+        int p_next = (int)blockIdx.x * TILE + m;
+        if (rows && p_next < n_total) p_next = __ldg(rows + p_next);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int j = tile * TILE + m;
             const bool valid = j < n_total;
-            const int p = (valid && rows) ? __ldg(rows + j) : j;
+            const int p = p_next;
+            {
+                const int jn = j + (int)gridDim.x * TILE;
+                p_next = (rows && jn < n_total) ? __ldg(rows + jn) : jn;
+            }
             float dO[NO_PAD], dAdir[NF];
             uint32_t rbits[NH / 32];
 #pragma unroll
@@ -304,6 +312,7 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                             r[k] = make_float4(dir[k].x + dy[4*k], dir[k].y + dy[4*k+1], dir[k].z + dy[4*k+2], dir[k].w + dy[4*k+3]);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) r[4 + k] = make_float4(dy[NF+4*k], dy[NF+4*k+1], dy[NF+4*k+2], dy[NF+4*k+3]);
+                        reinterpret_cast<int*>(r + 12)[0] = p;            // the row's particle, in the pad piece: no list lookups below
                     }
                     __syncwarp();
 #pragma unroll
@@ -311,7 +320,7 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                         const int idx = k * 32 + lane, row = idx / 12, cq = idx - 12 * row;
                         const int jr = jw + sub * 8 + row;
                         if (jr < n_total) {
-                            const size_t pr = rows ? (size_t)__ldg(rows + jr) : (size_t)jr;
+                            const size_t pr = (size_t)reinterpret_cast<const int*>(st4 + row * 13 + 12)[0];
                             const float4 v = st4[row * 13 + cq];
                             if (cq < 4) dA4[pr * 4 + cq] = v; else dY4[pr * 8 + (cq - 4)] = v;
                         }
