@@ -358,28 +358,40 @@ step_adjoint_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, co
     const int lane = threadIdx.x & 31, part = lane & 3, q = lane >> 2;
     const int64_t p = grp * PG + q;
     const int batches = group_slots[grp] >> 2;
-    const int64_t e0 = group_base[grp] + lane;
     const float4* __restrict__ G4 = reinterpret_cast<const float4*>(dY_s);      // row = 8 float4: x part 0..3, y part 4..7
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int jv = 0; float2 wa = make_float2(0.f, 0.f);
-    if (batches > 0) { jv = __ldcs(J + e0); wa = __ldcs(WA + e0); }
+    // Every lane of a quad reads its particle's list entries itself (same address: a broadcast inside the load; a warp = one group,
+    // so a slot's 8 entries are 32 / 64 contiguous bytes) instead of one lane per entry + 3 shuffles per pair: shuffles share the
+    // LSU pipe this sweep is bound by (0.1856 -> 0.1783 ms).  Not so in the fired-rows perception sweep, whose quads belong to
+    // different groups: there the direct reads would touch 4x the lines.
+    const int64_t eq = group_base[grp] + q;
+    int jn[4]; float2 wn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { jn[u] = 0; wn[u] = make_float2(0.f, 0.f); }
+    if (batches > 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { jn[u] = __ldcs(J + eq + u * PG); wn[u] = __ldcs(WA + eq + u * PG); }
+    }
 #pragma unroll 1
     for (int b = 0; b < batches; ++b) {
         float4 a[4], bb[4];
+        float2 wc[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int j = __shfl_sync(0xffffffffu, jv, u * PG + q);
+            const int j = jn[u];
+            wc[u] = wn[u];
             const size_t row = (size_t)j * 8;
-            // not fired: read a row of zeros instead (one shared, always-cached line) -- a select on the pointer, no divergent branch
             const float4* src = (FIRED && !(__ldg(flags_s + j) & 4)) ? g_zero_row : G4 + row;
             a[u] = __ldg(src + part); bb[u] = __ldg(src + 4 + part);
         }
-        const float2 wac = wa;
-        if (b + 1 < batches) { const int64_t e = e0 + (int64_t)(b + 1) * 32; jv = __ldcs(J + e); wa = __ldcs(WA + e); }
+        if (b + 1 < batches) {
+            const int64_t e = eq + (int64_t)(b + 1) * 32;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { jn[u] = __ldcs(J + e + u * PG); wn[u] = __ldcs(WA + e + u * PG); }
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const float wxs = __shfl_sync(0xffffffffu, wac.x, u * PG + q), wys = __shfl_sync(0xffffffffu, wac.y, u * PG + q);
-            const float2 wx = make_float2(wxs, wxs), wy = make_float2(wys, wys);
+            const float2 wx = make_float2(wc[u].x, wc[u].x), wy = make_float2(wc[u].y, wc[u].y);
             float2 t;
             t = ffma2(wx, make_float2(a[u].x, a[u].y), ffma2(wy, make_float2(bb[u].x, bb[u].y), make_float2(acc.x, acc.y))); acc.x = t.x; acc.y = t.y;
             t = ffma2(wx, make_float2(a[u].z, a[u].w), ffma2(wy, make_float2(bb[u].z, bb[u].w), make_float2(acc.z, acc.w))); acc.z = t.x; acc.w = t.y;
