@@ -394,18 +394,26 @@ step_mlp_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
             auto convert = [&](const uint32_t (&r)[16], const float* __restrict__ b1p, const float* __restrict__ w2p,
                                uint32_t (&hi)[16], uint32_t (&lo)[16]) -> uint32_t {
                 uint32_t bits = 0;
+                // descending j: the ReLU bit of element j is the SIGN of (0 - pre) -- set exactly when pre > 0, for +-0 too -- shifted
+                // into the word by one funnel shift per element (element 0 last: bit 0); bias / gate weights come four at a time
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    const float2 pre = fadd2(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), *reinterpret_cast<const float2*>(b1p + j));
-                    bits |= (pre.x > 0.f ? 1u : 0u) << j;
-                    bits |= (pre.y > 0.f ? 1u : 0u) << (j + 1);
-                    const float2 hv = make_float2(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f));
-                    o32p = ffma2(hv, *reinterpret_cast<const float2*>(w2p + j), o32p);
-                    const float2 h_ = make_float2(__uint_as_float((__float_as_uint(hv.x) + 0x1000u) & 0xffffe000u),
-                                                  __uint_as_float((__float_as_uint(hv.y) + 0x1000u) & 0xffffe000u));   // split_tf32
-                    const float2 l_ = fsub2(hv, h_);
-                    hi[j] = __float_as_uint(h_.x); hi[j + 1] = __float_as_uint(h_.y);
-                    lo[j] = __float_as_uint(l_.x); lo[j + 1] = __float_as_uint(l_.y);
+                for (int j4 = 12; j4 >= 0; j4 -= 4) {
+                    const float4 bq = *reinterpret_cast<const float4*>(b1p + j4), wq = *reinterpret_cast<const float4*>(w2p + j4);
+#pragma unroll
+                    for (int jj = 2; jj >= 0; jj -= 2) {
+                        const int j = j4 + jj;
+                        const float2 pre = fadd2(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), jj ? make_float2(bq.z, bq.w) : make_float2(bq.x, bq.y));
+                        const float2 npre = fsub2(make_float2(0.f, 0.f), pre);
+                        bits = __funnelshift_l(__float_as_uint(npre.y), bits, 1);
+                        bits = __funnelshift_l(__float_as_uint(npre.x), bits, 1);
+                        const float2 hv = make_float2(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f));
+                        o32p = ffma2(hv, jj ? make_float2(wq.z, wq.w) : make_float2(wq.x, wq.y), o32p);
+                        const float2 h_ = make_float2(__uint_as_float((__float_as_uint(hv.x) + 0x1000u) & 0xffffe000u),
+                                                      __uint_as_float((__float_as_uint(hv.y) + 0x1000u) & 0xffffe000u));   // split_tf32
+                        const float2 l_ = fsub2(hv, h_);
+                        hi[j] = __float_as_uint(h_.x); hi[j + 1] = __float_as_uint(h_.y);
+                        lo[j] = __float_as_uint(l_.x); lo[j + 1] = __float_as_uint(l_.y);
+                    }
                 }
                 return bits;
             };
