@@ -34,7 +34,7 @@ WANT = ["sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_ac
         "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 KEYS = {"step_perceive_pairs_kernel": "step_perceive", "step_perceive_pairs_fired_kernel": "step_perceive", "step_mlp_tc_kernel": "step_mlp", "step_bwd_tc_kernel": "step_bwd",
-        "mlp_wgrad_tc_kernel": "mlp_wgrad", "step_adjoint_pairs_kernel": "step_adjoint", "fire_fill_kernel": "fire_list",
+        "mlp_wgrad_tc_kernel": "mlp_wgrad", "step_adjoint_pairs_kernel": "step_adjoint", "fire_fill_kernel": "fire_list", "fire_list_onepass_kernel": "fire_list",
         "step_bwd_unfired_kernel": "step_bwd_unfired"}
 
 def full(src, txt, js, particles):
