@@ -242,3 +242,49 @@ def test_weight_gradient_accumulation_262144_rows_vs_fp64():
     print("\nweight gradient over 262,144 rows vs fp64:", {k: f"{v:.2e}" for k, v in errs.items()})
     for nm, e in errs.items():
         assert e <= GRAD_RTOL, f"{nm}: {e:.3e} (all {errs})"
+
+
+def test_weight_gradient_partials_over_a_series_of_calls_vs_fp64():
+    """sphnca_mlp_wgrad_list_partial x 3 (accumulate = 0, 1, 1: the steps of a rollout's backward, different row counts) +
+    ONE sphnca_mlp_wgrad_reduce == the fp64 sum of the three weight gradients, and == three sphnca_mlp_wgrad_list calls up to
+    fp32 summation order; a stream without rows in one of the calls keeps what the others gave it."""
+    import ctypes as C
+    from sphops import _lib, fused
+    gen = torch.Generator().manual_seed(7)
+    W = [t.to(DEV) for t in _weights("weights_zebra")]
+    R = 40_000
+    p = fused._step_params(*W, "gated", False, 1.0, 1.0)
+    nb = C.c_size_t(0)
+    _lib.check(_lib.lib.sphnca_mlp_wgrad_workspace_bytes(R, C.byref(nb)))
+    ws = torch.full((nb.value,), 0xA5, dtype=torch.uint8, device=DEV)      # garbage: the first call of a series must not read it
+    ws2 = torch.empty(nb.value, dtype=torch.uint8, device=DEV)
+    dW = [torch.zeros_like(t) for t in W]
+    dW_each = [torch.zeros_like(t) for t in W]
+    ref = None
+    W1, b1, W2, b2 = [t.double() for t in W]
+    for call, rows in enumerate((R, 37, 25_001)):                          # 37 rows: one 64-row chunk, every other stream idle
+        A_c = torch.rand(R, 16, generator=gen).to(DEV)
+        Y_c = (0.3 * torch.randn(R, 32, generator=gen)).to(DEV)
+        # same-sign gradients, zero on rows that hold an ill-conditioned hidden unit (see the test above: kink flips are not the subject)
+        Yc = torch.cat([A_c.cpu(), Y_c.cpu()], 1).double()
+        keep = ((Yc @ W1.cpu().t() + b1.cpu()).abs() / (Yc.abs() @ W1.cpu().abs().t() + b1.cpu().abs()) >= 1e-5).all(1)
+        dO = torch.zeros(R, 36)
+        dO[:, :33] = 1e-3 * (0.25 + torch.rand(R, 33, generator=gen))
+        dO[~keep] = 0.0
+        dO = dO.to(DEV)
+        count = torch.tensor([rows], dtype=torch.int32, device=DEV)
+        _lib.check(_lib.lib.sphnca_mlp_wgrad_list_partial(R, _lib.ptr(count), _lib.ptr(A_c), _lib.ptr(Y_c), _lib.ptr(dO), C.byref(p),
+                                                          1 if call else 0, _lib.ptr(ws), nb.value, _lib.stream_ptr()))
+        _lib.check(_lib.lib.sphnca_mlp_wgrad_list(R, _lib.ptr(count), _lib.ptr(A_c), _lib.ptr(Y_c), _lib.ptr(dO), C.byref(p),
+                                                  *[_lib.ptr(t) for t in dW_each], _lib.ptr(ws2), nb.value, _lib.stream_ptr()))
+        Yf = torch.cat([A_c[:rows], Y_c[:rows]], 1).double()
+        pre = Yf @ W1.t() + b1
+        dOd = dO[:rows, :33].double()
+        dH = (dOd @ W2) * (pre > 0)
+        part = [dH.t() @ Yf, dH.sum(0), dOd.t() @ torch.relu(pre), dOd.sum(0)]
+        ref = part if ref is None else [a + b for a, b in zip(ref, part)]
+    _lib.check(_lib.lib.sphnca_mlp_wgrad_reduce(R, C.byref(p), *[_lib.ptr(t) for t in dW], _lib.ptr(ws), nb.value, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    for t, e, r, nm in zip(dW, dW_each, ref, ("dW1", "db1", "dW2", "db2")):
+        assert rel_err(t, r) <= GRAD_RTOL, f"{nm}: series vs fp64 {rel_err(t, r):.3e}"
+        assert rel_err(t, e.double()) <= 2e-6, f"{nm}: series vs per-call reduction {rel_err(t, e.double()):.3e}"
