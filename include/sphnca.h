@@ -62,6 +62,8 @@ typedef struct sphnca_grid {
     double band_lo[3], band_hi[3];
 } sphnca_grid;
 
+/* 3: fire-list workspace = look-back state (zero before the first use, larger than in 2), sphnca_mlp_wgrad_list_partial /
+ * sphnca_mlp_wgrad_reduce added, W2 must be 16-byte aligned.  2: periodic grids, fire lists, pair lists. */
 int32_t sphnca_abi_version(void);
 const char* sphnca_last_error(void);
 /* number of kernels this library has launched so far in this process (all threads) */

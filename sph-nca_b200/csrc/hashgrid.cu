@@ -281,7 +281,7 @@ using namespace sphnca;
 
 extern "C" {
 
-int32_t sphnca_abi_version(void) { return 2; }
+int32_t sphnca_abi_version(void) { return 3; }
 const char* sphnca_last_error(void) { return sphnca::last_error(); }
 int64_t sphnca_launch_count(void) { return sphnca::launches(); }
 

@@ -17,7 +17,7 @@ def test_header_symbols_are_exported():
     assert declared, "no declarations found"
     assert set(L.DECLARED_SYMBOLS) == declared, (set(L.DECLARED_SYMBOLS) ^ declared)
     assert L.MISSING_SYMBOLS == (), f"not exported by libsphnca.so: {L.MISSING_SYMBOLS}"
-    assert L.lib.sphnca_abi_version() == 2
+    assert L.lib.sphnca_abi_version() == 3
 
 
 def test_public_names_match_reference():
