@@ -63,7 +63,7 @@ typedef struct sphnca_grid {
 } sphnca_grid;
 
 /* 3: fire-list workspace = look-back state (zero before the first use, larger than in 2), sphnca_mlp_wgrad_list_partial /
- * sphnca_mlp_wgrad_reduce added, W2 must be 16-byte aligned.  2: periodic grids, fire lists, pair lists. */
+ * sphnca_mlp_wgrad_reduce added, W2 must be 16-byte aligned, sphnca_step_params.dy_interleaved added (struct grows by 8 bytes).  2: periodic grids, fire lists, pair lists. */
 int32_t sphnca_abi_version(void);
 const char* sphnca_last_error(void);
 /* number of kernels this library has launched so far in this process (all threads) */
@@ -128,6 +128,12 @@ typedef struct sphnca_step_params {
     int32_t use_alpha;     /* nca.py:17-21 */
     float perception_scale;/* h*normalize_perception if >0 else 1 (nca.py:65-69) */
     float orig_rate;       /* self.fire_rate / fire_rate, 'orig' rule only (nca.py:108) */
+    /* Layout of the dL/dY rows (dY_s) that sphnca_step_bwd_list WRITES and sphnca_step_adjoint_pairs[_fired] READ -- the two ends
+     * of the fire-list backward.  0: the perception vector's own layout, [dYx (16) | dYy (16)].  1: per 4-channel quarter q the
+     * pair [dYx 4q..4q+3 | dYy 4q..4q+3]: the 4 lanes that gather a neighbour's row in the adjoint sweep then take their x and y
+     * quarters with ONE 32-byte load each (one L1 line lookup per row instead of two; same arithmetic, bit-identical results).
+     * Every other entry (sphnca_step_bwd, sphnca_step_adjoint, sphnca_step_bwd_unfired: zeros) uses layout 0 and ignores it. */
+    int32_t dy_interleaved;
 } sphnca_step_params;
 
 /* One forward step = sphnca_step_fwd then sphnca_step_mask (one kernel each).

@@ -339,14 +339,21 @@ step_perceive_pairs_fired_kernel(const int32_t* __restrict__ rows, const int32_t
     reinterpret_cast<float4*>(A_c + (size_t)j * NF)[part] = Ai;
 }
 
-__device__ float4 g_zero_row[8];      // 128 bytes of zeros: the dL/dY row of every particle that did not fire
+__device__ float4 g_zero_row[8];
+// 32 bytes in one load: the x and y quarters of an interleaved dL/dY row (sphnca_step_params.dy_interleaved)
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}      // 128 bytes of zeros: the dL/dY row of every particle that did not fire
 
 // Gather adjoint of the perception sweep from the pair lists (same output as step_adjoint_kernel).
 // FIRED (fire-list rollouts, firelist.cu): dL/dY of a particle that did not fire is exactly zero and its direct dL/dA part is
 // (living ? dL/dA_new : 0), so both are taken from the flag byte instead of from memory: the 128-byte row gather of a not-fired
 // neighbour (half of them at fire rate 0.5 -- this kernel is bound by the L1 data pipe) is skipped, and nobody has to write
 // those rows of dY_s / dAdir_s first.
-template <bool FIRED>
+// ILV: the dL/dY rows are [x quarter | y quarter] pairs (sphnca_step_params.dy_interleaved) -- a template parameter, not a branch
+// in the loop: with the branch the four gathers of a batch sit in four basic blocks and are no longer issued back to back.
+template <bool FIRED, bool ILV>
 __global__ void __launch_bounds__(128)
 step_adjoint_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, const int64_t* __restrict__ group_base,
                           const int32_t* __restrict__ J, const float2* __restrict__ WA, const float2* __restrict__ SXY,
@@ -358,7 +365,8 @@ step_adjoint_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, co
     const int lane = threadIdx.x & 31, part = lane & 3, q = lane >> 2;
     const int64_t p = grp * PG + q;
     const int batches = group_slots[grp] >> 2;
-    const float4* __restrict__ G4 = reinterpret_cast<const float4*>(dY_s);      // row = 8 float4: x part 0..3, y part 4..7
+    const float4* __restrict__ G4 = reinterpret_cast<const float4*>(dY_s);      // row = 8 float4: x part 0..3, y part 4..7 (or x|y pairs)
+    constexpr bool ilv = ILV;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     // Every lane of a quad reads its particle's list entries itself (same address: a broadcast inside the load; a warp = one group,
     // so a slot's 8 entries are 32 / 64 contiguous bytes) instead of one lane per entry + 3 shuffles per pair: shuffles share the
@@ -382,7 +390,8 @@ step_adjoint_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, co
             wc[u] = wn[u];
             const size_t row = (size_t)j * 8;
             const float4* src = (FIRED && !(__ldg(flags_s + j) & 4)) ? g_zero_row : G4 + row;
-            a[u] = __ldg(src + part); bb[u] = __ldg(src + 4 + part);
+            if (ilv) ldg256(src + 2 * part, a[u], bb[u]);     // one line lookup per row instead of two (0.174 -> 0.162 ms)
+            else { a[u] = __ldg(src + part); bb[u] = __ldg(src + 4 + part); }
         }
         if (b + 1 < batches) {
             const int64_t e = eq + (int64_t)(b + 1) * 32;
@@ -403,7 +412,8 @@ step_adjoint_pairs_kernel(int64_t n, const int32_t* __restrict__ group_slots, co
     float4 Gx, Gy, dir;
     const uint8_t fl_ = FIRED ? flags_s[p] : (uint8_t)4;
     if (fl_ & 4) {
-        Gx = __ldg(G4 + (size_t)p * 8 + part); Gy = __ldg(G4 + (size_t)p * 8 + 4 + part);
+        if (ilv) ldg256(G4 + (size_t)p * 8 + 2 * part, Gx, Gy);
+        else { Gx = __ldg(G4 + (size_t)p * 8 + part); Gy = __ldg(G4 + (size_t)p * 8 + 4 + part); }
         dir = __ldg(reinterpret_cast<const float4*>(dAdir_s) + (size_t)p * 4 + part);
     } else {
         Gx = make_float4(0.f, 0.f, 0.f, 0.f); Gy = Gx;
@@ -525,12 +535,12 @@ static int launch_adjoint_pairs(const sphnca_grid* g, const int32_t* group_slots
     if (gv.n == 0) return SPHNCA_OK;
     SPHNCA_CHECK_ARG(group_slots && group_base && J && WA && SXY && xv4 && dY_s && dAdir_s && dA_s, "NULL argument");
     const int blocks = (int)((gv.n + 31) / 32);           // one warp per group of 8 particles, 4 groups per CTA
-    if (flags_s != nullptr)
-        SPHNCA_LAUNCH(step_adjoint_pairs_kernel<true>, blocks, 128, 0, as_stream(stream_), gv.n, group_slots, group_base, J, (const float2*)WA,
-                      (const float2*)SXY, (const float4*)xv4, dY_s, dAdir_s, c, dA_s, flags_s, dAn_s);
-    else
-        SPHNCA_LAUNCH(step_adjoint_pairs_kernel<false>, blocks, 128, 0, as_stream(stream_), gv.n, group_slots, group_base, J, (const float2*)WA,
-                      (const float2*)SXY, (const float4*)xv4, dY_s, dAdir_s, c, dA_s, flags_s, dAn_s);
+#define SPHNCA_ADJ_LAUNCH(FIRED_, ILV_)                                                                                                  \
+    SPHNCA_LAUNCH((step_adjoint_pairs_kernel<FIRED_, ILV_>), blocks, 128, 0, as_stream(stream_), gv.n, group_slots, group_base, J,     \
+                  (const float2*)WA, (const float2*)SXY, (const float4*)xv4, dY_s, dAdir_s, c, dA_s, flags_s, dAn_s)
+    if (flags_s != nullptr) { if (c.dy_ilv) SPHNCA_ADJ_LAUNCH(true, true); else SPHNCA_ADJ_LAUNCH(true, false); }
+    else { if (c.dy_ilv) SPHNCA_ADJ_LAUNCH(false, true); else SPHNCA_ADJ_LAUNCH(false, false); }
+#undef SPHNCA_ADJ_LAUNCH
     SPHNCA_LAUNCH_CHECK();
     return SPHNCA_OK;
 }

@@ -303,6 +303,7 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                 float4* dA4 = reinterpret_cast<float4*>(dAdir_s);
                 float4* dY4 = reinterpret_cast<float4*>(dY_s);
                 const int jw = tile * TILE + (warp & 3) * 32;
+                const bool ilv = rows != nullptr && c.dy_ilv;     // list mode only: sphnca_step_bwd keeps the plain layout
 #pragma unroll 1
                 for (int sub = 0; sub < 4; ++sub) {
                     if ((lane >> 3) == sub) {
@@ -311,7 +312,8 @@ step_bwd_tc_kernel(int n_total, const float* __restrict__ A_s, const float* __re
                         for (int k = 0; k < 4; ++k)
                             r[k] = make_float4(dir[k].x + dy[4*k], dir[k].y + dy[4*k+1], dir[k].z + dy[4*k+2], dir[k].w + dy[4*k+3]);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) r[4 + k] = make_float4(dy[NF+4*k], dy[NF+4*k+1], dy[NF+4*k+2], dy[NF+4*k+3]);
+                        for (int k = 0; k < 8; ++k)      // dy_ilv: [x quarter | y quarter] pairs (sphnca_step_params.dy_interleaved)
+                            r[4 + (ilv ? ((k & 3) * 2 + (k >> 2)) : k)] = make_float4(dy[NF+4*k], dy[NF+4*k+1], dy[NF+4*k+2], dy[NF+4*k+3]);
                         reinterpret_cast<int*>(r + 12)[0] = p;            // the row's particle, in the pad piece: no list lookups below
                     }
                     __syncwarp();

@@ -16,6 +16,7 @@ struct StepConsts {
     float kg;          // spiky normalisation * perception scale
     int use_alpha, rule, n_out;
     float orig_rate;
+    int dy_ilv;        // sphnca_step_params.dy_interleaved
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -43,6 +44,7 @@ inline int make_consts(const sphnca_grid* g, const sphnca_step_params* p, StepCo
     c->kg = (float)(spiky_norm(g->dim, g->h) * (double)p->perception_scale);
     c->use_alpha = p->use_alpha; c->rule = p->update_rule; c->n_out = p->update_rule == 0 ? 2 * NF + 1 : NF;
     c->orig_rate = p->orig_rate;
+    c->dy_ilv = p->dy_interleaved ? 1 : 0;
     return SPHNCA_OK;
 }
 

@@ -34,6 +34,7 @@ class CStepParams(C.Structure):
         ("W1", C.c_void_p), ("b1", C.c_void_p), ("W2", C.c_void_p), ("b2", C.c_void_p),
         ("update_rule", C.c_int32), ("use_alpha", C.c_int32),
         ("perception_scale", C.c_float), ("orig_rate", C.c_float),
+        ("dy_interleaved", C.c_int32),
     ]
 
 

@@ -452,6 +452,9 @@ class _NCARollout(torch.autograd.Function):
         st = stream_ptr()
         recompute = ctx.taped == 2
         fl = ctx.fire_lists
+        # fire lists + pair lists: the data-gradient kernel writes the dL/dY rows as [x quarter | y quarter] pairs, the layout the
+        # list adjoint gathers with one 32-byte load per lane (include/sphnca.h: sphnca_step_params.dy_interleaved)
+        p.dy_interleaved = int(bool(fl) and ctx.pairs is not None)
         # The weight-gradient kernel of step k (tensor-core bound) and its adjoint sweep (latency bound) both depend on the
         # data-gradient kernel only: with OVERLAP_WGRAD the weight-gradient kernels run on a side stream (serialised there, so the
         # parameter gradients accumulate in the same fixed order) beside the adjoint sweep and the next step's data gradient.
@@ -685,6 +688,7 @@ def _microbatched_backward(ctx, dstates):
                 continue
             g, xv = sub.c_grid(), xv4[p0:p1]
             pl = _group_lists(sub, xv, use_alpha)
+            p.dy_interleaved = int(pl is not None)            # see _NCARollout.backward
             fb = work.fb
             gcur = dstates[K][p0:p1] if dstates[K] is not None else None
             wg_calls = 0                                      # a group's steps add to ITS partials (the stream count follows n)

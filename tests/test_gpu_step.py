@@ -465,6 +465,16 @@ def test_tile_sweeps_equal_gather_sweeps(kind):
         assert torch.equal(Y, res[0][0]), "perception from pair lists"
         assert torch.equal(fl, res[0][1]), "life mask from pair lists"
         assert torch.equal(dA, res[0][2]), "adjoint from pair lists"
+        # dL/dY rows as [x quarter | y quarter] pairs (sphnca_step_params.dy_interleaved: what sphnca_step_bwd_list writes when the
+        # flag is set): one 32-byte gather per lane instead of two 16-byte ones, same arithmetic
+        p_ilv = fused._step_params(*W, "gated", True, 1.7, 1.0); p_ilv.dy_interleaved = 1
+        dY_ilv = dY_s.view(N, 2, 4, 4).transpose(1, 2).contiguous().view(N, 32)
+        dA2 = torch.zeros(N, 16, device=DEV)
+        _lib.check(_lib.lib.sphnca_step_adjoint_pairs(grid.c_grid(), _lib.ptr(pl["slots"]), _lib.ptr(pl["base"]), _lib.ptr(pl["J"]),
+                                                      _lib.ptr(pl["WA"]), _lib.ptr(pl["SXY"]), _lib.ptr(xv4), _lib.ptr(dY_ilv), _lib.ptr(dAd_s),
+                                                      C.byref(p_ilv), _lib.ptr(dA2), st))
+        torch.cuda.synchronize()
+        assert torch.equal(dA2, res[0][2]), "adjoint from pair lists, interleaved dL/dY rows"
         # no alpha channel: the life mask comes from the flag the fill kernel evaluated once (the blur weights are not read)
         p0 = fused._step_params(*W, "gated", False, 1.7, 1.0)
         outs = []
