@@ -71,3 +71,21 @@ def test_bad_arguments_are_rejected_by_the_c_abi():
     sec = (C.c_int64 * 1)(4); dims = (C.c_int64 * 3)(2, 2, 2)
     rc = L.lib.sphnca_hashgrid_build(None, 4, 4, sec, 1, 0.5, dims, None, None, None, None, None, None, None, None, 0, None)
     assert rc == -1 and b"D must be 2 or 3" in L.lib.sphnca_last_error()
+
+
+def test_workspace_sizes_and_struct_layout_without_a_gpu():
+    """Host-only entries: the fire-list workspace holds one 8-byte state word per block of 1024 rows, one per group of 256
+    blocks and the two counters (include/sphnca.h: zero before the first use); struct sphnca_step_params is 56 bytes with
+    dy_interleaved behind orig_rate (ABI 3)."""
+    import ctypes as C
+    import sphops._lib as L
+    for n in (0, 1, 1024, 1025, 524_288, 262_145 * 1024, 2**31 - 1):
+        nb = C.c_size_t(0)
+        L.check(L.lib.sphnca_fire_list_workspace_bytes(n, C.byref(nb)))
+        blocks = (n + 1023) // 1024
+        assert nb.value == (blocks + (blocks + 255) // 256 + 1) * 8 and nb.value % 8 == 0, (n, nb.value)
+    assert L.lib.sphnca_fire_list_workspace_bytes(-1, C.byref(nb)) != 0
+    assert C.sizeof(L.CStepParams) == 56
+    assert L.CStepParams.dy_interleaved.offset == 48 and L.CStepParams.orig_rate.offset == 44
+    p = L.CStepParams()
+    assert p.dy_interleaved == 0            # every entry but the fire-list backward pair ignores it; default = plain layout
